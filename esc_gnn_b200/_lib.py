@@ -1,0 +1,70 @@
+"""ctypes binding of libescgnn_b200.so (C-ABI in include/escgnn_b200.h).
+
+There is NO CPU fallback: importing this module without the built library, or calling a device entry point
+without a CUDA device, raises.  Build with `python -m esc_gnn_b200.build` (or `__graft_entry__.build()`).
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libescgnn_b200.so')
+
+ERR_BITS = {1: 'sub_degree >= 200 (reference: F.one_hot(sub_degree, 200) raises)',
+            2: 'node id outside [0, num_nodes)',
+            4: 'resistance-distance bin outside the supported range / singular system',
+            8: 'use_rd on a non-symmetric edge multiset is not supported'}
+NUM_COUNTERS = 8
+RD_SLOTS = 12
+REC_IDX_BITS = 11
+
+_lib = None
+_vp, _i64, _i32, _u32p = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+# name -> (restype, argtypes); every symbol include/escgnn_b200.h declares
+SIGNATURES = {
+    'escgnn_version': (_i32, []),
+    'escgnn_rewrite_self_loops': (_i32, [_vp] * 4 + [_i64] + [_vp] * 5),
+    'escgnn_encode': (_i32, [_vp] * 4 + [_i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    'escgnn_encode_scratch_bytes': (_i64, [_i64, _i64, _i32]),
+    'escgnn_encode_rd_scratch_bytes': (_i64, [_i64, _i64, _i32]),
+    'escgnn_encode_rd': (_i32, [_vp] * 4 + [_i64, _i32, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    'escgnn_exclusive_scan_i32': (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    'escgnn_expand_records': (_i32, [_vp] * 6 + [_i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    'escgnn_ctx_create': (_vp, [_i32]),
+    'escgnn_ctx_destroy': (None, [_vp]),
+    'escgnn_encode_host_run': (_i32, [_vp] * 5 + [_i64, _i32, _i32, _i32, _i32, _i64p, _i64p, _u32p]),
+    'escgnn_encode_host_fetch': (_i32, [_vp] * 7),
+    'escgnn_encode_host_device_results': (_i32, [_vp] * 6),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('esc_gnn_b200: %s is missing -- build it with `python -m esc_gnn_b200.build`; '
+                               'there is no CPU fallback' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError = header and library disagree: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    names = {-1: 'bad argument', -2: 'graph too large for the kernels', -3: 'record capacity', -4: 'data error'}
+    if rc < 0:
+        raise RuntimeError('esc_gnn_b200.%s failed: %s' % (what, names.get(rc, rc)))
+    raise RuntimeError('esc_gnn_b200.%s failed: CUDA error %d' % (what, rc))
+
+
+def raise_data_errors(bits):
+    if not bits:
+        return
+    msgs = [m for b, m in ERR_BITS.items() if bits & b]
+    raise RuntimeError('esc_gnn_b200 encoder: ' + '; '.join(msgs))

@@ -1,0 +1,252 @@
+"""Drop-in for the reference's efficient structural-encoding transform, backed by the sm_100a kernels.
+
+`create_subgraphs` keeps the signature and output contract of
+/root/reference/utils_edge_efficient.py:20-152 (same keyword names, same `Data` fields `pos_enc`, `pos_index`,
+`pos_batch`, same self-loop rewrite of `edge_index` / `edge_attr`, same exceptions for the degenerate inputs).
+`encode_batch` is the batched entry the kernels really want: many graphs per launch, results left on the device
+in compact form for the model's bag-embed kernel, or expanded to the reference's int64 triple.
+
+No CPU fallback: without libescgnn_b200.so / a CUDA device these functions raise.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_ctx_cache = {}
+
+
+def _ctx(device_index):
+    c = _ctx_cache.get(device_index)
+    if c is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError('esc_gnn_b200: no CUDA device -- the encoder has no CPU fallback')
+        c = _lib.lib().escgnn_ctx_create(int(device_index))
+        if not c:
+            raise RuntimeError('esc_gnn_b200: escgnn_ctx_create failed on device %d' % device_index)
+        _ctx_cache[device_index] = c
+    return c
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class EncodedBatch(object):
+    """Result of `encode_batch`.
+
+    Reference-contract fields (int64): `edge_index` [2, E_out] (graph-local ids, after the self-loop rewrite),
+    `edge_ptr` [G+1], and -- when expanded -- `pos_enc`, `pos_index`, `pos_batch` [nnz].
+    Compact device fields (what the model consumes directly): `rec` uint32 [nnz] = index | count << 11,
+    `rec_off` int64 [E_out], `rec_nnz` int32 [E_out].
+    """
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def encode_batch_host(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=False, local_ordinals=False,
+                      device=0, out=None):
+    """HOST buffers in, HOST buffers out through the C-ABI host front end (H2D + kernels + D2H inside the call).
+
+    src/dst/edge_ptr/node_ptr: int64 numpy arrays or CPU tensors (graph-local node ids). Returns an EncodedBatch
+    of CPU tensors (pinned when `out` supplies pinned buffers)."""
+    L = _lib.lib()
+    src = torch.as_tensor(src, dtype=torch.int64).contiguous()
+    dst = torch.as_tensor(dst, dtype=torch.int64).contiguous()
+    edge_ptr = torch.as_tensor(edge_ptr, dtype=torch.int64).contiguous()
+    node_ptr = torch.as_tensor(node_ptr, dtype=torch.int64).contiguous()
+    G = edge_ptr.numel() - 1
+    c = _ctx(device)
+    e_out, nnz, bits = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_uint32(0)
+    rc = L.escgnn_encode_host_run(c, _ptr(src), _ptr(dst), _ptr(edge_ptr), _ptr(node_ptr), G, int(h), int(use_rd),
+                                  int(self_loop), int(local_ordinals), ctypes.byref(e_out), ctypes.byref(nnz),
+                                  ctypes.byref(bits))
+    if rc == -4:
+        _lib.raise_data_errors(bits.value)
+    _lib.check(rc, 'encode_host_run')
+    E, K = e_out.value, nnz.value
+    if out is not None:
+        ei, eptr = out['edge_index'][:, :E], out['edge_ptr'][:G + 1]
+        pe, pi, pb = out['pos_enc'][:K], out['pos_index'][:K], out['pos_batch'][:K]
+        ei0, ei1 = out['edge_index'][0], out['edge_index'][1]
+    else:
+        ei = torch.empty((2, E), dtype=torch.int64)
+        eptr = torch.empty(G + 1, dtype=torch.int64)
+        pe, pi, pb = (torch.empty(K, dtype=torch.int64) for _ in range(3))
+        ei0, ei1 = ei[0], ei[1]
+    _lib.check(L.escgnn_encode_host_fetch(c, _ptr(ei0), _ptr(ei1), _ptr(eptr), _ptr(pe), _ptr(pi), _ptr(pb)),
+               'encode_host_fetch')
+    return EncodedBatch(edge_index=ei, edge_ptr=eptr, pos_enc=pe, pos_index=pi, pos_batch=pb, num_edges=E, nnz=K)
+
+
+class _Timer(object):
+    """Optional CUDA-event brackets around the kernels of one encode_batch call (bench / profiling only)."""
+    def __init__(self, sink):
+        self.sink = sink
+
+    def __call__(self, name):
+        return _Span(self.sink, name)
+
+
+class _Span(object):
+    def __init__(self, sink, name):
+        self.sink, self.name = sink, name
+
+    def __enter__(self):
+        if self.sink is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.sink is not None:
+            self.b.record()
+            self.sink.setdefault(self.name, []).append((self.a, self.b))
+
+
+def encode_batch(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=False, expand=True, local_ordinals=False,
+                 max_nodes=None, max_edges=None, timings=None):
+    """DEVICE tensors in, DEVICE tensors out, on the current torch stream.
+
+    src/dst: int64 CUDA tensors [E_in] (graph-local ids); edge_ptr/node_ptr: int64 [G+1], CPU or CUDA
+    (`max_nodes` / `max_edges` must be given when they are CUDA tensors, so no sync is needed to size the launch).
+    One device->host read of two counters (total records, error bits) sizes the output."""
+    L = _lib.lib()
+    if not src.is_cuda:
+        raise RuntimeError('encode_batch needs CUDA tensors (use encode_batch_host for CPU buffers); no CPU fallback')
+    dev = src.device
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    G = edge_ptr.numel() - 1
+    if max_nodes is None or max_edges is None:
+        ep, npt = edge_ptr.cpu(), node_ptr.cpu()
+        nn = (npt[1:] - npt[:-1])
+        ee = (ep[1:] - ep[:-1])
+        max_nodes = int(nn.max()) if G else 0
+        max_edges = int((ee + nn).max() if self_loop else ee.max()) if G else 0
+        n_total = int(npt[-1])
+    else:
+        n_total = None
+    d_eptr = edge_ptr.to(dev, non_blocking=True)
+    d_nptr = node_ptr.to(dev, non_blocking=True)
+    E_in = src.numel()
+    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
+    span = _Timer(timings)
+    if self_loop:
+        if n_total is None:
+            n_total = int(node_ptr[-1])
+        e_cap = E_in + n_total
+        eo = torch.empty((2, e_cap), dtype=torch.int64, device=dev)
+        eo_ptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
+        tmp = torch.empty(4 * G + 8 * (G // 1024 + 2) + 64, dtype=torch.uint8, device=dev)
+        with span('rewrite'):
+            _lib.check(L.escgnn_rewrite_self_loops(_ptr(src), _ptr(dst), _ptr(d_eptr), _ptr(d_nptr), G,
+                                                   _ptr(eo_ptr), _ptr(eo[0]), _ptr(eo[1]), _ptr(tmp), stream),
+                       'rewrite_self_loops')
+        eo_src, eo_dst = eo[0], eo[1]
+    else:
+        e_cap = E_in
+        eo_src, eo_dst, eo_ptr = src.contiguous(), dst.contiguous(), d_eptr
+        eo = None
+    sb = L.escgnn_encode_scratch_bytes(max_nodes, max_edges, int(h))
+    if use_rd:
+        sb = max(sb, L.escgnn_encode_rd_scratch_bytes(max_nodes, max_edges, int(h)))
+    scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=dev)
+    rdh = None
+    if use_rd:
+        rdh = torch.empty((e_cap + 1, _lib.RD_SLOTS), dtype=torch.int16, device=dev)
+        with span('ego_rd'):
+            _lib.check(L.escgnn_encode_rd(_ptr(eo_src), _ptr(eo_dst), _ptr(eo_ptr), _ptr(d_nptr), G, int(h),
+                                          _ptr(rdh), _ptr(counters), max_nodes, max_edges, _ptr(scratch),
+                                          scratch.numel(), stream), 'encode_rd')
+    rec_off = torch.empty(e_cap + 1, dtype=torch.int64, device=dev)
+    rec_nnz = torch.empty(e_cap + 1, dtype=torch.int32, device=dev)
+    edge_graph = torch.empty(e_cap + 1, dtype=torch.int32, device=dev)
+    rec_cap = e_cap * 48 + 1024
+    for attempt in range(2):
+        rec = torch.empty(rec_cap, dtype=torch.int32, device=dev)
+        with span('ego_encode'):
+            _lib.check(L.escgnn_encode(_ptr(eo_src), _ptr(eo_dst), _ptr(eo_ptr), _ptr(d_nptr), G, int(h),
+                                       _ptr(rdh) if rdh is not None else None, _ptr(rec), rec_cap, _ptr(rec_off),
+                                       _ptr(rec_nnz), _ptr(edge_graph), _ptr(counters), max_nodes, max_edges,
+                                       _ptr(scratch), scratch.numel(), stream), 'encode')
+        tail = torch.cat([counters[:2], eo_ptr[G:G + 1]]).cpu()     # the one sync: nnz, error bits, E_out
+        nnz, bits, E = int(tail[0]), int(tail[1]), int(tail[2])
+        if nnz <= rec_cap:
+            break
+        rec_cap = nnz
+        counters[0] = 0
+        counters[2] = 0
+    _lib.raise_data_errors(bits)
+    res = EncodedBatch(edge_index=(eo[:, :E] if eo is not None else torch.stack([eo_src, eo_dst])), edge_ptr=eo_ptr,
+                       rec=rec, rec_off=rec_off[:E], rec_nnz=rec_nnz[:E], edge_graph=edge_graph[:E], num_edges=E,
+                       nnz=nnz, use_rd=bool(use_rd))
+    if expand:
+        out_off = torch.empty(E + 2, dtype=torch.int64, device=dev)
+        scan_tmp = torch.empty(E // 1024 + 4, dtype=torch.int64, device=dev)
+        with span('scan'):
+            _lib.check(L.escgnn_exclusive_scan_i32(_ptr(rec_nnz), E, _ptr(out_off), _ptr(scan_tmp), stream), 'scan')
+        trip = torch.empty((3, max(nnz, 1)), dtype=torch.int64, device=dev)
+        with span('expand'):
+            _lib.check(L.escgnn_expand_records(_ptr(rec), _ptr(rec_off), _ptr(rec_nnz), _ptr(edge_graph),
+                                               _ptr(eo_ptr), _ptr(out_off), E, int(use_rd), int(local_ordinals),
+                                               _ptr(trip[0]), _ptr(trip[1]), _ptr(trip[2]), stream),
+                       'expand_records')
+        res.pos_enc, res.pos_index, res.pos_batch = trip[0, :nnz], trip[1, :nnz], trip[2, :nnz]
+        res.out_off = out_off[:E + 1]
+    return res
+
+
+def create_subgraphs(data, h=1, sample_ratio=1.0, max_nodes_per_hop=None, node_label='hop', use_rd=False,
+                     subgraph_pretransform=None, data_name=None, self_loop=False):
+    """Same contract as the reference `create_subgraphs` (utils_edge_efficient.py:20-152).
+
+    `node_label` is accepted and ignored exactly like the reference (both BFS calls hard-code 'hop', :44-51);
+    `sample_ratio` / `data_name` are unused there too.  `max_nodes_per_hop` (random sampling, :235-237) and
+    `subgraph_pretransform` (k-GNN hook, :109-118) are outside the hot path and must stay None.
+    The resistance-distance block follows parity policy E5 (float64)."""
+    if max_nodes_per_hop is not None or subgraph_pretransform is not None:
+        raise NotImplementedError('max_nodes_per_hop / subgraph_pretransform are not part of the efficient hot path')
+    if type(h) == int:
+        h = [h]
+    assert hasattr(data, 'edge_index') and hasattr(data, 'num_nodes'), 'expected a PyG-style Data object'
+    x, edge_index, num_nodes = data.x, data.edge_index, data.num_nodes
+    if type(num_nodes) is torch.Tensor:
+        num_nodes = num_nodes.item()
+    num_nodes = int(num_nodes)
+    for h_ in h:
+        if h_ >= 5:      # F.one_hot(code, 1300) raises for distances up to h+1 = 6
+            raise RuntimeError('Class values must be smaller than num_classes.')
+    h_ = int(h[-1])      # the reference returns only the last h (:152 sits outside the loop)
+    edge_attr = data.edge_attr
+    if self_loop:        # E1 on the attributes (edge_index itself is rewritten on the device)
+        keep = edge_index[0] != edge_index[1]
+        if edge_attr is not None:
+            edge_attr = edge_attr[keep]
+            loop_attr = edge_attr.new_full((num_nodes, ) + tuple(edge_attr.size()[1:]), 1.)
+            edge_attr = torch.cat([edge_attr, loop_attr], dim=0)
+        n_out = int(keep.sum()) + num_nodes
+    else:
+        n_out = edge_index.size(1)
+    if n_out == 0:       # reference: torch.cat of an empty list (:146-151)
+        raise RuntimeError('torch.cat(): expected a non-empty list of Tensors')
+    if h_ < 1:
+        raise NotImplementedError('h must be >= 1')
+    ei = edge_index.to(torch.int64)
+    if ei.is_cuda:
+        eptr = torch.tensor([0, ei.size(1)], dtype=torch.int64)
+        nptr = torch.tensor([0, num_nodes], dtype=torch.int64)
+        r = encode_batch(ei[0].contiguous(), ei[1].contiguous(), eptr, nptr, h_, use_rd, self_loop,
+                         expand=True, local_ordinals=True)
+    else:
+        r = encode_batch_host(ei[0], ei[1], np.array([0, ei.size(1)], dtype=np.int64),
+                              np.array([0, num_nodes], dtype=np.int64), h_, use_rd, self_loop, local_ordinals=True,
+                              device=torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    kw = dict(pos_enc=r.pos_enc, pos_index=r.pos_index, pos_batch=r.pos_batch)
+    if not hasattr(data, 'pos'):
+        return data.__class__(data.x, r.edge_index, edge_attr, data.y, None, **kw)
+    if not hasattr(data, 'name'):
+        return data.__class__(data.x, r.edge_index, edge_attr, data.y, None, **kw)
+    return data.__class__(data.x, r.edge_index, edge_attr, data.y, pos=data.pos, name=data.name,
+                          node_type=data.node_type, **kw)

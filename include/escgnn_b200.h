@@ -1,0 +1,111 @@
+/* escgnn_b200 -- C-ABI of the B200-native ESC-GNN hot paths (libescgnn_b200.so).
+ *
+ * The reference (pkuyzy/ESC-GNN) is pure Python on these paths and has no native FFI boundary of its own
+ * (SURVEY.md section 8b); the entry points below are what a maintainer binds from Python (ctypes stub in
+ * INTEGRATION.md) to replace the bodies of the reference functions cited on each declaration.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every `d_` pointer is DEVICE memory, every `h_` pointer HOST memory
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); device entry points never synchronise
+ *   - return value: 0 on success, otherwise a cudaError_t (>0) or an ESCGNN_ERR_* code (<0); never throws
+ *   - data-dependent errors (degree >= 200, bad node id ...) are reported through `d_counters[ESCGNN_CTR_ERROR]`
+ */
+#ifndef ESCGNN_B200_H
+#define ESCGNN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESCGNN_ERR_BAD_ARG (-1)
+#define ESCGNN_ERR_TOO_LARGE (-2)     /* a graph exceeds the supported node/edge count of the kernels */
+#define ESCGNN_ERR_CAPACITY (-3)      /* caller-provided record capacity too small (required size reported) */
+#define ESCGNN_ERR_DATA (-4)          /* data-dependent error, see ESCGNN_CTR_ERROR bits */
+
+/* bits of d_counters[ESCGNN_CTR_ERROR] -- mirror the exceptions the reference raises */
+#define ESCGNN_DATA_DEG 1u            /* sub_degree >= 200: F.one_hot(..., 200) raises (utils_edge_efficient.py:128) */
+#define ESCGNN_DATA_NODE 2u           /* node id outside [0, N) */
+#define ESCGNN_DATA_RD 4u             /* rd bin outside the representable range (:131) / singular system */
+#define ESCGNN_DATA_ASYM 8u           /* use_rd on a non-symmetric edge multiset (unsupported, documented) */
+
+/* slots of the uint64 counter block every encoder launch works on (caller zeroes it, or uses *_host) */
+#define ESCGNN_CTR_NNZ 0              /* total records emitted (bump cursor) */
+#define ESCGNN_CTR_ERROR 1            /* OR of ESCGNN_DATA_* */
+#define ESCGNN_CTR_TICKET 2           /* persistent-CTA work ticket */
+#define ESCGNN_CTR_TICKET_RD 3
+#define ESCGNN_NUM_COUNTERS 8
+
+#define ESCGNN_RD_SLOTS 12            /* rd histogram slots kept per edge (bins 0..11; R(u,w) <= 2h+1 <= 9) */
+
+/* A record packs one non-zero of the per-edge encoding vector: index (11 bits, < 1800) | count << 11. */
+#define ESCGNN_REC_IDX_BITS 11
+
+int escgnn_version(void);
+
+/* ---- E1: self-loop rewrite.  Replaces utils_edge_efficient.py:33-38 (remove_self_loops + add_self_loops).
+ * Input: G graphs, graph-local int64 node ids, d_edge_ptr[G+1], d_node_ptr[G+1].
+ * Output: d_eo_ptr[G+1] and the rewritten edge list (capacity E_in + total nodes). With self_loop == 0 the
+ * caller aliases the input instead of calling this. d_tmp: scratch of 4*G + 8*(G/1024 + 2) + 16 bytes. */
+int escgnn_rewrite_self_loops(const int64_t* d_src, const int64_t* d_dst, const int64_t* d_edge_ptr,
+                              const int64_t* d_node_ptr, int64_t n_graphs, int64_t* d_eo_ptr, int64_t* d_eo_src,
+                              int64_t* d_eo_dst, void* d_tmp, void* stream);
+
+/* ---- E2-E4 (+E6 compact form): per-edge ego-net encoding.  Replaces utils_edge_efficient.py:41-90,122-144
+ * and k_hop_subgraph (:201-294).  One CTA per graph (persistent, ticketed); N bounded BFS per graph; warp per
+ * edge builds the histogram in shared memory and emits ascending (index,count) records.
+ *   d_eo_*      edge list after E1, d_eo_ptr[G+1] / d_node_ptr[G+1]
+ *   d_rdh       optional [E_out][ESCGNN_RD_SLOTS] uint16 rd histogram from escgnn_encode_rd (NULL = use_rd off)
+ *   d_rec       uint32 records, capacity rec_cap; d_rec_off[E_out] int64, d_rec_nnz[E_out] int32,
+ *               d_edge_graph[E_out] int32
+ *   d_counters  ESCGNN_NUM_COUNTERS uint64, zeroed by the caller; NNZ may exceed rec_cap (then nothing past the
+ *               capacity was written and the caller retries with a larger buffer)
+ *   d_scratch   global scratch for graphs that do not fit in shared memory (scratch_bytes, may be 0/NULL when
+ *               max_nodes/max_edges fit); max_nodes/max_edges: maxima over the batch (host knows them from ptrs) */
+int escgnn_encode(const int64_t* d_eo_src, const int64_t* d_eo_dst, const int64_t* d_eo_ptr,
+                  const int64_t* d_node_ptr, int64_t n_graphs, int h, const uint16_t* d_rdh, uint32_t* d_rec,
+                  int64_t rec_cap, int64_t* d_rec_off, int32_t* d_rec_nnz, int32_t* d_edge_graph,
+                  unsigned long long* d_counters, int64_t max_nodes, int64_t max_edges, void* d_scratch,
+                  int64_t scratch_bytes, void* stream);
+/* scratch bytes escgnn_encode / escgnn_encode_rd need for a batch with these maxima (0 if everything fits on chip) */
+int64_t escgnn_encode_scratch_bytes(int64_t max_nodes, int64_t max_edges, int h);
+int64_t escgnn_encode_rd_scratch_bytes(int64_t max_nodes, int64_t max_edges, int h);
+
+/* ---- E5: resistance-distance histogram per edge.  Replaces utils_edge_efficient.py:92-107,130-131 under parity
+ * policy E5 (float64 solve, bin = trunc((float)rd)).  Writes d_rdh[E_out][ESCGNN_RD_SLOTS]. */
+int escgnn_encode_rd(const int64_t* d_eo_src, const int64_t* d_eo_dst, const int64_t* d_eo_ptr,
+                     const int64_t* d_node_ptr, int64_t n_graphs, int h, uint16_t* d_rdh,
+                     unsigned long long* d_counters, int64_t max_nodes, int64_t max_edges, void* d_scratch,
+                     int64_t scratch_bytes, void* stream);
+
+/* ---- E6: expand compact records into the reference's int64 triple (pos_enc, pos_index, pos_batch), edges in
+ * order, indices ascending (utils_edge_efficient.py:139-151).  d_out_off[E_out+1] = exclusive scan of d_rec_nnz
+ * (escgnn_exclusive_scan_i32).  pos_batch = edge ordinal minus d_eo_ptr[graph] when local_ordinals != 0
+ * (per-graph Data), else the batch-wide ordinal (what batch.py:70-71 produces after collation). */
+int escgnn_exclusive_scan_i32(const int32_t* d_in, int64_t n, int64_t* d_out /* [n+1] */, int64_t* d_tmp /* [n/1024+2] */,
+                              void* stream);
+int escgnn_expand_records(const uint32_t* d_rec, const int64_t* d_rec_off, const int32_t* d_rec_nnz,
+                          const int32_t* d_edge_graph, const int64_t* d_eo_ptr, const int64_t* d_out_off,
+                          int64_t n_edges, int use_rd, int local_ordinals, int64_t* d_pos_enc, int64_t* d_pos_index,
+                          int64_t* d_pos_batch, void* stream);
+
+/* ---- Host-buffer front end (what `create_subgraphs` binds when the caller holds CPU tensors): H2D, E1, E5, E2-E4,
+ * scan, E6, D2H in one call on an internal stream with a grow-only device workspace.
+ * Two-step because the output size is data dependent: `_run` leaves results on the device and returns sizes,
+ * `_fetch` copies them into caller buffers of exactly those sizes. */
+typedef struct escgnn_ctx escgnn_ctx;
+escgnn_ctx* escgnn_ctx_create(int device);
+void escgnn_ctx_destroy(escgnn_ctx* ctx);
+int escgnn_encode_host_run(escgnn_ctx* ctx, const int64_t* h_src, const int64_t* h_dst, const int64_t* h_edge_ptr,
+                           const int64_t* h_node_ptr, int64_t n_graphs, int h, int use_rd, int self_loop,
+                           int local_ordinals, int64_t* out_num_edges, int64_t* out_nnz, uint32_t* out_error_bits);
+int escgnn_encode_host_fetch(escgnn_ctx* ctx, int64_t* h_eo_src, int64_t* h_eo_dst, int64_t* h_eo_ptr,
+                             int64_t* h_pos_enc, int64_t* h_pos_index, int64_t* h_pos_batch);
+/* device pointers of the last run's compact results (valid until the next run on this ctx) */
+int escgnn_encode_host_device_results(escgnn_ctx* ctx, const uint32_t** d_rec, const int64_t** d_rec_off,
+                                      const int32_t** d_rec_nnz, const int64_t** d_eo_src, const int64_t** d_eo_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESCGNN_B200_H */

@@ -1,0 +1,184 @@
+"""GPU parity of the sm_100a encoder (through the C-ABI) against the golden fixtures and the C oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(c, device='cpu'):
+    from esc_gnn_b200.data import Data
+    d = Data(x=torch.ones(c.n, 1), edge_index=torch.as_tensor(c.ei, dtype=torch.long, device=device))
+    d.num_nodes = c.n
+    return d
+
+
+@pytest.mark.parametrize('fname', G.FILES)
+def test_create_subgraphs_host_path_matches_reference_fixtures(fname):
+    from esc_gnn_b200.transform import create_subgraphs
+    for c in G.load(fname):
+        o = create_subgraphs(_data(c), c.h, use_rd=c.use_rd, self_loop=c.self_loop)
+        assert o.pos_enc.dtype == o.pos_index.dtype == o.pos_batch.dtype == torch.int64
+        G.check_against_case(c, o.edge_index.numpy(), o.pos_enc.numpy(), o.pos_index.numpy(), o.pos_batch.numpy())
+        if c.use_rd:     # rd block: bit-exact against the fp64 oracle (parity policy E5)
+            ref = c_oracle.encode_graph(c.ei, c.n, c.h, True, c.self_loop)
+            for got, want in zip((o.edge_index, o.pos_enc, o.pos_index, o.pos_batch), ref):
+                assert np.array_equal(got.numpy(), want), c.name
+
+
+@pytest.mark.parametrize('fname', ('kat1', 'edge_cases', 'cfg2', 'cfg4'))
+def test_create_subgraphs_device_path(fname):
+    from esc_gnn_b200.transform import create_subgraphs
+    for c in G.load(fname)[:30]:
+        o = create_subgraphs(_data(c, 'cuda'), c.h, use_rd=c.use_rd, self_loop=c.self_loop)
+        assert o.pos_enc.is_cuda
+        ref = c_oracle.encode_graph(c.ei, c.n, c.h, c.use_rd, c.self_loop)
+        for got, want in zip((o.edge_index, o.pos_enc, o.pos_index, o.pos_batch), ref):
+            assert np.array_equal(got.cpu().numpy(), want), c.name
+
+
+def _oracle_batch(src, dst, eptr, nptr, h, use_rd, self_loop):
+    eo, pe, pi, pb = [], [], [], []
+    base = 0
+    for g in range(len(nptr) - 1):
+        a, b = eptr[g], eptr[g + 1]
+        r = c_oracle.encode_graph(np.stack([src[a:b], dst[a:b]]), int(nptr[g + 1] - nptr[g]), h, use_rd, self_loop)
+        eo.append(r[0]); pe.append(r[1]); pi.append(r[2]); pb.append(r[3] + base)
+        base += r[0].shape[1]
+    return np.concatenate(eo, 1), np.concatenate(pe), np.concatenate(pi), np.concatenate(pb)
+
+
+@pytest.mark.parametrize('config,count', [(1, 96), (2, 256), (3, 32), (4, 64)])
+def test_batched_encoder_matches_oracle_on_config_shapes(config, count):
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.transform import encode_batch, encode_batch_host
+    fl = synth.ENCODER_FLAGS[config]
+    src, dst, eptr, nptr = synth.make_batch_arrays(config, 5000, count)
+    want = _oracle_batch(src, dst, eptr, nptr, fl['h'], fl['use_rd'], fl['self_loop'])
+    r = encode_batch(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), torch.as_tensor(eptr),
+                     torch.as_tensor(nptr), fl['h'], fl['use_rd'], fl['self_loop'])
+    for got, w in zip((r.edge_index, r.pos_enc, r.pos_index, r.pos_batch), want):
+        assert np.array_equal(got.cpu().numpy(), w)
+    rh = encode_batch_host(src, dst, eptr, nptr, fl['h'], fl['use_rd'], fl['self_loop'])
+    for got, w in zip((rh.edge_index, rh.pos_enc, rh.pos_index, rh.pos_batch), want):
+        assert np.array_equal(got.numpy(), w)
+    # compact records agree with the expanded triple
+    rec = r.rec.to(torch.int64) & 0xffffffff
+    k = 0
+    off, nz = r.rec_off.cpu().numpy(), r.rec_nnz.cpu().numpy()
+    recs = rec.cpu().numpy()
+    for e in (0, len(off) // 2, len(off) - 1):
+        seg = recs[off[e]:off[e] + nz[e]]
+        m = want[3] == e
+        assert np.array_equal(seg & 2047, want[2][m]) and np.array_equal(seg >> 11, want[1][m])
+
+
+@pytest.mark.parametrize('h,self_loop', [(1, False), (2, True), (3, False), (4, True)])
+def test_sweep_shapes_match_oracle(h, self_loop):
+    """Config 5 prefix: graphs of 25..500 nodes (shared-memory path with the 4-bit distance matrix)."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.transform import encode_batch
+    src, dst, eptr, nptr = synth.make_batch_arrays(5, 100 * h, 48)
+    want = _oracle_batch(src, dst, eptr, nptr, h, False, self_loop)
+    r = encode_batch(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), torch.as_tensor(eptr),
+                     torch.as_tensor(nptr), h, False, self_loop)
+    for got, w in zip((r.edge_index, r.pos_enc, r.pos_index, r.pos_batch), want):
+        assert np.array_equal(got.cpu().numpy(), w)
+
+
+def test_large_graph_uses_global_slab_and_matches_oracle():
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.transform import encode_batch
+    rng = np.random.Generator(np.random.PCG64(7))
+    parts = []
+    for n in (1500, 40, 900):
+        und = synth.random_graph(rng, n, int(1.2 * n))
+        parts.append((synth.symmetrise(und), n))
+    src = np.concatenate([p[0][0] for p in parts]); dst = np.concatenate([p[0][1] for p in parts])
+    eptr = np.cumsum([0] + [p[0].shape[1] for p in parts]); nptr = np.cumsum([0] + [p[1] for p in parts])
+    want = _oracle_batch(src, dst, eptr, nptr, 2, False, True)
+    r = encode_batch(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), torch.as_tensor(eptr),
+                     torch.as_tensor(nptr), 2, False, True)
+    for got, w in zip((r.edge_index, r.pos_enc, r.pos_index, r.pos_batch), want):
+        assert np.array_equal(got.cpu().numpy(), w)
+
+
+def test_rd_cta_mode_matches_oracle():
+    """Graphs too large for the warp-per-edge solver (n > ~40) go through the CTA-per-edge solver."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.transform import encode_batch
+    rng = np.random.Generator(np.random.PCG64(11))
+    parts = []
+    for n in (110, 20, 75, 130):
+        und = synth.random_graph(rng, n, n + 3, max_degree=4)
+        parts.append((synth.symmetrise(und), n))
+    src = np.concatenate([p[0][0] for p in parts]); dst = np.concatenate([p[0][1] for p in parts])
+    eptr = np.cumsum([0] + [p[0].shape[1] for p in parts]); nptr = np.cumsum([0] + [p[1] for p in parts])
+    for h, sl in ((3, False), (4, True)):
+        want = _oracle_batch(src, dst, eptr, nptr, h, True, sl)
+        r = encode_batch(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), torch.as_tensor(eptr),
+                         torch.as_tensor(nptr), h, True, sl)
+        for got, w in zip((r.edge_index, r.pos_enc, r.pos_index, r.pos_batch), want):
+            assert np.array_equal(got.cpu().numpy(), w)
+
+
+def test_invariants_at_full_batch_size():
+    """SURVEY KAT-3 on a BASELINE-sized batch (8192 ZINC-shaped graphs): size-independent properties."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.transform import encode_batch
+    pool = synth.make_batch_arrays(2, 0, 512)
+    reps = 16
+    src = np.tile(pool[0], reps); dst = np.tile(pool[1], reps)
+    eptr = np.concatenate([[0], np.cumsum(np.tile(np.diff(pool[2]), reps))])
+    nptr = np.concatenate([[0], np.cumsum(np.tile(np.diff(pool[3]), reps))])
+    r = encode_batch(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), torch.as_tensor(eptr),
+                     torch.as_tensor(nptr), 3, True, False)
+    E = r.num_edges
+    assert E == len(src)
+    pe, pi, pb = r.pos_enc, r.pos_index, r.pos_batch
+    assert bool((pb[1:] >= pb[:-1]).all())                                   # edges in order
+    same = pb[1:] == pb[:-1]
+    assert bool((pi[1:][same] > pi[:-1][same]).all())                        # ascending index inside an edge
+    def block_sum(lo, hi):
+        m = (pi >= lo) & (pi < hi)
+        return torch.zeros(E, dtype=torch.int64, device=pe.device).index_add_(0, pb[m], pe[m])
+    s_deg, s_d0, s_d1, s_rd = block_sum(0, 200), block_sum(200, 300), block_sum(300, 400), block_sum(400, 500)
+    assert bool((s_deg == s_d0).all() and (s_d0 == s_d1).all() and (s_d1 == s_rd).all())   # each = #S
+    one = torch.zeros(E, dtype=torch.int64, device=pe.device).index_add_(0, pb[pi == 200], pe[pi == 200])
+    assert bool((one == 1).all())                                            # exactly one node at d0 = 0 (u != v)
+    # periodicity: replica k equals replica 0
+    n0 = int((pb < pool[2][-1]).sum())
+    assert pe.numel() == n0 * reps
+    assert torch.equal(pe[:n0], pe[n0 * (reps - 1):]) and torch.equal(pi[:n0], pi[n0 * (reps - 1):])
+
+
+def test_error_behaviour_matches_reference():
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.transform import create_subgraphs
+    hub = torch.tensor([[0] * 210 + list(range(1, 211)), list(range(1, 211)) + [0] * 210])
+    d = Data(x=torch.ones(211, 1), edge_index=hub)
+    with pytest.raises(RuntimeError):
+        create_subgraphs(d, 1)                                   # degree >= 200: one_hot raises in the reference
+    with pytest.raises(RuntimeError):
+        create_subgraphs(Data(x=torch.ones(3, 1), edge_index=hub[:, :2]), 5)        # h >= 5
+    with pytest.raises(RuntimeError):
+        create_subgraphs(Data(x=torch.ones(3, 1), edge_index=torch.zeros((2, 0), dtype=torch.long)), 2)  # cat([])
+    with pytest.raises(RuntimeError):
+        create_subgraphs(Data(x=torch.ones(3, 1), edge_index=torch.tensor([[0, 1], [1, 2]])), 2, use_rd=True)
+    with pytest.raises(RuntimeError):
+        create_subgraphs(Data(x=torch.ones(2, 1), edge_index=torch.tensor([[0, 5], [1, 0]])), 2)         # bad id
+
+
+def test_edge_attr_self_loop_rewrite():
+    """E1 on attributes: loop rows dropped, N rows of 1.0 appended (PyG add_self_loops, utils_edge_efficient.py:35-36)."""
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.transform import create_subgraphs
+    ei = torch.tensor([[0, 0, 1, 1, 2], [0, 1, 0, 2, 1]])
+    ea = torch.arange(10, dtype=torch.float32).view(5, 2)
+    o = create_subgraphs(Data(x=torch.ones(3, 1), edge_index=ei, edge_attr=ea, y=torch.tensor([1.0])), 2, self_loop=True)
+    assert o.edge_index.tolist() == [[0, 1, 1, 2, 0, 1, 2], [1, 0, 2, 1, 0, 1, 2]]
+    assert torch.equal(o.edge_attr, torch.cat([ea[1:], torch.ones(3, 2)]))
+    assert o.pos is None and torch.equal(o.y, torch.tensor([1.0]))
