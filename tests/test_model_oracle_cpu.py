@@ -1,0 +1,75 @@
+"""CPU: the plain-PyTorch model oracle (oracle/model_ref.py) against fixtures produced by the reference classes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import model_util as MU
+
+FIX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'model.npz'))
+CPU_CASES = ('count_h64', 'zinc_l2', 'ogb', 'zinc')
+
+
+def run_case(model, variant, batch, name, rtol, atol, check_adam=True):
+    """Shared by the CPU oracle test and the GPU product test: everything the fixture pins."""
+    sd = MU.det_state(model.state_dict(), seed=1234)
+    sd = {k: v.to(next(model.parameters()).device) for k, v in sd.items()}
+    model.load_state_dict(sd)
+    model.train()
+    pred = model(batch)
+    loss = MU.loss_fn(variant, pred, batch.y)
+    loss.backward()
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), FIX[name + '/pred_train'], rtol=rtol, atol=atol)
+    assert abs(loss.item() - FIX[name + '/loss'][0]) <= rtol * abs(FIX[name + '/loss'][0]) + atol
+    grads = dict(model.named_parameters())
+    for k, want in zip(FIX[name + '/grad_keys'], FIX[name + '/grad_digest']):
+        got = MU.grad_digest(grads[str(k)].grad)
+        scale = max(want[1] / max(grads[str(k)].numel(), 1), 1e-6)         # mean |g|
+        np.testing.assert_allclose(got[2:], want[2:], rtol=20 * rtol, atol=20 * rtol * scale + atol * 1e-2, err_msg=str(k))
+        assert abs(got[1] - want[1]) <= 5 * rtol * want[1] + atol, k
+    sd1 = model.state_dict()
+    for k, want in zip(FIX[name + '/running_keys'], FIX[name + '/running_digest']):
+        np.testing.assert_allclose(MU.grad_digest(sd1[str(k)]), want, rtol=10 * rtol, atol=atol, err_msg=str(k))
+    model.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(model(batch).cpu().numpy(), FIX[name + '/pred_eval'], rtol=rtol, atol=atol)
+    if check_adam:
+        model.load_state_dict(sd)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        traj = []
+        for _ in range(3):
+            opt.zero_grad()
+            l = MU.loss_fn(variant, model(batch), batch.y)
+            l.backward()
+            opt.step()
+            traj.append(l.item())
+        np.testing.assert_allclose(traj, FIX[name + '/adam_losses'], rtol=50 * rtol, atol=atol)
+
+
+@pytest.mark.parametrize('name', CPU_CASES)
+def test_model_oracle_matches_reference_classes(name):
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    model = MU.build_oracle_model(variant, kw)
+    batch = MU.ref_batch(config, 100, count)
+    run_case(model, variant, batch, name, rtol=2e-5, atol=2e-5)
+
+
+def test_state_dict_keys_match_reference_contract():
+    """key names and shapes are the load/save compatibility contract."""
+    m = MU.build_oracle_model('count', dict(num_layers=5, hidden=256))
+    sd = m.state_dict()
+    assert sd['z_initial.weight'].shape == (1800, 256)
+    assert sd['conv1.lin.weight'].shape == (10, 256) and sd['conv1.eps'].shape == (1, )
+    assert sd['convs.3.nn.4.weight'].shape == (256, 256) and 'convs.3.nn.6.running_var' in sd
+    assert sd['lin1.weight'].shape == (256, 6 * 256) and sd['lin2.weight'].shape == (1, 256)
+    assert sum(p.numel() for p in m.parameters()) == 1857296
+    z = MU.build_oracle_model('zinc', dict(num_layers=5))
+    assert z.state_dict()['conv1.lin.weight'].shape == (32, 288) and z.state_dict()['lin1.weight'].shape == (256, 1280)
+    assert sum(p.numel() for p in z.parameters()) == 1773606
+    o = MU.build_oracle_model('ogb', MU.MODEL_CASES['ogb_full'][3])
+    assert sum(p.numel() for p in o.parameters()) == 5238907
+    assert 'gnn_node.convs.0.edge_encoder.bond_embedding_list.2.weight' in o.state_dict()
