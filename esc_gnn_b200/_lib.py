@@ -36,6 +36,15 @@ SIGNATURES = {
     'escgnn_encode_host_run': (_i32, [_vp] * 5 + [_i64, _i32, _i32, _i32, _i32, _i64p, _i64p, _u32p]),
     'escgnn_encode_host_fetch': (_i32, [_vp] * 7),
     'escgnn_encode_host_device_results': (_i32, [_vp] * 6),
+    'escgnn_csr_build': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'escgnn_sorted_ids_to_ptr': (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    'escgnn_bag_embed_fwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp]),
+    'escgnn_bag_embed_bwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp]),
+    'escgnn_gine_aggregate_fwd': (_i32, [_vp] * 6 + [_i64, _i32, _vp, _vp]),
+    'escgnn_gine_aggregate_bwd': (_i32, [_vp] * 7 + [_i64, _i32] + [_vp] * 5),
+    'escgnn_segment_pool_fwd': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    'escgnn_segment_pool_bwd': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    'escgnn_edge_distance': (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i32, ctypes.c_float, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -1,0 +1,364 @@
+// Sparse kernels of the NestedGIN_eff step -- fp32, HBM/L2-bound.
+//
+//   K3  bag_embed  fwd/bwd : z0[e] = sum_k cnt_k * W[idx_k]            (run_graphcount.py:155, zinc_models.py:590,
+//                                                                         ogb_mol_gnn.py:716) -- no [nnz,H] intermediate
+//   K4  gine_aggregate fwd : out[i] = (1+eps) x[i] + sum_{e: dst=i} relu(x[src_e] + ee[e])   (PyG GINEConv;
+//                            in-tree twin GraphGPS/graphgps/layer/gine_conv_layer.py:56-84; ogb_mol_gnn.py:346-358)
+//                            CSR-by-destination segmented sum, no atomics, 128-bit loads
+//   K5  gine_aggregate bwd : one pass over CSR-by-source: g_e[e] = g_out[dst_e] * [x[src]+ee > 0],
+//                            g_x[i] = (1+eps) g_out[i] + sum_{e: src=i} g_e[e],  d_eps = sum_i <g_out[i], x[i]>
+//   K7  segment_pool fwd/bwd (sum / mean over the sorted `batch` vector)  (run_graphcount.py:179, zinc_models.py:602)
+//   plus the index plumbing: deterministic CSR build from an int64 key vector, sorted-ids -> segment pointers.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/escgnn_b200.h"
+
+namespace escgnn {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---------------------------------------------------------------- index plumbing
+__global__ void count_keys_kernel(const int64_t* __restrict__ keys, int64_t e, int n, int* __restrict__ ptr,
+                                  unsigned long long* err) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = keys[i];
+        if (k < 0 || k >= n) { if (err) atomicOr(err, 1ull); continue; }
+        atomicAdd(&ptr[k + 1], 1);
+    }
+}
+
+// single block, in place: inclusive scan of ptr[0..n]
+__global__ void scan_ptr_kernel(int* ptr, int n1) {
+    __shared__ int s_warp[33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int carry = 0;
+    for (int i0 = 0; i0 < n1; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        int v = i < n1 ? ptr[i] : 0, incl = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(kFullMask, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < nw ? s_warp[lane] : 0, wi = w;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(kFullMask, wi, d); if (lane >= d) wi += t; }
+            if (lane < nw) s_warp[lane] = wi - w;
+            if (lane == 31) s_warp[32] = wi;
+        }
+        __syncthreads();
+        if (i < n1) ptr[i] = carry + s_warp[warp] + incl;
+        carry += s_warp[32];
+        __syncthreads();
+    }
+}
+
+__global__ void fill_perm_kernel(const int64_t* __restrict__ keys, int64_t e, int n, const int* __restrict__ ptr,
+                                 int* __restrict__ cursor, int* __restrict__ perm) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = keys[i];
+        if (k < 0 || k >= n) continue;
+        perm[ptr[k] + atomicAdd(&cursor[k], 1)] = (int)i;
+    }
+}
+
+// order every segment by edge id so the segmented float sums are run-to-run deterministic
+__global__ void sort_segments_kernel(const int* __restrict__ ptr, int n, int* __restrict__ perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = ptr[i], b = ptr[i + 1];
+    for (int p = a + 1; p < b; ++p) {
+        const int v = perm[p];
+        int q = p - 1;
+        while (q >= a && perm[q] > v) { perm[q + 1] = perm[q]; --q; }
+        perm[q + 1] = v;
+    }
+}
+
+__global__ void sorted_to_ptr_kernel(const int64_t* __restrict__ ids, int64_t n, int segs, int* __restrict__ ptr) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > segs) return;
+    int64_t lo = 0, hi = n;                  // first position with ids[pos] >= s
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (ids[mid] < s) lo = mid + 1; else hi = mid; }
+    ptr[s] = (int)lo;
+}
+
+// ---------------------------------------------------------------- K3 bag-embed
+// kRec: records come packed (index | count << 11) with per-edge (offset, count); else from the int64 triple + ptr.
+template <bool kRec>
+__global__ void __launch_bounds__(256)
+bag_embed_fwd_kernel(const float* __restrict__ W, int H, const int64_t* __restrict__ pos_index,
+                     const int64_t* __restrict__ pos_enc, const int* __restrict__ ptr,
+                     const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off,
+                     const int32_t* __restrict__ rec_nnz, int64_t n_edges, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n_edges) return;
+    int64_t a; int k;
+    if (kRec) { a = rec_off[e]; k = rec_nnz[e]; } else { a = ptr[e]; k = ptr[e + 1] - ptr[e]; }
+    const int chunks = H >> 2;
+    for (int c0 = 0; c0 < chunks; c0 += 64) {           // two float4 chunks per lane per pass
+        const int ca = c0 + lane, cb = c0 + 32 + lane;
+        float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = accA;
+        for (int j = 0; j < k; ++j) {
+            int idx; float cnt;
+            if (kRec) { const uint32_t r = rec[a + j]; idx = r & ((1u << ESCGNN_REC_IDX_BITS) - 1); cnt = (float)(r >> ESCGNN_REC_IDX_BITS); }
+            else { idx = (int)pos_index[a + j]; cnt = (float)pos_enc[a + j]; }
+            const float* row = W + (size_t)idx * H;
+            if (ca < chunks) { const float4 w = ld4(row + 4 * ca); accA.x += cnt * w.x; accA.y += cnt * w.y; accA.z += cnt * w.z; accA.w += cnt * w.w; }
+            if (cb < chunks) { const float4 w = ld4(row + 4 * cb); accB.x += cnt * w.x; accB.y += cnt * w.y; accB.z += cnt * w.z; accB.w += cnt * w.w; }
+        }
+        if (ca < chunks) st4(out + (size_t)e * H + 4 * ca, accA);
+        if (cb < chunks) st4(out + (size_t)e * H + 4 * cb, accB);
+    }
+}
+
+template <bool kRec>
+__global__ void __launch_bounds__(256)
+bag_embed_bwd_kernel(const float* __restrict__ g, int H, const int64_t* __restrict__ pos_index,
+                     const int64_t* __restrict__ pos_enc, const int* __restrict__ ptr,
+                     const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off,
+                     const int32_t* __restrict__ rec_nnz, int64_t n_edges, float* __restrict__ dW) {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n_edges) return;
+    int64_t a; int k;
+    if (kRec) { a = rec_off[e]; k = rec_nnz[e]; } else { a = ptr[e]; k = ptr[e + 1] - ptr[e]; }
+    const int chunks = H >> 2;
+    for (int c = lane; c < chunks; c += 32) {
+        const float4 gv = ld4(g + (size_t)e * H + 4 * c);
+        for (int j = 0; j < k; ++j) {
+            int idx; float cnt;
+            if (kRec) { const uint32_t r = rec[a + j]; idx = r & ((1u << ESCGNN_REC_IDX_BITS) - 1); cnt = (float)(r >> ESCGNN_REC_IDX_BITS); }
+            else { idx = (int)pos_index[a + j]; cnt = (float)pos_enc[a + j]; }
+            float4* dst = reinterpret_cast<float4*>(dW + (size_t)idx * H + 4 * c);
+            atomicAdd(dst, make_float4(cnt * gv.x, cnt * gv.y, cnt * gv.z, cnt * gv.w));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K4 / K5 GINE aggregation
+template <bool kVec>
+__global__ void __launch_bounds__(256)
+gine_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ee, const int64_t* __restrict__ src,
+                const int* __restrict__ dst_ptr, const int* __restrict__ dst_perm, const float* __restrict__ eps,
+                int n, int C, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float scale = 1.f + eps[0];
+    const int a = dst_ptr[i], b = dst_ptr[i + 1];
+    if (kVec) {
+        const int chunks = C >> 2;
+        for (int c = lane; c < chunks; c += 32) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = a; k < b; ++k) {
+                const int e = dst_perm[k];
+                const float4 xv = ld4(x + (size_t)src[e] * C + 4 * c), ev = ld4(ee + (size_t)e * C + 4 * c);
+                acc.x += fmaxf(xv.x + ev.x, 0.f); acc.y += fmaxf(xv.y + ev.y, 0.f);
+                acc.z += fmaxf(xv.z + ev.z, 0.f); acc.w += fmaxf(xv.w + ev.w, 0.f);
+            }
+            const float4 xi = ld4(x + (size_t)i * C + 4 * c);
+            st4(out + (size_t)i * C + 4 * c, make_float4(acc.x + scale * xi.x, acc.y + scale * xi.y,
+                                                          acc.z + scale * xi.z, acc.w + scale * xi.w));
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) {
+            float acc = 0.f;
+            for (int k = a; k < b; ++k) {
+                const int e = dst_perm[k];
+                acc += fmaxf(x[(size_t)src[e] * C + c] + ee[(size_t)e * C + c], 0.f);
+            }
+            out[(size_t)i * C + c] = acc + scale * x[(size_t)i * C + c];
+        }
+    }
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(256)
+gine_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ x, const float* __restrict__ ee,
+                const int64_t* __restrict__ dst, const int* __restrict__ src_ptr, const int* __restrict__ src_perm,
+                const float* __restrict__ eps, int n, int C, float* __restrict__ g_x, float* __restrict__ g_e,
+                float* __restrict__ dots) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float scale = 1.f + eps[0];
+    const int a = src_ptr[i], b = src_ptr[i + 1];
+    float dot = 0.f;
+    if (kVec) {
+        const int chunks = C >> 2;
+        for (int c = lane; c < chunks; c += 32) {
+            const float4 xi = ld4(x + (size_t)i * C + 4 * c);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = a; k < b; ++k) {
+                const int e = src_perm[k];
+                const float4 gv = ld4(g_out + (size_t)dst[e] * C + 4 * c), ev = ld4(ee + (size_t)e * C + 4 * c);
+                float4 m;
+                m.x = xi.x + ev.x > 0.f ? gv.x : 0.f; m.y = xi.y + ev.y > 0.f ? gv.y : 0.f;
+                m.z = xi.z + ev.z > 0.f ? gv.z : 0.f; m.w = xi.w + ev.w > 0.f ? gv.w : 0.f;
+                st4(g_e + (size_t)e * C + 4 * c, m);
+                acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+            }
+            const float4 gi = ld4(g_out + (size_t)i * C + 4 * c);
+            st4(g_x + (size_t)i * C + 4 * c, make_float4(acc.x + scale * gi.x, acc.y + scale * gi.y,
+                                                          acc.z + scale * gi.z, acc.w + scale * gi.w));
+            dot += gi.x * xi.x + gi.y * xi.y + gi.z * xi.z + gi.w * xi.w;
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) {
+            const float xi = x[(size_t)i * C + c];
+            float acc = 0.f;
+            for (int k = a; k < b; ++k) {
+                const int e = src_perm[k];
+                const float m = xi + ee[(size_t)e * C + c] > 0.f ? g_out[(size_t)dst[e] * C + c] : 0.f;
+                g_e[(size_t)e * C + c] = m;
+                acc += m;
+            }
+            const float gi = g_out[(size_t)i * C + c];
+            g_x[(size_t)i * C + c] = acc + scale * gi;
+            dot += gi * xi;
+        }
+    }
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) dot += __shfl_xor_sync(kFullMask, dot, d);
+    if (lane == 0) dots[i] = dot;
+}
+
+// deterministic single-block sum of a float vector into out[0] (optionally accumulating)
+__global__ void reduce_sum_kernel(const float* __restrict__ v, int64_t n, float* out, int accumulate) {
+    __shared__ float s[32];
+    float t = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) t += v[i];
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(kFullMask, t, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(kFullMask, t, d);
+        if (threadIdx.x == 0) out[0] = accumulate ? out[0] + t : t;
+    }
+}
+
+// ---------------------------------------------------------------- K7 segment pooling (sorted batch vector)
+__global__ void __launch_bounds__(256)
+segment_pool_fwd_kernel(const float* __restrict__ x, const int* __restrict__ ptr, int segs, int C, int mean,
+                        float* __restrict__ out) {
+    const int s = blockIdx.x;
+    const int a = ptr[s], b = ptr[s + 1];
+    const float inv = mean ? 1.f / (float)max(b - a, 1) : 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int i = a; i < b; ++i) acc += x[(size_t)i * C + c];
+        out[(size_t)s * C + c] = acc * inv;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+segment_pool_bwd_kernel(const float* __restrict__ g, const int* __restrict__ ptr, int segs, int C, int mean,
+                        float* __restrict__ gx) {
+    const int s = blockIdx.x;
+    const int a = ptr[s], b = ptr[s + 1];
+    const float inv = mean ? 1.f / (float)max(b - a, 1) : 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = g[(size_t)s * C + c] * inv;
+        for (int i = a; i < b; ++i) gx[(size_t)i * C + c] = v;
+    }
+}
+
+static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace escgnn
+
+using namespace escgnn;
+
+extern "C" {
+
+int escgnn_csr_build(const int64_t* d_keys, int64_t n_edges, int64_t n_nodes, int32_t* d_ptr, int32_t* d_perm,
+                     int32_t* d_tmp, unsigned long long* d_err, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_nodes < 0 || n_edges < 0 || n_nodes > 0x7ffffff0 || n_edges > 0x7ffffff0) return ESCGNN_ERR_BAD_ARG;
+    cudaMemsetAsync(d_ptr, 0, (size_t)(n_nodes + 1) * 4, st);
+    cudaMemsetAsync(d_tmp, 0, (size_t)(n_nodes + 1) * 4, st);
+    if (n_edges > 0) {
+        const unsigned gb = blocks_for(n_edges, 256) > 1184 ? 1184 : blocks_for(n_edges, 256);
+        count_keys_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_err);
+        scan_ptr_kernel<<<1, 1024, 0, st>>>(d_ptr, (int)n_nodes + 1);
+        fill_perm_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_tmp, d_perm);
+        sort_segments_kernel<<<blocks_for(n_nodes, 128), 128, 0, st>>>(d_ptr, (int)n_nodes, d_perm);
+    }
+    return (int)cudaGetLastError();
+}
+
+int escgnn_sorted_ids_to_ptr(const int64_t* d_ids, int64_t n, int64_t n_segments, int32_t* d_ptr, void* stream) {
+    if (n_segments < 0 || n > 0x7ffffff0) return ESCGNN_ERR_BAD_ARG;
+    sorted_to_ptr_kernel<<<blocks_for(n_segments + 1, 256), 256, 0, (cudaStream_t)stream>>>(d_ids, n, (int)n_segments,
+                                                                                            d_ptr);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_bag_embed_fwd(const float* d_weight, int hidden, const int64_t* d_pos_index, const int64_t* d_pos_enc,
+                         const int32_t* d_ptr, const uint32_t* d_rec, const int64_t* d_rec_off,
+                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_out, void* stream) {
+    if (hidden % 4 != 0) return ESCGNN_ERR_BAD_ARG;
+    if (n_edges <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_rec) bag_embed_fwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_weight, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_out);
+    else bag_embed_fwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_weight, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_out);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_bag_embed_bwd(const float* d_grad, int hidden, const int64_t* d_pos_index, const int64_t* d_pos_enc,
+                         const int32_t* d_ptr, const uint32_t* d_rec, const int64_t* d_rec_off,
+                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_grad_weight, void* stream) {
+    if (hidden % 4 != 0) return ESCGNN_ERR_BAD_ARG;
+    if (n_edges <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_rec) bag_embed_bwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_grad_weight);
+    else bag_embed_bwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_grad_weight);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_gine_aggregate_fwd(const float* d_x, const float* d_edge_feat, const int64_t* d_src, const int32_t* d_dst_ptr,
+                              const int32_t* d_dst_perm, const float* d_eps, int64_t n_nodes, int channels,
+                              float* d_out, void* stream) {
+    if (n_nodes <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels % 4 == 0) gine_fwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out);
+    else gine_fwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_gine_aggregate_bwd(const float* d_grad_out, const float* d_x, const float* d_edge_feat, const int64_t* d_dst,
+                              const int32_t* d_src_ptr, const int32_t* d_src_perm, const float* d_eps, int64_t n_nodes,
+                              int channels, float* d_grad_x, float* d_grad_edge_feat, float* d_node_dots,
+                              float* d_grad_eps, void* stream) {
+    if (n_nodes <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels % 4 == 0) gine_bwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots);
+    else gine_bwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots);
+    if (d_grad_eps) reduce_sum_kernel<<<1, 1024, 0, st>>>(d_node_dots, n_nodes, d_grad_eps, 0);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_segment_pool_fwd(const float* d_x, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
+                            float* d_out, void* stream) {
+    if (n_segments <= 0) return 0;
+    segment_pool_fwd_kernel<<<(unsigned)n_segments, 256, 0, (cudaStream_t)stream>>>(d_x, d_ptr, (int)n_segments, channels, mean, d_out);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_segment_pool_bwd(const float* d_grad, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
+                            float* d_grad_x, void* stream) {
+    if (n_segments <= 0) return 0;
+    segment_pool_bwd_kernel<<<(unsigned)n_segments, 256, 0, (cudaStream_t)stream>>>(d_grad, d_ptr, (int)n_segments, channels, mean, d_grad_x);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""Autograd bindings of the sm_100a model kernels (C-ABI in include/escgnn_b200.h), on the current torch stream.
+
+Every op raises when its inputs are not CUDA tensors: there is no CPU / eager fallback behind these functions.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('esc_gnn_b200 ops need CUDA tensors; there is no CPU fallback')
+
+
+class GraphIndex(object):
+    """Per-batch index structures built once on the device and shared by every layer:
+    CSR by destination (forward aggregation), CSR by source (backward), record ranges per edge, node ranges per graph."""
+
+    def __init__(self, edge_index, num_nodes, batch=None, num_graphs=None, pos_batch=None):
+        _need_cuda(edge_index)
+        L = _lib.lib()
+        dev = edge_index.device
+        st = _stream(edge_index)
+        ei = edge_index.contiguous()
+        self.src, self.dst = ei[0], ei[1]
+        self.num_nodes, self.num_edges = int(num_nodes), int(ei.size(1))
+        N, E = self.num_nodes, self.num_edges
+        buf = torch.empty(4 * (N + 1) + 2 * E + 2, dtype=torch.int32, device=dev)
+        self.dst_ptr, self.src_ptr = buf[:N + 1], buf[N + 1:2 * N + 2]
+        tmp_a, tmp_b = buf[2 * N + 2:3 * N + 3], buf[3 * N + 3:4 * N + 4]
+        self.dst_perm, self.src_perm = buf[4 * N + 4:4 * N + 4 + E], buf[4 * N + 4 + E:4 * N + 4 + 2 * E]
+        self.err = torch.zeros(1, dtype=torch.int64, device=dev)
+        _lib.check(L.escgnn_csr_build(_p(self.dst), E, N, _p(self.dst_ptr), _p(self.dst_perm), _p(tmp_a),
+                                      _p(self.err), st), 'csr_build')
+        _lib.check(L.escgnn_csr_build(_p(self.src), E, N, _p(self.src_ptr), _p(self.src_perm), _p(tmp_b),
+                                      _p(self.err), st), 'csr_build')
+        self.rec_ptr = None
+        if pos_batch is not None:
+            self.rec_ptr = torch.empty(E + 1, dtype=torch.int32, device=dev)
+            _lib.check(L.escgnn_sorted_ids_to_ptr(_p(pos_batch), pos_batch.numel(), E, _p(self.rec_ptr), st),
+                       'sorted_ids_to_ptr')
+        self.graph_ptr, self.num_graphs = None, None
+        if batch is not None:
+            if num_graphs is None:
+                num_graphs = int(batch[-1]) + 1          # the reference's own sync (PyG global_add_pool)
+            self.num_graphs = int(num_graphs)
+            self.graph_ptr = torch.empty(self.num_graphs + 1, dtype=torch.int32, device=dev)
+            _lib.check(L.escgnn_sorted_ids_to_ptr(_p(batch), batch.numel(), self.num_graphs, _p(self.graph_ptr), st),
+                       'sorted_ids_to_ptr')
+
+
+def graph_index(data):
+    """Index of a batch, cached on the batch object (edge_index / pos_batch / batch are immutable per batch)."""
+    idx = data.__dict__.get('_esc_index') if hasattr(data, '__dict__') else None
+    if idx is not None and idx.src.data_ptr() == data.edge_index[0].data_ptr():
+        return idx
+    n = data.x.size(0)
+    ng = getattr(data, 'num_graphs', None) if 'num_graphs' in dir(data) else None
+    idx = GraphIndex(data.edge_index, n, batch=data.batch, num_graphs=ng, pos_batch=data.pos_batch)
+    try:
+        object.__setattr__(data, '_esc_index', idx)
+    except Exception:
+        pass
+    return idx
+
+
+class _BagEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, pos_index, pos_enc, rec_ptr, n_edges):
+        _need_cuda(weight, pos_index, pos_enc, rec_ptr)
+        H = weight.size(1)
+        out = torch.empty((n_edges, H), dtype=torch.float32, device=weight.device)
+        w = weight.contiguous()
+        _lib.check(_lib.lib().escgnn_bag_embed_fwd(_p(w), H, _p(pos_index), _p(pos_enc), _p(rec_ptr), None, None, None,
+                                                   n_edges, _p(out), _stream(w)), 'bag_embed_fwd')
+        ctx.save_for_backward(pos_index, pos_enc, rec_ptr)
+        ctx.shape = tuple(weight.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pos_index, pos_enc, rec_ptr = ctx.saved_tensors
+        g = g.contiguous()
+        dW = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        _lib.check(_lib.lib().escgnn_bag_embed_bwd(_p(g), ctx.shape[1], _p(pos_index), _p(pos_enc), _p(rec_ptr), None,
+                                                   None, None, g.size(0), _p(dW), _stream(g)), 'bag_embed_bwd')
+        return dW, None, None, None, None
+
+
+def bag_embed(weight, pos_index, pos_enc, index):
+    """z0[e] = sum_k pos_enc[k] * weight[pos_index[k]] over the records of edge e (run_graphcount.py:155)."""
+    return _BagEmbed.apply(weight, pos_index.contiguous(), pos_enc.contiguous(), index.rec_ptr, index.num_edges)
+
+
+class _GineAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, edge_feat, eps, index):
+        _need_cuda(x, edge_feat, eps)
+        x, edge_feat = x.contiguous(), edge_feat.contiguous()
+        N, C = x.shape
+        assert edge_feat.shape == (index.num_edges, C) and N == index.num_nodes
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().escgnn_gine_aggregate_fwd(_p(x), _p(edge_feat), _p(index.src), _p(index.dst_ptr),
+                                                        _p(index.dst_perm), _p(eps), N, C, _p(out), _stream(x)),
+                   'gine_aggregate_fwd')
+        ctx.save_for_backward(x, edge_feat, eps)
+        ctx.index = index
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, edge_feat, eps = ctx.saved_tensors
+        index = ctx.index
+        g = g.contiguous()
+        N, C = x.shape
+        gx = torch.empty_like(x)
+        ge = torch.empty_like(edge_feat)
+        dots = torch.empty(N, dtype=torch.float32, device=x.device)
+        geps = torch.empty(1, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().escgnn_gine_aggregate_bwd(_p(g), _p(x), _p(edge_feat), _p(index.dst), _p(index.src_ptr),
+                                                        _p(index.src_perm), _p(eps), N, C, _p(gx), _p(ge), _p(dots),
+                                                        _p(geps), _stream(x)), 'gine_aggregate_bwd')
+        return gx, ge, geps, None
+
+
+def gine_aggregate(x, edge_feat, eps, index):
+    """(1+eps) x[i] + sum_{e: dst=i} relu(x[src_e] + edge_feat[e])  -- PyG GINEConv propagate + residual."""
+    return _GineAggregate.apply(x, edge_feat, eps, index)
+
+
+class _SegmentPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ptr, segs, mean):
+        _need_cuda(x, ptr)
+        x = x.contiguous()
+        out = torch.empty((segs, x.size(1)), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().escgnn_segment_pool_fwd(_p(x), _p(ptr), segs, x.size(1), int(mean), _p(out), _stream(x)),
+                   'segment_pool_fwd')
+        ctx.save_for_backward(ptr)
+        ctx.meta = (x.size(0), x.size(1), segs, int(mean))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (ptr, ) = ctx.saved_tensors
+        n, c, segs, mean = ctx.meta
+        g = g.contiguous()
+        gx = torch.zeros((n, c), dtype=torch.float32, device=g.device)
+        _lib.check(_lib.lib().escgnn_segment_pool_bwd(_p(g), _p(ptr), segs, c, mean, _p(gx), _stream(g)),
+                   'segment_pool_bwd')
+        return gx, None, None, None
+
+
+def global_add_pool(x, index):
+    return _SegmentPool.apply(x, index.graph_ptr, index.num_graphs, False)
+
+
+def global_mean_pool(x, index):
+    return _SegmentPool.apply(x, index.graph_ptr, index.num_graphs, True)

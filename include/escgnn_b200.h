@@ -105,6 +105,57 @@ int escgnn_encode_host_fetch(escgnn_ctx* ctx, int64_t* h_eo_src, int64_t* h_eo_d
 int escgnn_encode_host_device_results(escgnn_ctx* ctx, const uint32_t** d_rec, const int64_t** d_rec_off,
                                       const int32_t** d_rec_nnz, const int64_t** d_eo_src, const int64_t** d_eo_dst);
 
+/* ================= model step; fp32, row-major, device pointers ======== */
+
+/* Deterministic CSR of an int64 key vector (edge_index[1] for the forward aggregation, edge_index[0] for the
+ * backward): d_ptr[n_nodes+1], d_perm[n_edges] = edge ids grouped by key, ascending inside a group.
+ * d_tmp: n_nodes+1 int32 scratch. d_err (optional): bit 0 set when a key is outside [0, n_nodes). */
+int escgnn_csr_build(const int64_t* d_keys, int64_t n_edges, int64_t n_nodes, int32_t* d_ptr, int32_t* d_perm,
+                     int32_t* d_tmp, unsigned long long* d_err, void* stream);
+/* Segment pointers of a sorted id vector (pos_batch -> per-edge record ranges, batch -> per-graph node ranges;
+ * replaces the `int(batch.max())+1` + scatter bookkeeping of PyG global_add_pool). d_ptr[n_segments+1]. */
+int escgnn_sorted_ids_to_ptr(const int64_t* d_ids, int64_t n, int64_t n_segments, int32_t* d_ptr, void* stream);
+
+/* M1 sparse bag-embed.  Replaces global_add_pool(z_initial.weight[pos_index] * pos_enc[:,None], pos_batch)
+ * (run_graphcount.py:155, zinc_models.py:590, ogb_mol_gnn.py:716) without the [nnz,H] intermediate.
+ * Sparse operand either as the reference's int64 triple (d_pos_index, d_pos_enc, d_ptr from
+ * escgnn_sorted_ids_to_ptr(pos_batch)) or, when d_rec != NULL, as the encoder's packed records. hidden % 4 == 0.
+ * bwd accumulates into d_grad_weight [1800,hidden] (caller zeroes it). */
+int escgnn_bag_embed_fwd(const float* d_weight, int hidden, const int64_t* d_pos_index, const int64_t* d_pos_enc,
+                         const int32_t* d_ptr, const uint32_t* d_rec, const int64_t* d_rec_off,
+                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_out, void* stream);
+int escgnn_bag_embed_bwd(const float* d_grad, int hidden, const int64_t* d_pos_index, const int64_t* d_pos_enc,
+                         const int32_t* d_ptr, const uint32_t* d_rec, const int64_t* d_rec_off,
+                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_grad_weight, void* stream);
+
+/* M3 GINE aggregation.  Replaces PyG GINEConv.propagate + the (1+eps)*x residual (in-tree twin:
+ * GraphGPS/graphgps/layer/gine_conv_layer.py:56-84; ogb_mol_gnn.py:346-358):
+ *   out[i] = (1+eps) x[i] + sum_{e: dst_e = i} relu(x[src_e] + edge_feat[e]).
+ * d_src/d_dst: the int64 rows of edge_index; (d_dst_ptr, d_dst_perm) / (d_src_ptr, d_src_perm) from escgnn_csr_build.
+ * bwd writes d_grad_x [N,C], d_grad_edge_feat [E,C], per-node <g_out, x> into d_node_dots [N] and their sum into
+ * d_grad_eps[0] (optional). */
+int escgnn_gine_aggregate_fwd(const float* d_x, const float* d_edge_feat, const int64_t* d_src, const int32_t* d_dst_ptr,
+                              const int32_t* d_dst_perm, const float* d_eps, int64_t n_nodes, int channels,
+                              float* d_out, void* stream);
+int escgnn_gine_aggregate_bwd(const float* d_grad_out, const float* d_x, const float* d_edge_feat, const int64_t* d_dst,
+                              const int32_t* d_src_ptr, const int32_t* d_src_perm, const float* d_eps, int64_t n_nodes,
+                              int channels, float* d_grad_x, float* d_grad_edge_feat, float* d_node_dots,
+                              float* d_grad_eps, void* stream);
+
+/* M4 pooling over the sorted `batch` vector.  Replaces global_add_pool / global_mean_pool
+ * (run_graphcount.py:179, zinc_models.py:602, ogb_mol_gnn.py:124,768). mean divides by max(count,1). */
+int escgnn_segment_pool_fwd(const float* d_x, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
+                            float* d_out, void* stream);
+int escgnn_segment_pool_bwd(const float* d_grad, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
+                            float* d_grad_x, void* stream);
+
+/* D1 `Distance` edge transform.  Replaces distance.py:29-47: dist = ||pos[col]-pos[row]|| (squared != 0: its
+ * square), divided by the data maximum (norm != 0, max_value <= 0) or by max_value; d_rel (optional) receives
+ * pos[col]-pos[row] [E,dim]. d_max_scratch: one uint32. */
+int escgnn_edge_distance(const float* d_pos, int dim, const int64_t* d_row, const int64_t* d_col, int64_t n_edges,
+                         int squared, int norm, float max_value, float* d_dist, float* d_rel, unsigned* d_max_scratch,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

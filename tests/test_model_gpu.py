@@ -1,0 +1,126 @@
+"""GPU: the sm_100a model kernels and the three NestedGIN_eff variants against the torch oracle and the fixtures
+produced by the reference's own classes.  Tolerance: 1e-4 relative in fp32 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref
+from tests import model_util as MU
+from tests.test_batch_cpu import to_data
+from tests.test_model_oracle_cpu import run_case
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def product_batch(config, start, count):
+    from esc_gnn_b200.batch import Batch
+    return Batch.from_data_list([to_data(g) for g in MU.graph_dicts(config, start, count)]).to('cuda')
+
+
+def build_product_model(variant, kw):
+    from esc_gnn_b200 import graphcount_model, ogb_model, zinc_model
+    if variant == 'count':
+        return graphcount_model.NestedGIN_eff(None, kw['num_layers'], kw['hidden'], use_rd=True, graph_pred=False,
+                                              dropout=0, edge_nest=True, use_cycle=True)
+    if variant == 'zinc':
+        return zinc_model.NestedGIN_eff(None, kw['num_layers'])
+    return ogb_model.GNN('ogbg-molhiv', kw['num_tasks'], num_layer=kw['num_layer'], emb_dim=kw['emb_dim'],
+                         gnn_type='gin_eff', virtual_node=kw['virtual_node'], residual=kw['residual'],
+                         drop_ratio=kw['drop_ratio'])
+
+
+@pytest.mark.parametrize('name', list(MU.MODEL_CASES))
+def test_models_match_reference_class_fixtures(name):
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = build_product_model(variant, kw).cuda()
+    batch = product_batch(config, 100, count)
+    run_case(model, variant, batch, name, rtol=RTOL, atol=1e-5)
+
+
+def test_ops_against_torch_oracle():
+    from esc_gnn_b200 import ops
+    b = product_batch(2, 700, 40)
+    idx = ops.graph_index(b)
+    E, N = b.edge_index.size(1), b.x.size(0)
+    g = torch.Generator(device='cuda').manual_seed(3)
+    for H in (256, 300, 64):
+        W = torch.randn(1800, H, device='cuda', generator=g, requires_grad=True)
+        W2 = W.detach().clone().requires_grad_(True)
+        out = ops.bag_embed(W, b.pos_index, b.pos_enc, idx)
+        ref = model_ref.bag_embed(W2, b.pos_index, b.pos_enc, b.pos_batch)
+        torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-4)
+        go = torch.randn(E, H, device='cuda', generator=g)
+        out.backward(go); ref.backward(go)
+        torch.testing.assert_close(W.grad, W2.grad, rtol=1e-4, atol=1e-3)
+    for C in (256, 32, 10, 300):
+        x = torch.randn(N, C, device='cuda', generator=g, requires_grad=True)
+        e = torch.randn(E, C, device='cuda', generator=g, requires_grad=True)
+        eps = torch.tensor([0.3], device='cuda', requires_grad=True)
+        x2, e2, eps2 = (t.detach().clone().requires_grad_(True) for t in (x, e, eps))
+        out = ops.gine_aggregate(x, e, eps, idx)
+        msg = (x2[b.edge_index[0]] + e2).relu()
+        ref = torch.zeros_like(x2).index_add(0, b.edge_index[1], msg) + (1 + eps2) * x2
+        torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+        go = torch.randn(N, C, device='cuda', generator=g)
+        out.backward(go); ref.backward(go)
+        torch.testing.assert_close(x.grad, x2.grad, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(e.grad, e2.grad, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(eps.grad, eps2.grad, rtol=1e-4, atol=1e-3)
+    x = torch.randn(N, 96, device='cuda', generator=g, requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    for mean in (False, True):
+        out = (ops.global_mean_pool if mean else ops.global_add_pool)(x, idx)
+        ref = (model_ref.global_mean_pool if mean else model_ref.global_add_pool)(x2, b.batch)
+        torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+        go = torch.randn_like(out)
+        x.grad = None; x2.grad = None
+        out.backward(go); ref.backward(go)
+        torch.testing.assert_close(x.grad, x2.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_csr_build_is_sorted_and_complete():
+    from esc_gnn_b200 import ops
+    b = product_batch(1, 50, 30)
+    idx = ops.graph_index(b)
+    dst = b.edge_index[1].cpu().numpy(); src = b.edge_index[0].cpu().numpy()
+    for keys, ptr, perm in ((dst, idx.dst_ptr, idx.dst_perm), (src, idx.src_ptr, idx.src_perm)):
+        ptr, perm = ptr.cpu().numpy(), perm.cpu().numpy()
+        assert sorted(perm.tolist()) == list(range(len(keys)))
+        for i in range(len(ptr) - 1):
+            seg = perm[ptr[i]:ptr[i + 1]]
+            assert (keys[seg] == i).all() and (np.diff(seg) > 0).all()
+    assert int(idx.err[0]) == 0
+    assert np.array_equal(idx.rec_ptr.cpu().numpy(),
+                          np.searchsorted(b.pos_batch.cpu().numpy(), np.arange(len(dst) + 1)))
+
+
+def test_distance_transform_matches_reference_formula():
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.distance import Distance
+    g = torch.Generator().manual_seed(0)
+    pos = torch.randn(40, 3, generator=g)
+    ei = torch.randint(0, 40, (2, 200), generator=g)
+    ea = torch.randn(200, 4, generator=g)
+    for dev in ('cpu', 'cuda'):
+        for kw in (dict(), dict(norm=False), dict(squared=True), dict(relative_pos=True), dict(max_value=3.0),
+                   dict(cat=False)):
+            d = Data(x=torch.ones(40, 1), edge_index=ei.to(dev), edge_attr=ea.to(dev), pos=pos.to(dev))
+            out = Distance(**kw)(d).edge_attr.cpu()
+            row, col = ei
+            dist = ((pos[col] - pos[row]) ** 2).sum(1).view(-1, 1) if kw.get('squared') else \
+                torch.norm(pos[col] - pos[row], p=2, dim=-1).view(-1, 1)
+            if kw.get('norm', True):
+                dist = dist / (dist.max() if kw.get('max_value') is None else kw['max_value'])
+            want = torch.cat([ea, dist], -1) if kw.get('cat', True) else dist
+            if kw.get('relative_pos'):
+                want = torch.cat([want, pos[col] - pos[row]], -1)
+            torch.testing.assert_close(out, want, rtol=1e-6, atol=1e-6)
+
+
+def test_ops_refuse_cpu_tensors():
+    from esc_gnn_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.GraphIndex(torch.tensor([[0, 1], [1, 0]]), 2)
