@@ -1,0 +1,286 @@
+"""Headline benchmark: graphs/sec for ego-net encoding + NestedGIN_eff train step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic input: a batch of 256 ZINC-shaped raw graphs
+(BASELINE.json configs[1]; run_zinc.py:56 batch size) is structurally encoded (h=3, rd on, no self-loops;
+run_zinc.py:141-146), collated and run through one NestedGIN_eff train step (5 layers, hidden 256; forward, L1
+loss, backward, Adam).  `value` = graphs/s with the raw graphs already resident in HBM; `e2e` = the same step fed
+from pinned HOST buffers (H2D of the raw graphs and D2H of the loss inside the timed region).
+Multi-GPU: weak scaling, every rank encodes and trains on its own 256 graphs; the only exchange is one NCCL
+all-reduce of the flat gradient per step.
+
+`--impl reference` times the CPU restatement of the same step (oracle port: C encoder with OpenMP over graphs +
+plain-PyTorch NestedGIN_eff on all host threads); the unmodified Python reference cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIG, LAYERS, HIDDEN, BATCH, LR = 2, 5, 256, 256, 1e-3
+METRIC = 'graphs/sec, ego-net encoding + NestedGIN_eff train step'
+WORKLOAD = 'ZINC-shaped synthetic molecules (n~23, ~25 bonds), encode h=3 rd=on + NestedGIN_eff 5 layers hidden 256 train step, batch 256'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return json.load(open(path)).get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith('active')})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_step_factory(threads):
+    """The oracle port of one step on the host: C encoder (OpenMP over graphs) + torch CPU train step."""
+    import numpy as np
+    import torch
+    from esc_gnn_b200 import synth
+    from oracle import c_oracle, model_ref
+    from tests import model_util as MU
+    torch.set_num_threads(threads)
+    fl = synth.ENCODER_FLAGS[CONFIG]
+    model = model_ref.NestedGINEffZinc(LAYERS, HIDDEN)
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+    model.train()
+    cache = {}
+
+    def step(i, sample):
+        if i not in cache:                         # inputs prepared outside the timed region
+            arr = synth.make_batch_arrays(CONFIG, 10_000_000 + i * sample, sample)
+            cache[i] = (arr, MU.ref_batch(CONFIG, 10_000_000 + i * sample, sample))
+        (src, dst, eptr, nptr), batch = cache[i]
+        t0 = time.perf_counter()
+        c_oracle.encode_batch_digest(src, dst, eptr, nptr, fl['h'], fl['use_rd'], fl['self_loop'], threads=threads)
+        t1 = time.perf_counter()
+        opt.zero_grad()
+        loss = torch.nn.L1Loss()(model(batch), batch.y.view(-1, 1))
+        loss.backward()
+        opt.step()
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, loss.item()
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = BATCH if args.cpu_sample is None else args.cpu_sample
+    step = cpu_step_factory(threads)
+    for i in range(max(args.warmup, 1)):
+        step(i % 4, sample)
+    t_enc = t_trn = 0.0
+    for i in range(args.steps):
+        a, b, _ = step(i % 4, sample)
+        t_enc += a; t_trn += b
+    total = t_enc + t_trn
+    value = sample * args.steps / total
+    out = dict(impl='reference', metric=METRIC, value=value, unit='graphs/s', n_gpus=args.gpus, steps=args.steps,
+               warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype='int64+f64 (encode), f32 (model)', data='synthetic',
+               config=dict(workload=WORKLOAD, note='CPU oracle port; each step is a bounded sample of %d graphs of the workload' % sample),
+               cpu_baseline=dict(value=value, unit='graphs/s', cores=threads, kind='port',
+                                 sample='%d steps x %d ZINC-shaped graphs: C-oracle encode (OpenMP) + torch CPU train step' % (args.steps, sample),
+                                 encode_graphs_per_s=sample * args.steps / t_enc, train_graphs_per_s=sample * args.steps / t_trn),
+               e2e=dict(value=value, unit='graphs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------------- own arm (B200)
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from esc_gnn_b200 import _lib, ops, synth, zinc_model
+    from esc_gnn_b200.pipeline import RawBatch, TrainPipeline
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.backends.cuda.matmul.allow_tf32 = False          # fp32 parity with the reference's fp32 CPU path
+    torch.backends.cudnn.allow_tf32 = False
+    fl = synth.ENCODER_FLAGS[CONFIG]
+    torch.manual_seed(0)
+    model = zinc_model.NestedGIN_eff(None, LAYERS).cuda()
+    model.train()
+    loss_fn = lambda pred, y: torch.nn.functional.l1_loss(pred, y.view(-1, 1))
+    pipe = TrainPipeline(model, loss_fn, fl['h'], fl['use_rd'], fl['self_loop'], lr=LR, distributed=world > 1)
+    n_pool = min(args.steps + args.warmup, 12)
+    host_pool = [RawBatch.synth(CONFIG, rank * 1_000_000 + i * BATCH, BATCH) for i in range(n_pool)]
+    dev_pool = [b.cuda(non_blocking=False) for b in host_pool]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, pool, k_steps, timings):
+        evs = []
+        for i in range(k_steps):
+            flush.zero_()                                   # L2 flush between timed iterations (untimed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn(pool[i % len(pool)], timings)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    for i in range(max(args.warmup, 3)):                    # W >= 3 warm-up steps
+        pipe.step_device(dev_pool[i % n_pool])
+        pipe.step_host(host_pool[i % n_pool])
+    # ---- value: inputs resident in HBM
+    timings = {}
+    ops.TIMINGS = timings
+    launches0 = _lib.LAUNCHES['n']
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ms_value = timed(lambda b, t: pipe.step_device(b, timings=t), dev_pool, args.steps, timings)
+    barrier()
+    clk = clocks.stop()
+    launches = _lib.LAUNCHES['n'] - launches0
+    ops.TIMINGS = None
+    ms_value = max_over_ranks(ms_value)
+    # ---- e2e: raw graphs in pinned host memory, loss read back every step
+    barrier()
+    ms_e2e = timed(lambda b, t: pipe.step_host(b), host_pool, args.steps, None)
+    barrier()
+    ms_e2e = max_over_ranks(ms_e2e)
+    torch.cuda.synchronize()
+    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in timings.items()}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant hand-written kernel (B_enc = 16 E_in + 16 E_out + 24 nnz)
+    peak, peak_src = peaks()
+    top = max(kernel_ms, key=kernel_ms.get)
+    raw0 = dev_pool[0]
+    from esc_gnn_b200.pipeline import encode_and_collate
+    b0 = encode_and_collate(raw0, fl['h'], fl['use_rd'], fl['self_loop'])
+    e_in, e_out, nnz = raw0.src.numel(), b0.num_edges, b0.nnz
+    n_nodes = raw0.num_nodes
+    alg = {'ego_rd': 16 * e_in + 24 * e_out, 'ego_encode': 16 * e_in + 16 * e_out + 24 * nnz,
+           'bag_embed_fwd': 12 * nnz + 4 * e_out * HIDDEN, 'bag_embed_bwd': 12 * nnz + 4 * e_out * HIDDEN,
+           'gine_aggregate_fwd': LAYERS * (e_out * (2 * 4 * HIDDEN + 8) + 2 * 4 * n_nodes * HIDDEN),
+           'gine_aggregate_bwd': LAYERS * (e_out * (3 * 4 * HIDDEN + 8) + 4 * e_out * HIDDEN + 2 * 4 * n_nodes * HIDDEN)}
+    calls = {k: len(v) / args.steps for k, v in timings.items()}
+    per_launch_ms = kernel_ms[top] / max(calls[top], 1)
+    bytes_launch = alg.get(top, alg['ego_encode']) / max(calls[top], 1) if top.startswith(('gine', 'bag')) else alg.get(top, alg['ego_encode'])
+    achieved = bytes_launch / (per_launch_ms * 1e-3) / 1e9
+    roofline = dict(bound='hbm', kernel=top, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                    traffic=None, peak_source=peak_src, share_of_step=kernel_ms[top] / (ms_value / args.steps),
+                    algorithmic_bytes_per_launch=bytes_launch, launch_ms=per_launch_ms,
+                    note='ego_* kernels are issue-bound integer/fp64 graph kernels (ncu: ~84% issue-active), see DESIGN.md')
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        step = cpu_step_factory(threads)
+        sample = BATCH
+        step(0, sample)
+        t_enc = t_trn = 0.0
+        reps = 3
+        for i in range(reps):
+            a, b, _ = step(i % 2, sample)
+            t_enc += a; t_trn += b
+        cpu = dict(value=sample * reps / (t_enc + t_trn), unit='graphs/s', cores=threads, kind='port',
+                   sample='%d steps x %d ZINC-shaped graphs: C-oracle encode (OpenMP) + torch CPU NestedGIN_eff train step' % (reps, sample),
+                   encode_graphs_per_s=sample * reps / t_enc, train_graphs_per_s=sample * reps / t_trn)
+    graphs = BATCH * world * args.steps
+    h2d = host_pool[0].h2d_bytes()
+    out = dict(metric=METRIC, value=graphs / (ms_value * 1e-3), unit='graphs/s', n_gpus=world, steps=args.steps,
+               warmup=max(args.warmup, 3), ms_per_step=ms_value / args.steps, higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype='int64+f64 (encode), f32 (model)', data='synthetic',
+               config=dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism='dp%d' % world,
+                           l2='flushed between timed iterations (256 MB write)', lr=LR),
+               clocks=clk,
+               e2e=dict(value=graphs / (ms_e2e * 1e-3), unit='graphs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                        ms_per_step=ms_e2e / args.steps),
+               gpu_launches=launches, kernel_ms_per_step=kernel_ms, roofline=roofline, cpu_baseline=cpu,
+               shape=dict(graphs=BATCH, nodes=n_nodes, edges=e_out, nnz=nnz))
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--cpu-sample', type=int, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -44,6 +44,9 @@ SIGNATURES = {
     'escgnn_gine_aggregate_bwd': (_i32, [_vp] * 7 + [_i64, _i32] + [_vp] * 5),
     'escgnn_segment_pool_fwd': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     'escgnn_segment_pool_bwd': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    'escgnn_collate_edges': (_i32, [_vp] * 4 + [_i64, _vp, _vp, _vp]),
+    'escgnn_ptr_to_ids': (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    'escgnn_adam_step': (_i32, [_vp, _vp, _vp, _vp, _i64] + [ctypes.c_float] * 4 + [_i64, ctypes.c_float, _vp]),
     'escgnn_edge_distance': (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i32, ctypes.c_float, _vp, _vp, _vp, _vp]),
 }
 
@@ -63,8 +66,17 @@ def lib():
     return _lib
 
 
+# kernels launched by one successful call of each entry point (bench.py's `gpu_launches` evidence)
+KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'scan': 3, 'expand_records': 1,
+                    'csr_build': 4, 'sorted_ids_to_ptr': 1, 'bag_embed_fwd': 1, 'bag_embed_bwd': 1,
+                    'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
+                    'edge_distance': 2, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1}
+LAUNCHES = {'n': 0}
+
+
 def check(rc, what):
     if rc == 0:
+        LAUNCHES['n'] += KERNELS_PER_CALL.get(what, 1)
         return
     names = {-1: 'bad argument', -2: 'graph too large for the kernels', -3: 'record capacity', -4: 'data error'}
     if rc < 0:

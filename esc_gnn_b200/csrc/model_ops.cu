@@ -272,6 +272,25 @@ segment_pool_bwd_kernel(const float* __restrict__ g, const int* __restrict__ ptr
     }
 }
 
+// ---------------------------------------------------------------- device-side collation (batch.py:52-123 rules)
+__global__ void collate_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                     const int32_t* __restrict__ edge_graph, const int64_t* __restrict__ node_ptr,
+                                     int64_t e, int64_t* __restrict__ out_src, int64_t* __restrict__ out_dst) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t off = node_ptr[edge_graph[i]];       // edge_index += cumulative num_nodes (Data.__inc__)
+        out_src[i] = src[i] + off;
+        out_dst[i] = dst[i] + off;
+    }
+}
+
+__global__ void ptr_to_ids_kernel(const int64_t* __restrict__ ptr, int64_t segs, int64_t n, int64_t* __restrict__ ids) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = segs;                           // last segment with ptr[s] <= i
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (ptr[mid] <= i) lo = mid; else hi = mid; }
+        ids[i] = lo;
+    }
+}
+
 static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace escgnn
@@ -293,6 +312,21 @@ int escgnn_csr_build(const int64_t* d_keys, int64_t n_edges, int64_t n_nodes, in
         fill_perm_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_tmp, d_perm);
         sort_segments_kernel<<<blocks_for(n_nodes, 128), 128, 0, st>>>(d_ptr, (int)n_nodes, d_perm);
     }
+    return (int)cudaGetLastError();
+}
+
+int escgnn_collate_edges(const int64_t* d_src, const int64_t* d_dst, const int32_t* d_edge_graph,
+                         const int64_t* d_node_ptr, int64_t n_edges, int64_t* d_out_src, int64_t* d_out_dst, void* stream) {
+    if (n_edges <= 0) return 0;
+    unsigned b = blocks_for(n_edges, 256); if (b > 2368) b = 2368;
+    collate_edges_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, d_edge_graph, d_node_ptr, n_edges, d_out_src, d_out_dst);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64_t* d_ids, void* stream) {
+    if (n <= 0) return 0;
+    unsigned b = blocks_for(n, 256); if (b > 2368) b = 2368;
+    ptr_to_ids_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_ptr, n_segments, n, d_ids);
     return (int)cudaGetLastError();
 }
 

@@ -61,7 +61,7 @@ class NestedGIN_eff(torch.nn.Module):
             raise NotImplementedError('dense edge_pos is the legacy slow path (run_graphcount.py:142-146)')
         index = ops.graph_index(data)
         x, edge_index = data.x, data.edge_index
-        z_emb = self.z_embedding(ops.bag_embed(self.z_initial.weight, data.pos_index, data.pos_enc, index))
+        z_emb = self.z_embedding(ops.bag_embed_data(self.z_initial.weight, data, index))
         x = self.conv1(x, edge_index, z_emb, index)
         xs = [self.x_embedding(data.x), x]
         for conv in self.convs:

@@ -52,8 +52,7 @@ class GNN_node_efficient(torch.nn.Module):
         if self.virtual_node:
             vn = self.virtualnode_embedding.weight.expand(index.num_graphs, -1)
         h_list = [self.node_encoder(x)]
-        z_emb = self.z_embedding(ops.bag_embed(self.z_initial.weight, batched_data.pos_index, batched_data.pos_enc,
-                                               index))
+        z_emb = self.z_embedding(ops.bag_embed_data(self.z_initial.weight, batched_data, index))
         batch = batched_data.batch
         for layer in range(self.num_layer):
             if self.virtual_node:

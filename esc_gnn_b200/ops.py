@@ -17,6 +17,25 @@ def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+TIMINGS = None      # bench.py sets this to a dict to bracket every kernel call with CUDA events
+
+
+class _span(object):
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMINGS is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if TIMINGS is not None:
+            self.b.record()
+            TIMINGS.setdefault(self.name, []).append((self.a, self.b))
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -60,14 +79,29 @@ class GraphIndex(object):
                        'sorted_ids_to_ptr')
 
 
+def _field(data, name):
+    """Optional attribute of a Data-like object (our Data keeps fields in `_store`, PyG's raises AttributeError)."""
+    store = getattr(data, '_store', None)
+    if isinstance(store, dict):
+        return store.get(name)
+    try:
+        return getattr(data, name)
+    except AttributeError:
+        return None
+
+
 def graph_index(data):
     """Index of a batch, cached on the batch object (edge_index / pos_batch / batch are immutable per batch)."""
     idx = data.__dict__.get('_esc_index') if hasattr(data, '__dict__') else None
     if idx is not None and idx.src.data_ptr() == data.edge_index[0].data_ptr():
         return idx
     n = data.x.size(0)
-    ng = getattr(data, 'num_graphs', None) if 'num_graphs' in dir(data) else None
-    idx = GraphIndex(data.edge_index, n, batch=data.batch, num_graphs=ng, pos_batch=data.pos_batch)
+    try:
+        ng = data.num_graphs
+    except AttributeError:
+        ng = None
+    idx = GraphIndex(data.edge_index, n, batch=data.batch, num_graphs=ng,
+                     pos_batch=None if _field(data, 'rec') is not None else data.pos_batch)
     try:
         object.__setattr__(data, '_esc_index', idx)
     except Exception:
@@ -82,8 +116,9 @@ class _BagEmbed(torch.autograd.Function):
         H = weight.size(1)
         out = torch.empty((n_edges, H), dtype=torch.float32, device=weight.device)
         w = weight.contiguous()
-        _lib.check(_lib.lib().escgnn_bag_embed_fwd(_p(w), H, _p(pos_index), _p(pos_enc), _p(rec_ptr), None, None, None,
-                                                   n_edges, _p(out), _stream(w)), 'bag_embed_fwd')
+        with _span('bag_embed_fwd'):
+            _lib.check(_lib.lib().escgnn_bag_embed_fwd(_p(w), H, _p(pos_index), _p(pos_enc), _p(rec_ptr), None, None, None,
+                                                       n_edges, _p(out), _stream(w)), 'bag_embed_fwd')
         ctx.save_for_backward(pos_index, pos_enc, rec_ptr)
         ctx.shape = tuple(weight.shape)
         return out
@@ -93,9 +128,44 @@ class _BagEmbed(torch.autograd.Function):
         pos_index, pos_enc, rec_ptr = ctx.saved_tensors
         g = g.contiguous()
         dW = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
-        _lib.check(_lib.lib().escgnn_bag_embed_bwd(_p(g), ctx.shape[1], _p(pos_index), _p(pos_enc), _p(rec_ptr), None,
-                                                   None, None, g.size(0), _p(dW), _stream(g)), 'bag_embed_bwd')
+        with _span('bag_embed_bwd'):
+            _lib.check(_lib.lib().escgnn_bag_embed_bwd(_p(g), ctx.shape[1], _p(pos_index), _p(pos_enc), _p(rec_ptr), None,
+                                                       None, None, g.size(0), _p(dW), _stream(g)), 'bag_embed_bwd')
         return dW, None, None, None, None
+
+
+class _BagEmbedRec(torch.autograd.Function):
+    """Bag-embed straight from the encoder's packed records (no int64 triple in between)."""
+    @staticmethod
+    def forward(ctx, weight, rec, rec_off, rec_nnz, n_edges):
+        _need_cuda(weight, rec, rec_off, rec_nnz)
+        H = weight.size(1)
+        out = torch.empty((n_edges, H), dtype=torch.float32, device=weight.device)
+        w = weight.contiguous()
+        with _span('bag_embed_fwd'):
+            _lib.check(_lib.lib().escgnn_bag_embed_fwd(_p(w), H, None, None, None, _p(rec), _p(rec_off), _p(rec_nnz),
+                                                       n_edges, _p(out), _stream(w)), 'bag_embed_fwd')
+        ctx.save_for_backward(rec, rec_off, rec_nnz)
+        ctx.shape = tuple(weight.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rec, rec_off, rec_nnz = ctx.saved_tensors
+        g = g.contiguous()
+        dW = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        with _span('bag_embed_bwd'):
+            _lib.check(_lib.lib().escgnn_bag_embed_bwd(_p(g), ctx.shape[1], None, None, None, _p(rec), _p(rec_off),
+                                                       _p(rec_nnz), g.size(0), _p(dW), _stream(g)), 'bag_embed_bwd')
+        return dW, None, None, None, None
+
+
+def bag_embed_data(weight, data, index):
+    """Dispatch on what the batch carries: packed encoder records (native path) or the reference's int64 triple."""
+    rec = _field(data, 'rec')
+    if rec is not None:
+        return _BagEmbedRec.apply(weight, rec, data.rec_off, data.rec_nnz, index.num_edges)
+    return bag_embed(weight, data.pos_index, data.pos_enc, index)
 
 
 def bag_embed(weight, pos_index, pos_enc, index):
@@ -111,9 +181,10 @@ class _GineAggregate(torch.autograd.Function):
         N, C = x.shape
         assert edge_feat.shape == (index.num_edges, C) and N == index.num_nodes
         out = torch.empty_like(x)
-        _lib.check(_lib.lib().escgnn_gine_aggregate_fwd(_p(x), _p(edge_feat), _p(index.src), _p(index.dst_ptr),
-                                                        _p(index.dst_perm), _p(eps), N, C, _p(out), _stream(x)),
-                   'gine_aggregate_fwd')
+        with _span('gine_aggregate_fwd'):
+            _lib.check(_lib.lib().escgnn_gine_aggregate_fwd(_p(x), _p(edge_feat), _p(index.src), _p(index.dst_ptr),
+                                                            _p(index.dst_perm), _p(eps), N, C, _p(out), _stream(x)),
+                       'gine_aggregate_fwd')
         ctx.save_for_backward(x, edge_feat, eps)
         ctx.index = index
         return out
@@ -128,9 +199,10 @@ class _GineAggregate(torch.autograd.Function):
         ge = torch.empty_like(edge_feat)
         dots = torch.empty(N, dtype=torch.float32, device=x.device)
         geps = torch.empty(1, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().escgnn_gine_aggregate_bwd(_p(g), _p(x), _p(edge_feat), _p(index.dst), _p(index.src_ptr),
-                                                        _p(index.src_perm), _p(eps), N, C, _p(gx), _p(ge), _p(dots),
-                                                        _p(geps), _stream(x)), 'gine_aggregate_bwd')
+        with _span('gine_aggregate_bwd'):
+            _lib.check(_lib.lib().escgnn_gine_aggregate_bwd(_p(g), _p(x), _p(edge_feat), _p(index.dst), _p(index.src_ptr),
+                                                            _p(index.src_perm), _p(eps), N, C, _p(gx), _p(ge), _p(dots),
+                                                            _p(geps), _stream(x)), 'gine_aggregate_bwd')
         return gx, ge, geps, None
 
 
@@ -145,8 +217,9 @@ class _SegmentPool(torch.autograd.Function):
         _need_cuda(x, ptr)
         x = x.contiguous()
         out = torch.empty((segs, x.size(1)), dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().escgnn_segment_pool_fwd(_p(x), _p(ptr), segs, x.size(1), int(mean), _p(out), _stream(x)),
-                   'segment_pool_fwd')
+        with _span('segment_pool_fwd'):
+            _lib.check(_lib.lib().escgnn_segment_pool_fwd(_p(x), _p(ptr), segs, x.size(1), int(mean), _p(out), _stream(x)),
+                       'segment_pool_fwd')
         ctx.save_for_backward(ptr)
         ctx.meta = (x.size(0), x.size(1), segs, int(mean))
         return out
@@ -157,8 +230,9 @@ class _SegmentPool(torch.autograd.Function):
         n, c, segs, mean = ctx.meta
         g = g.contiguous()
         gx = torch.zeros((n, c), dtype=torch.float32, device=g.device)
-        _lib.check(_lib.lib().escgnn_segment_pool_bwd(_p(g), _p(ptr), segs, c, mean, _p(gx), _stream(g)),
-                   'segment_pool_bwd')
+        with _span('segment_pool_bwd'):
+            _lib.check(_lib.lib().escgnn_segment_pool_bwd(_p(g), _p(ptr), segs, c, mean, _p(gx), _stream(g)),
+                       'segment_pool_bwd')
         return gx, None, None, None
 
 

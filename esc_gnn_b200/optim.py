@@ -1,0 +1,59 @@
+"""Flat-buffer Adam on the sm_100a `adam_step` kernel, plus the data-parallel gradient exchange.
+
+All parameters are re-pointed at views of ONE contiguous fp32 buffer (and their .grad at views of one gradient
+buffer), so a step is one kernel launch and the data-parallel exchange is one NCCL all-reduce over NVLink.
+Update rule = torch.optim.Adam defaults (reference: run_graphcount.py:478, run_zinc.py:263, run_ogb_mol.py:436).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+class FlatAdam(object):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params or not self.params[0].is_cuda:
+            raise RuntimeError('FlatAdam needs CUDA parameters; there is no CPU fallback')
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        pad = [(-s) % 4 for s in sizes]                       # keep every tensor 16-byte aligned in the flat buffer
+        total = sum(s + q for s, q in zip(sizes, pad))
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        off = 0
+        for p, s, q in zip(self.params, sizes, pad):
+            self.flat[off:off + s].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + s].view(p.shape)
+            p.grad = self.grad[off:off + s].view(p.shape)
+            off += s + q
+        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self.param_groups = [dict(lr=lr)]
+
+    def zero_grad(self, set_to_none=False):
+        self.grad.zero_()
+        for p in self.params:                                 # autograd may have replaced .grad; keep the views
+            if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr() or \
+                    p.grad.data_ptr() >= self.grad.data_ptr() + self.grad.numel() * 4:
+                off = (p.data.data_ptr() - self.flat.data_ptr()) // 4
+                p.grad = self.grad[off:off + p.numel()].view(p.shape)
+
+    def all_reduce_grads(self, group=None):
+        """Data-parallel exchange: one sum all-reduce of the flat gradient (NCCL over NVLink); step() rescales."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            return dist.get_world_size(group)
+        return 1
+
+    def step(self, world_size=1):
+        self.t += 1
+        lr = self.param_groups[0]['lr']
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().escgnn_adam_step(P(self.flat), P(self.grad), P(self.exp_avg), P(self.exp_avg_sq),
+                                               self.flat.numel(), lr, self.betas[0], self.betas[1], self.eps, self.t,
+                                               1.0 / world_size, st), 'adam_step')

@@ -21,4 +21,4 @@ def run():
     loss = torch.nn.L1Loss()(model(batch), batch.y.view(-1, 1))
     loss.backward()
     assert torch.isfinite(loss) and model.z_initial.weight.grad.abs().sum() > 0
-    return float(loss)
+    return loss.item()

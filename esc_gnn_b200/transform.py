@@ -107,7 +107,7 @@ class _Span(object):
 
 
 def encode_batch(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=False, expand=True, local_ordinals=False,
-                 max_nodes=None, max_edges=None, timings=None):
+                 max_nodes=None, max_edges=None, n_total=None, timings=None):
     """DEVICE tensors in, DEVICE tensors out, on the current torch stream.
 
     src/dst: int64 CUDA tensors [E_in] (graph-local ids); edge_ptr/node_ptr: int64 [G+1], CPU or CUDA
@@ -126,8 +126,6 @@ def encode_batch(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=False,
         max_nodes = int(nn.max()) if G else 0
         max_edges = int((ee + nn).max() if self_loop else ee.max()) if G else 0
         n_total = int(npt[-1])
-    else:
-        n_total = None
     d_eptr = edge_ptr.to(dev, non_blocking=True)
     d_nptr = node_ptr.to(dev, non_blocking=True)
     E_in = src.numel()

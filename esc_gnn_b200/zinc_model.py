@@ -49,7 +49,7 @@ class NestedGIN_eff(torch.nn.Module):
             raise NotImplementedError('dense edge_pos is the legacy slow path (zinc_models.py:584-587)')
         index = ops.graph_index(data)
         x, edge_index = self.node_type_embedding(data.x), data.edge_index
-        z_emb = self.z_embedding(ops.bag_embed(self.z_initial.weight, data.pos_index, data.pos_enc, index))
+        z_emb = self.z_embedding(ops.bag_embed_data(self.z_initial.weight, data, index))
         z_emb = torch.cat((z_emb, self.edge_type_embedding(data.edge_attr)), dim=-1)
         x = self.conv1(x, edge_index, z_emb, index)
         xs = [x]

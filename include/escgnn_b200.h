@@ -156,6 +156,18 @@ int escgnn_edge_distance(const float* d_pos, int dim, const int64_t* d_row, cons
                          int squared, int norm, float max_value, float* d_dist, float* d_rel, unsigned* d_max_scratch,
                          void* stream);
 
+/* M5 Adam over one flat fp32 buffer (torch.optim.Adam rule, no amsgrad / weight decay; reference call sites
+ * run_graphcount.py:478,505, run_zinc.py:263, run_ogb_mol.py:436). `step` counts from 1; grad_scale multiplies
+ * the gradient first (1/world_size after a sum all-reduce). */
+int escgnn_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+
+/* B1 collation on the device (reference batch.py:52-123 + Data.__inc__): shift graph-local edge ids by the
+ * graph's node offset (d_edge_graph from escgnn_encode), and expand node_ptr into the `batch` vector. */
+int escgnn_collate_edges(const int64_t* d_src, const int64_t* d_dst, const int32_t* d_edge_graph,
+                         const int64_t* d_node_ptr, int64_t n_edges, int64_t* d_out_src, int64_t* d_out_dst, void* stream);
+int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64_t* d_ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,7 +63,8 @@ def ref_batch(config, start, count, **kw):
 
 def grad_digest(t):
     t = t.detach().double().flatten().cpu()
-    return np.array([t.sum().item(), t.abs().sum().item()] + t[:6].tolist() + [0.0] * max(0, 6 - t.numel()))
+    head = t[:6].tolist() + [0.0] * max(0, 6 - t.numel())
+    return np.array([t.sum().item(), t.abs().sum().item(), t.abs().max().item(), t.norm().item()] + head)
 
 
 MODEL_CASES = {
