@@ -36,16 +36,27 @@ SIGNATURES = {
     'escgnn_encode_host_run': (_i32, [_vp] * 5 + [_i64, _i32, _i32, _i32, _i32, _i64p, _i64p, _u32p]),
     'escgnn_encode_host_fetch': (_i32, [_vp] * 7),
     'escgnn_encode_host_device_results': (_i32, [_vp] * 6),
-    'escgnn_csr_build': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
-    'escgnn_sorted_ids_to_ptr': (_i32, [_vp, _i64, _i64, _vp, _vp]),
-    'escgnn_bag_embed_fwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp]),
-    'escgnn_bag_embed_bwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp]),
-    'escgnn_gine_aggregate_fwd': (_i32, [_vp] * 6 + [_i64, _i32, _vp, _vp]),
-    'escgnn_gine_aggregate_bwd': (_i32, [_vp] * 7 + [_i64, _i32] + [_vp] * 5),
+    'escgnn_csr_build': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'escgnn_sorted_ids_to_ptr': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    'escgnn_bag_embed_fwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp, _vp]),
+    'escgnn_bag_embed_bwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp, _vp]),
+    'escgnn_gine_aggregate_fwd': (_i32, [_vp] * 6 + [_i64, _i32, _vp, _vp, _vp]),
+    'escgnn_gine_aggregate_bwd': (_i32, [_vp] * 7 + [_i64, _i32] + [_vp] * 6),
     'escgnn_segment_pool_fwd': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     'escgnn_segment_pool_bwd': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
-    'escgnn_collate_edges': (_i32, [_vp] * 4 + [_i64, _vp, _vp, _vp]),
-    'escgnn_ptr_to_ids': (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    'escgnn_collate_edges': (_i32, [_vp] * 4 + [_i64, _vp, _vp, _vp, _vp]),
+    'escgnn_ptr_to_ids': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    'escgnn_dense_tile_rows': (_i32, []),
+    'escgnn_bn_act_fwd': (_i32, [_vp, _i32] + [_vp] * 7 + [_i32, ctypes.c_float, ctypes.c_float, _i32, _vp, _i32, _i32, _vp, _i32, _vp]),
+    'escgnn_bn_act_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _i32] + [_vp] * 4 + [_i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
+    'escgnn_act_fwd': (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp]),
+    'escgnn_act_bwd': (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp]),
+    'escgnn_colsum': (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
+    'escgnn_embedding_fwd': (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp]),
+    'escgnn_embedding_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    'escgnn_loss_fwd_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+    'escgnn_adam_step_device': (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'escgnn_make_dims': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     'escgnn_adam_step': (_i32, [_vp, _vp, _vp, _vp, _i64] + [ctypes.c_float] * 4 + [_i64, ctypes.c_float, _vp]),
     'escgnn_edge_distance': (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i32, ctypes.c_float, _vp, _vp, _vp, _vp]),
 }
@@ -70,7 +81,9 @@ def lib():
 KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'scan': 3, 'expand_records': 1,
                     'csr_build': 4, 'sorted_ids_to_ptr': 1, 'bag_embed_fwd': 1, 'bag_embed_bwd': 1,
                     'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
-                    'edge_distance': 2, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1}
+                    'edge_distance': 2, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 2, 'bn_act_bwd': 2,
+                    'act_fwd': 1, 'act_bwd': 1, 'colsum': 2, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
+                    'make_dims': 1, 'adam_step_device': 2}
 LAUNCHES = {'n': 0}
 
 

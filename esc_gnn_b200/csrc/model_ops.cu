@@ -22,8 +22,14 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ---------------------------------------------------------------- index plumbing
+// actual count = *d_count when given (static-shape engine), else the host value
+__device__ __forceinline__ int64_t dyn(int64_t host_n, const int* d_count) {
+    return d_count ? (int64_t)min((long long)*d_count, (long long)host_n) : host_n;
+}
+
 __global__ void count_keys_kernel(const int64_t* __restrict__ keys, int64_t e, int n, int* __restrict__ ptr,
-                                  unsigned long long* err) {
+                                  unsigned long long* err, const int* d_count) {
+    e = dyn(e, d_count);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = keys[i];
         if (k < 0 || k >= n) { if (err) atomicOr(err, 1ull); continue; }
@@ -58,7 +64,8 @@ __global__ void scan_ptr_kernel(int* ptr, int n1) {
 }
 
 __global__ void fill_perm_kernel(const int64_t* __restrict__ keys, int64_t e, int n, const int* __restrict__ ptr,
-                                 int* __restrict__ cursor, int* __restrict__ perm) {
+                                 int* __restrict__ cursor, int* __restrict__ perm, const int* d_count) {
+    e = dyn(e, d_count);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = keys[i];
         if (k < 0 || k >= n) continue;
@@ -79,9 +86,11 @@ __global__ void sort_segments_kernel(const int* __restrict__ ptr, int n, int* __
     }
 }
 
-__global__ void sorted_to_ptr_kernel(const int64_t* __restrict__ ids, int64_t n, int segs, int* __restrict__ ptr) {
+__global__ void sorted_to_ptr_kernel(const int64_t* __restrict__ ids, int64_t n, int segs, int* __restrict__ ptr,
+                                     const int* d_count) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s > segs) return;
+    n = dyn(n, d_count);
     int64_t lo = 0, hi = n;                  // first position with ids[pos] >= s
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (ids[mid] < s) lo = mid + 1; else hi = mid; }
     ptr[s] = (int)lo;
@@ -94,12 +103,15 @@ __global__ void __launch_bounds__(256)
 bag_embed_fwd_kernel(const float* __restrict__ W, int H, const int64_t* __restrict__ pos_index,
                      const int64_t* __restrict__ pos_enc, const int* __restrict__ ptr,
                      const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off,
-                     const int32_t* __restrict__ rec_nnz, int64_t n_edges, float* __restrict__ out) {
+                     const int32_t* __restrict__ rec_nnz, int64_t n_edges, float* __restrict__ out,
+                     const int* d_count) {
     const int lane = threadIdx.x & 31;
     const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= n_edges) return;
-    int64_t a; int k;
-    if (kRec) { a = rec_off[e]; k = rec_nnz[e]; } else { a = ptr[e]; k = ptr[e + 1] - ptr[e]; }
+    int64_t a = 0; int k = 0;
+    if (e < dyn(n_edges, d_count)) {          // rows beyond the actual count are written as zeros
+        if (kRec) { a = rec_off[e]; k = rec_nnz[e]; } else { a = ptr[e]; k = ptr[e + 1] - ptr[e]; }
+    }
     const int chunks = H >> 2;
     for (int c0 = 0; c0 < chunks; c0 += 64) {           // two float4 chunks per lane per pass
         const int ca = c0 + lane, cb = c0 + 32 + lane;
@@ -122,10 +134,11 @@ __global__ void __launch_bounds__(256)
 bag_embed_bwd_kernel(const float* __restrict__ g, int H, const int64_t* __restrict__ pos_index,
                      const int64_t* __restrict__ pos_enc, const int* __restrict__ ptr,
                      const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off,
-                     const int32_t* __restrict__ rec_nnz, int64_t n_edges, float* __restrict__ dW) {
+                     const int32_t* __restrict__ rec_nnz, int64_t n_edges, float* __restrict__ dW,
+                     const int* d_count) {
     const int lane = threadIdx.x & 31;
     const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (e >= n_edges) return;
+    if (e >= dyn(n_edges, d_count)) return;
     int64_t a; int k;
     if (kRec) { a = rec_off[e]; k = rec_nnz[e]; } else { a = ptr[e]; k = ptr[e + 1] - ptr[e]; }
     const int chunks = H >> 2;
@@ -146,10 +159,14 @@ template <bool kVec>
 __global__ void __launch_bounds__(256)
 gine_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ee, const int64_t* __restrict__ src,
                 const int* __restrict__ dst_ptr, const int* __restrict__ dst_perm, const float* __restrict__ eps,
-                int n, int C, float* __restrict__ out) {
+                int n, int C, float* __restrict__ out, const int* d_count) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
+    if (i >= dyn(n, d_count)) {               // padded rows stay zero
+        for (int c = lane; c < C; c += 32) out[(size_t)i * C + c] = 0.f;
+        return;
+    }
     const float scale = 1.f + eps[0];
     const int a = dst_ptr[i], b = dst_ptr[i + 1];
     if (kVec) {
@@ -183,10 +200,15 @@ __global__ void __launch_bounds__(256)
 gine_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ x, const float* __restrict__ ee,
                 const int64_t* __restrict__ dst, const int* __restrict__ src_ptr, const int* __restrict__ src_perm,
                 const float* __restrict__ eps, int n, int C, float* __restrict__ g_x, float* __restrict__ g_e,
-                float* __restrict__ dots) {
+                float* __restrict__ dots, const int* d_count) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
+    if (i >= dyn(n, d_count)) {
+        for (int c = lane; c < C; c += 32) g_x[(size_t)i * C + c] = 0.f;
+        if (lane == 0) dots[i] = 0.f;
+        return;
+    }
     const float scale = 1.f + eps[0];
     const int a = src_ptr[i], b = src_ptr[i + 1];
     float dot = 0.f;
@@ -275,7 +297,9 @@ segment_pool_bwd_kernel(const float* __restrict__ g, const int* __restrict__ ptr
 // ---------------------------------------------------------------- device-side collation (batch.py:52-123 rules)
 __global__ void collate_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                      const int32_t* __restrict__ edge_graph, const int64_t* __restrict__ node_ptr,
-                                     int64_t e, int64_t* __restrict__ out_src, int64_t* __restrict__ out_dst) {
+                                     int64_t e, int64_t* __restrict__ out_src, int64_t* __restrict__ out_dst,
+                                     const int* d_count) {
+    e = dyn(e, d_count);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t off = node_ptr[edge_graph[i]];       // edge_index += cumulative num_nodes (Data.__inc__)
         out_src[i] = src[i] + off;
@@ -283,11 +307,21 @@ __global__ void collate_edges_kernel(const int64_t* __restrict__ src, const int6
     }
 }
 
-__global__ void ptr_to_ids_kernel(const int64_t* __restrict__ ptr, int64_t segs, int64_t n, int64_t* __restrict__ ids) {
+__global__ void ptr_to_ids_kernel(const int64_t* __restrict__ ptr, int64_t segs, int64_t n, int64_t* __restrict__ ids,
+                                  const int* d_count) {
+    n = dyn(n, d_count);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t lo = 0, hi = segs;                           // last segment with ptr[s] <= i
         while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (ptr[mid] <= i) lo = mid; else hi = mid; }
         ids[i] = lo;
+    }
+}
+
+__global__ void make_dims_kernel(const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int64_t g,
+                                 const unsigned long long* __restrict__ counters, int* __restrict__ dims) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        dims[0] = (int)node_ptr[g]; dims[1] = (int)eo_ptr[g]; dims[2] = (int)g;
+        dims[3] = counters ? (int)counters[ESCGNN_CTR_NNZ] : 0;
     }
 }
 
@@ -300,83 +334,93 @@ using namespace escgnn;
 extern "C" {
 
 int escgnn_csr_build(const int64_t* d_keys, int64_t n_edges, int64_t n_nodes, int32_t* d_ptr, int32_t* d_perm,
-                     int32_t* d_tmp, unsigned long long* d_err, void* stream) {
+                     int32_t* d_tmp, unsigned long long* d_err, const int* d_count, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_nodes < 0 || n_edges < 0 || n_nodes > 0x7ffffff0 || n_edges > 0x7ffffff0) return ESCGNN_ERR_BAD_ARG;
     cudaMemsetAsync(d_ptr, 0, (size_t)(n_nodes + 1) * 4, st);
     cudaMemsetAsync(d_tmp, 0, (size_t)(n_nodes + 1) * 4, st);
     if (n_edges > 0) {
         const unsigned gb = blocks_for(n_edges, 256) > 1184 ? 1184 : blocks_for(n_edges, 256);
-        count_keys_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_err);
+        count_keys_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_err, d_count);
         scan_ptr_kernel<<<1, 1024, 0, st>>>(d_ptr, (int)n_nodes + 1);
-        fill_perm_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_tmp, d_perm);
+        fill_perm_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_tmp, d_perm, d_count);
         sort_segments_kernel<<<blocks_for(n_nodes, 128), 128, 0, st>>>(d_ptr, (int)n_nodes, d_perm);
     }
     return (int)cudaGetLastError();
 }
 
 int escgnn_collate_edges(const int64_t* d_src, const int64_t* d_dst, const int32_t* d_edge_graph,
-                         const int64_t* d_node_ptr, int64_t n_edges, int64_t* d_out_src, int64_t* d_out_dst, void* stream) {
+                         const int64_t* d_node_ptr, int64_t n_edges, int64_t* d_out_src, int64_t* d_out_dst,
+                         const int* d_count, void* stream) {
     if (n_edges <= 0) return 0;
     unsigned b = blocks_for(n_edges, 256); if (b > 2368) b = 2368;
-    collate_edges_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, d_edge_graph, d_node_ptr, n_edges, d_out_src, d_out_dst);
+    collate_edges_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, d_edge_graph, d_node_ptr, n_edges, d_out_src, d_out_dst, d_count);
     return (int)cudaGetLastError();
 }
 
-int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64_t* d_ids, void* stream) {
+int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t n_graphs,
+                     const unsigned long long* d_counters, int* d_dims, void* stream) {
+    make_dims_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_eo_ptr, d_node_ptr, n_graphs, d_counters, d_dims);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64_t* d_ids, const int* d_count,
+                      void* stream) {
     if (n <= 0) return 0;
     unsigned b = blocks_for(n, 256); if (b > 2368) b = 2368;
-    ptr_to_ids_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_ptr, n_segments, n, d_ids);
+    ptr_to_ids_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_ptr, n_segments, n, d_ids, d_count);
     return (int)cudaGetLastError();
 }
 
-int escgnn_sorted_ids_to_ptr(const int64_t* d_ids, int64_t n, int64_t n_segments, int32_t* d_ptr, void* stream) {
+int escgnn_sorted_ids_to_ptr(const int64_t* d_ids, int64_t n, int64_t n_segments, int32_t* d_ptr, const int* d_count,
+                             void* stream) {
     if (n_segments < 0 || n > 0x7ffffff0) return ESCGNN_ERR_BAD_ARG;
     sorted_to_ptr_kernel<<<blocks_for(n_segments + 1, 256), 256, 0, (cudaStream_t)stream>>>(d_ids, n, (int)n_segments,
-                                                                                            d_ptr);
+                                                                                            d_ptr, d_count);
     return (int)cudaGetLastError();
 }
 
 int escgnn_bag_embed_fwd(const float* d_weight, int hidden, const int64_t* d_pos_index, const int64_t* d_pos_enc,
                          const int32_t* d_ptr, const uint32_t* d_rec, const int64_t* d_rec_off,
-                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_out, void* stream) {
+                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_out, const int* d_count, void* stream) {
     if (hidden % 4 != 0) return ESCGNN_ERR_BAD_ARG;
     if (n_edges <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d_rec) bag_embed_fwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_weight, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_out);
-    else bag_embed_fwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_weight, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_out);
+    if (d_rec) bag_embed_fwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_weight, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_out, d_count);
+    else bag_embed_fwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_weight, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_out, d_count);
     return (int)cudaGetLastError();
 }
 
 int escgnn_bag_embed_bwd(const float* d_grad, int hidden, const int64_t* d_pos_index, const int64_t* d_pos_enc,
                          const int32_t* d_ptr, const uint32_t* d_rec, const int64_t* d_rec_off,
-                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_grad_weight, void* stream) {
+                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_grad_weight, const int* d_count,
+                         void* stream) {
     if (hidden % 4 != 0) return ESCGNN_ERR_BAD_ARG;
     if (n_edges <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d_rec) bag_embed_bwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_grad_weight);
-    else bag_embed_bwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_grad_weight);
+    if (d_rec) bag_embed_bwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_grad_weight, d_count);
+    else bag_embed_bwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_grad_weight, d_count);
     return (int)cudaGetLastError();
 }
 
 int escgnn_gine_aggregate_fwd(const float* d_x, const float* d_edge_feat, const int64_t* d_src, const int32_t* d_dst_ptr,
                               const int32_t* d_dst_perm, const float* d_eps, int64_t n_nodes, int channels,
-                              float* d_out, void* stream) {
+                              float* d_out, const int* d_count, void* stream) {
     if (n_nodes <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (channels % 4 == 0) gine_fwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out);
-    else gine_fwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out);
+    if (channels % 4 == 0) gine_fwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count);
+    else gine_fwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count);
     return (int)cudaGetLastError();
 }
 
 int escgnn_gine_aggregate_bwd(const float* d_grad_out, const float* d_x, const float* d_edge_feat, const int64_t* d_dst,
                               const int32_t* d_src_ptr, const int32_t* d_src_perm, const float* d_eps, int64_t n_nodes,
                               int channels, float* d_grad_x, float* d_grad_edge_feat, float* d_node_dots,
-                              float* d_grad_eps, void* stream) {
+                              float* d_grad_eps, const int* d_count, void* stream) {
     if (n_nodes <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (channels % 4 == 0) gine_bwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots);
-    else gine_bwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots);
+    if (channels % 4 == 0) gine_bwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count);
+    else gine_bwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count);
     if (d_grad_eps) reduce_sum_kernel<<<1, 1024, 0, st>>>(d_node_dots, n_nodes, d_grad_eps, 0);
     return (int)cudaGetLastError();
 }

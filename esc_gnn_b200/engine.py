@@ -1,0 +1,398 @@
+"""Static-shape training engine: the whole hot path of one step as ONE replayable CUDA graph.
+
+    raw graphs (static input buffers) -> E1/E5/E2-E4 encoding -> device collation -> CSR builds ->
+    NestedGIN_eff forward -> loss -> hand-written backward -> (gradient all-reduce) -> Adam
+
+Why: at the reference's batch sizes (256 graphs = ~6k nodes, ~12k edges) a step is a few hundred microseconds of
+GPU work, and an eager autograd step spends >85% of its time in launch latency.  Every buffer here is
+allocated once at a fixed capacity, every kernel reads the actual sizes (nodes, edges, graphs, records) from a
+4-int device array, so the captured graph is valid for every batch and the host does nothing per step but copy the
+raw graphs into the input buffers and replay.
+
+The engine reads and updates the SAME parameters as the drop-in `NestedGIN_eff` module it is built from (they are
+views into FlatAdam's flat buffer), so `state_dict()` / checkpoints stay interchangeable with the reference's
+(run_zinc.py:257-262, run_graphcount.py:464-476).  Forward semantics: zinc_models.py:579-611 and
+run_graphcount.py:134-194; train step: run_zinc.py:266-289.
+
+Dense contractions go through `torch.addmm` / `torch.mm` into preallocated outputs (cuBLAS fp32) in this round;
+everything else is the hand-written sm_100a kernels of csrc/*.cu.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .optim import FlatAdam
+
+ACT = {'none': 0, 'relu': 1, 'elu': 2}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _Ctx(object):
+    """Allocation + launch helpers shared by the tapes."""
+
+    def __init__(self, device, caps):
+        self.dev = device
+        self.caps = dict(caps)                       # 'N', 'E', 'B', 'nnz', 'E_in'
+        self.dims = torch.zeros(4, dtype=torch.int32, device=device)      # N, E, B, nnz
+        self.rows = {'N': self.dims[0:1], 'E': self.dims[1:2], 'B': self.dims[2:3]}
+        tile = _lib.lib().escgnn_dense_tile_rows()
+        max_tiles = (max(self.caps['N'], self.caps['E'], self.caps['B']) + tile - 1) // tile
+        self.partial = torch.zeros(max_tiles * 2 * 2048, dtype=torch.float32, device=device)
+        self.L = _lib.lib()
+
+    def st(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def buf(self, kind, cols, dtype=torch.float32):
+        return torch.zeros((self.caps[kind], cols), dtype=dtype, device=self.dev)
+
+
+class StaticTrainEngine(object):
+    """One NestedGIN_eff variant ('zinc' or 'count') at a fixed capacity."""
+
+    def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
+                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True):
+        if variant not in ('zinc', 'count'):
+            raise NotImplementedError('engine variants: zinc, count (the OGB model runs through the module path)')
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError('StaticTrainEngine needs a CUDA model; there is no CPU fallback')
+        self.model, self.variant, self.flags = model, variant, dict(flags)
+        self.opt = FlatAdam(model.parameters(), lr=lr)
+        self.distributed, self.use_graph = distributed, use_graph
+        dev = p0.device
+        self.G = int(max_graphs)
+        self.max_n, self.max_e = int(max_nodes_per_graph), int(max_edges_per_graph)   # per-graph maxima (after E1)
+        e_in_cap = int(edges_cap)
+        e_cap = e_in_cap + (int(nodes_cap) if flags['self_loop'] else 0)
+        self.c = c = _Ctx(dev, dict(N=int(nodes_cap), E=e_cap, B=self.G, nnz=e_cap * records_per_edge, E_in=e_in_cap))
+        i64 = torch.int64
+        # ---- static input buffers (the only thing the host touches per step)
+        self.in_src = torch.zeros(e_in_cap, dtype=i64, device=dev)
+        self.in_dst = torch.zeros(e_in_cap, dtype=i64, device=dev)
+        self.in_eptr = torch.zeros(self.G + 1, dtype=i64, device=dev)
+        self.in_nptr = torch.zeros(self.G + 1, dtype=i64, device=dev)
+        if variant == 'zinc':
+            self.in_x = torch.zeros(c.caps['N'], dtype=i64, device=dev)
+            self.in_ea = torch.zeros(c.caps['E'], dtype=i64, device=dev)
+            self.in_y = torch.zeros(self.G, dtype=torch.float32, device=dev)
+        else:
+            self.in_x = torch.zeros((c.caps['N'], 10), dtype=torch.float32, device=dev)
+            self.in_ea = None
+            self.in_y = torch.zeros(c.caps['N'], dtype=torch.float32, device=dev)
+        # ---- encoder state
+        self.counters = torch.zeros(_lib.NUM_COUNTERS, dtype=i64, device=dev)
+        if flags['self_loop']:
+            self.eo = torch.zeros((2, e_cap), dtype=i64, device=dev)
+            self.eo_ptr = torch.zeros(self.G + 1, dtype=i64, device=dev)
+            self.rw_tmp = torch.zeros(4 * self.G + 8 * (self.G // 1024 + 2) + 64, dtype=torch.uint8, device=dev)
+        sb = c.L.escgnn_encode_scratch_bytes(self.max_n, self.max_e, flags['h'])
+        if flags['use_rd']:
+            sb = max(sb, c.L.escgnn_encode_rd_scratch_bytes(self.max_n, self.max_e, flags['h']))
+        self.scratch = torch.zeros(max(sb, 16), dtype=torch.uint8, device=dev)
+        self.rdh = torch.zeros((e_cap + 1, _lib.RD_SLOTS), dtype=torch.int16, device=dev) if flags['use_rd'] else None
+        self.rec = torch.zeros(c.caps['nnz'], dtype=torch.int32, device=dev)
+        self.rec_off = torch.zeros(e_cap + 1, dtype=i64, device=dev)
+        self.rec_nnz = torch.zeros(e_cap + 1, dtype=torch.int32, device=dev)
+        self.edge_graph = torch.zeros(e_cap + 1, dtype=torch.int32, device=dev)
+        # ---- collated graph + indices
+        N, E = c.caps['N'], c.caps['E']
+        self.ei = torch.zeros((2, E), dtype=i64, device=dev)
+        self.batch = torch.zeros(N, dtype=i64, device=dev)
+        self.idx_buf = torch.zeros(4 * (N + 1) + 2 * E + 2, dtype=torch.int32, device=dev)
+        b = self.idx_buf
+        self.dst_ptr, self.src_ptr = b[:N + 1], b[N + 1:2 * N + 2]
+        self.tmp_a, self.tmp_b = b[2 * N + 2:3 * N + 3], b[3 * N + 3:4 * N + 4]
+        self.dst_perm, self.src_perm = b[4 * N + 4:4 * N + 4 + E], b[4 * N + 4 + E:4 * N + 4 + 2 * E]
+        self.graph_ptr = torch.zeros(self.G + 1, dtype=torch.int32, device=dev)
+        self.idx_err = torch.zeros(1, dtype=i64, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.fwd, self.bwd = [], []
+        self._build_model_tape()
+        self.graph = None
+        self.steps = 0
+
+    # ------------------------------------------------------------------ primitive ops (append to the tapes)
+    def _linear(self, x, lin, kind, out=None, dx=None, dx_accumulate=False, need_dx=True):
+        """y = x W^T + b over capacity rows.  Returns (y, dy) buffers; backward fills W.grad, b.grad and dx."""
+        c = self.c
+        W, bvec = lin.weight, lin.bias
+        y = out if out is not None else c.buf(kind, W.size(0))
+        dy = c.buf(kind, W.size(0))
+        self.fwd.append(lambda: torch.addmm(bvec, x, W.t(), out=y))
+
+        def back():
+            torch.mm(dy.t(), x, out=W.grad)
+            _lib.check(c.L.escgnn_colsum(_p(dy), dy.stride(0), _p(c.rows[kind]), c.caps[kind], dy.size(1), _p(c.partial),
+                                         _p(bvec.grad), c.st()), 'colsum')
+            if need_dx:
+                if dx_accumulate:
+                    dx.addmm_(dy, W)
+                else:
+                    torch.mm(dy, W, out=dx)
+        self.bwd.append(back)
+        return y, dy
+
+    def _bn_act(self, x, dx, bn, act, kind, out, dout, dout2=None, use_bn=True):
+        """out = act(BN(x)) (training mode).  Backward: dx from dout (+ dout2)."""
+        c = self.c
+        C = x.size(1)
+        if not use_bn:
+            self.fwd.append(lambda: _lib.check(c.L.escgnn_act_fwd(_p(x), x.stride(0), ACT[act], _p(c.rows[kind]),
+                                                                  c.caps[kind], C, _p(out), out.stride(0), c.st()), 'act_fwd'))
+            self.bwd.append(lambda: _lib.check(c.L.escgnn_act_bwd(_p(x), x.stride(0), _p(dout), dout.stride(0), ACT[act],
+                                                                  _p(c.rows[kind]), c.caps[kind], C, _p(dx), dx.stride(0),
+                                                                  c.st()), 'act_bwd'))
+            return
+        mean = torch.zeros(C, dtype=torch.float32, device=c.dev)
+        rstd = torch.ones(C, dtype=torch.float32, device=c.dev)
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_bn_act_fwd(
+            _p(x), x.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(rstd),
+            _p(c.partial), ACT[act], bn.eps, bn.momentum, 1, _p(c.rows[kind]), c.caps[kind], C, _p(out), out.stride(0),
+            c.st()), 'bn_act_fwd'))
+        self.fwd.append(lambda: bn.num_batches_tracked.add_(1))
+        self.bwd.append(lambda: _lib.check(c.L.escgnn_bn_act_bwd(
+            _p(x), x.stride(0), _p(dout), dout.stride(0), _p(dout2), dout2.stride(0) if dout2 is not None else 0, _p(mean),
+            _p(rstd), _p(bn.weight), _p(bn.bias), ACT[act], 1, _p(c.partial), _p(c.rows[kind]), c.caps[kind], C,
+            _p(bn.weight.grad), _p(bn.bias.grad), _p(dx), dx.stride(0), c.st()), 'bn_act_bwd'))
+
+    def _embedding(self, table, idx, kind, out):
+        c = self.c
+        C = table.weight.size(1)
+        cols = 1 if idx.dim() == 1 else idx.size(1)
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_embedding_fwd(_p(table.weight), _p(idx), cols, None, _p(c.rows[kind]),
+                                                                    c.caps[kind], C, _p(out), out.stride(0), c.st()),
+                                           'embedding_fwd'))
+        return C
+
+    def _embedding_bwd(self, table, idx, kind, dout):
+        c = self.c
+        C = table.weight.size(1)
+        cols = 1 if idx.dim() == 1 else idx.size(1)
+        self.bwd.append(lambda: _lib.check(c.L.escgnn_embedding_bwd(_p(dout), dout.stride(0), _p(idx), cols, None,
+                                                                    _p(c.rows[kind]), c.caps[kind], C, _p(table.weight.grad),
+                                                                    c.st()), 'embedding_bwd'))
+
+    def _gine(self, x, dx, ee, dee, eps, out, dout, dx_second=None):
+        """out = (1+eps) x + sum relu(x_src + ee).  Backward writes dx (or dx_second when dx already has an owner)."""
+        c = self.c
+        C = x.size(1)
+        assert x.is_contiguous() or x.stride(0) == C, 'gine kernels read dense rows'
+        dots = torch.zeros(c.caps['N'], dtype=torch.float32, device=c.dev)
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_gine_aggregate_fwd(
+            _p(x), _p(ee), _p(self.ei[0]), _p(self.dst_ptr), _p(self.dst_perm), _p(eps), c.caps['N'], C, _p(out),
+            _p(c.rows['N']), c.st()), 'gine_aggregate_fwd'))
+
+        def back():
+            dee.zero_()                                    # rows past the edge count must stay zero for the weight GEMMs
+            _lib.check(c.L.escgnn_gine_aggregate_bwd(
+                _p(dout), _p(x), _p(ee), _p(self.ei[1]), _p(self.src_ptr), _p(self.src_perm), _p(eps), c.caps['N'], C,
+                _p(dx), _p(dee), _p(dots), _p(eps.grad), _p(c.rows['N']), c.st()), 'gine_aggregate_bwd')
+        self.bwd.append(back)
+
+    # ------------------------------------------------------------------ model tape
+    def _build_model_tape(self):
+        m, c = self.model, self.c
+        H = m.z_initial.weight.size(1)
+        act = 'elu' if self.variant == 'zinc' else 'relu'
+        convs = [m.conv1] + list(m.convs)
+        Lh = len(convs)
+        # node input
+        if self.variant == 'zinc':
+            x0 = c.buf('N', 32)
+            self._embedding(m.node_type_embedding, self.in_x, 'N', x0)
+            dx0 = c.buf('N', 32)
+            self._embedding_bwd(m.node_type_embedding, self.in_x, 'N', dx0)
+            edge_dim = H + 32
+        else:
+            x0, dx0, edge_dim = self.in_x, c.buf('N', 10), H
+        # M1 bag-embed + M2 z_embedding
+        z0, dz0 = c.buf('E', H), c.buf('E', H)
+        W0 = m.z_initial.weight
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_bag_embed_fwd(_p(W0), H, None, None, None, _p(self.rec), _p(self.rec_off),
+                                                                    _p(self.rec_nnz), c.caps['E'], _p(z0), _p(c.rows['E']),
+                                                                    c.st()), 'bag_embed_fwd'))
+        self.bwd.append(lambda: _lib.check(c.L.escgnn_bag_embed_bwd(_p(dz0), H, None, None, None, _p(self.rec), _p(self.rec_off),
+                                                                    _p(self.rec_nnz), c.caps['E'], _p(W0.grad), _p(c.rows['E']),
+                                                                    c.st()), 'bag_embed_bwd'))
+        z1, dz1 = c.buf('E', H), c.buf('E', H)
+        self._bn_act(z0, dz0, m.z_embedding[1], act, 'E', z1, dz1)
+        z2, dz2 = self._linear(z1, m.z_embedding[3], 'E', dx=dz1)
+        zcat, dzcat = c.buf('E', edge_dim), c.buf('E', edge_dim)
+        self._bn_act(z2, dz2, m.z_embedding[5], act, 'E', zcat[:, :H], dzcat[:, :H])
+        if self.variant == 'zinc':
+            self._embedding(m.edge_type_embedding, self.in_ea, 'E', zcat[:, H:])
+            self._embedding_bwd(m.edge_type_embedding, self.in_ea, 'E', dzcat[:, H:])
+        # JK buffer: [x_embedding(x) | x1 .. xL] for count, [x1 .. xL] for zinc
+        jk_slots = Lh + (1 if self.variant == 'count' else 0)
+        xs, dxs = c.buf('N', jk_slots * H), c.buf('N', jk_slots * H)
+        slot0 = 0
+        if self.variant == 'count':       # xs[0] = x_embedding(data.x)   (run_graphcount.py:166)
+            seq = m.x_embedding
+            dxin = c.buf('N', 10)
+            a, da = self._linear(x0, seq[0], 'N', dx=dxin, need_dx=False)
+            b_, db_ = c.buf('N', H), c.buf('N', H)
+            self._bn_act(a, da, seq[2], act, 'N', b_, db_)
+            d_, dd_ = self._linear(b_, seq[4], 'N', dx=db_)
+            self._bn_act(d_, dd_, seq[6], act, 'N', xs[:, 0:H], dxs[:, 0:H])
+            slot0 = 1
+        # M3 GINE layers
+        x_prev, dx_prev = x0, dx0
+        layer_dx_from_next = [None] * Lh          # gradient flowing into layer l's output from layer l+1's aggregation
+        self.fwd.append(lambda: dzcat.zero_())    # every conv.lin backward accumulates into it
+        for l, conv in enumerate(convs):
+            cin = conv.lin.weight.size(0)
+            ee, dee = self._linear(zcat, conv.lin, 'E', dx=dzcat, dx_accumulate=True)
+            agg, dagg = c.buf('N', cin), c.buf('N', cin)
+            # x_prev for l >= 1 is a strided slice of xs: the aggregation kernels want dense rows -> keep a dense copy
+            if l == 0:
+                xin, dxin_buf = x_prev, dx_prev
+            else:
+                xin = c.buf('N', H)
+                src_slice = xs[:, (slot0 + l - 1) * H:(slot0 + l) * H]
+                self.fwd.append(lambda a=xin, b=src_slice: a.copy_(b))
+                dxin_buf = c.buf('N', H)
+                layer_dx_from_next[l - 1] = dxin_buf
+            self._gine(xin, dxin_buf, ee, dee, conv.eps, agg, dagg)
+            seq = conv.nn
+            h1, dh1 = self._linear(agg, seq[0], 'N', dx=dagg)
+            h2, dh2 = c.buf('N', H), c.buf('N', H)
+            self._bn_act(h1, dh1, seq[2], act, 'N', h2, dh2)
+            h3, dh3 = self._linear(h2, seq[4], 'N', dx=dh2)
+            out_slice = xs[:, (slot0 + l) * H:(slot0 + l + 1) * H]
+            dout_slice = dxs[:, (slot0 + l) * H:(slot0 + l + 1) * H]
+            # the last BN of layer l: its backward needs layer l+1's dx, which is only known after the loop wiring;
+            # register forward now, backward through a late-bound closure
+            self._bn_act_late(h3, dh3, seq[6], act, out_slice, dout_slice, layer_dx_from_next, l)
+        # M4 readout
+        if self.variant == 'zinc':
+            pooled, dpooled = c.buf('B', Lh * H), c.buf('B', Lh * H)
+            self.fwd.append(lambda: _lib.check(c.L.escgnn_segment_pool_fwd(_p(xs), _p(self.graph_ptr), self.G, Lh * H, 0,
+                                                                           _p(pooled), c.st()), 'segment_pool_fwd'))
+            self.bwd.append(lambda: _lib.check(c.L.escgnn_segment_pool_bwd(_p(dpooled), _p(self.graph_ptr), self.G, Lh * H, 0,
+                                                                           _p(dxs), c.st()), 'segment_pool_bwd'))
+            head_in, dhead_in, kind = pooled, dpooled, 'B'
+        else:
+            head_in, dhead_in, kind = xs, dxs, 'N'
+        p1, dp1 = self._linear(head_in, m.lin1, kind, dx=dhead_in)
+        p2, dp2 = c.buf(kind, H), c.buf(kind, H)
+        self._bn_act(p1, dp1, m.bn_lin1, act, kind, p2, dp2, use_bn=(self.G > 1 or kind == 'N'))
+        pred, dpred = self._linear(p2, m.lin2, kind, dx=dp2)
+        self.pred = pred
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_loss_fwd_bwd(_p(pred), pred.stride(0), _p(self.in_y), 0, _p(c.rows[kind]),
+                                                                   c.caps[kind], 1, _p(self.loss), _p(dpred), dpred.stride(0),
+                                                                   c.st()), 'loss_fwd_bwd'))
+
+    def _bn_act_late(self, x, dx, bn, act, out, dout, dx_from_next, l):
+        """Like _bn_act, but the second gradient source (next layer's aggregation) is resolved when the tape runs."""
+        c = self.c
+        C = x.size(1)
+        mean = torch.zeros(C, dtype=torch.float32, device=c.dev)
+        rstd = torch.ones(C, dtype=torch.float32, device=c.dev)
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_bn_act_fwd(
+            _p(x), x.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(rstd),
+            _p(c.partial), ACT[act], bn.eps, bn.momentum, 1, _p(c.rows['N']), c.caps['N'], C, _p(out), out.stride(0),
+            c.st()), 'bn_act_fwd'))
+        self.fwd.append(lambda: bn.num_batches_tracked.add_(1))
+
+        def back():
+            d2 = dx_from_next[l]
+            _lib.check(c.L.escgnn_bn_act_bwd(
+                _p(x), x.stride(0), _p(dout), dout.stride(0), _p(d2), d2.stride(0) if d2 is not None else 0, _p(mean), _p(rstd),
+                _p(bn.weight), _p(bn.bias), ACT[act], 1, _p(c.partial), _p(c.rows['N']), c.caps['N'], C, _p(bn.weight.grad),
+                _p(bn.bias.grad), _p(dx), dx.stride(0), c.st()), 'bn_act_bwd')
+        self.bwd.append(back)
+
+    # ------------------------------------------------------------------ one step
+    def _encode_and_index(self):
+        c, L, fl, G = self.c, self.c.L, self.flags, self.G
+        st = c.st()
+        self.counters.zero_()
+        if fl['self_loop']:
+            _lib.check(L.escgnn_rewrite_self_loops(_p(self.in_src), _p(self.in_dst), _p(self.in_eptr), _p(self.in_nptr), G,
+                                                   _p(self.eo_ptr), _p(self.eo[0]), _p(self.eo[1]), _p(self.rw_tmp), st),
+                       'rewrite_self_loops')
+            es, ed, ep = self.eo[0], self.eo[1], self.eo_ptr
+        else:
+            es, ed, ep = self.in_src, self.in_dst, self.in_eptr
+        if fl['use_rd']:
+            _lib.check(L.escgnn_encode_rd(_p(es), _p(ed), _p(ep), _p(self.in_nptr), G, fl['h'], _p(self.rdh), _p(self.counters),
+                                          self.max_n, self.max_e, _p(self.scratch), self.scratch.numel(), st), 'encode_rd')
+        _lib.check(L.escgnn_encode(_p(es), _p(ed), _p(ep), _p(self.in_nptr), G, fl['h'], _p(self.rdh), _p(self.rec),
+                                   self.rec.numel(), _p(self.rec_off), _p(self.rec_nnz), _p(self.edge_graph),
+                                   _p(self.counters), self.max_n, self.max_e, _p(self.scratch), self.scratch.numel(), st),
+                   'encode')
+        _lib.check(L.escgnn_make_dims(_p(ep), _p(self.in_nptr), G, _p(self.counters), _p(c.dims), st), 'make_dims')
+        N, E = c.caps['N'], c.caps['E']
+        _lib.check(L.escgnn_collate_edges(_p(es), _p(ed), _p(self.edge_graph), _p(self.in_nptr), E, _p(self.ei[0]),
+                                          _p(self.ei[1]), _p(c.rows['E']), st), 'collate_edges')
+        _lib.check(L.escgnn_ptr_to_ids(_p(self.in_nptr), G, N, _p(self.batch), _p(c.rows['N']), st), 'ptr_to_ids')
+        _lib.check(L.escgnn_csr_build(_p(self.ei[1]), E, N, _p(self.dst_ptr), _p(self.dst_perm), _p(self.tmp_a),
+                                      _p(self.idx_err), _p(c.rows['E']), st), 'csr_build')
+        _lib.check(L.escgnn_csr_build(_p(self.ei[0]), E, N, _p(self.src_ptr), _p(self.src_perm), _p(self.tmp_b),
+                                      _p(self.idx_err), _p(c.rows['E']), st), 'csr_build')
+        _lib.check(L.escgnn_sorted_ids_to_ptr(_p(self.batch), N, G, _p(self.graph_ptr), _p(c.rows['N']), st),
+                   'sorted_ids_to_ptr')
+
+    def _run(self):
+        """The whole step as a fixed launch sequence (run eagerly, or captured once and replayed)."""
+        self._encode_and_index()
+        self.opt.grad.zero_()
+        for f in self.fwd:
+            f()
+        for b in reversed(self.bwd):
+            b()
+        if self.distributed:
+            self.opt.all_reduce_grads()
+        self.opt.step_device()
+
+    def load(self, raw):
+        """Copy one RawBatch (pinned host or device) into the static input buffers (async on the current stream)."""
+        e, g = raw.src.numel(), raw.num_graphs
+        if g != self.G:
+            raise ValueError('engine built for %d graphs per step, got %d' % (self.G, g))
+        if e > self.c.caps['E_in'] or raw.num_nodes > self.c.caps['N'] or raw.max_nodes > self.max_n or \
+                (raw.max_loop_edges if self.flags['self_loop'] else raw.max_in_edges) > self.max_e:
+            raise ValueError('batch exceeds the engine capacity')
+        self.in_src[:e].copy_(raw.src, non_blocking=True)
+        self.in_dst[:e].copy_(raw.dst, non_blocking=True)
+        self.in_eptr.copy_(raw.edge_ptr, non_blocking=True)
+        self.in_nptr.copy_(raw.node_ptr, non_blocking=True)
+        n = raw.num_nodes
+        self.in_x[:n].copy_(raw.x, non_blocking=True)
+        if self.in_ea is not None:
+            self.in_ea[:raw.edge_attr.size(0)].copy_(raw.edge_attr, non_blocking=True)
+        self.in_y[:raw.y.numel()].copy_(raw.y.view(-1), non_blocking=True)
+
+    def step(self, raw):
+        """One full step on `raw`; returns the loss as a device tensor (read it with .item() when needed)."""
+        world = 1
+        if self.distributed:
+            import torch.distributed as dist
+            world = dist.get_world_size()
+        self.opt.sync_hyper(world)
+        self.load(raw)
+        if not self.use_graph or self.steps < 2:     # eager warm-up (cuBLAS handles / workspaces) before the capture
+            self._run()
+        else:
+            if self.graph is None:
+                torch.cuda.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._run()
+            self.graph.replay()
+        self.steps += 1
+        return self.loss
+
+    def check_errors(self):
+        """Lazy data-error check (degree >= 200, bad ids, capacity): one sync, call it once per epoch."""
+        cnt = self.counters.cpu()
+        _lib.raise_data_errors(int(cnt[1]))
+        if int(cnt[0]) > self.rec.numel():
+            raise RuntimeError('engine record capacity exceeded: %d > %d' % (int(cnt[0]), self.rec.numel()))
+        if int(self.idx_err.cpu()[0]):
+            raise RuntimeError('edge_index out of range after collation')

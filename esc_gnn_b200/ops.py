@@ -61,13 +61,13 @@ class GraphIndex(object):
         self.dst_perm, self.src_perm = buf[4 * N + 4:4 * N + 4 + E], buf[4 * N + 4 + E:4 * N + 4 + 2 * E]
         self.err = torch.zeros(1, dtype=torch.int64, device=dev)
         _lib.check(L.escgnn_csr_build(_p(self.dst), E, N, _p(self.dst_ptr), _p(self.dst_perm), _p(tmp_a),
-                                      _p(self.err), st), 'csr_build')
+                                      _p(self.err), None, st), 'csr_build')
         _lib.check(L.escgnn_csr_build(_p(self.src), E, N, _p(self.src_ptr), _p(self.src_perm), _p(tmp_b),
-                                      _p(self.err), st), 'csr_build')
+                                      _p(self.err), None, st), 'csr_build')
         self.rec_ptr = None
         if pos_batch is not None:
             self.rec_ptr = torch.empty(E + 1, dtype=torch.int32, device=dev)
-            _lib.check(L.escgnn_sorted_ids_to_ptr(_p(pos_batch), pos_batch.numel(), E, _p(self.rec_ptr), st),
+            _lib.check(L.escgnn_sorted_ids_to_ptr(_p(pos_batch), pos_batch.numel(), E, _p(self.rec_ptr), None, st),
                        'sorted_ids_to_ptr')
         self.graph_ptr, self.num_graphs = None, None
         if batch is not None:
@@ -75,7 +75,8 @@ class GraphIndex(object):
                 num_graphs = int(batch[-1]) + 1          # the reference's own sync (PyG global_add_pool)
             self.num_graphs = int(num_graphs)
             self.graph_ptr = torch.empty(self.num_graphs + 1, dtype=torch.int32, device=dev)
-            _lib.check(L.escgnn_sorted_ids_to_ptr(_p(batch), batch.numel(), self.num_graphs, _p(self.graph_ptr), st),
+            _lib.check(L.escgnn_sorted_ids_to_ptr(_p(batch), batch.numel(), self.num_graphs, _p(self.graph_ptr), None,
+                                                  st),
                        'sorted_ids_to_ptr')
 
 
@@ -118,7 +119,7 @@ class _BagEmbed(torch.autograd.Function):
         w = weight.contiguous()
         with _span('bag_embed_fwd'):
             _lib.check(_lib.lib().escgnn_bag_embed_fwd(_p(w), H, _p(pos_index), _p(pos_enc), _p(rec_ptr), None, None, None,
-                                                       n_edges, _p(out), _stream(w)), 'bag_embed_fwd')
+                                                       n_edges, _p(out), None, _stream(w)), 'bag_embed_fwd')
         ctx.save_for_backward(pos_index, pos_enc, rec_ptr)
         ctx.shape = tuple(weight.shape)
         return out
@@ -130,7 +131,7 @@ class _BagEmbed(torch.autograd.Function):
         dW = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
         with _span('bag_embed_bwd'):
             _lib.check(_lib.lib().escgnn_bag_embed_bwd(_p(g), ctx.shape[1], _p(pos_index), _p(pos_enc), _p(rec_ptr), None,
-                                                       None, None, g.size(0), _p(dW), _stream(g)), 'bag_embed_bwd')
+                                                       None, None, g.size(0), _p(dW), None, _stream(g)), 'bag_embed_bwd')
         return dW, None, None, None, None
 
 
@@ -144,7 +145,7 @@ class _BagEmbedRec(torch.autograd.Function):
         w = weight.contiguous()
         with _span('bag_embed_fwd'):
             _lib.check(_lib.lib().escgnn_bag_embed_fwd(_p(w), H, None, None, None, _p(rec), _p(rec_off), _p(rec_nnz),
-                                                       n_edges, _p(out), _stream(w)), 'bag_embed_fwd')
+                                                       n_edges, _p(out), None, _stream(w)), 'bag_embed_fwd')
         ctx.save_for_backward(rec, rec_off, rec_nnz)
         ctx.shape = tuple(weight.shape)
         return out
@@ -156,7 +157,7 @@ class _BagEmbedRec(torch.autograd.Function):
         dW = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
         with _span('bag_embed_bwd'):
             _lib.check(_lib.lib().escgnn_bag_embed_bwd(_p(g), ctx.shape[1], None, None, None, _p(rec), _p(rec_off),
-                                                       _p(rec_nnz), g.size(0), _p(dW), _stream(g)), 'bag_embed_bwd')
+                                                       _p(rec_nnz), g.size(0), _p(dW), None, _stream(g)), 'bag_embed_bwd')
         return dW, None, None, None, None
 
 
@@ -183,7 +184,7 @@ class _GineAggregate(torch.autograd.Function):
         out = torch.empty_like(x)
         with _span('gine_aggregate_fwd'):
             _lib.check(_lib.lib().escgnn_gine_aggregate_fwd(_p(x), _p(edge_feat), _p(index.src), _p(index.dst_ptr),
-                                                            _p(index.dst_perm), _p(eps), N, C, _p(out), _stream(x)),
+                                                            _p(index.dst_perm), _p(eps), N, C, _p(out), None, _stream(x)),
                        'gine_aggregate_fwd')
         ctx.save_for_backward(x, edge_feat, eps)
         ctx.index = index
@@ -202,7 +203,7 @@ class _GineAggregate(torch.autograd.Function):
         with _span('gine_aggregate_bwd'):
             _lib.check(_lib.lib().escgnn_gine_aggregate_bwd(_p(g), _p(x), _p(edge_feat), _p(index.dst), _p(index.src_ptr),
                                                             _p(index.src_perm), _p(eps), N, C, _p(gx), _p(ge), _p(dots),
-                                                            _p(geps), _stream(x)), 'gine_aggregate_bwd')
+                                                            _p(geps), None, _stream(x)), 'gine_aggregate_bwd')
         return gx, ge, geps, None
 
 

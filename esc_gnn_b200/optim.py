@@ -32,6 +32,10 @@ class FlatAdam(object):
             off += s + q
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
         self.param_groups = [dict(lr=lr)]
+        # device-side hyper-parameters / step counter (graph-capturable path)
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, 1.0, 1.0, 1.0, 0.0], dtype=torch.float32, device=dev)
+        self.state = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._hyper_host = (lr, 1.0)
 
     def zero_grad(self, set_to_none=False):
         self.grad.zero_()
@@ -48,6 +52,22 @@ class FlatAdam(object):
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
             return dist.get_world_size(group)
         return 1
+
+    def step_device(self, world_size=1):
+        """Adam with the step counter in device memory: identical launches every step, safe inside a CUDA graph.
+        (A learning-rate or world-size change is pushed with one small copy OUTSIDE the captured region.)"""
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().escgnn_adam_step_device(P(self.flat), P(self.grad), P(self.exp_avg), P(self.exp_avg_sq),
+                                                      self.flat.numel(), P(self.hyper), P(self.state), st),
+                   'adam_step_device')
+
+    def sync_hyper(self, world_size=1):
+        want = (self.param_groups[0]['lr'], 1.0 / world_size)
+        if want != self._hyper_host:
+            self.hyper[0] = want[0]
+            self.hyper[4] = want[1]
+            self._hyper_host = want
 
     def step(self, world_size=1):
         self.t += 1

@@ -83,9 +83,9 @@ def encode_and_collate(raw, h, use_rd, self_loop, timings=None):
     st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     ei = torch.empty((2, E), dtype=torch.int64, device=dev)
     _lib.check(L.escgnn_collate_edges(_p(r.edge_index[0]), _p(r.edge_index[1]), _p(r.edge_graph), _p(raw.node_ptr), E,
-                                      _p(ei[0]), _p(ei[1]), st), 'collate_edges')
+                                      _p(ei[0]), _p(ei[1]), None, st), 'collate_edges')
     batch = torch.empty(raw.num_nodes, dtype=torch.int64, device=dev)
-    _lib.check(L.escgnn_ptr_to_ids(_p(raw.node_ptr), raw.num_graphs, raw.num_nodes, _p(batch), st), 'ptr_to_ids')
+    _lib.check(L.escgnn_ptr_to_ids(_p(raw.node_ptr), raw.num_graphs, raw.num_nodes, _p(batch), None, st), 'ptr_to_ids')
     edge_attr = raw.edge_attr
     if self_loop and edge_attr is not None:          # E1 on attributes: synthetic graphs carry no loops
         tail = edge_attr.new_full((raw.num_nodes, ) + tuple(edge_attr.shape[1:]), 1)

@@ -105,16 +105,20 @@ int escgnn_encode_host_fetch(escgnn_ctx* ctx, int64_t* h_eo_src, int64_t* h_eo_d
 int escgnn_encode_host_device_results(escgnn_ctx* ctx, const uint32_t** d_rec, const int64_t** d_rec_off,
                                       const int32_t** d_rec_nnz, const int64_t** d_eo_src, const int64_t** d_eo_dst);
 
-/* ================= model step; fp32, row-major, device pointers ======== */
+/* ================= model step; fp32, row-major, device pointers ========
+ * Static-shape convention: where an entry point takes `const int* d_count` (may be NULL), the size argument before
+ * it is a CAPACITY and the actual count is read from device memory, so one captured CUDA graph serves every batch;
+ * rows between the count and the capacity are written as zeros. */
 
 /* Deterministic CSR of an int64 key vector (edge_index[1] for the forward aggregation, edge_index[0] for the
  * backward): d_ptr[n_nodes+1], d_perm[n_edges] = edge ids grouped by key, ascending inside a group.
  * d_tmp: n_nodes+1 int32 scratch. d_err (optional): bit 0 set when a key is outside [0, n_nodes). */
 int escgnn_csr_build(const int64_t* d_keys, int64_t n_edges, int64_t n_nodes, int32_t* d_ptr, int32_t* d_perm,
-                     int32_t* d_tmp, unsigned long long* d_err, void* stream);
+                     int32_t* d_tmp, unsigned long long* d_err, const int* d_count, void* stream);
 /* Segment pointers of a sorted id vector (pos_batch -> per-edge record ranges, batch -> per-graph node ranges;
  * replaces the `int(batch.max())+1` + scatter bookkeeping of PyG global_add_pool). d_ptr[n_segments+1]. */
-int escgnn_sorted_ids_to_ptr(const int64_t* d_ids, int64_t n, int64_t n_segments, int32_t* d_ptr, void* stream);
+int escgnn_sorted_ids_to_ptr(const int64_t* d_ids, int64_t n, int64_t n_segments, int32_t* d_ptr, const int* d_count,
+                             void* stream);
 
 /* M1 sparse bag-embed.  Replaces global_add_pool(z_initial.weight[pos_index] * pos_enc[:,None], pos_batch)
  * (run_graphcount.py:155, zinc_models.py:590, ogb_mol_gnn.py:716) without the [nnz,H] intermediate.
@@ -123,10 +127,11 @@ int escgnn_sorted_ids_to_ptr(const int64_t* d_ids, int64_t n, int64_t n_segments
  * bwd accumulates into d_grad_weight [1800,hidden] (caller zeroes it). */
 int escgnn_bag_embed_fwd(const float* d_weight, int hidden, const int64_t* d_pos_index, const int64_t* d_pos_enc,
                          const int32_t* d_ptr, const uint32_t* d_rec, const int64_t* d_rec_off,
-                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_out, void* stream);
+                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_out, const int* d_count, void* stream);
 int escgnn_bag_embed_bwd(const float* d_grad, int hidden, const int64_t* d_pos_index, const int64_t* d_pos_enc,
                          const int32_t* d_ptr, const uint32_t* d_rec, const int64_t* d_rec_off,
-                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_grad_weight, void* stream);
+                         const int32_t* d_rec_nnz, int64_t n_edges, float* d_grad_weight, const int* d_count,
+                         void* stream);
 
 /* M3 GINE aggregation.  Replaces PyG GINEConv.propagate + the (1+eps)*x residual (in-tree twin:
  * GraphGPS/graphgps/layer/gine_conv_layer.py:56-84; ogb_mol_gnn.py:346-358):
@@ -136,11 +141,11 @@ int escgnn_bag_embed_bwd(const float* d_grad, int hidden, const int64_t* d_pos_i
  * d_grad_eps[0] (optional). */
 int escgnn_gine_aggregate_fwd(const float* d_x, const float* d_edge_feat, const int64_t* d_src, const int32_t* d_dst_ptr,
                               const int32_t* d_dst_perm, const float* d_eps, int64_t n_nodes, int channels,
-                              float* d_out, void* stream);
+                              float* d_out, const int* d_count, void* stream);
 int escgnn_gine_aggregate_bwd(const float* d_grad_out, const float* d_x, const float* d_edge_feat, const int64_t* d_dst,
                               const int32_t* d_src_ptr, const int32_t* d_src_perm, const float* d_eps, int64_t n_nodes,
                               int channels, float* d_grad_x, float* d_grad_edge_feat, float* d_node_dots,
-                              float* d_grad_eps, void* stream);
+                              float* d_grad_eps, const int* d_count, void* stream);
 
 /* M4 pooling over the sorted `batch` vector.  Replaces global_add_pool / global_mean_pool
  * (run_graphcount.py:179, zinc_models.py:602, ogb_mol_gnn.py:124,768). mean divides by max(count,1). */
@@ -161,12 +166,56 @@ int escgnn_edge_distance(const float* d_pos, int dim, const int64_t* d_row, cons
  * the gradient first (1/world_size after a sum all-reduce). */
 int escgnn_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, float lr,
                      float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+/* same update with the step counter and hyper-parameters in device memory (graph-capturable):
+ * d_hyper[7] = {lr, beta1, beta2, eps, grad_scale, bc1 (out), sqrt(bc2) (out)}, d_state[1] = step (incremented). n % 4 == 0. */
+int escgnn_adam_step_device(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                            float* d_hyper, long long* d_state, void* stream);
 
 /* B1 collation on the device (reference batch.py:52-123 + Data.__inc__): shift graph-local edge ids by the
  * graph's node offset (d_edge_graph from escgnn_encode), and expand node_ptr into the `batch` vector. */
 int escgnn_collate_edges(const int64_t* d_src, const int64_t* d_dst, const int32_t* d_edge_graph,
-                         const int64_t* d_node_ptr, int64_t n_edges, int64_t* d_out_src, int64_t* d_out_dst, void* stream);
-int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64_t* d_ids, void* stream);
+                         const int64_t* d_node_ptr, int64_t n_edges, int64_t* d_out_src, int64_t* d_out_dst,
+                         const int* d_count, void* stream);
+int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64_t* d_ids, const int* d_count,
+                      void* stream);
+/* d_dims[4] = {total nodes, total edges after E1, graphs, records}: the device-side sizes the static-shape
+ * entry points read through their d_count / d_rows arguments (no host sync between encoder and model). */
+int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t n_graphs,
+                     const unsigned long long* d_counters, int* d_dims, void* stream);
+
+/* ---- dense row-wise kernels of the static-shape engine (M2, M4, M5); `d_rows` = actual row count on the device,
+ * rows_cap = capacity; ld* = leading dimensions (outputs can be column slices of a wider buffer = free concat) ---- */
+int escgnn_dense_tile_rows(void);     /* rows per reduction tile: d_partial needs ceil(rows_cap/tile) * 2 * channels floats */
+/* training-mode BatchNorm1d + activation (act: 0 none, 1 ReLU, 2 ELU). Replaces the BN,act pairs of
+ * nn.Sequential(Linear,Dropout,BN,act,...) (run_graphcount.py:54-61,78-87; zinc_models.py:513-522). Updates the
+ * running statistics like torch (momentum, unbiased variance); saves mean / rstd for the backward. */
+int escgnn_bn_act_fwd(const float* d_x, int ldx, const float* d_gamma, const float* d_beta, float* d_running_mean,
+                      float* d_running_var, float* d_mean, float* d_rstd, float* d_partial, int act, float eps,
+                      float momentum, int training, const int* d_rows, int rows_cap, int channels, float* d_y, int ldy,
+                      void* stream);
+/* backward through activation + BatchNorm; the incoming gradient is d_dy (+ d_dy2 when not NULL: the second
+ * consumer of a concatenated layer output). Writes d_dx, d_dgamma, d_dbeta. */
+int escgnn_bn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, const float* d_dy2, int lddy2,
+                      const float* d_mean, const float* d_rstd, const float* d_gamma, const float* d_beta, int act,
+                      int training, float* d_partial, const int* d_rows, int rows_cap, int channels, float* d_dgamma,
+                      float* d_dbeta, float* d_dx, int lddx, void* stream);
+int escgnn_act_fwd(const float* d_x, int ldx, int act, const int* d_rows, int rows_cap, int channels, float* d_y, int ldy,
+                   void* stream);
+int escgnn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, int act, const int* d_rows, int rows_cap,
+                   int channels, float* d_dx, int lddx, void* stream);
+/* ordered column sum over the valid rows (bias gradients of nn.Linear) */
+int escgnn_colsum(const float* d_x, int ldx, const int* d_rows, int rows_cap, int channels, float* d_partial, float* d_out,
+                  void* stream);
+/* sum of per-column embeddings: y[r] = sum_k table[idx[r,k] + col_offsets[k]] (nn.Embedding when idx_cols == 1;
+ * AtomEncoder / BondEncoder of ogb_mol_gnn.py:264-282 otherwise); bwd accumulates into d_dtable (caller zeroes) */
+int escgnn_embedding_fwd(const float* d_table, const int64_t* d_idx, int idx_cols, const int64_t* d_col_offsets,
+                         const int* d_rows, int rows_cap, int channels, float* d_y, int ldy, void* stream);
+int escgnn_embedding_bwd(const float* d_dy, int lddy, const int64_t* d_idx, int idx_cols, const int64_t* d_col_offsets,
+                         const int* d_rows, int rows_cap, int channels, float* d_dtable, void* stream);
+/* loss + its gradient: kind 0 = L1Loss mean (run_graphcount.py:498, run_zinc.py:283); kind 1 = BCEWithLogitsLoss
+ * over labelled targets y == y (run_ogb_mol.py:58-74) */
+int escgnn_loss_fwd_bwd(const float* d_pred, int ldp, const float* d_target, int kind, const int* d_rows, int rows_cap,
+                        int n_targets, float* d_loss, float* d_dpred, int lddp, void* stream);
 
 #ifdef __cplusplus
 }
