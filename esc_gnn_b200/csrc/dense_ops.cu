@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ partial, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* running_mean, float* running_var, float* __restrict__ mean_out,
                   float* __restrict__ rstd_out, int act, float eps, float momentum, int training,
-                  const int* __restrict__ d_rows, int C, float* __restrict__ y, int ldy) {
+                  const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ y, int ldy) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
+    const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = min(*d_rows, rows_cap);
     const int tiles = (rows + kTileRows - 1) / kTileRows;
     float mean = 0.f, rstd = 1.f, g = 1.f, bt = 0.f;
     if (c < C) {
@@ -89,7 +89,7 @@ bn_act_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
     }
     if (c >= C) return;
     const float sc = rstd * g, sh = bt - mean * sc;
-    for (int r = r0 + warp; r < r0 + kTileRows; r += 8) {
+    for (int r = r0 + warp; r < min(r0 + kTileRows, rows_cap); r += 8) {
         float o = 0.f;
         if (r < rows) o = act_fwd(x[(size_t)r * ldx + c] * sc + sh, act);
         y[(size_t)r * ldy + c] = o;               // rows >= actual count are zeroed (inert in the next GEMM)
@@ -126,10 +126,11 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy,
                         const float* __restrict__ dy2, int lddy2, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                        int act, int training, const float* __restrict__ partial, const int* __restrict__ d_rows, int C,
-                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx, int lddx) {
+                        int act, int training, const float* __restrict__ partial, const int* __restrict__ d_rows,
+                        int rows_cap, int C, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx,
+                        int lddx) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
+    const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = min(*d_rows, rows_cap);
     if (c >= C) return;
     const int tiles = (rows + kTileRows - 1) / kTileRows;
     float s1 = 0.f, s2 = 0.f;
@@ -138,7 +139,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ x, int ldx, const float* __res
     const float mu = mean[c], rs = rstd[c], g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
     const float inv_m = training ? 1.f / (float)max(rows, 1) : 0.f;
     const float m1 = s1 * inv_m, m2 = s2 * inv_m, k = g * rs;
-    for (int r = r0 + warp; r < r0 + kTileRows; r += 8) {
+    for (int r = r0 + warp; r < min(r0 + kTileRows, rows_cap); r += 8) {
         float o = 0.f;
         if (r < rows) {
             const float xhat = (x[(size_t)r * ldx + c] - mu) * rs;
@@ -153,19 +154,20 @@ bn_act_bwd_apply_kernel(const float* __restrict__ x, int ldx, const float* __res
 
 // activation only (no BatchNorm): y = act(x), rows beyond the count zeroed; backward: dx = dy * act'(x)
 __global__ void __launch_bounds__(256)
-act_fwd_kernel(const float* __restrict__ x, int ldx, int act, const int* __restrict__ d_rows, int C, float* __restrict__ y, int ldy) {
+act_fwd_kernel(const float* __restrict__ x, int ldx, int act, const int* __restrict__ d_rows, int rows_cap, int C,
+               float* __restrict__ y, int ldy) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
+    const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = min(*d_rows, rows_cap);
     if (c >= C) return;
-    for (int r = r0 + warp; r < r0 + kTileRows; r += 8) y[(size_t)r * ldy + c] = r < rows ? act_fwd(x[(size_t)r * ldx + c], act) : 0.f;
+    for (int r = r0 + warp; r < min(r0 + kTileRows, rows_cap); r += 8) y[(size_t)r * ldy + c] = r < rows ? act_fwd(x[(size_t)r * ldx + c], act) : 0.f;
 }
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy, int act,
-               const int* __restrict__ d_rows, int C, float* __restrict__ dx, int lddx) {
+               const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ dx, int lddx) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
+    const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = min(*d_rows, rows_cap);
     if (c >= C) return;
-    for (int r = r0 + warp; r < r0 + kTileRows; r += 8)
+    for (int r = r0 + warp; r < min(r0 + kTileRows, rows_cap); r += 8)
         dx[(size_t)r * lddx + c] = r < rows ? dy[(size_t)r * lddy + c] * act_grad(x[(size_t)r * ldx + c], act) : 0.f;
 }
 
@@ -264,7 +266,7 @@ int escgnn_bn_act_fwd(const float* d_x, int ldx, const float* d_gamma, const flo
     const dim3 g = tile_grid(rows_cap, channels);
     if (training) colstats_kernel<<<g, 256, 0, st>>>(d_x, ldx, d_rows, channels, d_partial);
     bn_act_fwd_kernel<<<g, 256, 0, st>>>(d_x, ldx, d_partial, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd,
-                                         act, eps, momentum, training, d_rows, channels, d_y, ldy);
+                                         act, eps, momentum, training, d_rows, rows_cap, channels, d_y, ldy);
     return (int)cudaGetLastError();
 }
 
@@ -277,19 +279,19 @@ int escgnn_bn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, co
     bn_act_bwd_reduce_kernel<<<g, 256, 0, st>>>(d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
                                                 d_rows, channels, d_partial);
     bn_act_bwd_apply_kernel<<<g, 256, 0, st>>>(d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
-                                               training, d_partial, d_rows, channels, d_dgamma, d_dbeta, d_dx, lddx);
+                                               training, d_partial, d_rows, rows_cap, channels, d_dgamma, d_dbeta, d_dx, lddx);
     return (int)cudaGetLastError();
 }
 
 int escgnn_act_fwd(const float* d_x, int ldx, int act, const int* d_rows, int rows_cap, int channels, float* d_y, int ldy,
                    void* stream) {
-    act_fwd_kernel<<<tile_grid(rows_cap, channels), 256, 0, (cudaStream_t)stream>>>(d_x, ldx, act, d_rows, channels, d_y, ldy);
+    act_fwd_kernel<<<tile_grid(rows_cap, channels), 256, 0, (cudaStream_t)stream>>>(d_x, ldx, act, d_rows, rows_cap, channels, d_y, ldy);
     return (int)cudaGetLastError();
 }
 
 int escgnn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, int act, const int* d_rows, int rows_cap,
                    int channels, float* d_dx, int lddx, void* stream) {
-    act_bwd_kernel<<<tile_grid(rows_cap, channels), 256, 0, (cudaStream_t)stream>>>(d_x, ldx, d_dy, lddy, act, d_rows, channels, d_dx, lddx);
+    act_bwd_kernel<<<tile_grid(rows_cap, channels), 256, 0, (cudaStream_t)stream>>>(d_x, ldx, d_dy, lddy, act, d_rows, rows_cap, channels, d_dx, lddx);
     return (int)cudaGetLastError();
 }
 

@@ -283,6 +283,8 @@ class StaticTrainEngine(object):
         self._bn_act(p1, dp1, m.bn_lin1, act, kind, p2, dp2, use_bn=(self.G > 1 or kind == 'N'))
         pred, dpred = self._linear(p2, m.lin2, kind, dx=dp2)
         self.pred = pred
+        self.debug_buffers = dict(head_in=head_in, dhead_in=dhead_in, p1=p1, dp1=dp1, p2=p2, dp2=dp2, pred=pred, dpred=dpred,
+                                  xs=xs, dxs=dxs, zcat=zcat, dzcat=dzcat)
         self.fwd.append(lambda: _lib.check(c.L.escgnn_loss_fwd_bwd(_p(pred), pred.stride(0), _p(self.in_y), 0, _p(c.rows[kind]),
                                                                    c.caps[kind], 1, _p(self.loss), _p(dpred), dpred.stride(0),
                                                                    c.st()), 'loss_fwd_bwd'))
@@ -338,6 +340,7 @@ class StaticTrainEngine(object):
         _lib.check(L.escgnn_sorted_ids_to_ptr(_p(self.batch), N, G, _p(self.graph_ptr), _p(c.rows['N']), st),
                    'sorted_ids_to_ptr')
 
+    @torch.no_grad()
     def _run(self):
         """The whole step as a fixed launch sequence (run eagerly, or captured once and replayed)."""
         self._encode_and_index()
