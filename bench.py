@@ -141,7 +141,8 @@ def run_own(args):
     import torch
     import torch.distributed as dist
     from esc_gnn_b200 import _lib, ops, synth, zinc_model
-    from esc_gnn_b200.pipeline import RawBatch, TrainPipeline
+    from esc_gnn_b200.engine import StaticTrainEngine
+    from esc_gnn_b200.pipeline import RawBatch
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -156,11 +157,13 @@ def run_own(args):
     torch.manual_seed(0)
     model = zinc_model.NestedGIN_eff(None, LAYERS).cuda()
     model.train()
-    loss_fn = lambda pred, y: torch.nn.functional.l1_loss(pred, y.view(-1, 1))
-    pipe = TrainPipeline(model, loss_fn, fl['h'], fl['use_rd'], fl['self_loop'], lr=LR, distributed=world > 1)
     n_pool = min(args.steps + args.warmup, 12)
     host_pool = [RawBatch.synth(CONFIG, rank * 1_000_000 + i * BATCH, BATCH) for i in range(n_pool)]
     dev_pool = [b.cuda(non_blocking=False) for b in host_pool]
+    nodes_cap = int(max(b.num_nodes for b in host_pool) * 1.04) + 64
+    edges_cap = int(max(b.src.numel() for b in host_pool) * 1.04) + 128
+    eng = StaticTrainEngine(model, 'zinc', fl, max_graphs=BATCH, max_nodes_per_graph=40, max_edges_per_graph=96,
+                            nodes_cap=nodes_cap, edges_cap=edges_cap, lr=LR, distributed=world > 1, use_graph=True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')     # > 126 MB L2
 
     def barrier():
@@ -169,13 +172,13 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, pool, k_steps, timings):
+    def timed(step_fn, pool, k_steps):
         evs = []
         for i in range(k_steps):
             flush.zero_()                                   # L2 flush between timed iterations (untimed)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            step_fn(pool[i % len(pool)], timings)
+            step_fn(pool[i % len(pool)])
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
@@ -188,53 +191,69 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    for i in range(max(args.warmup, 3)):                    # W >= 3 warm-up steps
-        pipe.step_device(dev_pool[i % n_pool])
-        pipe.step_host(host_pool[i % n_pool])
+    for i in range(max(args.warmup, 3) + 2):                # W >= 3 warm-up steps (+2 eager steps before the graph capture)
+        eng.step(dev_pool[i % n_pool])
+        float(eng.step(host_pool[i % n_pool]).item())
+    eng.check_errors()
     # ---- value: inputs resident in HBM
-    timings = {}
-    ops.TIMINGS = timings
     launches0 = _lib.LAUNCHES['n']
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    ms_value = timed(lambda b, t: pipe.step_device(b, timings=t), dev_pool, args.steps, timings)
+    ms_value = timed(lambda b: eng.step(b), dev_pool, args.steps)
     barrier()
     clk = clocks.stop()
-    launches = _lib.LAUNCHES['n'] - launches0
-    ops.TIMINGS = None
     ms_value = max_over_ranks(ms_value)
     # ---- e2e: raw graphs in pinned host memory, loss read back every step
     barrier()
-    ms_e2e = timed(lambda b, t: pipe.step_host(b), host_pool, args.steps, None)
+    ms_e2e = timed(lambda b: float(eng.step(b).item()), host_pool, args.steps)
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
+    eng.check_errors()
+    # ---- per-kernel durations: the same launch sequence run eagerly with a CUDA event after every launch
+    eng.use_graph = False
+    prof_steps = min(args.steps, 10)
+    _lib.PROFILE = []
+    launches_a = _lib.LAUNCHES['n']
+    for i in range(prof_steps):
+        flush.zero_()
+        eng.step(dev_pool[i % n_pool])
     torch.cuda.synchronize()
-    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in timings.items()}
+    launches_per_step = (_lib.LAUNCHES['n'] - launches_a) // prof_steps
+    marks, _lib.PROFILE = _lib.PROFILE, None
+    eng.use_graph = True
+    kernel_ms, calls = {}, {}
+    for (l0, e0), (l1, e1) in zip(marks[:-1], marks[1:]):
+        if l1 == 'start':
+            continue
+        kernel_ms[l1] = kernel_ms.get(l1, 0.0) + e0.elapsed_time(e1) / prof_steps
+        calls[l1] = calls.get(l1, 0) + 1.0 / prof_steps
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     # ---- roofline of the dominant hand-written kernel (B_enc = 16 E_in + 16 E_out + 24 nnz)
     peak, peak_src = peaks()
-    top = max(kernel_ms, key=kernel_ms.get)
-    raw0 = dev_pool[0]
-    from esc_gnn_b200.pipeline import encode_and_collate
-    b0 = encode_and_collate(raw0, fl['h'], fl['use_rd'], fl['self_loop'])
-    e_in, e_out, nnz = raw0.src.numel(), b0.num_edges, b0.nnz
-    n_nodes = raw0.num_nodes
-    alg = {'ego_rd': 16 * e_in + 24 * e_out, 'ego_encode': 16 * e_in + 16 * e_out + 24 * nnz,
-           'bag_embed_fwd': 12 * nnz + 4 * e_out * HIDDEN, 'bag_embed_bwd': 12 * nnz + 4 * e_out * HIDDEN,
-           'gine_aggregate_fwd': LAYERS * (e_out * (2 * 4 * HIDDEN + 8) + 2 * 4 * n_nodes * HIDDEN),
-           'gine_aggregate_bwd': LAYERS * (e_out * (3 * 4 * HIDDEN + 8) + 4 * e_out * HIDDEN + 2 * 4 * n_nodes * HIDDEN)}
-    calls = {k: len(v) / args.steps for k, v in timings.items()}
+    dims = eng.c.dims.cpu().tolist()
+    n_nodes, e_out, nnz = dims[0], dims[1], dims[3]
+    e_in = e_out
+    own = {k: v for k, v in kernel_ms.items() if not k.startswith(('gemm', 'memset', 'copy', 'misc'))}
+    top = max(own, key=own.get)
+    H2 = HIDDEN
+    alg = {'encode_rd': 16 * e_in + 24 * e_out, 'encode': 16 * e_in + 16 * e_out + 24 * nnz,
+           'bag_embed_fwd': 12 * nnz + 4 * e_out * H2, 'bag_embed_bwd': 12 * nnz + 4 * e_out * H2,
+           'gine_aggregate_fwd': e_out * (2 * 4 * H2 + 8) + 2 * 4 * n_nodes * H2,
+           'gine_aggregate_bwd': e_out * (3 * 4 * H2 + 8) + 4 * e_out * H2 + 2 * 4 * n_nodes * H2,
+           'bn_act_fwd': 3 * 4 * e_out * H2, 'bn_act_bwd': 5 * 4 * e_out * H2}
     per_launch_ms = kernel_ms[top] / max(calls[top], 1)
-    bytes_launch = alg.get(top, alg['ego_encode']) / max(calls[top], 1) if top.startswith(('gine', 'bag')) else alg.get(top, alg['ego_encode'])
+    bytes_launch = alg.get(top, alg['encode'])
     achieved = bytes_launch / (per_launch_ms * 1e-3) / 1e9
+    sum_ms = sum(kernel_ms.values())
     roofline = dict(bound='hbm', kernel=top, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                    traffic=None, peak_source=peak_src, share_of_step=kernel_ms[top] / (ms_value / args.steps),
+                    traffic=None, peak_source=peak_src, share_of_step=kernel_ms[top] / sum_ms,
                     algorithmic_bytes_per_launch=bytes_launch, launch_ms=per_launch_ms,
-                    note='ego_* kernels are issue-bound integer/fp64 graph kernels (ncu: ~84% issue-active), see DESIGN.md')
+                    note='share_of_step is over the event-bracketed eager replay of the same launch sequence; '
+                         'ego_* kernels are issue-bound integer / fp64 graph kernels (profiles/), see DESIGN.md')
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -250,6 +269,7 @@ def run_own(args):
         cpu = dict(value=sample * reps / (t_enc + t_trn), unit='graphs/s', cores=threads, kind='port',
                    sample='%d steps x %d ZINC-shaped graphs: C-oracle encode (OpenMP) + torch CPU NestedGIN_eff train step' % (reps, sample),
                    encode_graphs_per_s=sample * reps / t_enc, train_graphs_per_s=sample * reps / t_trn)
+    launches = launches_per_step * args.steps
     graphs = BATCH * world * args.steps
     h2d = host_pool[0].h2d_bytes()
     out = dict(metric=METRIC, value=graphs / (ms_value * 1e-3), unit='graphs/s', n_gpus=world, steps=args.steps,
@@ -260,8 +280,10 @@ def run_own(args):
                clocks=clk,
                e2e=dict(value=graphs / (ms_e2e * 1e-3), unit='graphs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                         ms_per_step=ms_e2e / args.steps),
-               gpu_launches=launches, kernel_ms_per_step=kernel_ms, roofline=roofline, cpu_baseline=cpu,
-               shape=dict(graphs=BATCH, nodes=n_nodes, edges=e_out, nnz=nnz))
+               gpu_launches=launches, kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
+               roofline=roofline, cpu_baseline=cpu,
+               shape=dict(graphs=BATCH, nodes=n_nodes, edges=e_out, nnz=nnz, nodes_cap=nodes_cap, edges_cap=edges_cap),
+               engine='one CUDA graph per step (encode+collate+fwd+bwd+Adam); GEMMs via cuBLAS fp32 this round')
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -85,11 +85,22 @@ KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'scan'
                     'act_fwd': 1, 'act_bwd': 1, 'colsum': 2, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
                     'make_dims': 1, 'adam_step_device': 2}
 LAUNCHES = {'n': 0}
+PROFILE = None      # bench.py: a list; every mark() appends (label, cuda event) -> per-kernel durations by differencing
+
+
+def mark(label):
+    if PROFILE is not None:
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        PROFILE.append((label, ev))
 
 
 def check(rc, what):
     if rc == 0:
         LAUNCHES['n'] += KERNELS_PER_CALL.get(what, 1)
+        if PROFILE is not None:
+            mark(what)
         return
     names = {-1: 'bad argument', -2: 'graph too large for the kernels', -3: 'record capacity', -4: 'data error'}
     if rc < 0:

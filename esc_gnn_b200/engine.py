@@ -123,10 +123,11 @@ class StaticTrainEngine(object):
         W, bvec = lin.weight, lin.bias
         y = out if out is not None else c.buf(kind, W.size(0))
         dy = c.buf(kind, W.size(0))
-        self.fwd.append(lambda: torch.addmm(bvec, x, W.t(), out=y))
+        self.fwd.append(lambda: (torch.addmm(bvec, x, W.t(), out=y), _lib.mark('gemm_fwd')))
 
         def back():
             torch.mm(dy.t(), x, out=W.grad)
+            _lib.mark('gemm_wgrad')
             _lib.check(c.L.escgnn_colsum(_p(dy), dy.stride(0), _p(c.rows[kind]), c.caps[kind], dy.size(1), _p(c.partial),
                                          _p(bvec.grad), c.st()), 'colsum')
             if need_dx:
@@ -134,6 +135,7 @@ class StaticTrainEngine(object):
                     dx.addmm_(dy, W)
                 else:
                     torch.mm(dy, W, out=dx)
+                _lib.mark('gemm_dgrad')
         self.bwd.append(back)
         return y, dy
 
@@ -154,7 +156,7 @@ class StaticTrainEngine(object):
             _p(x), x.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(rstd),
             _p(c.partial), ACT[act], bn.eps, bn.momentum, 1, _p(c.rows[kind]), c.caps[kind], C, _p(out), out.stride(0),
             c.st()), 'bn_act_fwd'))
-        self.fwd.append(lambda: bn.num_batches_tracked.add_(1))
+        self.fwd.append(lambda: (bn.num_batches_tracked.add_(1), _lib.mark('misc')))
         self.bwd.append(lambda: _lib.check(c.L.escgnn_bn_act_bwd(
             _p(x), x.stride(0), _p(dout), dout.stride(0), _p(dout2), dout2.stride(0) if dout2 is not None else 0, _p(mean),
             _p(rstd), _p(bn.weight), _p(bn.bias), ACT[act], 1, _p(c.partial), _p(c.rows[kind]), c.caps[kind], C,
@@ -189,6 +191,7 @@ class StaticTrainEngine(object):
 
         def back():
             dee.zero_()                                    # rows past the edge count must stay zero for the weight GEMMs
+            _lib.mark('memset')
             _lib.check(c.L.escgnn_gine_aggregate_bwd(
                 _p(dout), _p(x), _p(ee), _p(self.ei[1]), _p(self.src_ptr), _p(self.src_perm), _p(eps), c.caps['N'], C,
                 _p(dx), _p(dee), _p(dots), _p(eps.grad), _p(c.rows['N']), c.st()), 'gine_aggregate_bwd')
@@ -243,7 +246,7 @@ class StaticTrainEngine(object):
         # M3 GINE layers
         x_prev, dx_prev = x0, dx0
         layer_dx_from_next = [None] * Lh          # gradient flowing into layer l's output from layer l+1's aggregation
-        self.fwd.append(lambda: dzcat.zero_())    # every conv.lin backward accumulates into it
+        self.fwd.append(lambda: (dzcat.zero_(), _lib.mark('memset')))    # every conv.lin backward accumulates into it
         for l, conv in enumerate(convs):
             cin = conv.lin.weight.size(0)
             ee, dee = self._linear(zcat, conv.lin, 'E', dx=dzcat, dx_accumulate=True)
@@ -254,7 +257,7 @@ class StaticTrainEngine(object):
             else:
                 xin = c.buf('N', H)
                 src_slice = xs[:, (slot0 + l - 1) * H:(slot0 + l) * H]
-                self.fwd.append(lambda a=xin, b=src_slice: a.copy_(b))
+                self.fwd.append(lambda a=xin, b=src_slice: (a.copy_(b), _lib.mark('copy')))
                 dxin_buf = c.buf('N', H)
                 layer_dx_from_next[l - 1] = dxin_buf
             self._gine(xin, dxin_buf, ee, dee, conv.eps, agg, dagg)
@@ -299,7 +302,7 @@ class StaticTrainEngine(object):
             _p(x), x.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(rstd),
             _p(c.partial), ACT[act], bn.eps, bn.momentum, 1, _p(c.rows['N']), c.caps['N'], C, _p(out), out.stride(0),
             c.st()), 'bn_act_fwd'))
-        self.fwd.append(lambda: bn.num_batches_tracked.add_(1))
+        self.fwd.append(lambda: (bn.num_batches_tracked.add_(1), _lib.mark('misc')))
 
         def back():
             d2 = dx_from_next[l]
@@ -314,6 +317,7 @@ class StaticTrainEngine(object):
         c, L, fl, G = self.c, self.c.L, self.flags, self.G
         st = c.st()
         self.counters.zero_()
+        _lib.mark('memset')
         if fl['self_loop']:
             _lib.check(L.escgnn_rewrite_self_loops(_p(self.in_src), _p(self.in_dst), _p(self.in_eptr), _p(self.in_nptr), G,
                                                    _p(self.eo_ptr), _p(self.eo[0]), _p(self.eo[1]), _p(self.rw_tmp), st),
@@ -343,8 +347,10 @@ class StaticTrainEngine(object):
     @torch.no_grad()
     def _run(self):
         """The whole step as a fixed launch sequence (run eagerly, or captured once and replayed)."""
+        _lib.mark('start')
         self._encode_and_index()
         self.opt.grad.zero_()
+        _lib.mark('memset')
         for f in self.fwd:
             f()
         for b in reversed(self.bwd):
