@@ -55,6 +55,10 @@ SIGNATURES = {
     'escgnn_embedding_fwd': (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     'escgnn_embedding_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     'escgnn_loss_fwd_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+    'escgnn_gemm_tf32x3': (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    'escgnn_gemm_workspace_floats': (_i64, [_i32, _i32, _i32]),
+    'escgnn_tf32_split_lo': (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp]),
+    'escgnn_gemm_simple': (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     'escgnn_adam_step_device': (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'escgnn_make_dims': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     'escgnn_adam_step': (_i32, [_vp, _vp, _vp, _vp, _i64] + [ctypes.c_float] * 4 + [_i64, ctypes.c_float, _vp]),
@@ -83,7 +87,7 @@ KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'scan'
                     'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
                     'edge_distance': 2, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 2, 'bn_act_bwd': 2,
                     'act_fwd': 1, 'act_bwd': 1, 'colsum': 2, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
-                    'make_dims': 1, 'adam_step_device': 2}
+                    'make_dims': 1, 'adam_step_device': 2, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1}
 LAUNCHES = {'n': 0}
 PROFILE = None      # bench.py: a list; every mark() appends (label, cuda event) -> per-kernel durations by differencing
 
