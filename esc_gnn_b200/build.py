@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    subprocess.check_call([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart', '-lcuda'])
+    subprocess.check_call([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart'])
     return LIB
 
 

@@ -54,13 +54,15 @@ __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
 }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | SW128 (2) <<61
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (the only layout tf32 MN-major operands may use,
+// cutlass sm100_common.inl:92; it pairs with TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3fff);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;
     return d;
 }
 
@@ -163,10 +165,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     const uint32_t ab = pass == 2 ? a_lo : a_hi, bb = pass == 1 ? b_lo : b_hi;
                     #pragma unroll
                     for (int k = 0; k < kBlockK / 8; ++k) {
-                        // K-major: 8 rows x 128 B atoms, next 8-row group 1024 B further; a K step of 8 tf32 = +32 B.
-                        // MN-major: 32(MN) x 8(K) atoms of 1024 B; next MN atom one slab (4096 B) further; K step = +1024 B.
-                        const uint64_t ad = A_MN ? make_desc(ab + k * 1024, kSlabBytes, 1024) : make_desc(ab + k * 32, 0, 1024);
-                        const uint64_t bd = B_MN ? make_desc(bb + k * 1024, kSlabBytes, 1024) : make_desc(bb + k * 32, 0, 1024);
+                        // K-major (SW128): 8 rows x 128 B atoms, next 8-row group 1024 B further (SBO); a K step of 8 tf32 = +32 B.
+                        // MN-major (SW128 / 32 B atoms): 32(MN) x 4(K) atoms of 512 B; next K group 512 B further (SBO), next
+                        // MN atom one slab (4096 B) further (LBO); a K step of 8 = +1024 B.
+                        const uint64_t ad = A_MN ? make_desc(ab + k * 1024, kSlabBytes, 512, 1) : make_desc(ab + k * 32, 0, 1024, 2);
+                        const uint64_t bd = B_MN ? make_desc(bb + k * 1024, kSlabBytes, 512, 1) : make_desc(bb + k * 32, 0, 1024, 2);
                         mma_tf32(tmem_d, ad, bd, idesc, (i | pass | k) ? 1u : 0u);
                     }
                 }
@@ -286,14 +289,34 @@ gemm_simple_kernel(const float* __restrict__ A, int lda, int a_mn, const float* 
         }
 }
 
+// cuTensorMapEncodeTiled is a driver entry point: fetch it through the runtime so the library has no link-time
+// dependency on libcuda (it must load on machines without a driver, e.g. for the symbol check of the CPU test suite)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
 // 2-D fp32 tensor map, 128-byte swizzle; inner extent / stride in elements
-int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+             bool mn_major = false) {
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {ld * sizeof(float)};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return 699;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
@@ -305,8 +328,12 @@ int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& 
     constexpr int STAGES = stage <= 48 * 1024 ? 4 : (stage <= 64 * 1024 ? 3 : 2);
     const int smem = STAGES * stage + 1024;
     auto kern = gemm_tf32x3_kernel<BLOCK_N, A_MN, B_MN, STAGES>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
+    static bool configured = false;          // once per instantiation (keeps stream capture free of attribute calls)
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
     kern<<<grid, kThreads, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
     return (int)cudaGetLastError();
 }
@@ -354,12 +381,12 @@ int64_t escgnn_gemm_workspace_floats(int M, int N, int K) {
     return splits > 1 ? (int64_t)splits * M * N : 0;
 }
 
-int escgnn_gemm_tf32x3(const float* d_a_hi, const float* d_a_lo, int lda, int a_mn_major, const float* d_b_hi,
-                       const float* d_b_lo, int ldb, int b_mn_major, float* d_c, int ldc, const float* d_bias, int M, int N,
-                       int K, int accumulate, float* d_workspace, int64_t workspace_floats, void* stream) {
+int escgnn_gemm_tf32x3(const float* d_a_hi, int lda, const float* d_a_lo, int lda_lo, int a_mn_major, const float* d_b_hi,
+                       int ldb, const float* d_b_lo, int ldb_lo, int b_mn_major, float* d_c, int ldc, const float* d_bias,
+                       int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    if ((lda & 3) || (ldb & 3) || ((uintptr_t)d_a_hi & 15) || ((uintptr_t)d_a_lo & 15) || ((uintptr_t)d_b_hi & 15) ||
-        ((uintptr_t)d_b_lo & 15))
+    if ((lda & 3) || (ldb & 3) || (lda_lo & 3) || (ldb_lo & 3) || ((uintptr_t)d_a_hi & 15) || ((uintptr_t)d_a_lo & 15) ||
+        ((uintptr_t)d_b_hi & 15) || ((uintptr_t)d_b_lo & 15))
         return ESCGNN_ERR_BAD_ARG;            // TMA needs 16-byte aligned bases and row pitches
     cudaStream_t st = (cudaStream_t)stream;
     // BLOCK_N: a multiple of 32 (MN-major slabs are 32 wide) covering N in as few equal tiles as possible
@@ -386,14 +413,14 @@ int escgnn_gemm_tf32x3(const float* d_a_hi, const float* d_a_lo, int lda, int a_
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc = 0;
     if (!a_mn_major) {      // [M, K] row-major: inner = K
-        rc |= make_map(&a_hi, d_a_hi, K, M, lda, kBlockK, kBlockM); rc |= make_map(&a_lo, d_a_lo, K, M, lda, kBlockK, kBlockM);
+        rc |= make_map(&a_hi, d_a_hi, K, M, lda, kBlockK, kBlockM); rc |= make_map(&a_lo, d_a_lo, K, M, lda_lo, kBlockK, kBlockM);
     } else {                // [K, M] row-major: inner = M
-        rc |= make_map(&a_hi, d_a_hi, M, K, lda, 32, kBlockK); rc |= make_map(&a_lo, d_a_lo, M, K, lda, 32, kBlockK);
+        rc |= make_map(&a_hi, d_a_hi, M, K, lda, 32, kBlockK, true); rc |= make_map(&a_lo, d_a_lo, M, K, lda_lo, 32, kBlockK, true);
     }
     if (!b_mn_major) {
-        rc |= make_map(&b_hi, d_b_hi, K, N, ldb, kBlockK, block_n); rc |= make_map(&b_lo, d_b_lo, K, N, ldb, kBlockK, block_n);
+        rc |= make_map(&b_hi, d_b_hi, K, N, ldb, kBlockK, block_n); rc |= make_map(&b_lo, d_b_lo, K, N, ldb_lo, kBlockK, block_n);
     } else {
-        rc |= make_map(&b_hi, d_b_hi, N, K, ldb, 32, kBlockK); rc |= make_map(&b_lo, d_b_lo, N, K, ldb, 32, kBlockK);
+        rc |= make_map(&b_hi, d_b_hi, N, K, ldb, 32, kBlockK, true); rc |= make_map(&b_lo, d_b_lo, N, K, ldb_lo, 32, kBlockK, true);
     }
     if (rc) return rc;
     dim3 grid((unsigned)tiles_m, (unsigned)n_tiles, (unsigned)splits);

@@ -14,8 +14,9 @@ views into FlatAdam's flat buffer), so `state_dict()` / checkpoints stay interch
 (run_zinc.py:257-262, run_graphcount.py:464-476).  Forward semantics: zinc_models.py:579-611 and
 run_graphcount.py:134-194; train step: run_zinc.py:266-289.
 
-Dense contractions go through `torch.addmm` / `torch.mm` into preallocated outputs (cuBLAS fp32) in this round;
-everything else is the hand-written sm_100a kernels of csrc/*.cu.
+Dense contractions (every nn.Linear forward / dgrad / wgrad) run on the hand-written tcgen05 3xTF32 GEMM
+(csrc/gemm_tf32x3.cu: TMA -> shared memory -> tcgen05.mma -> TMEM); everything else is the hand-written sm_100a
+kernels of csrc/*.cu.  No library GEMM is on the path.
 """
 import ctypes
 
@@ -55,7 +56,7 @@ class StaticTrainEngine(object):
     """One NestedGIN_eff variant ('zinc' or 'count') at a fixed capacity."""
 
     def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
-                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True):
+                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True):
         if variant not in ('zinc', 'count'):
             raise NotImplementedError('engine variants: zinc, count (the OGB model runs through the module path)')
         p0 = next(model.parameters())
@@ -111,31 +112,71 @@ class StaticTrainEngine(object):
         self.graph_ptr = torch.zeros(self.G + 1, dtype=torch.int32, device=dev)
         self.idx_err = torch.zeros(1, dtype=i64, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.tensor_cores = tensor_cores
+        self.flat_lo = torch.zeros_like(self.opt.flat)
+        self._lo_cache = {}
+        ws = max(c.L.escgnn_gemm_workspace_floats(1024, 2048, max(c.caps['E'], c.caps['N'])), 1)
+        self.gemm_ws = torch.zeros(ws, dtype=torch.float32, device=dev)
         self.fwd, self.bwd = [], []
         self._build_model_tape()
         self.graph = None
         self.steps = 0
 
     # ------------------------------------------------------------------ primitive ops (append to the tapes)
+    # ---- dense contractions: tcgen05 3xTF32 GEMM (csrc/gemm_tf32x3.cu); CUDA-core kernel for 10-wide odd shapes
+    def _lo_of(self, t, rows_kind):
+        """Low tf32 plane of an activation buffer, computed once per step the first time a GEMM needs it (forward tape)."""
+        key = (t.data_ptr(), tuple(t.shape), t.stride(0))
+        hit = self._lo_cache.get(key)
+        if hit is None:
+            c = self.c
+            lo = torch.zeros((t.size(0), t.size(1)), dtype=torch.float32, device=c.dev)
+            self.fwd.append(lambda: _lib.check(c.L.escgnn_tf32_split_lo(_p(t), t.stride(0), _p(lo), lo.stride(0), t.size(0),
+                                                                        t.size(1), c.st()), 'tf32_split_lo'))
+            self._lo_cache[key] = hit = lo
+        return hit
+
+    def _weight_lo(self, W):
+        off = (W.data_ptr() - self.opt.flat.data_ptr()) // 4
+        return self.flat_lo[off:off + W.numel()].view(W.shape)
+
+    def _gemm(self, tag, A, A_lo, a_mn, B, B_lo, b_mn, C, bias, M, N, K, accumulate):
+        c = self.c
+        ok = all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (A, A_lo, B, B_lo)) and self.tensor_cores
+        if ok:
+            _lib.check(c.L.escgnn_gemm_tf32x3(_p(A), A.stride(0), _p(A_lo), A_lo.stride(0), int(a_mn), _p(B), B.stride(0),
+                                              _p(B_lo), B_lo.stride(0), int(b_mn), _p(C), C.stride(0), _p(bias), M, N, K,
+                                              int(accumulate), _p(self.gemm_ws), self.gemm_ws.numel(), c.st()), 'gemm_tf32x3')
+        else:
+            _lib.check(c.L.escgnn_gemm_simple(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
+                                              _p(bias), M, N, K, int(accumulate), c.st()), 'gemm_simple')
+        _lib.mark(tag)
+
     def _linear(self, x, lin, kind, out=None, dx=None, dx_accumulate=False, need_dx=True):
         """y = x W^T + b over capacity rows.  Returns (y, dy) buffers; backward fills W.grad, b.grad and dx."""
         c = self.c
         W, bvec = lin.weight, lin.bias
-        y = out if out is not None else c.buf(kind, W.size(0))
-        dy = c.buf(kind, W.size(0))
-        self.fwd.append(lambda: (torch.addmm(bvec, x, W.t(), out=y), _lib.mark('gemm_fwd')))
+        n_out, k_in, rows = W.size(0), W.size(1), c.caps[kind]
+        y = out if out is not None else c.buf(kind, n_out)
+        dy = c.buf(kind, n_out)
+        W_lo = self._weight_lo(W)
+        aligned = k_in % 4 == 0 and x.stride(0) % 4 == 0 and self.tensor_cores
+        x_lo = self._lo_of(x, kind) if aligned else x
+        dy_lo = c.buf(kind, n_out) if n_out % 4 == 0 else dy
+        # forward: Y[rows, n_out] = X[rows, k_in] W[n_out, k_in]^T + b          (A, B K-major)
+        self.fwd.append(lambda: self._gemm('gemm_fwd', x, x_lo, False, W, W_lo, False, y, bvec, rows, n_out, k_in, False))
 
         def back():
-            torch.mm(dy.t(), x, out=W.grad)
-            _lib.mark('gemm_wgrad')
+            if dy_lo is not dy and self.tensor_cores:
+                _lib.check(c.L.escgnn_tf32_split_lo(_p(dy), dy.stride(0), _p(dy_lo), dy_lo.stride(0), rows, n_out, c.st()),
+                           'tf32_split_lo')
+            # wgrad: dW[n_out, k_in] = dY^T X   (A = dY stored [rows, n_out] = MN-major, B = X stored [rows, k_in] = MN-major)
+            self._gemm('gemm_wgrad', dy, dy_lo, True, x, x_lo, True, W.grad, None, n_out, k_in, rows, False)
             _lib.check(c.L.escgnn_colsum(_p(dy), dy.stride(0), _p(c.rows[kind]), c.caps[kind], dy.size(1), _p(c.partial),
                                          _p(bvec.grad), c.st()), 'colsum')
             if need_dx:
-                if dx_accumulate:
-                    dx.addmm_(dy, W)
-                else:
-                    torch.mm(dy, W, out=dx)
-                _lib.mark('gemm_dgrad')
+                # dgrad: dX[rows, k_in] = dY W      (A = dY K-major, B = W stored [n_out, k_in] = MN-major for this product)
+                self._gemm('gemm_dgrad', dy, dy_lo, False, W, W_lo, True, dx, None, rows, k_in, n_out, dx_accumulate)
         self.bwd.append(back)
         return y, dy
 
@@ -348,6 +389,10 @@ class StaticTrainEngine(object):
     def _run(self):
         """The whole step as a fixed launch sequence (run eagerly, or captured once and replayed)."""
         _lib.mark('start')
+        if self.tensor_cores:      # low tf32 plane of every parameter in one launch (weights changed in the last Adam step)
+            _lib.check(self.c.L.escgnn_tf32_split_lo(_p(self.opt.flat), self.opt.flat.numel(), _p(self.flat_lo),
+                                                     self.opt.flat.numel(), 1, self.opt.flat.numel(), self.c.st()),
+                       'tf32_split_lo')
         self._encode_and_index()
         self.opt.grad.zero_()
         _lib.mark('memset')
