@@ -93,6 +93,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_bias[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
     const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -100,6 +101,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int num_kb = max(kb_end - kb_begin, 0);
     constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
 
+    for (int i = threadIdx.x; i < BLOCK_N; i += kThreads)
+        s_bias[i] = (p.bias && !p.partial && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
@@ -205,16 +208,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
             if (row_ok) {
-                #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c + j;
-                    if (n < p.N) {
-                        float r = __uint_as_float(v[j]);
-                        if (!p.partial) {
-                            if (p.bias) r += p.bias[n];
-                            if (p.accumulate) r += out[n];
+                const int nb = n0 + c;
+                const bool acc = p.accumulate && !p.partial;
+                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(out + nb) & 15) == 0)) {
+                    #pragma unroll
+                    for (int j = 0; j < 32; j += 4) {            // 128 contiguous bytes per thread, 16-byte stores
+                        float4 r = make_float4(__uint_as_float(v[j]) + s_bias[c + j], __uint_as_float(v[j + 1]) + s_bias[c + j + 1],
+                                               __uint_as_float(v[j + 2]) + s_bias[c + j + 2], __uint_as_float(v[j + 3]) + s_bias[c + j + 3]);
+                        float4* dst = reinterpret_cast<float4*>(out + nb + j);
+                        if (acc) { const float4 o = *dst; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+                        *dst = r;
+                    }
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nb + j;
+                        if (n < p.N) {
+                            float r = __uint_as_float(v[j]) + s_bias[c + j];
+                            if (acc) r += out[n];
+                            out[n] = r;
                         }
-                        out[n] = r;
                     }
                 }
             }

@@ -115,8 +115,7 @@ class StaticTrainEngine(object):
         self.tensor_cores = tensor_cores
         self.flat_lo = torch.zeros_like(self.opt.flat)
         self._lo_cache = {}
-        ws = max(c.L.escgnn_gemm_workspace_floats(1024, 2048, max(c.caps['E'], c.caps['N'])), 1)
-        self.gemm_ws = torch.zeros(ws, dtype=torch.float32, device=dev)
+        self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
         self.fwd, self.bwd = [], []
         self._build_model_tape()
         self.graph = None
@@ -146,11 +145,10 @@ class StaticTrainEngine(object):
         if ok:
             _lib.check(c.L.escgnn_gemm_tf32x3(_p(A), A.stride(0), _p(A_lo), A_lo.stride(0), int(a_mn), _p(B), B.stride(0),
                                               _p(B_lo), B_lo.stride(0), int(b_mn), _p(C), C.stride(0), _p(bias), M, N, K,
-                                              int(accumulate), _p(self.gemm_ws), self.gemm_ws.numel(), c.st()), 'gemm_tf32x3')
+                                              int(accumulate), _p(self.gemm_ws), self.gemm_ws.numel(), c.st()), tag)
         else:
             _lib.check(c.L.escgnn_gemm_simple(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
-                                              _p(bias), M, N, K, int(accumulate), c.st()), 'gemm_simple')
-        _lib.mark(tag)
+                                              _p(bias), M, N, K, int(accumulate), c.st()), tag + '_simple')
 
     def _linear(self, x, lin, kind, out=None, dx=None, dx_accumulate=False, need_dx=True):
         """y = x W^T + b over capacity rows.  Returns (y, dy) buffers; backward fills W.grad, b.grad and dx."""
