@@ -384,8 +384,8 @@ class StaticTrainEngine(object):
                    'sorted_ids_to_ptr')
 
     @torch.no_grad()
-    def _run(self):
-        """The whole step as a fixed launch sequence (run eagerly, or captured once and replayed)."""
+    def _run_main(self):
+        """Everything up to the gradients as a fixed launch sequence (run eagerly, or captured once and replayed)."""
         _lib.mark('start')
         if self.tensor_cores:      # low tf32 plane of every parameter in one launch (weights changed in the last Adam step)
             _lib.check(self.c.L.escgnn_tf32_split_lo(_p(self.opt.flat), self.opt.flat.numel(), _p(self.flat_lo),
@@ -398,9 +398,16 @@ class StaticTrainEngine(object):
             f()
         for b in reversed(self.bwd):
             b()
+
+    @torch.no_grad()
+    def _run_opt(self):
+        self.opt.step_device()
+
+    def _run(self):
+        self._run_main()
         if self.distributed:
             self.opt.all_reduce_grads()
-        self.opt.step_device()
+        self._run_opt()
 
     def load(self, raw):
         """Copy one RawBatch (pinned host or device) into the static input buffers (async on the current stream)."""
@@ -428,15 +435,24 @@ class StaticTrainEngine(object):
             world = dist.get_world_size()
         self.opt.sync_hyper(world)
         self.load(raw)
-        if not self.use_graph or self.steps < 2:     # eager warm-up (cuBLAS handles / workspaces) before the capture
+        if not self.use_graph or self.steps < 2:     # eager warm-up before the capture
             self._run()
         else:
             if self.graph is None:
                 torch.cuda.synchronize()
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
-                    self._run()
+                    self._run_main()
+                    if not self.distributed:
+                        self._run_opt()
+                if self.distributed:             # the NCCL exchange stays outside the captured graphs
+                    self.graph_opt = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph_opt):
+                        self._run_opt()
             self.graph.replay()
+            if self.distributed:
+                self.opt.all_reduce_grads()
+                self.graph_opt.replay()
         self.steps += 1
         return self.loss
 
