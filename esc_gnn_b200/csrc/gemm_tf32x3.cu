@@ -11,9 +11,10 @@
 //
 // Shape: one CTA per 128 x BLOCK_N output tile (x split-K slice); 6 warps: TMA producer, MMA issuer (+TMEM allocator),
 // 4 epilogue warps (one per TMEM lane quarter).  Operand tiles arrive by TMA (cp.async.bulk.tensor, 128-byte swizzle) into
-// a 2-4 stage shared-memory ring guarded by mbarriers; `tcgen05.mma.kind::tf32` (M=128, N=BLOCK_N, K=8) is issued by one
+// a shared-memory ring guarded by mbarriers; `tcgen05.mma.kind::tf32` (M=128, N=BLOCK_N<=128, K=8) is issued by one
 // thread; the accumulator lives in TMEM and is read back with tcgen05.ld for the epilogue.  The "hi" operand is the raw
-// fp32 array (the tensor core ignores the 13 low mantissa bits), the "lo" plane is x - tf32_trunc(x) (exact in fp32).
+// fp32 tile (the tensor core ignores the 13 low mantissa bits); the "lo" plane x - tf32_trunc(x) (exact in fp32) is
+// produced ON CHIP by the four epilogue warps while the tiles sit in shared memory, so only fp32 A and B are ever read.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -82,30 +83,38 @@ struct Params {
     int accumulate;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2..5 = tf32 splitters during the main loop, then epilogue.
+// Shared memory: STAGES raw stages {A 16 KB, B BLOCK_N*128 B} filled by TMA, ONE lo buffer of the same shape written by the
+// splitter warps (lo = x - trunc_tf32(x), element-wise, so the swizzled placement is simply preserved).  Two CTAs are
+// resident per SM (<= 113 KB each): while one waits on TMA / split / epilogue the other keeps the tensor pipe busy.
 template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Params p) {
+__global__ void __launch_bounds__(kThreads, 2)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int kABytes = kBlockM * 128;           // 16 KB per plane
+    constexpr int kABytes = kBlockM * 128;           // 16 KB
     constexpr int kBBytes = BLOCK_N * 128;
-    constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    constexpr int kStageBytes = kABytes + kBBytes;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    uint8_t* lo_buf = smem + (size_t)STAGES * kStageBytes;
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar, lo_free_bar, tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_bias[256];
+    __shared__ float s_bias[BLOCK_N];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
     const int num_kb = max(kb_end - kb_begin, 0);
-    constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+    constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : 128;
 
     for (int i = threadIdx.x; i < BLOCK_N; i += kThreads)
         s_bias[i] = (p.bias && !p.partial && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
+        mbar_init(&split_bar, 128); mbar_init(&lo_free_bar, 1); mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -122,31 +131,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         if (lane == 0) {
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
                 uint8_t* st = smem + (size_t)s * kStageBytes;
                 mbar_expect_tx(&full_bar[s], kStageBytes);
                 const int k0 = (kb_begin + i) * kBlockK;
-                if (!A_MN) {            // A stored [M, K]: box {32 k, 128 rows}
-                    tma_load_2d(st, &tmA_hi, &full_bar[s], k0, m0);
-                    tma_load_2d(st + kABytes, &tmA_lo, &full_bar[s], k0, m0);
-                } else {                // A stored [K, M]: four slabs {32 m, 32 k}
+                if (!A_MN) tma_load_2d(st, &tmA, &full_bar[s], k0, m0);              // A stored [M, K]: box {32 k, 128 rows}
+                else {                                                                 // A stored [K, M]: four slabs {32 m, 32 k}
                     #pragma unroll
-                    for (int j = 0; j < kBlockM / 32; ++j) {
-                        tma_load_2d(st + j * kSlabBytes, &tmA_hi, &full_bar[s], m0 + 32 * j, k0);
-                        tma_load_2d(st + kABytes + j * kSlabBytes, &tmA_lo, &full_bar[s], m0 + 32 * j, k0);
-                    }
+                    for (int j = 0; j < kBlockM / 32; ++j) tma_load_2d(st + j * kSlabBytes, &tmA, &full_bar[s], m0 + 32 * j, k0);
                 }
-                uint8_t* sb = st + 2 * kABytes;
-                if (!B_MN) {
-                    tma_load_2d(sb, &tmB_hi, &full_bar[s], k0, n0);
-                    tma_load_2d(sb + kBBytes, &tmB_lo, &full_bar[s], k0, n0);
-                } else {
+                uint8_t* sb = st + kABytes;
+                if (!B_MN) tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+                else {
                     #pragma unroll
-                    for (int j = 0; j < BLOCK_N / 32; ++j) {
-                        tma_load_2d(sb + j * kSlabBytes, &tmB_hi, &full_bar[s], n0 + 32 * j, k0);
-                        tma_load_2d(sb + kBBytes + j * kSlabBytes, &tmB_lo, &full_bar[s], n0 + 32 * j, k0);
-                    }
+                    for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * kSlabBytes, &tmB, &full_bar[s], n0 + 32 * j, k0);
                 }
             }
         }
@@ -156,13 +154,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            const uint32_t a_lo = smem_u32(lo_buf), b_lo = a_lo + kABytes;
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(&full_bar[s], (i / STAGES) & 1);       // raw tiles landed (hi operands)
+                mbar_wait(&split_bar, i & 1);                    // lo planes of this k-block written
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes), a_lo = a_hi + kABytes;
-                const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + kBBytes;
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes), b_hi = a_hi + kABytes;
                 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t ab = pass == 2 ? a_lo : a_hi, bb = pass == 1 ? b_lo : b_hi;
@@ -176,12 +174,33 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         mma_tf32(tmem_d, ad, bd, idesc, (i | pass | k) ? 1u : 0u);
                     }
                 }
-                tcgen05_commit(&empty_bar[s]);          // frees the stage once these MMAs have read it
+                tcgen05_commit(&empty_bar[s]);          // raw stage reusable once these MMAs have read it
+                tcgen05_commit(&lo_free_bar);           // ... and so is the lo buffer
             }
             tcgen05_commit(&tmem_full_bar);             // accumulator complete
         }
     } else {
-        // ===== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====
+        // ===== splitters (main loop), then epilogue: 4 warps, TMEM lane quarter = warp % 4 =====
+        const int t = threadIdx.x - 64;                 // 0..127
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(&full_bar[s], (i / STAGES) & 1);
+            mbar_wait(&lo_free_bar, (i & 1) ^ 1);       // previous k-block's MMAs are done with the lo buffer
+            const float4* src = reinterpret_cast<const float4*>(smem + (size_t)s * kStageBytes);
+            float4* dst = reinterpret_cast<float4*>(lo_buf);
+            #pragma unroll 4
+            for (int q = t; q < kStageBytes / 16; q += 128) {
+                const float4 v = src[q];
+                float4 r;
+                r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                dst[q] = r;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to tcgen05.mma
+            mbar_arrive(&split_bar);
+        }
         const int q = warp & 3;
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -335,11 +354,10 @@ int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const Params& p,
-           dim3 grid, cudaStream_t st) {
-    constexpr int stage = 2 * kBlockM * 128 + 2 * BLOCK_N * 128;
-    constexpr int STAGES = stage <= 48 * 1024 ? 4 : (stage <= 64 * 1024 ? 3 : 2);
-    const int smem = STAGES * stage + 1024;
+int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+    constexpr int stage = kBlockM * 128 + BLOCK_N * 128;
+    constexpr int STAGES = 2;                                   // 2 raw stages + 1 lo buffer = 3 * stage <= 96 KB -> 2 CTAs / SM
+    const int smem = (STAGES + 1) * stage + 1024;
     auto kern = gemm_tf32x3_kernel<BLOCK_N, A_MN, B_MN, STAGES>;
     static bool configured = false;          // once per instantiation (keeps stream capture free of attribute calls)
     if (!configured) {
@@ -347,21 +365,33 @@ int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& 
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    kern<<<grid, kThreads, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    kern<<<grid, kThreads, smem, st>>>(a, b, p);
     return (int)cudaGetLastError();
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch_n(int block_n, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-               const Params& p, dim3 grid, cudaStream_t st) {
+int dispatch_n(int block_n, const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
     switch (block_n) {
-        case 32: return launch<32, A_MN, B_MN>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
-        case 64: return launch<64, A_MN, B_MN>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
-        case 96: return launch<96, A_MN, B_MN>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
-        case 128: return launch<128, A_MN, B_MN>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
-        case 160: return launch<160, A_MN, B_MN>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
-        default: return launch<256, A_MN, B_MN>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+        case 32: return launch<32, A_MN, B_MN>(a, b, p, grid, st);
+        case 64: return launch<64, A_MN, B_MN>(a, b, p, grid, st);
+        case 96: return launch<96, A_MN, B_MN>(a, b, p, grid, st);
+        default: return launch<128, A_MN, B_MN>(a, b, p, grid, st);
     }
+}
+
+// tile width along N: a multiple of 32 (MN-major slabs are 32 wide), at most 128, as few equal tiles as possible
+int pick_block_n(int N) {
+    const int tiles = (N + 127) / 128;
+    int bn = ((N + tiles - 1) / tiles + 31) / 32 * 32;
+    return bn > 128 ? 128 : bn;
+}
+
+int pick_splits(int tiles, int kb_total, int M, int N, int64_t workspace_floats) {
+    if (tiles >= 96 || kb_total < 16) return 1;
+    int splits = 296 / tiles;
+    if (splits > kb_total / 4) splits = kb_total / 4;
+    if ((int64_t)splits * M * N > workspace_floats) splits = (int)(workspace_floats / ((int64_t)M * N));
+    return splits < 1 ? 1 : splits;
 }
 
 }  // namespace
@@ -385,62 +415,44 @@ int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d
     return (int)cudaGetLastError();
 }
 
-/* how many floats of split-K workspace a call with these sizes needs (0 = no split) */
+/* how many floats of split-K workspace a call with these sizes can use (0 = never splits) */
 int64_t escgnn_gemm_workspace_floats(int M, int N, int K) {
-    const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + 255) / 256);
+    const int block_n = pick_block_n(N);
+    const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + block_n - 1) / block_n);
     const int kb = (K + kBlockK - 1) / kBlockK;
-    if (tiles >= 64 || kb < 16) return 0;
-    int splits = 148 / tiles; if (splits > kb / 4) splits = kb / 4; if (splits < 1) splits = 1;
+    const int splits = pick_splits(tiles, kb, M, N, (int64_t)1 << 40);
     return splits > 1 ? (int64_t)splits * M * N : 0;
 }
 
-int escgnn_gemm_tf32x3(const float* d_a_hi, int lda, const float* d_a_lo, int lda_lo, int a_mn_major, const float* d_b_hi,
-                       int ldb, const float* d_b_lo, int ldb_lo, int b_mn_major, float* d_c, int ldc, const float* d_bias,
-                       int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats, void* stream) {
+int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,
+                       const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats,
+                       void* stream) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    if ((lda & 3) || (ldb & 3) || (lda_lo & 3) || (ldb_lo & 3) || ((uintptr_t)d_a_hi & 15) || ((uintptr_t)d_a_lo & 15) ||
-        ((uintptr_t)d_b_hi & 15) || ((uintptr_t)d_b_lo & 15))
+    if ((lda & 3) || (ldb & 3) || ((uintptr_t)d_a & 15) || ((uintptr_t)d_b & 15))
         return ESCGNN_ERR_BAD_ARG;            // TMA needs 16-byte aligned bases and row pitches
     cudaStream_t st = (cudaStream_t)stream;
-    // BLOCK_N: a multiple of 32 (MN-major slabs are 32 wide) covering N in as few equal tiles as possible
-    int n_tiles = (N + 255) / 256;
-    int block_n = ((N + n_tiles - 1) / n_tiles + 31) / 32 * 32;
-    if (block_n > 160 && block_n < 256) block_n = 256;
-    if (block_n == 192 || block_n == 224) block_n = 256;
-    const int tiles_m = (M + kBlockM - 1) / kBlockM;
-    n_tiles = (N + block_n - 1) / block_n;
+    const int block_n = pick_block_n(N);
+    const int tiles_m = (M + kBlockM - 1) / kBlockM, n_tiles = (N + block_n - 1) / block_n;
     const int kb_total = (K + kBlockK - 1) / kBlockK;
-    int splits = 1;
-    if (tiles_m * n_tiles < 64 && kb_total >= 16 && d_workspace) {
-        splits = 148 / (tiles_m * n_tiles);
-        if (splits > kb_total / 4) splits = kb_total / 4;
-        if ((int64_t)splits * M * N > workspace_floats) splits = (int)(workspace_floats / ((int64_t)M * N));
-        if (splits < 1) splits = 1;
-    }
+    int splits = d_workspace ? pick_splits(tiles_m * n_tiles, kb_total, M, N, workspace_floats) : 1;
     Params p;
     p.C = d_c; p.ldc = ldc; p.bias = d_bias; p.M = M; p.N = N; p.K = K;
     p.kb_total = kb_total; p.kb_per_split = (kb_total + splits - 1) / splits;
     splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.partial = splits > 1 ? d_workspace : nullptr;
     p.accumulate = accumulate;
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap a, b;
     int rc = 0;
-    if (!a_mn_major) {      // [M, K] row-major: inner = K
-        rc |= make_map(&a_hi, d_a_hi, K, M, lda, kBlockK, kBlockM); rc |= make_map(&a_lo, d_a_lo, K, M, lda_lo, kBlockK, kBlockM);
-    } else {                // [K, M] row-major: inner = M
-        rc |= make_map(&a_hi, d_a_hi, M, K, lda, 32, kBlockK, true); rc |= make_map(&a_lo, d_a_lo, M, K, lda_lo, 32, kBlockK, true);
-    }
-    if (!b_mn_major) {
-        rc |= make_map(&b_hi, d_b_hi, K, N, ldb, kBlockK, block_n); rc |= make_map(&b_lo, d_b_lo, K, N, ldb_lo, kBlockK, block_n);
-    } else {
-        rc |= make_map(&b_hi, d_b_hi, N, K, ldb, 32, kBlockK, true); rc |= make_map(&b_lo, d_b_lo, N, K, ldb_lo, 32, kBlockK, true);
-    }
+    if (!a_mn_major) rc |= make_map(&a, d_a, K, M, lda, kBlockK, kBlockM);          // [M, K] row-major: inner = K
+    else rc |= make_map(&a, d_a, M, K, lda, 32, kBlockK, true);                     // [K, M] row-major: inner = M
+    if (!b_mn_major) rc |= make_map(&b, d_b, K, N, ldb, kBlockK, block_n);
+    else rc |= make_map(&b, d_b, N, K, ldb, 32, kBlockK, true);
     if (rc) return rc;
     dim3 grid((unsigned)tiles_m, (unsigned)n_tiles, (unsigned)splits);
-    if (!a_mn_major && !b_mn_major) rc = dispatch_n<false, false>(block_n, a_hi, a_lo, b_hi, b_lo, p, grid, st);
-    else if (!a_mn_major && b_mn_major) rc = dispatch_n<false, true>(block_n, a_hi, a_lo, b_hi, b_lo, p, grid, st);
-    else if (a_mn_major && !b_mn_major) rc = dispatch_n<true, false>(block_n, a_hi, a_lo, b_hi, b_lo, p, grid, st);
-    else rc = dispatch_n<true, true>(block_n, a_hi, a_lo, b_hi, b_lo, p, grid, st);
+    if (!a_mn_major && !b_mn_major) rc = dispatch_n<false, false>(block_n, a, b, p, grid, st);
+    else if (!a_mn_major && b_mn_major) rc = dispatch_n<false, true>(block_n, a, b, p, grid, st);
+    else if (a_mn_major && !b_mn_major) rc = dispatch_n<true, false>(block_n, a, b, p, grid, st);
+    else rc = dispatch_n<true, true>(block_n, a, b, p, grid, st);
     if (rc) return rc;
     if (splits > 1) {
         int64_t blocks = ((int64_t)M * N + 255) / 256;

@@ -113,8 +113,6 @@ class StaticTrainEngine(object):
         self.idx_err = torch.zeros(1, dtype=i64, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.tensor_cores = tensor_cores
-        self.flat_lo = torch.zeros_like(self.opt.flat)
-        self._lo_cache = {}
         self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
         self.fwd, self.bwd = [], []
         self._build_model_tape()
@@ -123,29 +121,13 @@ class StaticTrainEngine(object):
 
     # ------------------------------------------------------------------ primitive ops (append to the tapes)
     # ---- dense contractions: tcgen05 3xTF32 GEMM (csrc/gemm_tf32x3.cu); CUDA-core kernel for 10-wide odd shapes
-    def _lo_of(self, t, rows_kind):
-        """Low tf32 plane of an activation buffer, computed once per step the first time a GEMM needs it (forward tape)."""
-        key = (t.data_ptr(), tuple(t.shape), t.stride(0))
-        hit = self._lo_cache.get(key)
-        if hit is None:
-            c = self.c
-            lo = torch.zeros((t.size(0), t.size(1)), dtype=torch.float32, device=c.dev)
-            self.fwd.append(lambda: _lib.check(c.L.escgnn_tf32_split_lo(_p(t), t.stride(0), _p(lo), lo.stride(0), t.size(0),
-                                                                        t.size(1), c.st()), 'tf32_split_lo'))
-            self._lo_cache[key] = hit = lo
-        return hit
-
-    def _weight_lo(self, W):
-        off = (W.data_ptr() - self.opt.flat.data_ptr()) // 4
-        return self.flat_lo[off:off + W.numel()].view(W.shape)
-
-    def _gemm(self, tag, A, A_lo, a_mn, B, B_lo, b_mn, C, bias, M, N, K, accumulate):
+    def _gemm(self, tag, A, a_mn, B, b_mn, C, bias, M, N, K, accumulate):
         c = self.c
-        ok = all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (A, A_lo, B, B_lo)) and self.tensor_cores
+        ok = all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (A, B)) and self.tensor_cores
         if ok:
-            _lib.check(c.L.escgnn_gemm_tf32x3(_p(A), A.stride(0), _p(A_lo), A_lo.stride(0), int(a_mn), _p(B), B.stride(0),
-                                              _p(B_lo), B_lo.stride(0), int(b_mn), _p(C), C.stride(0), _p(bias), M, N, K,
-                                              int(accumulate), _p(self.gemm_ws), self.gemm_ws.numel(), c.st()), tag)
+            _lib.check(c.L.escgnn_gemm_tf32x3(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
+                                              _p(bias), M, N, K, int(accumulate), _p(self.gemm_ws), self.gemm_ws.numel(),
+                                              c.st()), tag)
         else:
             _lib.check(c.L.escgnn_gemm_simple(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
                                               _p(bias), M, N, K, int(accumulate), c.st()), tag + '_simple')
@@ -157,24 +139,17 @@ class StaticTrainEngine(object):
         n_out, k_in, rows = W.size(0), W.size(1), c.caps[kind]
         y = out if out is not None else c.buf(kind, n_out)
         dy = c.buf(kind, n_out)
-        W_lo = self._weight_lo(W)
-        aligned = k_in % 4 == 0 and x.stride(0) % 4 == 0 and self.tensor_cores
-        x_lo = self._lo_of(x, kind) if aligned else x
-        dy_lo = c.buf(kind, n_out) if n_out % 4 == 0 else dy
         # forward: Y[rows, n_out] = X[rows, k_in] W[n_out, k_in]^T + b          (A, B K-major)
-        self.fwd.append(lambda: self._gemm('gemm_fwd', x, x_lo, False, W, W_lo, False, y, bvec, rows, n_out, k_in, False))
+        self.fwd.append(lambda: self._gemm('gemm_fwd', x, False, W, False, y, bvec, rows, n_out, k_in, False))
 
         def back():
-            if dy_lo is not dy and self.tensor_cores:
-                _lib.check(c.L.escgnn_tf32_split_lo(_p(dy), dy.stride(0), _p(dy_lo), dy_lo.stride(0), rows, n_out, c.st()),
-                           'tf32_split_lo')
             # wgrad: dW[n_out, k_in] = dY^T X   (A = dY stored [rows, n_out] = MN-major, B = X stored [rows, k_in] = MN-major)
-            self._gemm('gemm_wgrad', dy, dy_lo, True, x, x_lo, True, W.grad, None, n_out, k_in, rows, False)
+            self._gemm('gemm_wgrad', dy, True, x, True, W.grad, None, n_out, k_in, rows, False)
             _lib.check(c.L.escgnn_colsum(_p(dy), dy.stride(0), _p(c.rows[kind]), c.caps[kind], dy.size(1), _p(c.partial),
                                          _p(bvec.grad), c.st()), 'colsum')
             if need_dx:
                 # dgrad: dX[rows, k_in] = dY W      (A = dY K-major, B = W stored [n_out, k_in] = MN-major for this product)
-                self._gemm('gemm_dgrad', dy, dy_lo, False, W, W_lo, True, dx, None, rows, k_in, n_out, dx_accumulate)
+                self._gemm('gemm_dgrad', dy, False, W, True, dx, None, rows, k_in, n_out, dx_accumulate)
         self.bwd.append(back)
         return y, dy
 
@@ -387,10 +362,6 @@ class StaticTrainEngine(object):
     def _run_main(self):
         """Everything up to the gradients as a fixed launch sequence (run eagerly, or captured once and replayed)."""
         _lib.mark('start')
-        if self.tensor_cores:      # low tf32 plane of every parameter in one launch (weights changed in the last Adam step)
-            _lib.check(self.c.L.escgnn_tf32_split_lo(_p(self.opt.flat), self.opt.flat.numel(), _p(self.flat_lo),
-                                                     self.opt.flat.numel(), 1, self.opt.flat.numel(), self.c.st()),
-                       'tf32_split_lo')
         self._encode_and_index()
         self.opt.grad.zero_()
         _lib.mark('memset')

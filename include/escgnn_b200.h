@@ -221,13 +221,14 @@ int escgnn_loss_fwd_bwd(const float* d_pred, int ldp, const float* d_target, int
  * Replaces nn.Linear forward / dgrad / wgrad (run_graphcount.py:54-118, zinc_models.py:513-566, GINEConv.lin).
  *   a_mn_major == 0: A is [M,K] row-major (lda);  != 0: A is stored [K,M] row-major (i.e. the caller holds A^T)
  *   b_mn_major == 0: B is [N,K] row-major (ldb);  != 0: B is stored [K,N] row-major
- * d_*_hi is the fp32 operand itself, d_*_lo its low plane from escgnn_tf32_split_lo (x - tf32_trunc(x)).
- * every pitch (lda, lda_lo, ldb, ldb_lo) a multiple of 4 and every base 16-byte aligned (TMA). Rows of A beyond M read as zero. Split-K (used when the
- * output is small and K long, e.g. wgrad) needs d_workspace of escgnn_gemm_workspace_floats(M,N,K) floats. */
-int escgnn_gemm_tf32x3(const float* d_a_hi, int lda, const float* d_a_lo, int lda_lo, int a_mn_major, const float* d_b_hi,
-                       int ldb, const float* d_b_lo, int ldb_lo, int b_mn_major, float* d_c, int ldc, const float* d_bias,
-                       int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats, void* stream);
+ * Operands are plain fp32; the low tf32 planes are produced on chip. lda / ldb multiples of 4 and 16-byte aligned bases
+ * (TMA). Rows beyond the tensor extents read as zero. Split-K (small output, long K: wgrad) uses d_workspace
+ * (escgnn_gemm_workspace_floats(M,N,K) floats; NULL disables it) with an ordered reduction. */
+int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,
+                       const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats,
+                       void* stream);
 int64_t escgnn_gemm_workspace_floats(int M, int N, int K);
+/* x - tf32_trunc(x): the low plane of the 3xTF32 split (diagnostics; the GEMM computes it on chip) */
 int escgnn_tf32_split_lo(const float* d_x, int ldx, float* d_lo, int ldlo, int64_t rows, int cols, void* stream);
 /* CUDA-core GEMM with the same contract (any strides): odd shapes (K or N = 10, 1) and the test reference */
 int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,

@@ -37,10 +37,8 @@ def run_gemm(A, B, a_mn, b_mn, bias=None, C0=None, simple=False):
         return C
     ws_n = L.escgnn_gemm_workspace_floats(M, N, K)
     ws = torch.empty(max(ws_n, 1), device='cuda')
-    Al, Bl = _lo(As), _lo(Bs)          # keep both alive: the caching allocator would hand B's plane A's freed block
-    _lib.check(L.escgnn_gemm_tf32x3(_p(As), As.stride(0), _p(Al), Al.stride(0), int(a_mn), _p(Bs), Bs.stride(0), _p(Bl), Bl.stride(0), int(b_mn),
-                                    _p(C), N, _p(bias), M, N, K, int(C0 is not None), _p(ws) if ws_n else None, ws_n, _st()),
-               'gemm_tf32x3')
+    _lib.check(L.escgnn_gemm_tf32x3(_p(As), As.stride(0), int(a_mn), _p(Bs), Bs.stride(0), int(b_mn), _p(C), N, _p(bias), M, N, K,
+                                    int(C0 is not None), _p(ws) if ws_n else None, ws_n, _st()), 'gemm_tf32x3')
     return C
 
 
