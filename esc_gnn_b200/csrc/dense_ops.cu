@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int kTileRows = 128;     // rows per CTA
+constexpr int kTileRows = 128;     // rows per CTA (512 was measured slower: too few CTAs in flight)
 constexpr int kCols = 32;          // columns per CTA (one per lane)
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -50,6 +50,7 @@ colstats_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ d_
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
     float a = 0.f, b = 0.f;
     if (c < C)
+        #pragma unroll 8
         for (int r = r0 + warp; r < min(r0 + kTileRows, rows); r += 8) { const float v = x[(size_t)r * ldx + c]; a += v; b += v * v; }
     cta_reduce2(a, b, s);
     if (warp == 0 && c < C) { partial[((size_t)blockIdx.y * 2 + 0) * C + c] = a; partial[((size_t)blockIdx.y * 2 + 1) * C + c] = b; }
@@ -89,6 +90,7 @@ bn_act_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
     }
     if (c >= C) return;
     const float sc = rstd * g, sh = bt - mean * sc;
+    #pragma unroll 8
     for (int r = r0 + warp; r < min(r0 + kTileRows, rows_cap); r += 8) {
         float o = 0.f;
         if (r < rows) o = act_fwd(x[(size_t)r * ldx + c] * sc + sh, act);
@@ -108,6 +110,7 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ x, int ldx, const float* __re
     float a = 0.f, b = 0.f;
     if (c < C) {
         const float mu = mean[c], rs = rstd[c], g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+        #pragma unroll 4
         for (int r = r0 + warp; r < min(r0 + kTileRows, rows); r += 8) {
             const float xhat = (x[(size_t)r * ldx + c] - mu) * rs;
             float d = dy[(size_t)r * lddy + c];
@@ -139,6 +142,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ x, int ldx, const float* __res
     const float mu = mean[c], rs = rstd[c], g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
     const float inv_m = training ? 1.f / (float)max(rows, 1) : 0.f;
     const float m1 = s1 * inv_m, m2 = s2 * inv_m, k = g * rs;
+    #pragma unroll 4
     for (int r = r0 + warp; r < min(r0 + kTileRows, rows_cap); r += 8) {
         float o = 0.f;
         if (r < rows) {

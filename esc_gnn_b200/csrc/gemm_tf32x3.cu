@@ -91,8 +91,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Shared memory: STAGES raw stages {A 16 KB, B BLOCK_N*128 B} filled by TMA, ONE lo buffer of the same shape written by the
 // splitter warps (lo = x - trunc_tf32(x), element-wise, so the swizzled placement is simply preserved).  Two CTAs are
 // resident per SM (<= 113 KB each): while one waits on TMA / split / epilogue the other keeps the tensor pipe busy.
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS>
+__global__ void __launch_bounds__(kThreads, LO_BUFS == 1 ? 2 : 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int kABytes = kBlockM * 128;           // 16 KB
@@ -100,7 +100,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr int kStageBytes = kABytes + kBBytes;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* lo_buf = smem + (size_t)STAGES * kStageBytes;
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar, lo_free_bar, tmem_full_bar;
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[LO_BUFS], lo_free_bar[LO_BUFS], tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ float s_bias[BLOCK_N];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,7 +114,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         s_bias[i] = (p.bias && !p.partial && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&split_bar, 128); mbar_init(&lo_free_bar, 1); mbar_init(&tmem_full_bar, 1);
+        for (int b = 0; b < LO_BUFS; ++b) { mbar_init(&split_bar[b], 128); mbar_init(&lo_free_bar[b], 1); }
+        mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -154,11 +155,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-            const uint32_t a_lo = smem_u32(lo_buf), b_lo = a_lo + kABytes;
             for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
+                const int s = i % STAGES, lb = i % LO_BUFS;
+                const uint32_t a_lo = smem_u32(lo_buf + (size_t)lb * kStageBytes), b_lo = a_lo + kABytes;
                 mbar_wait(&full_bar[s], (i / STAGES) & 1);       // raw tiles landed (hi operands)
-                mbar_wait(&split_bar, i & 1);                    // lo planes of this k-block written
+                mbar_wait(&split_bar[lb], (i / LO_BUFS) & 1);    // lo planes of this k-block written
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes), b_hi = a_hi + kABytes;
                 #pragma unroll
@@ -175,7 +176,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
                 tcgen05_commit(&empty_bar[s]);          // raw stage reusable once these MMAs have read it
-                tcgen05_commit(&lo_free_bar);           // ... and so is the lo buffer
+                tcgen05_commit(&lo_free_bar[lb]);       // ... and so is the lo buffer
             }
             tcgen05_commit(&tmem_full_bar);             // accumulator complete
         }
@@ -183,11 +184,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ===== splitters (main loop), then epilogue: 4 warps, TMEM lane quarter = warp % 4 =====
         const int t = threadIdx.x - 64;                 // 0..127
         for (int i = 0; i < num_kb; ++i) {
-            const int s = i % STAGES;
+            const int s = i % STAGES, lb = i % LO_BUFS;
             mbar_wait(&full_bar[s], (i / STAGES) & 1);
-            mbar_wait(&lo_free_bar, (i & 1) ^ 1);       // previous k-block's MMAs are done with the lo buffer
+            mbar_wait(&lo_free_bar[lb], ((i / LO_BUFS) & 1) ^ 1);     // the MMAs that last read this lo buffer are done
             const float4* src = reinterpret_cast<const float4*>(smem + (size_t)s * kStageBytes);
-            float4* dst = reinterpret_cast<float4*>(lo_buf);
+            float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kStageBytes);
             #pragma unroll 4
             for (int q = t; q < kStageBytes / 16; q += 128) {
                 const float4 v = src[q];
@@ -199,7 +200,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 dst[q] = r;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to tcgen05.mma
-            mbar_arrive(&split_bar);
+            mbar_arrive(&split_bar[lb]);
         }
         const int q = warp & 3;
         mbar_wait(&tmem_full_bar, 0);
@@ -353,12 +354,13 @@ int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+// two shared-memory plans: "dual" = 2 raw stages + 1 lo buffer (<= 96 KB, two CTAs per SM hide each other's latencies),
+// "deep" = 4 raw stages + 2 lo buffers (<= 192 KB, one CTA per SM, split overlaps the MMAs of the previous k-block)
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS>
+int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
     constexpr int stage = kBlockM * 128 + BLOCK_N * 128;
-    constexpr int STAGES = 2;                                   // 2 raw stages + 1 lo buffer = 3 * stage <= 96 KB -> 2 CTAs / SM
-    const int smem = (STAGES + 1) * stage + 1024;
-    auto kern = gemm_tf32x3_kernel<BLOCK_N, A_MN, B_MN, STAGES>;
+    const int smem = (STAGES + LO_BUFS) * stage + 1024;
+    auto kern = gemm_tf32x3_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS>;
     static bool configured = false;          // once per instantiation (keeps stream capture free of attribute calls)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -367,6 +369,15 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 gri
     }
     kern<<<grid, kThreads, smem, st>>>(a, b, p);
     return (int)cudaGetLastError();
+}
+
+int g_gemm_plan = -1;      // -1 auto, 0 dual, 1 deep (escgnn_gemm_set_plan; experiments / tests)
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+    const int ctas = (int)(grid.x * grid.y * grid.z);
+    const bool deep = g_gemm_plan >= 0 ? g_gemm_plan == 1 : (ctas <= 148 && grid.z == 1);   // one wave at 1 CTA/SM: deeper ring
+    return deep ? launch_cfg<BLOCK_N, A_MN, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg<BLOCK_N, A_MN, B_MN, 2, 1>(a, b, p, grid, st);
 }
 
 template <bool A_MN, bool B_MN>
@@ -414,6 +425,8 @@ int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d
     gemm_simple_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, lda, a_mn_major, d_b, ldb, b_mn_major, d_c, ldc, d_bias, M, N, K, accumulate);
     return (int)cudaGetLastError();
 }
+
+int escgnn_gemm_set_plan(int plan) { g_gemm_plan = plan; return 0; }
 
 /* how many floats of split-K workspace a call with these sizes can use (0 = never splits) */
 int64_t escgnn_gemm_workspace_floats(int M, int N, int K) {

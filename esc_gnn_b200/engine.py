@@ -114,8 +114,14 @@ class StaticTrainEngine(object):
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.tensor_cores = tensor_cores
         self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
-        self.fwd, self.bwd = [], []
+        # weight / bias gradients are off the critical path (only Adam consumes them): they run on a side stream that
+        # forks from the backward chain wherever a dY becomes available and joins before the optimiser
+        self.side = torch.cuda.Stream(device=dev)
+        self.side_partial = torch.zeros_like(c.partial)
+        self._side_used = False
+        self.fwd, self.bwd, self._bns = [], [], []
         self._build_model_tape()
+        self._bn_synced = 0
         self.graph = None
         self.steps = 0
 
@@ -132,25 +138,70 @@ class StaticTrainEngine(object):
             _lib.check(c.L.escgnn_gemm_simple(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
                                               _p(bias), M, N, K, int(accumulate), c.st()), tag + '_simple')
 
-    def _linear(self, x, lin, kind, out=None, dx=None, dx_accumulate=False, need_dx=True):
-        """y = x W^T + b over capacity rows.  Returns (y, dy) buffers; backward fills W.grad, b.grad and dx."""
+    # ---- graph branches: work that is off the critical path runs on the side stream (captured as a parallel branch)
+    def _fork(self, fn):
+        """Run fn on the side stream after everything issued so far on the main stream; returns its completion event."""
+        main = torch.cuda.current_stream(self.c.dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            fn()
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self._side_used = True
+        return done
+
+    def _join(self):
+        if self._side_used:
+            done = torch.cuda.Event()
+            done.record(self.side)
+            torch.cuda.current_stream(self.c.dev).wait_event(done)
+            self._side_used = False
+
+    def _linear(self, x, lin, kind, out=None, dx=None, dx_accumulate=False, need_dx=True, feeds_bn=False, branch=False):
+        """y = x W^T + b over capacity rows.  Returns (y, dy) buffers; backward fills W.grad, b.grad and dx.
+
+        feeds_bn: the output goes straight into a training-mode BatchNorm.  Its bias gradient is sum_rows(dBN/dx), which
+        is identically zero (BN subtracts the batch mean), so the column-sum kernels are skipped and b.grad stays at the
+        zero the step starts from; torch computes the same quantity as ~1e-9 rounding noise.
+        branch: nothing downstream on the critical path needs this layer's output immediately (the conv.lin edge
+        projections: every layer's depends only on z): forward and dgrad run on the side stream as well; the caller waits on
+        the returned events."""
         c = self.c
         W, bvec = lin.weight, lin.bias
         n_out, k_in, rows = W.size(0), W.size(1), c.caps[kind]
         y = out if out is not None else c.buf(kind, n_out)
         dy = c.buf(kind, n_out)
         # forward: Y[rows, n_out] = X[rows, k_in] W[n_out, k_in]^T + b          (A, B K-major)
-        self.fwd.append(lambda: self._gemm('gemm_fwd', x, False, W, False, y, bvec, rows, n_out, k_in, False))
+        fwd_gemm = lambda: self._gemm('gemm_fwd', x, False, W, False, y, bvec, rows, n_out, k_in, False)
+        fwd_event = [None]
+        if branch:
+            self.fwd.append(lambda: fwd_event.__setitem__(0, self._fork(fwd_gemm)))
+        else:
+            self.fwd.append(fwd_gemm)
 
-        def back():
+        def grads():
             # wgrad: dW[n_out, k_in] = dY^T X   (A = dY stored [rows, n_out] = MN-major, B = X stored [rows, k_in] = MN-major)
             self._gemm('gemm_wgrad', dy, True, x, True, W.grad, None, n_out, k_in, rows, False)
-            _lib.check(c.L.escgnn_colsum(_p(dy), dy.stride(0), _p(c.rows[kind]), c.caps[kind], dy.size(1), _p(c.partial),
-                                         _p(bvec.grad), c.st()), 'colsum')
-            if need_dx:
-                # dgrad: dX[rows, k_in] = dY W      (A = dY K-major, B = W stored [n_out, k_in] = MN-major for this product)
-                self._gemm('gemm_dgrad', dy, False, W, True, dx, None, rows, k_in, n_out, dx_accumulate)
+            if not feeds_bn:
+                _lib.check(c.L.escgnn_colsum(_p(dy), dy.stride(0), _p(c.rows[kind]), c.caps[kind], dy.size(1),
+                                             _p(self.side_partial), _p(bvec.grad), c.st()), 'colsum')
+
+        def dgrad():
+            # dgrad: dX[rows, k_in] = dY W      (A = dY K-major, B = W stored [n_out, k_in] = MN-major for this product)
+            self._gemm('gemm_dgrad', dy, False, W, True, dx, None, rows, k_in, n_out, dx_accumulate)
+
+        def back():
+            if branch:
+                self._fork(lambda: (grads(), dgrad() if need_dx else None))
+            else:
+                self._fork(grads)                   # weight / bias gradients: only Adam consumes them
+                if need_dx:
+                    dgrad()
         self.bwd.append(back)
+        if branch:
+            return y, dy, fwd_event
         return y, dy
 
     def _bn_act(self, x, dx, bn, act, kind, out, dout, dout2=None, use_bn=True):
@@ -170,7 +221,7 @@ class StaticTrainEngine(object):
             _p(x), x.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(rstd),
             _p(c.partial), ACT[act], bn.eps, bn.momentum, 1, _p(c.rows[kind]), c.caps[kind], C, _p(out), out.stride(0),
             c.st()), 'bn_act_fwd'))
-        self.fwd.append(lambda: (bn.num_batches_tracked.add_(1), _lib.mark('misc')))
+        self._bns.append(bn)
         self.bwd.append(lambda: _lib.check(c.L.escgnn_bn_act_bwd(
             _p(x), x.stride(0), _p(dout), dout.stride(0), _p(dout2), dout2.stride(0) if dout2 is not None else 0, _p(mean),
             _p(rstd), _p(bn.weight), _p(bn.bias), ACT[act], 1, _p(c.partial), _p(c.rows[kind]), c.caps[kind], C,
@@ -238,7 +289,7 @@ class StaticTrainEngine(object):
                                                                     c.st()), 'bag_embed_bwd'))
         z1, dz1 = c.buf('E', H), c.buf('E', H)
         self._bn_act(z0, dz0, m.z_embedding[1], act, 'E', z1, dz1)
-        z2, dz2 = self._linear(z1, m.z_embedding[3], 'E', dx=dz1)
+        z2, dz2 = self._linear(z1, m.z_embedding[3], 'E', dx=dz1, feeds_bn=True)
         zcat, dzcat = c.buf('E', edge_dim), c.buf('E', edge_dim)
         self._bn_act(z2, dz2, m.z_embedding[5], act, 'E', zcat[:, :H], dzcat[:, :H])
         if self.variant == 'zinc':
@@ -251,19 +302,21 @@ class StaticTrainEngine(object):
         if self.variant == 'count':       # xs[0] = x_embedding(data.x)   (run_graphcount.py:166)
             seq = m.x_embedding
             dxin = c.buf('N', 10)
-            a, da = self._linear(x0, seq[0], 'N', dx=dxin, need_dx=False)
+            a, da = self._linear(x0, seq[0], 'N', dx=dxin, need_dx=False, feeds_bn=True)
             b_, db_ = c.buf('N', H), c.buf('N', H)
             self._bn_act(a, da, seq[2], act, 'N', b_, db_)
-            d_, dd_ = self._linear(b_, seq[4], 'N', dx=db_)
+            d_, dd_ = self._linear(b_, seq[4], 'N', dx=db_, feeds_bn=True)
             self._bn_act(d_, dd_, seq[6], act, 'N', xs[:, 0:H], dxs[:, 0:H])
             slot0 = 1
         # M3 GINE layers
         x_prev, dx_prev = x0, dx0
+        self.bwd.append(self._join)               # (runs after every conv backward) dzcat is complete before z_embedding's backward
         layer_dx_from_next = [None] * Lh          # gradient flowing into layer l's output from layer l+1's aggregation
         self.fwd.append(lambda: (dzcat.zero_(), _lib.mark('memset')))    # every conv.lin backward accumulates into it
         for l, conv in enumerate(convs):
             cin = conv.lin.weight.size(0)
-            ee, dee = self._linear(zcat, conv.lin, 'E', dx=dzcat, dx_accumulate=True)
+            ee, dee, ee_ready = self._linear(zcat, conv.lin, 'E', dx=dzcat, dx_accumulate=True, branch=True)
+            self.fwd.append(lambda ev=ee_ready: torch.cuda.current_stream(c.dev).wait_event(ev[0]))
             agg, dagg = c.buf('N', cin), c.buf('N', cin)
             # x_prev for l >= 1 is a strided slice of xs: the aggregation kernels want dense rows -> keep a dense copy
             if l == 0:
@@ -276,10 +329,10 @@ class StaticTrainEngine(object):
                 layer_dx_from_next[l - 1] = dxin_buf
             self._gine(xin, dxin_buf, ee, dee, conv.eps, agg, dagg)
             seq = conv.nn
-            h1, dh1 = self._linear(agg, seq[0], 'N', dx=dagg)
+            h1, dh1 = self._linear(agg, seq[0], 'N', dx=dagg, feeds_bn=True)
             h2, dh2 = c.buf('N', H), c.buf('N', H)
             self._bn_act(h1, dh1, seq[2], act, 'N', h2, dh2)
-            h3, dh3 = self._linear(h2, seq[4], 'N', dx=dh2)
+            h3, dh3 = self._linear(h2, seq[4], 'N', dx=dh2, feeds_bn=True)
             out_slice = xs[:, (slot0 + l) * H:(slot0 + l + 1) * H]
             dout_slice = dxs[:, (slot0 + l) * H:(slot0 + l + 1) * H]
             # the last BN of layer l: its backward needs layer l+1's dx, which is only known after the loop wiring;
@@ -295,9 +348,10 @@ class StaticTrainEngine(object):
             head_in, dhead_in, kind = pooled, dpooled, 'B'
         else:
             head_in, dhead_in, kind = xs, dxs, 'N'
-        p1, dp1 = self._linear(head_in, m.lin1, kind, dx=dhead_in)
+        head_bn = self.G > 1 or kind == 'N'
+        p1, dp1 = self._linear(head_in, m.lin1, kind, dx=dhead_in, feeds_bn=head_bn)
         p2, dp2 = c.buf(kind, H), c.buf(kind, H)
-        self._bn_act(p1, dp1, m.bn_lin1, act, kind, p2, dp2, use_bn=(self.G > 1 or kind == 'N'))
+        self._bn_act(p1, dp1, m.bn_lin1, act, kind, p2, dp2, use_bn=head_bn)
         pred, dpred = self._linear(p2, m.lin2, kind, dx=dp2)
         self.pred = pred
         self.debug_buffers = dict(head_in=head_in, dhead_in=dhead_in, p1=p1, dp1=dp1, p2=p2, dp2=dp2, pred=pred, dpred=dpred,
@@ -316,7 +370,7 @@ class StaticTrainEngine(object):
             _p(x), x.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(rstd),
             _p(c.partial), ACT[act], bn.eps, bn.momentum, 1, _p(c.rows['N']), c.caps['N'], C, _p(out), out.stride(0),
             c.st()), 'bn_act_fwd'))
-        self.fwd.append(lambda: (bn.num_batches_tracked.add_(1), _lib.mark('misc')))
+        self._bns.append(bn)
 
         def back():
             d2 = dx_from_next[l]
@@ -369,6 +423,7 @@ class StaticTrainEngine(object):
             f()
         for b in reversed(self.bwd):
             b()
+        self._join()                                 # every weight gradient is in place before the optimiser / exchange
 
     @torch.no_grad()
     def _run_opt(self):
@@ -426,6 +481,14 @@ class StaticTrainEngine(object):
                 self.graph_opt.replay()
         self.steps += 1
         return self.loss
+
+    def sync_counters(self):
+        """BatchNorm `num_batches_tracked` is bookkeeping only (momentum is fixed): advanced lazily, outside the graph."""
+        d = self.steps - self._bn_synced
+        if d:
+            for bn in self._bns:
+                bn.num_batches_tracked.add_(d)
+            self._bn_synced = self.steps
 
     def check_errors(self):
         """Lazy data-error check (degree >= 200, bad ids, capacity): one sync, call it once per epoch."""

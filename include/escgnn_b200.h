@@ -228,6 +228,8 @@ int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d
                        const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats,
                        void* stream);
 int64_t escgnn_gemm_workspace_floats(int M, int N, int K);
+/* shared-memory plan of the GEMM: -1 auto, 0 = 2 stages + 1 lo buffer (2 CTAs/SM), 1 = 4 stages + 2 lo buffers (1 CTA/SM) */
+int escgnn_gemm_set_plan(int plan);
 /* x - tf32_trunc(x): the low plane of the 3xTF32 split (diagnostics; the GEMM computes it on chip) */
 int escgnn_tf32_split_lo(const float* d_x, int ldx, float* d_lo, int ldlo, int64_t rows, int cols, void* stream);
 /* CUDA-core GEMM with the same contract (any strides): odd shapes (K or N = 10, 1) and the test reference */
