@@ -210,24 +210,10 @@ def run_own(args):
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
     eng.check_errors()
-    # ---- per-kernel durations: the same launch sequence run eagerly with a CUDA event after every launch
-    eng.use_graph = False
-    prof_steps = min(args.steps, 10)
-    _lib.PROFILE = []
+    # ---- per-kernel device times: the step captured once more on one stream with an event after every launch, replayed
     launches_a = _lib.LAUNCHES['n']
-    for i in range(prof_steps):
-        flush.zero_()
-        eng.step(dev_pool[i % n_pool])
-    torch.cuda.synchronize()
-    launches_per_step = (_lib.LAUNCHES['n'] - launches_a) // prof_steps
-    marks, _lib.PROFILE = _lib.PROFILE, None
-    eng.use_graph = True
-    kernel_ms, calls = {}, {}
-    for (l0, e0), (l1, e1) in zip(marks[:-1], marks[1:]):
-        if l1 == 'start':
-            continue
-        kernel_ms[l1] = kernel_ms.get(l1, 0.0) + e0.elapsed_time(e1) / prof_steps
-        calls[l1] = calls.get(l1, 0) + 1.0 / prof_steps
+    kernel_ms, calls = eng.profile(dev_pool[0], reps=min(args.steps, 10), flush=flush)
+    launches_per_step = _lib.LAUNCHES['n'] - launches_a
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -252,8 +238,8 @@ def run_own(args):
     roofline = dict(bound='hbm', kernel=top, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                     traffic=None, peak_source=peak_src, share_of_step=kernel_ms[top] / sum_ms,
                     algorithmic_bytes_per_launch=bytes_launch, launch_ms=per_launch_ms,
-                    note='share_of_step is over the event-bracketed eager replay of the same launch sequence; '
-                         'ego_* kernels are issue-bound integer / fp64 graph kernels (profiles/), see DESIGN.md')
+                    note='kernel times: graph replay of the same launch sequence on one stream with an event after every launch '
+                         '(the timed step overlaps weight-gradient work on a second graph branch)')
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

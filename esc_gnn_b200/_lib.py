@@ -40,6 +40,7 @@ SIGNATURES = {
     'escgnn_sorted_ids_to_ptr': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
     'escgnn_bag_embed_fwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp, _vp]),
     'escgnn_bag_embed_bwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp, _vp]),
+    'escgnn_bag_embed_bwd_sorted': (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'escgnn_gine_aggregate_fwd': (_i32, [_vp] * 6 + [_i64, _i32, _vp, _vp, _vp]),
     'escgnn_gine_aggregate_bwd': (_i32, [_vp] * 7 + [_i64, _i32] + [_vp] * 6),
     'escgnn_segment_pool_fwd': (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
@@ -88,15 +89,16 @@ KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'scan'
                     'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
                     'edge_distance': 2, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 2, 'bn_act_bwd': 2,
                     'act_fwd': 1, 'act_bwd': 1, 'colsum': 2, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
-                    'make_dims': 1, 'adam_step_device': 2, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1}
+                    'make_dims': 1, 'adam_step_device': 2, 'bag_embed_bwd_sorted': 4, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1}
 LAUNCHES = {'n': 0}
 PROFILE = None      # bench.py: a list; every mark() appends (label, cuda event) -> per-kernel durations by differencing
+PROFILE_EXTERNAL = False   # record graph-capturable ("external") events: per-kernel device times of a REPLAYED graph
 
 
 def mark(label):
     if PROFILE is not None:
         import torch
-        ev = torch.cuda.Event(enable_timing=True)
+        ev = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
         ev.record()
         PROFILE.append((label, ev))
 

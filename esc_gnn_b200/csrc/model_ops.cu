@@ -154,6 +154,130 @@ bag_embed_bwd_kernel(const float* __restrict__ g, int H, const int64_t* __restri
     }
 }
 
+// ---------------------------------------------------------------- K3 backward, index-major (no hot-row atomics)
+// dW[idx] += cnt * g[e] has ~30 records per edge and a few indices (d0 = 0, d1 = 1, degree 2 ...) present in EVERY edge, so
+// per-record atomics serialise on those rows.  Instead the records are transposed once per step into index-major order
+// (count -> scan -> fill, shared-memory histograms, one global atomic per (CTA, index)), then reduced in balanced chunks of
+// consecutive records: a warp accumulates a run of equal indices in registers and touches global memory once per run.
+constexpr int kBagRows = 1800;         // z_initial has 1800 rows (run_graphcount.py:51-53)
+constexpr int kBagChunk = 64;          // sorted records per warp in the reduction
+
+__global__ void __launch_bounds__(256)
+bag_count_kernel(const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off, const int32_t* __restrict__ rec_nnz,
+                 int64_t n_edges, const int* d_count, int* __restrict__ counts) {
+    __shared__ int hist[kBagRows];
+    for (int i = threadIdx.x; i < kBagRows; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t e_end = dyn(n_edges, d_count);
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < e_end; e += wpg) {
+        const int64_t a = rec_off[e]; const int k = rec_nnz[e];
+        for (int j = lane; j < k; j += 32) atomicAdd(&hist[rec[a + j] & ((1u << ESCGNN_REC_IDX_BITS) - 1)], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBagRows; i += blockDim.x) if (hist[i]) atomicAdd(&counts[i], hist[i]);
+}
+
+// single block: ptr = exclusive scan of counts (ptr[1800] = total records); cursors zeroed
+__global__ void __launch_bounds__(1024)
+bag_scan_kernel(const int* __restrict__ counts, int* __restrict__ ptr, int* __restrict__ cursor) {
+    __shared__ int s_warp[33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int carry = 0;
+    for (int i0 = 0; i0 < kBagRows; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const int v = i < kBagRows ? counts[i] : 0;
+        int incl = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(kFullMask, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane], wi = w;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(kFullMask, wi, d); if (lane >= d) wi += t; }
+            s_warp[lane] = wi - w;
+            if (lane == 31) s_warp[32] = wi;
+        }
+        __syncthreads();
+        if (i < kBagRows) { ptr[i] = carry + s_warp[warp] + incl - v; cursor[i] = 0; }
+        carry += s_warp[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ptr[kBagRows] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+bag_fill_kernel(const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off, const int32_t* __restrict__ rec_nnz,
+                int64_t n_edges, const int* d_count, const int* __restrict__ ptr, int* __restrict__ cursor,
+                int* __restrict__ sorted_edge, float* __restrict__ sorted_cnt) {
+    __shared__ int hist[kBagRows], base[kBagRows];
+    for (int i = threadIdx.x; i < kBagRows; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t e_all = dyn(n_edges, d_count);
+    const int64_t per = (e_all + gridDim.x - 1) / gridDim.x;
+    const int64_t e_lo = (int64_t)blockIdx.x * per, e_hi = min(e_lo + per, e_all);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int64_t e = e_lo + warp; e < e_hi; e += nw) {
+        const int64_t a = rec_off[e]; const int k = rec_nnz[e];
+        for (int j = lane; j < k; j += 32) atomicAdd(&hist[rec[a + j] & ((1u << ESCGNN_REC_IDX_BITS) - 1)], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBagRows; i += blockDim.x) {
+        const int c = hist[i];
+        base[i] = c ? ptr[i] + atomicAdd(&cursor[i], c) : 0;      // this CTA's contiguous range inside index i's segment
+        hist[i] = 0;
+    }
+    __syncthreads();
+    for (int64_t e = e_lo + warp; e < e_hi; e += nw) {
+        const int64_t a = rec_off[e]; const int k = rec_nnz[e];
+        for (int j = lane; j < k; j += 32) {
+            const uint32_t r = rec[a + j];
+            const int idx = r & ((1u << ESCGNN_REC_IDX_BITS) - 1);
+            const int pos = base[idx] + atomicAdd(&hist[idx], 1);
+            sorted_edge[pos] = (int)e;
+            sorted_cnt[pos] = (float)(r >> ESCGNN_REC_IDX_BITS);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bag_reduce_kernel(const float* __restrict__ g, int H, const int* __restrict__ ptr, const int* __restrict__ sorted_edge,
+                  const float* __restrict__ sorted_cnt, float* __restrict__ dW) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int total = ptr[kBagRows];
+    const int64_t p0 = chunk * kBagChunk;
+    if (p0 >= total) return;
+    const int p1 = (int)min((int64_t)total, p0 + kBagChunk);
+    int lo = 0, hi = kBagRows;                       // index owning record p0: last idx with ptr[idx] <= p0
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ptr[mid] <= p0) lo = mid; else hi = mid; }
+    int idx = lo, seg_end = ptr[idx + 1];
+    const int chunks = H >> 2;
+    for (int c0 = 0; c0 < chunks; c0 += 64) {
+        const int ca = c0 + lane, cb = c0 + 32 + lane;
+        float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = accA;
+        int cur = idx, cur_end = seg_end;
+        for (int p = (int)p0; p < p1; ++p) {
+            while (p >= cur_end) {                   // run of `cur` ends: flush (also skips empty indices)
+                float* row = dW + (size_t)cur * H;
+                if (ca < chunks && (accA.x != 0.f || accA.y != 0.f || accA.z != 0.f || accA.w != 0.f)) atomicAdd(reinterpret_cast<float4*>(row + 4 * ca), accA);
+                if (cb < chunks && (accB.x != 0.f || accB.y != 0.f || accB.z != 0.f || accB.w != 0.f)) atomicAdd(reinterpret_cast<float4*>(row + 4 * cb), accB);
+                accA = make_float4(0.f, 0.f, 0.f, 0.f); accB = accA;
+                ++cur; cur_end = ptr[cur + 1];
+            }
+            const float cnt = sorted_cnt[p];
+            const float* grow = g + (size_t)sorted_edge[p] * H;
+            if (ca < chunks) { const float4 v = ld4(grow + 4 * ca); accA.x += cnt * v.x; accA.y += cnt * v.y; accA.z += cnt * v.z; accA.w += cnt * v.w; }
+            if (cb < chunks) { const float4 v = ld4(grow + 4 * cb); accB.x += cnt * v.x; accB.y += cnt * v.y; accB.z += cnt * v.z; accB.w += cnt * v.w; }
+        }
+        float* row = dW + (size_t)cur * H;
+        if (ca < chunks) atomicAdd(reinterpret_cast<float4*>(row + 4 * ca), accA);
+        if (cb < chunks) atomicAdd(reinterpret_cast<float4*>(row + 4 * cb), accB);
+    }
+}
+
 // ---------------------------------------------------------------- K4 / K5 GINE aggregation
 template <bool kVec>
 __global__ void __launch_bounds__(256)
@@ -400,6 +524,24 @@ int escgnn_bag_embed_bwd(const float* d_grad, int hidden, const int64_t* d_pos_i
     cudaStream_t st = (cudaStream_t)stream;
     if (d_rec) bag_embed_bwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_grad_weight, d_count);
     else bag_embed_bwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_grad_weight, d_count);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_bag_embed_bwd_sorted(const float* d_grad, int hidden, const uint32_t* d_rec, const int64_t* d_rec_off,
+                                const int32_t* d_rec_nnz, int64_t n_edges, int64_t rec_cap, float* d_grad_weight,
+                                int32_t* d_work /* 3*1800 + 1 ints */, int32_t* d_sorted_edge, float* d_sorted_cnt,
+                                const int* d_count, void* stream) {
+    if (hidden % 4 != 0) return ESCGNN_ERR_BAD_ARG;
+    if (n_edges <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* counts = d_work; int* ptr = d_work + kBagRows; int* cursor = d_work + 2 * kBagRows + 1;
+    cudaMemsetAsync(counts, 0, kBagRows * sizeof(int), st);
+    unsigned gb = blocks_for(n_edges, 8 * 16); if (gb > 296) gb = 296; if (gb < 1) gb = 1;
+    bag_count_kernel<<<gb, 256, 0, st>>>(d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, counts);
+    bag_scan_kernel<<<1, 1024, 0, st>>>(counts, ptr, cursor);
+    bag_fill_kernel<<<gb, 256, 0, st>>>(d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, ptr, cursor, d_sorted_edge, d_sorted_cnt);
+    const int64_t chunks = (rec_cap + kBagChunk - 1) / kBagChunk;
+    bag_reduce_kernel<<<blocks_for(chunks, 8), 256, 0, st>>>(d_grad, hidden, ptr, d_sorted_edge, d_sorted_cnt, d_grad_weight);
     return (int)cudaGetLastError();
 }
 

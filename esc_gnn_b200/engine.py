@@ -119,6 +119,7 @@ class StaticTrainEngine(object):
         self.side = torch.cuda.Stream(device=dev)
         self.side_partial = torch.zeros_like(c.partial)
         self._side_used = False
+        self.inline_branches = False
         self.fwd, self.bwd, self._bns = [], [], []
         self._build_model_tape()
         self._bn_synced = 0
@@ -142,6 +143,11 @@ class StaticTrainEngine(object):
     def _fork(self, fn):
         """Run fn on the side stream after everything issued so far on the main stream; returns its completion event."""
         main = torch.cuda.current_stream(self.c.dev)
+        if self.inline_branches:                  # profiling: one stream, so every interval belongs to exactly one kernel
+            fn()
+            done = torch.cuda.Event()
+            done.record(main)
+            return done
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(self.side):
@@ -284,9 +290,12 @@ class StaticTrainEngine(object):
         self.fwd.append(lambda: _lib.check(c.L.escgnn_bag_embed_fwd(_p(W0), H, None, None, None, _p(self.rec), _p(self.rec_off),
                                                                     _p(self.rec_nnz), c.caps['E'], _p(z0), _p(c.rows['E']),
                                                                     c.st()), 'bag_embed_fwd'))
-        self.bwd.append(lambda: _lib.check(c.L.escgnn_bag_embed_bwd(_p(dz0), H, None, None, None, _p(self.rec), _p(self.rec_off),
-                                                                    _p(self.rec_nnz), c.caps['E'], _p(W0.grad), _p(c.rows['E']),
-                                                                    c.st()), 'bag_embed_bwd'))
+        bag_work = torch.zeros(3 * 1800 + 8, dtype=torch.int32, device=c.dev)
+        bag_edge = torch.zeros(c.caps['nnz'], dtype=torch.int32, device=c.dev)
+        bag_cnt = torch.zeros(c.caps['nnz'], dtype=torch.float32, device=c.dev)
+        self.bwd.append(lambda: _lib.check(c.L.escgnn_bag_embed_bwd_sorted(
+            _p(dz0), H, _p(self.rec), _p(self.rec_off), _p(self.rec_nnz), c.caps['E'], c.caps['nnz'], _p(W0.grad), _p(bag_work),
+            _p(bag_edge), _p(bag_cnt), _p(c.rows['E']), c.st()), 'bag_embed_bwd_sorted'))
         z1, dz1 = c.buf('E', H), c.buf('E', H)
         self._bn_act(z0, dz0, m.z_embedding[1], act, 'E', z1, dz1)
         z2, dz2 = self._linear(z1, m.z_embedding[3], 'E', dx=dz1, feeds_bn=True)
@@ -481,6 +490,37 @@ class StaticTrainEngine(object):
                 self.graph_opt.replay()
         self.steps += 1
         return self.loss
+
+    def profile(self, raw, reps=10, flush=None):
+        """Per-kernel DEVICE times of the captured step: the same launch sequence captured once more on a single stream
+        with a graph-capturable event after every launch, replayed `reps` times (parameters are restored afterwards).
+        Returns ({label: ms per step}, {label: launches per step})."""
+        import copy
+        saved = (self.opt.flat.clone(), self.opt.exp_avg.clone(), self.opt.exp_avg_sq.clone(), self.opt.state.clone(),
+                 [(b.running_mean.clone(), b.running_var.clone()) for b in self._bns])
+        self.load(raw)
+        torch.cuda.synchronize()
+        _lib.PROFILE, _lib.PROFILE_EXTERNAL, self.inline_branches = [], True, True
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run_main()
+            self._run_opt()
+            _lib.mark('end')
+        marks, _lib.PROFILE, _lib.PROFILE_EXTERNAL, self.inline_branches = _lib.PROFILE, None, False, False
+        ms, calls = {}, {}
+        for _ in range(reps):
+            if flush is not None:
+                flush.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            for (l0, e0), (l1, e1) in zip(marks[:-1], marks[1:]):
+                ms[l1] = ms.get(l1, 0.0) + e0.elapsed_time(e1) / reps
+                calls[l1] = calls.get(l1, 0) + 1.0 / reps
+        self.opt.flat.copy_(saved[0]); self.opt.exp_avg.copy_(saved[1]); self.opt.exp_avg_sq.copy_(saved[2])
+        self.opt.state.copy_(saved[3])
+        for b, (rm, rv) in zip(self._bns, saved[4]):
+            b.running_mean.copy_(rm); b.running_var.copy_(rv)
+        return ms, calls
 
     def sync_counters(self):
         """BatchNorm `num_batches_tracked` is bookkeeping only (momentum is fixed): advanced lazily, outside the graph."""

@@ -133,6 +133,14 @@ int escgnn_bag_embed_bwd(const float* d_grad, int hidden, const int64_t* d_pos_i
                          const int32_t* d_rec_nnz, int64_t n_edges, float* d_grad_weight, const int* d_count,
                          void* stream);
 
+/* Same gradient, index-major: the records are transposed on the device (count / scan / fill) and reduced in balanced
+ * chunks, so the indices present in every edge do not serialise on atomics. Packed records only. rec_cap bounds the
+ * record count (grid sizing); d_work: 3*1800+1 int32; d_sorted_edge / d_sorted_cnt: rec_cap entries each. */
+int escgnn_bag_embed_bwd_sorted(const float* d_grad, int hidden, const uint32_t* d_rec, const int64_t* d_rec_off,
+                                const int32_t* d_rec_nnz, int64_t n_edges, int64_t rec_cap, float* d_grad_weight,
+                                int32_t* d_work, int32_t* d_sorted_edge, float* d_sorted_cnt, const int* d_count,
+                                void* stream);
+
 /* M3 GINE aggregation.  Replaces PyG GINEConv.propagate + the (1+eps)*x residual (in-tree twin:
  * GraphGPS/graphgps/layer/gine_conv_layer.py:56-84; ogb_mol_gnn.py:346-358):
  *   out[i] = (1+eps) x[i] + sum_{e: dst_e = i} relu(x[src_e] + edge_feat[e]).

@@ -214,3 +214,26 @@ def test_static_engine_handles_varying_batches_under_one_graph():
     with torch.no_grad():
         pg, pe = eng_g.model(b), eng_e.model(b)
     assert (pg - pe).abs().max().item() <= 2e-3 * max(1.0, pe.abs().max().item())
+
+
+def test_bag_embed_backward_index_major_matches_atomic_version():
+    import ctypes
+    from esc_gnn_b200 import _lib, synth
+    from esc_gnn_b200.transform import encode_batch
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    src, dst, eptr, nptr = synth.make_batch_arrays(2, 4000, 64)
+    r = encode_batch(torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), torch.as_tensor(eptr), torch.as_tensor(nptr),
+                     3, True, False, expand=True)
+    E, H = r.num_edges, 256
+    g = torch.randn(E + 50, H, device='cuda')
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    d_count = torch.tensor([E], dtype=torch.int32, device='cuda')
+    dW = torch.zeros(1800, H, device='cuda')
+    work = torch.zeros(3 * 1800 + 8, dtype=torch.int32, device='cuda')
+    cap = r.nnz + 1000
+    se, sc = torch.zeros(cap, dtype=torch.int32, device='cuda'), torch.zeros(cap, device='cuda')
+    _lib.check(_lib.lib().escgnn_bag_embed_bwd_sorted(P(g), H, P(r.rec), P(r.rec_off), P(r.rec_nnz), E + 50, cap, P(dW), P(work), P(se),
+                                                      P(sc), P(d_count), st), 'bag_embed_bwd_sorted')
+    ref = torch.zeros(1800, H, device='cuda', dtype=torch.float64)
+    ref.index_add_(0, r.pos_index, g[r.pos_batch].double() * r.pos_enc.view(-1, 1).double())
+    torch.testing.assert_close(dW.double(), ref, rtol=1e-5, atol=1e-4)
