@@ -283,12 +283,12 @@ template <bool kVec>
 __global__ void __launch_bounds__(256)
 gine_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ee, const int64_t* __restrict__ src,
                 const int* __restrict__ dst_ptr, const int* __restrict__ dst_perm, const float* __restrict__ eps,
-                int n, int C, float* __restrict__ out, const int* d_count) {
+                int n, int C, float* __restrict__ out, const int* d_count, int ldx, int lde, int ldo) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     if (i >= dyn(n, d_count)) {               // padded rows stay zero
-        for (int c = lane; c < C; c += 32) out[(size_t)i * C + c] = 0.f;
+        for (int c = lane; c < C; c += 32) out[(size_t)i * ldo + c] = 0.f;
         return;
     }
     const float scale = 1.f + eps[0];
@@ -299,12 +299,12 @@ gine_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ee, const
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int k = a; k < b; ++k) {
                 const int e = dst_perm[k];
-                const float4 xv = ld4(x + (size_t)src[e] * C + 4 * c), ev = ld4(ee + (size_t)e * C + 4 * c);
+                const float4 xv = ld4(x + (size_t)src[e] * ldx + 4 * c), ev = ld4(ee + (size_t)e * lde + 4 * c);
                 acc.x += fmaxf(xv.x + ev.x, 0.f); acc.y += fmaxf(xv.y + ev.y, 0.f);
                 acc.z += fmaxf(xv.z + ev.z, 0.f); acc.w += fmaxf(xv.w + ev.w, 0.f);
             }
-            const float4 xi = ld4(x + (size_t)i * C + 4 * c);
-            st4(out + (size_t)i * C + 4 * c, make_float4(acc.x + scale * xi.x, acc.y + scale * xi.y,
+            const float4 xi = ld4(x + (size_t)i * ldx + 4 * c);
+            st4(out + (size_t)i * ldo + 4 * c, make_float4(acc.x + scale * xi.x, acc.y + scale * xi.y,
                                                           acc.z + scale * xi.z, acc.w + scale * xi.w));
         }
     } else {
@@ -312,9 +312,9 @@ gine_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ee, const
             float acc = 0.f;
             for (int k = a; k < b; ++k) {
                 const int e = dst_perm[k];
-                acc += fmaxf(x[(size_t)src[e] * C + c] + ee[(size_t)e * C + c], 0.f);
+                acc += fmaxf(x[(size_t)src[e] * ldx + c] + ee[(size_t)e * lde + c], 0.f);
             }
-            out[(size_t)i * C + c] = acc + scale * x[(size_t)i * C + c];
+            out[(size_t)i * ldo + c] = acc + scale * x[(size_t)i * ldx + c];
         }
     }
 }
@@ -324,12 +324,12 @@ __global__ void __launch_bounds__(256)
 gine_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ x, const float* __restrict__ ee,
                 const int64_t* __restrict__ dst, const int* __restrict__ src_ptr, const int* __restrict__ src_perm,
                 const float* __restrict__ eps, int n, int C, float* __restrict__ g_x, float* __restrict__ g_e,
-                float* __restrict__ dots, const int* d_count) {
+                float* __restrict__ dots, const int* d_count, int ldx, int lde, int ldg, int ldgx) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     if (i >= dyn(n, d_count)) {
-        for (int c = lane; c < C; c += 32) g_x[(size_t)i * C + c] = 0.f;
+        for (int c = lane; c < C; c += 32) g_x[(size_t)i * ldgx + c] = 0.f;
         if (lane == 0) dots[i] = 0.f;
         return;
     }
@@ -339,34 +339,34 @@ gine_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ x, co
     if (kVec) {
         const int chunks = C >> 2;
         for (int c = lane; c < chunks; c += 32) {
-            const float4 xi = ld4(x + (size_t)i * C + 4 * c);
+            const float4 xi = ld4(x + (size_t)i * ldx + 4 * c);
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int k = a; k < b; ++k) {
                 const int e = src_perm[k];
-                const float4 gv = ld4(g_out + (size_t)dst[e] * C + 4 * c), ev = ld4(ee + (size_t)e * C + 4 * c);
+                const float4 gv = ld4(g_out + (size_t)dst[e] * ldg + 4 * c), ev = ld4(ee + (size_t)e * lde + 4 * c);
                 float4 m;
                 m.x = xi.x + ev.x > 0.f ? gv.x : 0.f; m.y = xi.y + ev.y > 0.f ? gv.y : 0.f;
                 m.z = xi.z + ev.z > 0.f ? gv.z : 0.f; m.w = xi.w + ev.w > 0.f ? gv.w : 0.f;
-                st4(g_e + (size_t)e * C + 4 * c, m);
+                st4(g_e + (size_t)e * lde + 4 * c, m);
                 acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
             }
-            const float4 gi = ld4(g_out + (size_t)i * C + 4 * c);
-            st4(g_x + (size_t)i * C + 4 * c, make_float4(acc.x + scale * gi.x, acc.y + scale * gi.y,
+            const float4 gi = ld4(g_out + (size_t)i * ldg + 4 * c);
+            st4(g_x + (size_t)i * ldgx + 4 * c, make_float4(acc.x + scale * gi.x, acc.y + scale * gi.y,
                                                           acc.z + scale * gi.z, acc.w + scale * gi.w));
             dot += gi.x * xi.x + gi.y * xi.y + gi.z * xi.z + gi.w * xi.w;
         }
     } else {
         for (int c = lane; c < C; c += 32) {
-            const float xi = x[(size_t)i * C + c];
+            const float xi = x[(size_t)i * ldx + c];
             float acc = 0.f;
             for (int k = a; k < b; ++k) {
                 const int e = src_perm[k];
-                const float m = xi + ee[(size_t)e * C + c] > 0.f ? g_out[(size_t)dst[e] * C + c] : 0.f;
-                g_e[(size_t)e * C + c] = m;
+                const float m = xi + ee[(size_t)e * lde + c] > 0.f ? g_out[(size_t)dst[e] * ldg + c] : 0.f;
+                g_e[(size_t)e * lde + c] = m;
                 acc += m;
             }
-            const float gi = g_out[(size_t)i * C + c];
-            g_x[(size_t)i * C + c] = acc + scale * gi;
+            const float gi = g_out[(size_t)i * ldg + c];
+            g_x[(size_t)i * ldgx + c] = acc + scale * gi;
             dot += gi * xi;
         }
     }
@@ -545,13 +545,30 @@ int escgnn_bag_embed_bwd_sorted(const float* d_grad, int hidden, const uint32_t*
     return (int)cudaGetLastError();
 }
 
+int escgnn_gine_aggregate_fwd_ld(const float* d_x, int ldx, const float* d_edge_feat, int lde, const int64_t* d_src,
+                                 const int32_t* d_dst_ptr, const int32_t* d_dst_perm, const float* d_eps, int64_t n_nodes,
+                                 int channels, float* d_out, int ldo, const int* d_count, void* stream);
+int escgnn_gine_aggregate_bwd_ld(const float* d_grad_out, int ldg, const float* d_x, int ldx, const float* d_edge_feat, int lde,
+                                 const int64_t* d_dst, const int32_t* d_src_ptr, const int32_t* d_src_perm, const float* d_eps,
+                                 int64_t n_nodes, int channels, float* d_grad_x, int ldgx, float* d_grad_edge_feat,
+                                 float* d_node_dots, float* d_grad_eps, const int* d_count, void* stream);
+
 int escgnn_gine_aggregate_fwd(const float* d_x, const float* d_edge_feat, const int64_t* d_src, const int32_t* d_dst_ptr,
                               const int32_t* d_dst_perm, const float* d_eps, int64_t n_nodes, int channels,
                               float* d_out, const int* d_count, void* stream) {
+    return escgnn_gine_aggregate_fwd_ld(d_x, channels, d_edge_feat, channels, d_src, d_dst_ptr, d_dst_perm, d_eps, n_nodes, channels,
+                                        d_out, channels, d_count, stream);
+}
+
+int escgnn_gine_aggregate_fwd_ld(const float* d_x, int ldx, const float* d_edge_feat, int lde, const int64_t* d_src,
+                                 const int32_t* d_dst_ptr, const int32_t* d_dst_perm, const float* d_eps, int64_t n_nodes,
+                                 int channels, float* d_out, int ldo, const int* d_count, void* stream) {
     if (n_nodes <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (channels % 4 == 0) gine_fwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count);
-    else gine_fwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count);
+    const bool vec = channels % 4 == 0 && ldx % 4 == 0 && lde % 4 == 0 && ldo % 4 == 0 &&
+                     (((uintptr_t)d_x | (uintptr_t)d_edge_feat | (uintptr_t)d_out) & 15) == 0;
+    if (vec) gine_fwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count, ldx, lde, ldo);
+    else gine_fwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count, ldx, lde, ldo);
     return (int)cudaGetLastError();
 }
 
@@ -559,10 +576,22 @@ int escgnn_gine_aggregate_bwd(const float* d_grad_out, const float* d_x, const f
                               const int32_t* d_src_ptr, const int32_t* d_src_perm, const float* d_eps, int64_t n_nodes,
                               int channels, float* d_grad_x, float* d_grad_edge_feat, float* d_node_dots,
                               float* d_grad_eps, const int* d_count, void* stream) {
+    return escgnn_gine_aggregate_bwd_ld(d_grad_out, channels, d_x, channels, d_edge_feat, channels, d_dst, d_src_ptr, d_src_perm, d_eps,
+                                        n_nodes, channels, d_grad_x, channels, d_grad_edge_feat, d_node_dots, d_grad_eps, d_count,
+                                        stream);
+}
+
+int escgnn_gine_aggregate_bwd_ld(const float* d_grad_out, int ldg, const float* d_x, int ldx, const float* d_edge_feat, int lde,
+                                 const int64_t* d_dst, const int32_t* d_src_ptr, const int32_t* d_src_perm, const float* d_eps,
+                                 int64_t n_nodes, int channels, float* d_grad_x, int ldgx, float* d_grad_edge_feat,
+                                 float* d_node_dots, float* d_grad_eps, const int* d_count, void* stream) {
     if (n_nodes <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (channels % 4 == 0) gine_bwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count);
-    else gine_bwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count);
+    const bool vec = channels % 4 == 0 && ldx % 4 == 0 && lde % 4 == 0 && ldg % 4 == 0 && ldgx % 4 == 0 &&
+                     (((uintptr_t)d_x | (uintptr_t)d_edge_feat | (uintptr_t)d_grad_out | (uintptr_t)d_grad_x |
+                       (uintptr_t)d_grad_edge_feat) & 15) == 0;
+    if (vec) gine_bwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count, ldx, lde, ldg, ldgx);
+    else gine_bwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count, ldx, lde, ldg, ldgx);
     if (d_grad_eps) reduce_sum_kernel<<<1, 1024, 0, st>>>(d_node_dots, n_nodes, d_grad_eps, 0);
     return (int)cudaGetLastError();
 }

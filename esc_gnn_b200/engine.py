@@ -63,7 +63,11 @@ class StaticTrainEngine(object):
         if not p0.is_cuda:
             raise RuntimeError('StaticTrainEngine needs a CUDA model; there is no CPU fallback')
         self.model, self.variant, self.flags = model, variant, dict(flags)
-        self.opt = FlatAdam(model.parameters(), lr=lr)
+        # the edge projections `conv.lin` of ALL layers read the same z, so they are one GEMM against the row-concatenation
+        # of their weights: lay those tensors out adjacently (256-wide layers first, the narrow first layer last)
+        self.lin_convs = list(model.convs) + [model.conv1]
+        self.opt = FlatAdam(model.parameters(), lr=lr, first=[cv.lin.weight for cv in self.lin_convs] +
+                            [cv.lin.bias for cv in self.lin_convs])
         self.distributed, self.use_graph = distributed, use_graph
         dev = p0.device
         self.G = int(max_graphs)
@@ -116,6 +120,7 @@ class StaticTrainEngine(object):
         self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
         # weight / bias gradients are off the critical path (only Adam consumes them): they run on a side stream that
         # forks from the backward chain wherever a dY becomes available and joins before the optimiser
+        self.gemm_ws_side = torch.zeros_like(self.gemm_ws)
         self.side = torch.cuda.Stream(device=dev)
         self.side_partial = torch.zeros_like(c.partial)
         self._side_used = False
@@ -132,9 +137,10 @@ class StaticTrainEngine(object):
         c = self.c
         ok = all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (A, B)) and self.tensor_cores
         if ok:
+            # split-K partials: one workspace per stream (GEMMs of the two graph branches may run concurrently)
+            ws = self.gemm_ws_side if torch.cuda.current_stream(c.dev) == self.side else self.gemm_ws
             _lib.check(c.L.escgnn_gemm_tf32x3(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
-                                              _p(bias), M, N, K, int(accumulate), _p(self.gemm_ws), self.gemm_ws.numel(),
-                                              c.st()), tag)
+                                              _p(bias), M, N, K, int(accumulate), _p(ws), ws.numel(), c.st()), tag)
         else:
             _lib.check(c.L.escgnn_gemm_simple(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
                                               _p(bias), M, N, K, int(accumulate), c.st()), tag + '_simple')
@@ -250,23 +256,19 @@ class StaticTrainEngine(object):
                                                                     _p(c.rows[kind]), c.caps[kind], C, _p(table.weight.grad),
                                                                     c.st()), 'embedding_bwd'))
 
-    def _gine(self, x, dx, ee, dee, eps, out, dout, dx_second=None):
-        """out = (1+eps) x + sum relu(x_src + ee).  Backward writes dx (or dx_second when dx already has an owner)."""
+    def _gine(self, x, dx, ee, dee, eps, out, dout):
+        """out = (1+eps) x + sum relu(x_src + ee).  x / ee / dee may be column slices (leading dimensions are passed).
+        dee rows past the edge count are kept zero by the caller (one memset of the whole projection buffer per step)."""
         c = self.c
         C = x.size(1)
-        assert x.is_contiguous() or x.stride(0) == C, 'gine kernels read dense rows'
         dots = torch.zeros(c.caps['N'], dtype=torch.float32, device=c.dev)
-        self.fwd.append(lambda: _lib.check(c.L.escgnn_gine_aggregate_fwd(
-            _p(x), _p(ee), _p(self.ei[0]), _p(self.dst_ptr), _p(self.dst_perm), _p(eps), c.caps['N'], C, _p(out),
-            _p(c.rows['N']), c.st()), 'gine_aggregate_fwd'))
-
-        def back():
-            dee.zero_()                                    # rows past the edge count must stay zero for the weight GEMMs
-            _lib.mark('memset')
-            _lib.check(c.L.escgnn_gine_aggregate_bwd(
-                _p(dout), _p(x), _p(ee), _p(self.ei[1]), _p(self.src_ptr), _p(self.src_perm), _p(eps), c.caps['N'], C,
-                _p(dx), _p(dee), _p(dots), _p(eps.grad), _p(c.rows['N']), c.st()), 'gine_aggregate_bwd')
-        self.bwd.append(back)
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_gine_aggregate_fwd_ld(
+            _p(x), x.stride(0), _p(ee), ee.stride(0), _p(self.ei[0]), _p(self.dst_ptr), _p(self.dst_perm), _p(eps), c.caps['N'], C,
+            _p(out), out.stride(0), _p(c.rows['N']), c.st()), 'gine_aggregate_fwd_ld'))
+        self.bwd.append(lambda: _lib.check(c.L.escgnn_gine_aggregate_bwd_ld(
+            _p(dout), dout.stride(0), _p(x), x.stride(0), _p(ee), ee.stride(0), _p(self.ei[1]), _p(self.src_ptr),
+            _p(self.src_perm), _p(eps), c.caps['N'], C, _p(dx), dx.stride(0), _p(dee), _p(dots), _p(eps.grad), _p(c.rows['N']),
+            c.st()), 'gine_aggregate_bwd_ld'))
 
     # ------------------------------------------------------------------ model tape
     def _build_model_tape(self):
@@ -320,20 +322,43 @@ class StaticTrainEngine(object):
         # M3 GINE layers
         x_prev, dx_prev = x0, dx0
         self.bwd.append(self._join)               # (runs after every conv backward) dzcat is complete before z_embedding's backward
+        # ---- edge projections of every layer in one GEMM: ee_all[E, sum C_in] = zcat @ W_cat^T + b_cat
+        col, off = {}, 0
+        for cv in self.lin_convs:
+            col[id(cv)] = off
+            off += cv.lin.weight.size(0)
+        n_tot, ld_all = off, (off + 3) // 4 * 4
+        flat, gflat = self.opt.flat, self.opt.grad
+        w0 = (self.lin_convs[0].lin.weight.data_ptr() - flat.data_ptr()) // 4
+        b0 = (self.lin_convs[0].lin.bias.data_ptr() - flat.data_ptr()) // 4
+        W_cat, dW_cat = flat[w0:w0 + n_tot * edge_dim].view(n_tot, edge_dim), gflat[w0:w0 + n_tot * edge_dim].view(n_tot, edge_dim)
+        b_cat, db_cat = flat[b0:b0 + n_tot], gflat[b0:b0 + n_tot]
+        assert self.lin_convs[-1].lin.weight.data_ptr() == W_cat[col[id(self.lin_convs[-1])]].data_ptr(), 'lin weights not adjacent'
+        assert self.lin_convs[-1].lin.bias.data_ptr() == b_cat[col[id(self.lin_convs[-1])]:].data_ptr(), 'lin biases not adjacent'
+        ee_all, dee_all = c.buf('E', ld_all), c.buf('E', ld_all)
+        E_rows = c.caps['E']
+        ee_ready = [None]
+        self.fwd.append(lambda: ee_ready.__setitem__(0, self._fork(
+            lambda: self._gemm('gemm_fwd', zcat, False, W_cat, False, ee_all, b_cat, E_rows, n_tot, edge_dim, False))))
+        self.fwd.append(lambda: (dee_all.zero_(), _lib.mark('memset')))    # rows past the edge count stay zero for the GEMMs below
+
+        def proj_back():                          # runs after every layer's backward has filled its slice of dee_all
+            self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, False),
+                                _lib.check(c.L.escgnn_colsum(_p(dee_all), dee_all.stride(0), _p(c.rows['E']), E_rows, n_tot,
+                                                             _p(self.side_partial), _p(db_cat), c.st()), 'colsum')))
+            self._gemm('gemm_dgrad', dee_all, False, W_cat, True, dzcat, None, E_rows, edge_dim, n_tot, False)
+        self.bwd.append(proj_back)
         layer_dx_from_next = [None] * Lh          # gradient flowing into layer l's output from layer l+1's aggregation
-        self.fwd.append(lambda: (dzcat.zero_(), _lib.mark('memset')))    # every conv.lin backward accumulates into it
         for l, conv in enumerate(convs):
             cin = conv.lin.weight.size(0)
-            ee, dee, ee_ready = self._linear(zcat, conv.lin, 'E', dx=dzcat, dx_accumulate=True, branch=True)
-            self.fwd.append(lambda ev=ee_ready: torch.cuda.current_stream(c.dev).wait_event(ev[0]))
+            c0 = col[id(conv)]
+            ee, dee = ee_all[:, c0:c0 + cin], dee_all[:, c0:c0 + cin]
             agg, dagg = c.buf('N', cin), c.buf('N', cin)
-            # x_prev for l >= 1 is a strided slice of xs: the aggregation kernels want dense rows -> keep a dense copy
             if l == 0:
                 xin, dxin_buf = x_prev, dx_prev
-            else:
-                xin = c.buf('N', H)
-                src_slice = xs[:, (slot0 + l - 1) * H:(slot0 + l) * H]
-                self.fwd.append(lambda a=xin, b=src_slice: (a.copy_(b), _lib.mark('copy')))
+                self.fwd.append(lambda: torch.cuda.current_stream(c.dev).wait_event(ee_ready[0]))
+            else:                                  # the previous layer's output is a column slice of the JK buffer
+                xin = xs[:, (slot0 + l - 1) * H:(slot0 + l) * H]
                 dxin_buf = c.buf('N', H)
                 layer_dx_from_next[l - 1] = dxin_buf
             self._gine(xin, dxin_buf, ee, dee, conv.eps, agg, dagg)

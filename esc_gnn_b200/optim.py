@@ -12,8 +12,13 @@ from . import _lib
 
 
 class FlatAdam(object):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
-        self.params = [p for p in params if p.requires_grad]
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, first=()):
+        """`first`: parameters to lay out first and in this order (tensors the engine wants adjacent in memory, e.g. the
+        edge-projection weights of all layers so they form ONE [sum C_in, edge_dim] operand); the rest keep their order."""
+        params = [p for p in params if p.requires_grad]
+        head = [p for p in first if p.requires_grad]
+        ids = {id(p) for p in head}
+        self.params = head + [p for p in params if id(p) not in ids]
         if not self.params or not self.params[0].is_cuda:
             raise RuntimeError('FlatAdam needs CUDA parameters; there is no CPU fallback')
         dev = self.params[0].device

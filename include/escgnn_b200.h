@@ -155,6 +155,16 @@ int escgnn_gine_aggregate_bwd(const float* d_grad_out, const float* d_x, const f
                               int channels, float* d_grad_x, float* d_grad_edge_feat, float* d_node_dots,
                               float* d_grad_eps, const int* d_count, void* stream);
 
+/* the same with explicit leading dimensions: x / out / gradients may be column slices of wider buffers (the JK concat
+ * buffer, one projection of all layers' edge features), so no slice is ever copied */
+int escgnn_gine_aggregate_fwd_ld(const float* d_x, int ldx, const float* d_edge_feat, int lde, const int64_t* d_src,
+                                 const int32_t* d_dst_ptr, const int32_t* d_dst_perm, const float* d_eps, int64_t n_nodes,
+                                 int channels, float* d_out, int ldo, const int* d_count, void* stream);
+int escgnn_gine_aggregate_bwd_ld(const float* d_grad_out, int ldg, const float* d_x, int ldx, const float* d_edge_feat, int lde,
+                                 const int64_t* d_dst, const int32_t* d_src_ptr, const int32_t* d_src_perm, const float* d_eps,
+                                 int64_t n_nodes, int channels, float* d_grad_x, int ldgx, float* d_grad_edge_feat,
+                                 float* d_node_dots, float* d_grad_eps, const int* d_count, void* stream);
+
 /* M4 pooling over the sorted `batch` vector.  Replaces global_add_pool / global_mean_pool
  * (run_graphcount.py:179, zinc_models.py:602, ogb_mol_gnn.py:124,768). mean divides by max(count,1). */
 int escgnn_segment_pool_fwd(const float* d_x, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
