@@ -232,14 +232,34 @@ def run_own(args):
            'gine_aggregate_bwd': e_out * (3 * 4 * H2 + 8) + 4 * e_out * H2 + 2 * 4 * n_nodes * H2,
            'bn_act_fwd': 3 * 4 * e_out * H2, 'bn_act_bwd': 5 * 4 * e_out * H2}
     per_launch_ms = kernel_ms[top] / max(calls[top], 1)
-    bytes_launch = alg.get(top, alg['encode'])
-    achieved = bytes_launch / (per_launch_ms * 1e-3) / 1e9
     sum_ms = sum(kernel_ms.values())
-    roofline = dict(bound='hbm', kernel=top, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                    traffic=None, peak_source=peak_src, share_of_step=kernel_ms[top] / sum_ms,
-                    algorithmic_bytes_per_launch=bytes_launch, launch_ms=per_launch_ms,
-                    note='kernel times: graph replay of the same launch sequence on one stream with an event after every launch '
-                         '(the timed step overlaps weight-gradient work on a second graph branch)')
+    if top.startswith('gemm'):
+        # dense contraction: useful flops of the Linear layers of one step, 1/3 each for fwd, dgrad, wgrad
+        L1 = LAYERS - 1
+        flops = 2.0 * (e_out * H2 * H2 + e_out * (H2 + 32) * (32 + L1 * H2) + n_nodes * (32 * H2 + H2 * H2) +
+                       L1 * n_nodes * 2 * H2 * H2 + BATCH * (LAYERS * H2 * H2 + H2))
+        pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops_sustained', 1388.2) \
+            if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 1400.0
+        achieved = flops / (kernel_ms[top] * 1e-3) / 1e12
+        roofline = dict(bound='tensor', kernel=top + ' (gemm_tf32x3_kernel)', achieved=achieved, peak=pk, unit='TFLOP/s',
+                        frac=achieved / pk, traffic=None, peak_source=peak_src + ' dense bf16, sustained',
+                        share_of_step=kernel_ms[top] / sum_ms, algorithmic_flops_per_step=flops, launches_per_step=calls[top],
+                        launch_ms=per_launch_ms,
+                        note='useful fp32-equivalent flops; the kernel issues 3 tf32 MMA passes per product and tf32 runs at half '
+                             'the bf16 rate, so 1/6 of this peak is the ceiling of a 3xTF32 scheme')
+    else:
+        bytes_launch = alg.get(top, alg['encode'])
+        achieved = bytes_launch / (per_launch_ms * 1e-3) / 1e9
+        roofline = dict(bound='hbm', kernel=top, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                        traffic=None, peak_source=peak_src, share_of_step=kernel_ms[top] / sum_ms,
+                        algorithmic_bytes_per_launch=bytes_launch, launch_ms=per_launch_ms)
+    roofline['how'] = ('kernel times: graph replay of the same launch sequence on one stream with a CUDA event after every '
+                       'launch (the timed step overlaps weight-gradient work on a second graph branch)')
+    enc_ms = kernel_ms.get('encode', 0) + kernel_ms.get('encode_rd', 0)
+    roofline['encoder'] = dict(kernels='ego_rd + ego_encode', ms_per_step=enc_ms, contract_bytes=alg['encode'],
+                               achieved_GBps=alg['encode'] / (enc_ms * 1e-3) / 1e9 if enc_ms else None,
+                               frac_of_hbm=alg['encode'] / (enc_ms * 1e-3) / 1e9 / peak if enc_ms else None,
+                               note='issue-bound integer / fp64 kernels (profiles/): the byte roofline is not what limits them')
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -80,9 +80,7 @@ ego_encode_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict_
             if (u == v && lane == 0) {          // phantom duplicate root: degree 0, z = (0,0)
                 fresh += hist_add(hist, 0) + hist_add(hist, kBinZ0) + hist_add(hist, kBinZ1);
             }
-            for (int w = lane; w < n; w += 32) {
-                const uint32_t du = nib(rowU, w), dv = nib(rowV, w);
-                if (du == kFar && dv == kFar) continue;
+            auto visit = [&](int w, uint32_t du, uint32_t dv) {       // one member w of S = B_u U B_v
                 const int z0 = min((int)du, H + 1), z1 = min((int)dv, H + 1);
                 fresh += hist_add(hist, kBinZ0 + z0) + hist_add(hist, kBinZ1 + z1);
                 const int cbase = kBinCode + (z0 * B + z1) * B * B;
@@ -98,6 +96,24 @@ ego_encode_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict_
                     fresh += hist_add(hist, cbase + min((int)bu, H + 1) * B + min((int)bv, H + 1));
                 }
                 if (deg >= 200) deg_err = true; else fresh += hist_add(hist, deg);
+            };
+            if (n <= kWideNodes) {                       // small graphs: one node per lane
+                for (int w = lane; w < n; w += 32) {
+                    const uint32_t du = nib(rowU, w), dv = nib(rowV, w);
+                    if (du == kFar && dv == kFar) continue;
+                    visit(w, du, dv);
+                }
+            } else {                                     // large graphs: one distance word (8 nodes) per lane, members only
+                for (int wi = lane; wi < rw; wi += 32) {
+                    const uint32_t xu = rowU[wi], xv = rowV[wi];
+                    uint32_t m = nibbles_near(xu) | nibbles_near(xv);
+                    while (m) {
+                        const int sh = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int w = wi * 8 + (sh >> 2);
+                        if (w < n) visit(w, (xu >> sh) & 15u, (xv >> sh) & 15u);
+                    }
+                }
             }
             // rd block comes pre-binned from K1b
             uint32_t rdc = 0;
@@ -120,27 +136,24 @@ ego_encode_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict_
             __syncwarp();
             // ---- ascending emission; each lane owns one word = two consecutive bins; table is zeroed on the way
             int pos = 0;
+            const unsigned lt = (1u << lane) - 1u;
             auto emit_words = [&](int w_lo, int w_hi, auto bin_to_index) {
                 for (int w0 = w_lo; w0 < w_hi; w0 += 32) {
                     const int wi = w0 + lane;
                     uint32_t word = 0;
-                    if (wi < w_hi) { word = hist[wi]; if (word) hist[wi] = 0; }
+                    if (wi < w_hi) word = hist[wi];
+                    const unsigned any = __ballot_sync(kFull, word != 0u);
+                    if (any == 0u) continue;                       // most 32-word spans of the code block are empty
+                    if (word) hist[wi] = 0;
                     const uint32_t c0 = word & 0xffffu, c1 = word >> 16;
-                    const int mine = (c0 != 0) + (c1 != 0);
-                    int incl = mine;
-                    #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int t = __shfl_up_sync(kFull, incl, d);
-                        if (lane >= d) incl += t;
-                    }
-                    const int total = __shfl_sync(kFull, incl, 31);
-                    if (total == 0) continue;
-                    int p = pos + incl - mine;
+                    const unsigned m0 = __ballot_sync(kFull, c0 != 0u), m1 = __ballot_sync(kFull, c1 != 0u);
+                    // records of lower lanes come first; inside a lane the even bin precedes the odd one
+                    int p = pos + __popc(m0 & lt) + __popc(m1 & lt);
                     if (room) {
                         if (c0) rec[off + p++] = (uint32_t)bin_to_index(2 * wi) | (c0 << ESCGNN_REC_IDX_BITS);
                         if (c1) rec[off + p] = (uint32_t)bin_to_index(2 * wi + 1) | (c1 << ESCGNN_REC_IDX_BITS);
                     }
-                    pos += total;
+                    pos += __popc(m0) + __popc(m1);
                 }
             };
             emit_words(0, deg_words, [](int b) { return b; });                           // degree   [0,200)

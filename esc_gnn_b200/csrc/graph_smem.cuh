@@ -50,6 +50,16 @@ __device__ __forceinline__ uint32_t nib(const uint32_t* row, int w) {
     return (row[w >> 3] >> ((w & 7) << 2)) & 15u;
 }
 
+// SWAR over the 8 nibbles of a word: bit 4k set where nibble k == v
+__device__ __forceinline__ uint32_t nibbles_equal(uint32_t word, uint32_t v) {
+    const uint32_t y = word ^ (v * 0x11111111u);            // matching nibbles become 0
+    return ~(y | (y >> 1) | (y >> 2) | (y >> 3)) & 0x11111111u;
+}
+// bit 4k set where nibble k != 15 (node within h hops)
+__device__ __forceinline__ uint32_t nibbles_near(uint32_t word) { return ~nibbles_equal(word, kFar) & 0x11111111u; }
+
+constexpr int kWideNodes = 64;      // graphs above this size scan 8 nodes per lane (one distance word) instead of 1
+
 // Build both CSRs and run the N bounded BFS.  All threads of the CTA call this; `base` points at the graph's
 // working set (shared or global), `s_misc` at >= 2 ints of shared scratch.  Returns false (uniformly) when the
 // edge list holds a node id outside [0, n) (error bit already raised).
@@ -128,8 +138,7 @@ __device__ bool load_graph(GraphView& g, unsigned char* base, const int64_t* __r
         __syncwarp();
         for (int level = 0; level < H; ++level) {
             bool grew = false;
-            for (int w = lane; w < n; w += 32) {
-                if (((row[w >> 3] >> ((w & 7) << 2)) & 15u) != (uint32_t)level) continue;
+            auto expand = [&](int w) {
                 const uint32_t a = g.in_ptr[w], b = g.in_ptr[w + 1];
                 for (uint32_t k = a; k < b; ++k) {
                     const int s = g.in_adj[k];
@@ -138,6 +147,19 @@ __device__ bool load_graph(GraphView& g, unsigned char* base, const int64_t* __r
                         // 15 -> level+1: clearing the zero bits of (level+1) is idempotent among same-level racers
                         atomicAnd(const_cast<uint32_t*>(&row[s >> 3]), ~((15u ^ (uint32_t)(level + 1)) << sh));
                         grew = true;
+                    }
+                }
+            };
+            if (n <= kWideNodes) {
+                for (int w = lane; w < n; w += 32)
+                    if (((row[w >> 3] >> ((w & 7) << 2)) & 15u) == (uint32_t)level) expand(w);
+            } else {                                   // frontier = nibbles equal to `level`, 8 nodes per lane per step
+                for (int wi = lane; wi < rw; wi += 32) {
+                    uint32_t m = nibbles_equal(row[wi], (uint32_t)level);
+                    while (m) {
+                        const int w = wi * 8 + ((__ffs(m) - 1) >> 2);
+                        m &= m - 1;
+                        if (w < n) expand(w);
                     }
                 }
             }
