@@ -26,6 +26,7 @@ SIGNATURES = {
     'escgnn_version': (_i32, []),
     'escgnn_rewrite_self_loops': (_i32, [_vp] * 4 + [_i64] + [_vp] * 5),
     'escgnn_encode': (_i32, [_vp] * 4 + [_i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    'escgnn_encode_subset': (_i32, [_vp] * 4 + [_i64, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     'escgnn_encode_scratch_bytes': (_i64, [_i64, _i64, _i32]),
     'escgnn_encode_rd_scratch_bytes': (_i64, [_i64, _i64, _i32]),
     'escgnn_encode_rd': (_i32, [_vp] * 4 + [_i64, _i32, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
@@ -86,7 +87,7 @@ def lib():
 
 
 # kernels launched by one successful call of each entry point (bench.py's `gpu_launches` evidence)
-KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'scan': 3, 'expand_records': 1,
+KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'encode_subset': 1, 'scan': 3, 'expand_records': 1,
                     'csr_build': 4, 'sorted_ids_to_ptr': 1, 'bag_embed_fwd': 1, 'bag_embed_bwd': 1,
                     'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'gine_aggregate_fwd_ld': 1, 'gine_aggregate_bwd_ld': 2, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
                     'edge_distance': 2, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 2, 'bn_act_bwd': 2,

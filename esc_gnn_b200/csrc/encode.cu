@@ -29,14 +29,14 @@ __device__ __forceinline__ int hist_add(uint32_t* hist, int b) {
     return ((old >> ((b & 1) << 4)) & 0xffffu) == 0u;
 }
 
-template <int H>
-__global__ void __launch_bounds__(256)
+template <int H, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 ego_encode_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo_dst,
                   const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int n_graphs,
                   const uint16_t* __restrict__ rdh, uint32_t* __restrict__ rec, long long rec_cap,
                   int64_t* __restrict__ rec_off, int32_t* __restrict__ rec_nnz, int32_t* __restrict__ edge_graph,
                   unsigned long long* counters, long long graph_smem_bytes, unsigned char* scratch,
-                  long long slab_bytes) {
+                  long long slab_bytes, const int32_t* __restrict__ graph_ids) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     __shared__ int s_misc[2];
@@ -54,8 +54,8 @@ ego_encode_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict_
         __syncthreads();
         if (tid == 0) s_ticket = (int)atomicAdd(&counters[ESCGNN_CTR_TICKET], 1ull);
         __syncthreads();
-        const int gi = s_ticket;
-        if (gi >= n_graphs) break;
+        if (s_ticket >= n_graphs) break;
+        const int gi = graph_ids ? graph_ids[s_ticket] : s_ticket;      // size-class launches walk an id list
         const long long e0 = eo_ptr[gi];
         const int e = (int)(eo_ptr[gi + 1] - e0);
         const int n = (int)(node_ptr[gi + 1] - node_ptr[gi]);
@@ -295,12 +295,12 @@ __global__ void expand_records_kernel(const uint32_t* __restrict__ rec, const in
     }
 }
 
-template <int H>
-static int launch_encode(const int64_t* eo_src, const int64_t* eo_dst, const int64_t* eo_ptr, const int64_t* node_ptr,
+template <int H, int kThreads>
+static int launch_encode_t(const int64_t* eo_src, const int64_t* eo_dst, const int64_t* eo_ptr, const int64_t* node_ptr,
                          int64_t n_graphs, const uint16_t* rdh, uint32_t* rec, int64_t rec_cap, int64_t* rec_off,
                          int32_t* rec_nnz, int32_t* edge_graph, unsigned long long* counters, int64_t max_nodes,
-                         int64_t max_edges, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
-    constexpr int kThreads = 256, kNw = kThreads / 32;
+                         int64_t max_edges, void* scratch, int64_t scratch_bytes, const int32_t* graph_ids, cudaStream_t st) {
+    constexpr int kNw = kThreads / 32;
     const int64_t hist_bytes = align16((int64_t)kNw * Bins<H>::kWords * 4);
     const int64_t need = GraphLayout(max_nodes, max_edges).total;
     int dev = 0, sms = 148, smem_optin = 0;
@@ -314,7 +314,7 @@ static int launch_encode(const int64_t* eo_src, const int64_t* eo_dst, const int
         graph_bytes = cap < 64 * 1024 ? cap : 64 * 1024;
     }
     const int64_t smem = hist_bytes + graph_bytes;
-    auto kern = ego_encode_kernel<H>;
+    auto kern = ego_encode_kernel<H, kThreads>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     int occ = 1;
@@ -330,11 +330,25 @@ static int launch_encode(const int64_t* eo_src, const int64_t* eo_dst, const int
         const int64_t fit = scratch_bytes / slab;
         if (grid > fit) grid = fit;
     }
+    cudaMemsetAsync(counters + ESCGNN_CTR_TICKET, 0, sizeof(unsigned long long), st);     // every launch starts its own queue
     kern<<<(unsigned)grid, kThreads, (size_t)smem, st>>>(eo_src, eo_dst, eo_ptr, node_ptr, (int)n_graphs, rdh, rec,
                                                           (long long)rec_cap, rec_off, rec_nnz, edge_graph, counters,
                                                           (long long)graph_bytes, (unsigned char*)scratch,
-                                                          (long long)slab);
+                                                          (long long)slab, graph_ids);
     return (int)cudaGetLastError();
+}
+
+// large graphs get 16 warps per CTA: their distance matrix allows one CTA per SM, so parallelism has to come from warps
+template <int H>
+static int launch_encode(const int64_t* eo_src, const int64_t* eo_dst, const int64_t* eo_ptr, const int64_t* node_ptr,
+                         int64_t n_graphs, const uint16_t* rdh, uint32_t* rec, int64_t rec_cap, int64_t* rec_off,
+                         int32_t* rec_nnz, int32_t* edge_graph, unsigned long long* counters, int64_t max_nodes,
+                         int64_t max_edges, void* scratch, int64_t scratch_bytes, const int32_t* graph_ids, cudaStream_t st) {
+    if (max_nodes > 160)
+        return launch_encode_t<H, 512>(eo_src, eo_dst, eo_ptr, node_ptr, n_graphs, rdh, rec, rec_cap, rec_off, rec_nnz, edge_graph,
+                                        counters, max_nodes, max_edges, scratch, scratch_bytes, graph_ids, st);
+    return launch_encode_t<H, 256>(eo_src, eo_dst, eo_ptr, node_ptr, n_graphs, rdh, rec, rec_cap, rec_off, rec_nnz, edge_graph,
+                                   counters, max_nodes, max_edges, scratch, scratch_bytes, graph_ids, st);
 }
 
 }  // namespace escgnn
@@ -342,6 +356,12 @@ static int launch_encode(const int64_t* eo_src, const int64_t* eo_dst, const int
 using namespace escgnn;
 
 extern "C" {
+
+int escgnn_encode_subset(const int64_t* d_eo_src, const int64_t* d_eo_dst, const int64_t* d_eo_ptr,
+                         const int64_t* d_node_ptr, int64_t n_graphs, const int32_t* d_graph_ids, int h, const uint16_t* d_rdh,
+                         uint32_t* d_rec, int64_t rec_cap, int64_t* d_rec_off, int32_t* d_rec_nnz, int32_t* d_edge_graph,
+                         unsigned long long* d_counters, int64_t max_nodes, int64_t max_edges, void* d_scratch,
+                         int64_t scratch_bytes, void* stream);
 
 int escgnn_version(void) { return 100; }
 
@@ -385,13 +405,22 @@ int escgnn_encode(const int64_t* d_eo_src, const int64_t* d_eo_dst, const int64_
                   int64_t rec_cap, int64_t* d_rec_off, int32_t* d_rec_nnz, int32_t* d_edge_graph,
                   unsigned long long* d_counters, int64_t max_nodes, int64_t max_edges, void* d_scratch,
                   int64_t scratch_bytes, void* stream) {
+    return escgnn_encode_subset(d_eo_src, d_eo_dst, d_eo_ptr, d_node_ptr, n_graphs, nullptr, h, d_rdh, d_rec, rec_cap, d_rec_off,
+                                d_rec_nnz, d_edge_graph, d_counters, max_nodes, max_edges, d_scratch, scratch_bytes, stream);
+}
+
+int escgnn_encode_subset(const int64_t* d_eo_src, const int64_t* d_eo_dst, const int64_t* d_eo_ptr,
+                         const int64_t* d_node_ptr, int64_t n_graphs, const int32_t* d_graph_ids, int h, const uint16_t* d_rdh,
+                         uint32_t* d_rec, int64_t rec_cap, int64_t* d_rec_off, int32_t* d_rec_nnz, int32_t* d_edge_graph,
+                         unsigned long long* d_counters, int64_t max_nodes, int64_t max_edges, void* d_scratch,
+                         int64_t scratch_bytes, void* stream) {
     if (n_graphs <= 0) return 0;
     if (h < 1 || h > 4) return ESCGNN_ERR_BAD_ARG;            // reference: one_hot(code, 1300) raises for h >= 5
     if (max_nodes > 65535 || max_edges > 65535) return ESCGNN_ERR_TOO_LARGE;
     cudaStream_t st = (cudaStream_t)stream;
 #define ESC_GO(H) launch_encode<H>(d_eo_src, d_eo_dst, d_eo_ptr, d_node_ptr, n_graphs, d_rdh, d_rec, rec_cap, \
                                    d_rec_off, d_rec_nnz, d_edge_graph, d_counters, max_nodes, max_edges, d_scratch, \
-                                   scratch_bytes, st)
+                                   scratch_bytes, d_graph_ids, st)
     switch (h) {
         case 1: return ESC_GO(1);
         case 2: return ESC_GO(2);

@@ -119,13 +119,26 @@ def encode_batch(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=False,
     dev = src.device
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     G = edge_ptr.numel() - 1
+    classes = None
     if max_nodes is None or max_edges is None:
         ep, npt = edge_ptr.cpu(), node_ptr.cpu()
         nn = (npt[1:] - npt[:-1])
         ee = (ep[1:] - ep[:-1])
+        eo_n = (ee + nn) if self_loop else ee
         max_nodes = int(nn.max()) if G else 0
-        max_edges = int((ee + nn).max() if self_loop else ee.max()) if G else 0
+        max_edges = int(eo_n.max()) if G else 0
         n_total = int(npt[-1])
+        if G and max_nodes > 96:
+            # size classes by on-chip footprint (distance matrix ~ n^2/2 bytes): one launch per class keeps the occupancy of
+            # the small graphs independent of the largest graph in the batch
+            foot = (nn * ((nn + 7) // 8) * 4 + 4 * eo_n + 8 * nn).numpy()
+            bounds = [8 << 10, 24 << 10, 56 << 10, 1 << 62]
+            classes, lo = [], 0
+            for hi in bounds:
+                ids = np.nonzero((foot > lo) & (foot <= hi))[0]
+                lo = hi
+                if ids.size:
+                    classes.append((torch.as_tensor(ids.astype(np.int32)).to(src.device), int(nn[ids].max()), int(eo_n[ids].max())))
     d_eptr = edge_ptr.to(dev, non_blocking=True)
     d_nptr = node_ptr.to(dev, non_blocking=True)
     E_in = src.numel()
@@ -165,10 +178,12 @@ def encode_batch(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=False,
     for attempt in range(2):
         rec = torch.empty(rec_cap, dtype=torch.int32, device=dev)
         with span('ego_encode'):
-            _lib.check(L.escgnn_encode(_ptr(eo_src), _ptr(eo_dst), _ptr(eo_ptr), _ptr(d_nptr), G, int(h),
-                                       _ptr(rdh) if rdh is not None else None, _ptr(rec), rec_cap, _ptr(rec_off),
-                                       _ptr(rec_nnz), _ptr(edge_graph), _ptr(counters), max_nodes, max_edges,
-                                       _ptr(scratch), scratch.numel(), stream), 'encode')
+            for ids, cn, ce in (classes or [(None, max_nodes, max_edges)]):
+                _lib.check(L.escgnn_encode_subset(_ptr(eo_src), _ptr(eo_dst), _ptr(eo_ptr), _ptr(d_nptr),
+                                                  ids.numel() if ids is not None else G, _ptr(ids) if ids is not None else None,
+                                                  int(h), _ptr(rdh) if rdh is not None else None, _ptr(rec), rec_cap,
+                                                  _ptr(rec_off), _ptr(rec_nnz), _ptr(edge_graph), _ptr(counters), cn, ce,
+                                                  _ptr(scratch), scratch.numel(), stream), 'encode_subset')
         tail = torch.cat([counters[:2], eo_ptr[G:G + 1]]).cpu()     # the one sync: nnz, error bits, E_out
         nnz, bits, E = int(tail[0]), int(tail[1]), int(tail[2])
         if nnz <= rec_cap:

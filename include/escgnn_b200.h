@@ -67,6 +67,14 @@ int escgnn_encode(const int64_t* d_eo_src, const int64_t* d_eo_dst, const int64_
                   int64_t rec_cap, int64_t* d_rec_off, int32_t* d_rec_nnz, int32_t* d_edge_graph,
                   unsigned long long* d_counters, int64_t max_nodes, int64_t max_edges, void* d_scratch,
                   int64_t scratch_bytes, void* stream);
+/* The same over a SUBSET of the batch's graphs (d_graph_ids[n_graphs], int32): callers bucket graphs by size and launch
+ * once per bucket, so small graphs are not forced to the shared-memory footprint (= occupancy) of the largest one.
+ * max_nodes / max_edges are the maxima over the subset. All subsets share the record buffer and the counters. */
+int escgnn_encode_subset(const int64_t* d_eo_src, const int64_t* d_eo_dst, const int64_t* d_eo_ptr,
+                         const int64_t* d_node_ptr, int64_t n_graphs, const int32_t* d_graph_ids, int h, const uint16_t* d_rdh,
+                         uint32_t* d_rec, int64_t rec_cap, int64_t* d_rec_off, int32_t* d_rec_nnz, int32_t* d_edge_graph,
+                         unsigned long long* d_counters, int64_t max_nodes, int64_t max_edges, void* d_scratch,
+                         int64_t scratch_bytes, void* stream);
 /* scratch bytes escgnn_encode / escgnn_encode_rd need for a batch with these maxima (0 if everything fits on chip) */
 int64_t escgnn_encode_scratch_bytes(int64_t max_nodes, int64_t max_edges, int h);
 int64_t escgnn_encode_rd_scratch_bytes(int64_t max_nodes, int64_t max_edges, int h);

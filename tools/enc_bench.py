@@ -31,12 +31,12 @@ def run(config, graphs, h=None, use_rd=None, self_loop=None, iters=5, pool=256):
     te, tn = torch.as_tensor(eptr), torch.as_tensor(nptr)
     mn = int(np.diff(nptr).max()); me = int((np.diff(eptr) + (np.diff(nptr) if fl['self_loop'] else 0)).max())
     for _ in range(2):
-        r = encode_batch(ds, dd, te, tn, max_nodes=mn, max_edges=me, **fl)
+        r = encode_batch(ds, dd, te, tn, **fl)
     torch.cuda.synchronize()
     tim = {}
     t0 = time.perf_counter()
     for _ in range(iters):
-        r = encode_batch(ds, dd, te, tn, max_nodes=mn, max_edges=me, timings=tim, **fl)
+        r = encode_batch(ds, dd, te, tn, timings=tim, **fl)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / iters
     ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in tim.items()}
