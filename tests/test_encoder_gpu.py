@@ -182,3 +182,24 @@ def test_edge_attr_self_loop_rewrite():
     assert o.edge_index.tolist() == [[0, 1, 1, 2, 0, 1, 2], [1, 0, 2, 1, 0, 1, 2]]
     assert torch.equal(o.edge_attr, torch.cat([ea[1:], torch.ones(3, 2)]))
     assert o.pos is None and torch.equal(o.y, torch.tensor([1.0]))
+
+
+def test_pre_transform_batched_equals_per_graph_calls():
+    """N1: the batched dataset pre_transform returns the same per-graph Data as calling create_subgraphs on each graph."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.dataset import pre_transform_batched
+    from esc_gnn_b200.transform import create_subgraphs
+    graphs = []
+    for i in range(37):
+        g = synth.make_graph(4 if i % 2 else 1, 900 + i)
+        graphs.append(Data(x=torch.as_tensor(g['x']), edge_index=torch.as_tensor(g['edge_index']),
+                           edge_attr=torch.as_tensor(g['edge_attr']).float() if 'edge_attr' in g else None,
+                           y=torch.as_tensor(g['y'])))
+    for sl, rd in ((True, True), (False, False)):
+        got = pre_transform_batched(graphs, h=3, use_rd=rd, self_loop=sl, chunk=16)
+        for d, o in zip(graphs, got):
+            w = create_subgraphs(d, 3, use_rd=rd, self_loop=sl)
+            for k in ('edge_index', 'pos_enc', 'pos_index', 'pos_batch'):
+                assert torch.equal(o[k], w[k]), k
+            assert (o.edge_attr is None) == (w.edge_attr is None) and (o.edge_attr is None or torch.equal(o.edge_attr, w.edge_attr))
