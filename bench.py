@@ -62,6 +62,11 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
@@ -117,9 +122,11 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     sample = BATCH if args.cpu_sample is None else args.cpu_sample
     step = cpu_step_factory(threads)
-    for i in range(max(args.warmup, 1)):
+    steps_ref = min(args.steps, 40)                      # ~0.25 s per CPU step: keeps the default run within a minute
+    for i in range(min(max(args.warmup, 1), 3)):
         step(i % 4, sample)
     t_enc = t_trn = 0.0
+    args.steps = steps_ref
     for i in range(args.steps):
         a, b, _ = step(i % 4, sample)
         t_enc += a; t_trn += b
@@ -191,24 +198,25 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
+    clocks = ClockSampler(local)        # sampled from the warm-up to the end of the timed regions (the GPU is under load throughout)
+    clocks.start()
+    clocks.wait_first()
     for i in range(max(args.warmup, 3) + 2):                # W >= 3 warm-up steps (+2 eager steps before the graph capture)
         eng.step(dev_pool[i % n_pool])
         float(eng.step(host_pool[i % n_pool]).item())
     eng.check_errors()
     # ---- value: inputs resident in HBM
     launches0 = _lib.LAUNCHES['n']
-    clocks = ClockSampler(local)
     barrier()
-    clocks.start()
     ms_value = timed(lambda b: eng.step(b), dev_pool, args.steps)
     barrier()
-    clk = clocks.stop()
     ms_value = max_over_ranks(ms_value)
     # ---- e2e: raw graphs in pinned host memory, loss read back every step
     barrier()
     ms_e2e = timed(lambda b: float(eng.step(b).item()), host_pool, args.steps)
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
+    clk = clocks.stop()
     eng.check_errors()
     # ---- per-kernel device times: the step captured once more on one stream with an event after every launch, replayed
     launches_a = _lib.LAUNCHES['n']
@@ -298,8 +306,8 @@ def run_own(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -1,5 +1,6 @@
 // K1b `ego_rd`: resistance-distance histogram of every directed edge's union subgraph (E5).
 //
+// Both directions of an undirected edge share S and F, so each unordered pair is solved once (full selected inverse).
 // Replaces /root/reference/utils_edge_efficient.py:92-107 (float32 scipy laplacian -> pinv per edge) and :130-131
 // (one_hot(rd.long(), 100)) under parity policy E5: float64 arithmetic, bin = trunc((float)rd).
 //
@@ -39,9 +40,25 @@ template <bool kCta> __device__ __forceinline__ double group_sum(double v, doubl
     return t;
 }
 
-// One edge (u, v): fills hist[ESCGNN_RD_SLOTS] (shared, ints, zeroed here). Returns error bits (uniform in group).
+// 64-bit "which rows k of column c are non-zero" mask for the warp-per-pair solver (m <= 64): rows lane and lane + 32
+__device__ __forceinline__ unsigned long long column_mask(const double* M, int m, int c, int first_row, int lane) {
+    const int r0 = lane, r1 = lane + 32;
+    const bool a = r0 >= first_row && r0 < m && M[tidx(r0, c)] != 0.0;
+    const bool b = r1 >= first_row && r1 < m && M[tidx(r1, c)] != 0.0;
+    return (unsigned long long)__ballot_sync(kFull, a) | ((unsigned long long)__ballot_sync(kFull, b) << 32);
+}
+
+// One unordered pair {u, v} (or the self-loop edge u == v): fills hist_u[ESCGNN_RD_SLOTS] = rd histogram of the directed edge
+// (u, v) and hist_v = that of (v, u) -- both directions share S and F, only the root differs.
+//   u != v : ground u.  M = L without row/col u (SPD, and as sparse as the molecule), Z = M^-1:
+//            R(u,w) = Z_ww,  R(v,w) = Z_vv + Z_ww - 2 Z_vw,  R(v,u) = Z_vv.
+//   u == v : phantom root: Z = (L_ball + J/m)^-1, rd(w) = pinv(L)_ww = Z_ww - 1/m, rd(phantom) = 0.
+// LDL^T in place on the packed lower triangle, then the Takahashi recurrence Z_ij = delta_ij/D_j - (1/D_j) sum_{k>j} Z_ik W_kj
+// from the last column back.  The warp-per-pair variant walks only the NON-ZERO entries of each factor column (ballot
+// masks): molecular graphs are nearly trees, so a column holds 1-3 entries instead of m/2.
+// Returns error bits (uniform in the group).
 template <int H, bool kCta>
-__device__ unsigned rd_edge(const GraphView& g, int u, int v, double* M, uint16_t* sub, int* hist, double* s_red,
+__device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_t* sub, int* hist_u, int* hist_v, double* s_red,
                             int* s_cnt) {
     const int gt = kCta ? threadIdx.x : (threadIdx.x & 31);        // thread id inside the group
     const int gn = kCta ? blockDim.x : 32;                         // group size
@@ -50,8 +67,8 @@ __device__ unsigned rd_edge(const GraphView& g, int u, int v, double* M, uint16_
     const uint32_t* rowU = g.dist + (size_t)u * rw;
     const uint32_t* rowV = g.dist + (size_t)v * rw;
     const bool phantom = u == v;
+    if (gt < ESCGNN_RD_SLOTS) { hist_u[gt] = 0; hist_v[gt] = 0; }
     // ---- matrix index of every member of S (node order); u is grounded (no row) unless phantom
-    if (gt < ESCGNN_RD_SLOTS) hist[gt] = 0;
     int m = 0;
     if (!kCta || threadIdx.x < 32) {
         for (int w0 = 0; w0 < n; w0 += 32) {
@@ -66,20 +83,16 @@ __device__ unsigned rd_edge(const GraphView& g, int u, int v, double* M, uint16_
     }
     group_sync<kCta>();
     if (kCta) m = *s_cnt;
-    if (m == 0) {                                   // S = {u} only (cannot happen for an edge, kept for safety)
-        if (gt == 0) hist[0] = 1;
-        group_sync<kCta>();
-        return 0u;
-    }
     const double fill = phantom ? 1.0 / (double)m : 0.0;
     for (int t = gt; t < (int)tri(m); t += gn) M[t] = fill;
     group_sync<kCta>();
-    // ---- assemble: thread owning node w writes row sub[w] (diagonal = degree in F without loops)
+    // ---- assemble: the thread owning node w writes row sub[w] (diagonal = degree in F without loops)
     for (int w = gt; w < n; w += gn) {
         const int i = sub[w];
         if (i == 0xffff) continue;
         const uint32_t du = nib(rowU, w), dv = nib(rowV, w);
         double deg = 0.0;
+        double* rowi = M + tidx(i, 0);
         const uint32_t ka = g.out_ptr[w], kb = g.out_ptr[w + 1];
         for (uint32_t k = ka; k < kb; ++k) {
             const int b = g.out_adj[k];
@@ -88,9 +101,9 @@ __device__ unsigned rd_edge(const GraphView& g, int u, int v, double* M, uint16_
             if (!((du != kFar && bu != kFar) || (dv != kFar && bv != kFar))) continue;
             deg += 1.0;
             const int j = sub[b];
-            if (j != 0xffff && j < i) M[tidx(i, j)] -= 1.0;
+            if (j != 0xffff && j < i) rowi[j] -= 1.0;
         }
-        M[tidx(i, i)] += deg;
+        rowi[i] += deg;
     }
     group_sync<kCta>();
     // ---- LDL^T, column k keeps W_ik = L_ik * D_k (unscaled), diagonal keeps D_k
@@ -99,51 +112,118 @@ __device__ unsigned rd_edge(const GraphView& g, int u, int v, double* M, uint16_
         const double d = M[tidx(k, k)];
         if (!(d > 1e-12)) { bad = true; break; }                      // uniform: every thread reads the same value
         const double invd = 1.0 / d;
-        for (int i = k + 1 + gt; i < m; i += gn) {
-            const double f = M[tidx(i, k)] * invd;
-            if (f != 0.0) {
-                double* row = M + tidx(i, 0);
-                for (int j = k + 1; j <= i; ++j) row[j] -= f * M[tidx(j, k)];
+        if (!kCta && m <= 64) {
+            const unsigned long long nz = column_mask(M, m, k, k + 1, lane);       // rows j > k with W_jk != 0
+            const bool dense_col = 2 * __popcll(nz) > m - k;                        // uniform: walk the column contiguously
+            for (int i = k + 1 + ((lane - k - 1) & 31); i < m; i += 32) {             // rows owned by this lane (i % 32 == lane)
+                if (!((nz >> i) & 1ull)) continue;
+                double* rowi = M + tidx(i, 0);
+                const double f = rowi[k] * invd;
+                if (dense_col) {
+                    int p = tidx(k + 1, k);
+                    for (int j = k + 1; j <= i; ++j) { rowi[j] -= f * M[p]; p += j + 1; }
+                } else {
+                    unsigned long long todo = nz & ((i >= 63 ? ~0ull : ((1ull << (i + 1)) - 1ull)));   // j <= i
+                    while (todo) {
+                        const int jj = __ffsll((long long)todo) - 1;
+                        todo &= todo - 1;
+                        rowi[jj] -= f * M[tidx(jj, k)];
+                    }
+                }
+            }
+        } else {
+            for (int i = k + 1 + gt; i < m; i += gn) {
+                double* rowi = M + tidx(i, 0);
+                const double f = rowi[k] * invd;
+                if (f != 0.0) {
+                    int p = tidx(k + 1, k);                                // M[j][k], advancing one row at a time
+                    for (int j = k + 1; j <= i; ++j) { rowi[j] -= f * M[p]; p += j + 1; }
+                }
             }
         }
         group_sync<kCta>();
     }
     if (bad) return ESCGNN_DATA_RD;
-    // ---- Takahashi: columns from the last to the first; Z overwrites the factor column by column
+    // ---- Takahashi, columns from the last to the first; Z overwrites the factor column by column
     for (int j = m - 1; j >= 0; --j) {
         const double invd = 1.0 / M[tidx(j, j)];
         double part = 0.0;                      // sum_k W_kj * Z_kj over the rows this thread owns
         double zmine[4];                        // up to 4 rows per thread in flight (m <= 4 * group size)
         int cnt = 0;
-        for (int i = j + 1 + gt; i < m; i += gn) {
-            double acc = 0.0;
-            for (int k = j + 1; k < m; ++k) {
-                const double z = k <= i ? M[tidx(i, k)] : M[tidx(k, i)];
-                acc += z * M[tidx(k, j)];
+        if (!kCta && m <= 64) {
+            const unsigned long long nz = column_mask(M, m, j, j + 1, lane);       // rows k > j with W_kj != 0
+            const bool dense_col = 2 * __popcll(nz) > m - j;
+            for (int i = j + 1 + ((lane - j - 1) & 31); i < m; i += 32) {
+                const double* rowi = M + tidx(i, 0);
+                double acc = 0.0;
+                if (dense_col) {
+                    int pj = tidx(j + 1, j);
+                    for (int k = j + 1; k <= i; ++k) { acc += rowi[k] * M[pj]; pj += k + 1; }
+                    int pi = tidx(i + 1, i);
+                    for (int k = i + 1; k < m; ++k) { acc += M[pi] * M[pj]; pi += k + 1; pj += k + 1; }
+                } else {
+                    unsigned long long todo = nz;
+                    while (todo) {
+                        const int k = __ffsll((long long)todo) - 1;
+                        todo &= todo - 1;
+                        const double z = k <= i ? rowi[k] : M[tidx(k, i)];
+                        acc += z * M[tidx(k, j)];
+                    }
+                }
+                const double zij = -acc * invd;
+                part += rowi[j] * zij;
+                if (cnt < 4) zmine[cnt] = zij;
+                ++cnt;
             }
-            const double zij = -acc * invd;
-            part += M[tidx(i, j)] * zij;
-            if (cnt < 4) zmine[cnt] = zij;
-            ++cnt;
+        } else {
+            for (int i = j + 1 + gt; i < m; i += gn) {
+                const double* rowi = M + tidx(i, 0);
+                double acc = 0.0;
+                int pj = tidx(j + 1, j);                                   // W[k][j]
+                for (int k = j + 1; k <= i; ++k) { acc += rowi[k] * M[pj]; pj += k + 1; }          // Z_ik with k <= i: row i
+                int pi = tidx(i + 1, i);                                   // Z_ki with k > i: column i
+                for (int k = i + 1; k < m; ++k) { acc += M[pi] * M[pj]; pi += k + 1; pj += k + 1; }
+                const double zij = -acc * invd;
+                part += rowi[j] * zij;
+                if (cnt < 4) zmine[cnt] = zij;
+                ++cnt;
+            }
         }
         const double s = group_sum<kCta>(part, s_red);     // (also orders the reads of column j before its overwrite)
         group_sync<kCta>();
         cnt = 0;
-        for (int i = j + 1 + gt; i < m; i += gn) { M[tidx(i, j)] = zmine[cnt < 4 ? cnt : 3]; ++cnt; }
+        if (!kCta && m <= 64) { for (int i = j + 1 + ((lane - j - 1) & 31); i < m; i += 32) { M[tidx(i, j)] = zmine[cnt < 4 ? cnt : 3]; ++cnt; } }
+        else { for (int i = j + 1 + gt; i < m; i += gn) { M[tidx(i, j)] = zmine[cnt < 4 ? cnt : 3]; ++cnt; } }
         if (gt == 0) M[tidx(j, j)] = invd - invd * s;
         group_sync<kCta>();
     }
     // ---- bin: trunc((float)rd)   (torch.FloatTensor(...) then .long(), utils_edge_efficient.py:105,131)
     unsigned err = 0;
+    const int iv = phantom ? 0 : sub[v];
+    const double zvv = phantom ? 0.0 : M[tidx(iv, iv)];
     for (int w = gt; w < n; w += gn) {
         const int i = sub[w];
         if (i == 0xffff) continue;
-        const double rd = M[tidx(i, i)] - fill;
-        const float rf = (float)rd;
-        const int b = (int)truncf(rf);
-        if (b < 0 || b >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD; else atomicAdd(&hist[b], 1);
+        const double zww = M[tidx(i, i)];
+        if (phantom) {
+            const int b = (int)truncf((float)(zww - fill));
+            if (b < 0 || b >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD; else atomicAdd(&hist_u[b], 1);
+        } else {
+            const double zvw = i >= iv ? M[tidx(i, iv)] : M[tidx(iv, i)];
+            const int bu = (int)truncf((float)zww);                                        // R(u, w), u grounded
+            const int bv = w == v ? 0 : (int)truncf((float)(zvv + zww - 2.0 * zvw));        // R(v, w)
+            if (bu < 0 || bu >= ESCGNN_RD_SLOTS || bv < 0 || bv >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD;
+            else { atomicAdd(&hist_u[bu], 1); atomicAdd(&hist_v[bv], 1); }
+        }
     }
-    if (gt == 0) atomicAdd(&hist[0], 1);           // the grounded root u (rd = 0) or the phantom root (rd = 0)
+    if (gt == 0) {
+        if (phantom) atomicAdd(&hist_u[0], 1);             // the phantom root itself (rd = 0)
+        else {
+            atomicAdd(&hist_u[0], 1);                      // rd_u(u) = 0
+            const int b = (int)truncf((float)zvv);          // rd_v(u) = R(v, u) = Z_vv
+            if (b < 0 || b >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD; else atomicAdd(&hist_v[b], 1);
+        }
+    }
     group_sync<kCta>();
     return err;
 }
@@ -158,7 +238,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     __shared__ int s_misc[2];
-    __shared__ int s_hist[8][ESCGNN_RD_SLOTS];
+    __shared__ int s_hist[8][2][ESCGNN_RD_SLOTS];
     __shared__ double s_red[8];
     __shared__ int s_cnt;
     __shared__ unsigned s_err;
@@ -213,22 +293,49 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
             uint16_t* sub = sub_region + (size_t)warp * sub_stride;
             for (int ed = warp; ed < e; ed += nw) {
                 const int u = (int)eo_src[e0 + ed], v = (int)eo_dst[e0 + ed];
-                err |= rd_edge<H, false>(g, u, v, M, sub, s_hist[warp], nullptr, nullptr);
-                if (lane < ESCGNN_RD_SLOTS)
-                    rdh[(size_t)(e0 + ed) * ESCGNN_RD_SLOTS + lane] = (uint16_t)s_hist[warp][lane];
+                if (u > v) continue;                                   // handled together with its reverse edge (v, u)
+                // the first occurrence of (u, v) does the work for every copy of (u, v) and (v, u) in the edge list
+                bool first = true;
+                for (int q0 = 0; q0 < ed && first; q0 += 32) {
+                    const int q = q0 + lane;
+                    const bool dup = q < ed && (int)eo_src[e0 + q] == u && (int)eo_dst[e0 + q] == v;
+                    if (__any_sync(kFull, dup)) first = false;
+                }
+                if (!first) continue;
+                err |= rd_pair<H, false>(g, u, v, M, sub, s_hist[warp][0], s_hist[warp][1], nullptr, nullptr);
+                for (int q0 = 0; q0 < e; q0 += 32) {
+                    const int q = q0 + lane;
+                    if (q < e) {
+                        const int a = (int)eo_src[e0 + q], b = (int)eo_dst[e0 + q];
+                        const int which = (a == u && b == v) ? 0 : ((a == v && b == u) ? 1 : -1);
+                        if (which >= 0)
+                            for (int t = 0; t < ESCGNN_RD_SLOTS; ++t)
+                                rdh[(size_t)(e0 + q) * ESCGNN_RD_SLOTS + t] = (uint16_t)s_hist[warp][which][t];
+                    }
+                }
                 __syncwarp();
             }
         } else {
-            // whole CTA per edge; matrix in shared memory when it fits, else in the global slab
+            // whole CTA per pair; matrix in shared memory when it fits, else in the global slab
             double* M = need <= mat_region_doubles ? mat_region
                                                    : reinterpret_cast<double*>(slab + slab_graph_bytes);
             uint16_t* sub = (n <= nw * sub_stride) ? sub_region
                                                    : reinterpret_cast<uint16_t*>(slab + slab_graph_bytes + align16(need * 8));
             for (int ed = 0; ed < e; ++ed) {
                 const int u = (int)eo_src[e0 + ed], v = (int)eo_dst[e0 + ed];
-                err |= rd_edge<H, true>(g, u, v, M, sub, s_hist[0], s_red, &s_cnt);
-                if (tid < ESCGNN_RD_SLOTS)
-                    rdh[(size_t)(e0 + ed) * ESCGNN_RD_SLOTS + tid] = (uint16_t)s_hist[0][tid];
+                if (u > v) continue;
+                bool first = true;
+                for (int q = tid; q < ed; q += blockDim.x)
+                    if ((int)eo_src[e0 + q] == u && (int)eo_dst[e0 + q] == v) first = false;
+                if (__syncthreads_or(!first)) continue;
+                err |= rd_pair<H, true>(g, u, v, M, sub, s_hist[0][0], s_hist[0][1], s_red, &s_cnt);
+                for (int q = tid; q < e; q += blockDim.x) {
+                    const int a = (int)eo_src[e0 + q], b = (int)eo_dst[e0 + q];
+                    const int which = (a == u && b == v) ? 0 : ((a == v && b == u) ? 1 : -1);
+                    if (which >= 0)
+                        for (int t = 0; t < ESCGNN_RD_SLOTS; ++t)
+                            rdh[(size_t)(e0 + q) * ESCGNN_RD_SLOTS + t] = (uint16_t)s_hist[0][which][t];
+                }
                 __syncthreads();
             }
         }
