@@ -31,7 +31,7 @@ class GINEConv(torch.nn.Module):
         if edge_dim is not None:
             first = self.nn[0]
             in_channels = first.in_features if hasattr(first, 'in_features') else first.in_channels
-            self.lin = torch.nn.Linear(edge_dim, in_channels)
+            self.lin = ops.Linear(edge_dim, in_channels)
         else:
             self.lin = None
         self.reset_parameters()
@@ -77,14 +77,14 @@ class SumEmbedding(torch.nn.Module):
 class GINConv_eff(torch.nn.Module):
     def __init__(self, dataset, emb_dim, bond_dims=(5, 6, 2)):
         super(GINConv_eff, self).__init__()
-        self.mlp = torch.nn.Sequential(torch.nn.Linear(emb_dim, 2 * emb_dim), torch.nn.BatchNorm1d(2 * emb_dim),
-                                       torch.nn.ReLU(), torch.nn.Linear(2 * emb_dim, emb_dim))
+        self.mlp = torch.nn.Sequential(ops.Linear(emb_dim, 2 * emb_dim), ops.BatchNorm1d(2 * emb_dim),
+                                       torch.nn.ReLU(), ops.Linear(2 * emb_dim, emb_dim))
         self.eps = torch.nn.Parameter(torch.Tensor([0]))
         if dataset.startswith('ogbg-mol'):
             self.edge_encoder = SumEmbedding(bond_dims, emb_dim, 'bond_embedding_list')
         elif dataset.startswith('ogbg-ppa'):
-            self.edge_encoder = torch.nn.Linear(7, emb_dim)
-        self.edge_encoder_pos = torch.nn.Linear(emb_dim, emb_dim)
+            self.edge_encoder = ops.Linear(7, emb_dim)
+        self.edge_encoder_pos = ops.Linear(emb_dim, emb_dim)
 
     def forward(self, x, edge_index, edge_attr, edge_pos, index=None):
         if index is None:

@@ -2,8 +2,10 @@
 /root/reference/run_graphcount.py:39-194, running on the sm_100a kernels (bag-embed, GINE aggregation, pooling)."""
 import torch
 import torch.nn.functional as F
-from torch.nn import BatchNorm1d as BN
-from torch.nn import Dropout, Linear, ReLU, Sequential
+from torch.nn import Dropout, ReLU, Sequential
+
+from .ops import BatchNorm1d as BN
+from .ops import Linear
 
 from . import ops
 from .gine import GINEConv
@@ -40,8 +42,8 @@ class NestedGIN_eff(torch.nn.Module):
         self.convs = torch.nn.ModuleList()
         for _ in range(num_layers - 1):
             self.convs.append(GINEConv(_mlp(hidden, hidden, dropout), train_eps=True, edge_dim=hidden))
-        self.lin1 = torch.nn.Linear(num_layers * hidden + hidden, hidden)
-        self.bn_lin1 = torch.nn.BatchNorm1d(hidden, eps=1e-5, momentum=0.1)
+        self.lin1 = ops.Linear(num_layers * hidden + hidden, hidden)
+        self.bn_lin1 = ops.BatchNorm1d(hidden, eps=1e-5, momentum=0.1)
         self.lin2 = Linear(hidden, 1) if use_cycle else Linear(hidden, dataset.num_classes)
 
     def reset_parameters(self):

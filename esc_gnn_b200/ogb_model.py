@@ -35,13 +35,13 @@ class GNN_node_efficient(torch.nn.Module):
         self.batch_norms = torch.nn.ModuleList()
         for _ in range(num_layer):
             self.convs.append(GINConv_eff(dataset, emb_dim))
-            self.batch_norms.append(torch.nn.BatchNorm1d(emb_dim))
+            self.batch_norms.append(ops.BatchNorm1d(emb_dim))
         if self.virtual_node:
             self.mlp_virtualnode_list = torch.nn.ModuleList()
             for _ in range(num_layer - 1):
                 self.mlp_virtualnode_list.append(torch.nn.Sequential(
-                    torch.nn.Linear(emb_dim, 2 * emb_dim), torch.nn.BatchNorm1d(2 * emb_dim), torch.nn.ReLU(),
-                    torch.nn.Linear(2 * emb_dim, emb_dim), torch.nn.BatchNorm1d(emb_dim), torch.nn.ReLU()))
+                    ops.Linear(emb_dim, 2 * emb_dim), ops.BatchNorm1d(2 * emb_dim), torch.nn.ReLU(),
+                    ops.Linear(2 * emb_dim, emb_dim), ops.BatchNorm1d(emb_dim), torch.nn.ReLU()))
 
     def forward(self, batched_data, index=None):
         if hasattr(batched_data, 'edge_pos'):
@@ -92,7 +92,7 @@ class GNN(torch.nn.Module):
         self.gnn_node = GNN_node_efficient(dataset, num_layer, emb_dim, JK=JK, drop_ratio=drop_ratio,
                                            residual=residual, gnn_type=gnn_type, virtual_node=virtual_node,
                                            use_rd=use_rd, use_rp=use_rp, RNI=RNI)
-        self.graph_pred_linear = torch.nn.Linear(emb_dim, num_tasks)
+        self.graph_pred_linear = ops.Linear(emb_dim, num_tasks)
 
     def forward(self, data, x=None, edge_index=None, edge_attr=None, batch=None, perturb=None):
         if perturb is not None:

@@ -243,3 +243,109 @@ def global_add_pool(x, index):
 
 def global_mean_pool(x, index):
     return _SegmentPool.apply(x, index.graph_ptr, index.num_graphs, True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Dense layers of the drop-in modules on the hand-written kernels (same parameters / state_dict keys as torch.nn)
+_GEMM_WS = {}
+
+
+def _gemm_ws(dev):
+    ws = _GEMM_WS.get(dev)
+    if ws is None:
+        ws = _GEMM_WS[dev] = torch.empty(4 * 1024 * 1024, dtype=torch.float32, device=dev)
+    return ws
+
+
+def _gemm(A, a_mn, B, b_mn, C, bias, M, N, K, accumulate=False):
+    """C[M,N] (+)= op(A) op(B)^T (+bias): tcgen05 3xTF32 kernel when TMA alignment allows, CUDA-core kernel otherwise."""
+    L = _lib.lib()
+    st = _stream(C)
+    if all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (A, B)):
+        ws = _gemm_ws(C.device)
+        _lib.check(L.escgnn_gemm_tf32x3(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0), _p(bias),
+                                        M, N, K, int(accumulate), _p(ws), ws.numel(), st), 'gemm_tf32x3')
+    else:
+        _lib.check(L.escgnn_gemm_simple(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0), _p(bias),
+                                        M, N, K, int(accumulate), st), 'gemm_simple')
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x, weight)
+        x = x.contiguous()
+        M, K = x.shape
+        N = weight.size(0)
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        if M:
+            _gemm(x, False, weight, False, y, bias, M, N, K)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = weight.size(0)
+        dx = torch.zeros_like(x)
+        dw = torch.zeros_like(weight)
+        if M:
+            _gemm(dy, False, weight, True, dx, None, M, K, N)        # dX = dY W        (W read as an MN-major operand)
+            _gemm(dy, True, x, True, dw, None, N, K, M)              # dW = dY^T X      (both operands MN-major, split-K)
+        db = dy.sum(0) if ctx.has_bias else None
+        return dx, dw, db
+
+
+class Linear(torch.nn.Linear):
+    """torch.nn.Linear whose forward / dgrad / wgrad run on the tcgen05 3xTF32 GEMM (csrc/gemm_tf32x3.cu)."""
+    def forward(self, x):
+        if x.dim() != 2 or not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError('esc_gnn_b200.ops.Linear needs a 2-D fp32 CUDA input; there is no CPU fallback')
+        return _LinearFn.apply(x, self.weight, self.bias)
+
+
+class _BatchNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, training):
+        _need_cuda(x, weight)
+        x = x.contiguous()
+        rows, C = x.shape
+        L = _lib.lib()
+        d_rows = torch.tensor([rows], dtype=torch.int32, device=x.device)
+        tile = L.escgnn_dense_tile_rows()
+        partial = torch.empty(((rows + tile - 1) // tile + 1) * 2 * C, dtype=torch.float32, device=x.device)
+        mean, rstd = torch.empty(C, device=x.device), torch.empty(C, device=x.device)
+        y = torch.empty_like(x)
+        _lib.check(L.escgnn_bn_act_fwd(_p(x), C, _p(weight), _p(bias), _p(running_mean), _p(running_var), _p(mean), _p(rstd),
+                                       _p(partial), 0, eps, momentum, int(training), _p(d_rows), rows, C, _p(y), C, _stream(x)),
+                   'bn_act_fwd')
+        ctx.save_for_backward(x, weight, bias, mean, rstd, d_rows, partial)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, rstd, d_rows, partial = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows, C = x.shape
+        dx, dg, db = torch.empty_like(x), torch.empty(C, device=x.device), torch.empty(C, device=x.device)
+        _lib.check(_lib.lib().escgnn_bn_act_bwd(_p(x), C, _p(dy), C, None, 0, _p(mean), _p(rstd), _p(weight), _p(bias), 0,
+                                                int(ctx.training), _p(partial), _p(d_rows), rows, C, _p(dg), _p(db), _p(dx), C,
+                                                _stream(x)), 'bn_act_bwd')
+        return dx, dg, db, None, None, None, None, None
+
+
+class BatchNorm1d(torch.nn.BatchNorm1d):
+    """torch.nn.BatchNorm1d (affine, running stats, fixed momentum) on the bn_act kernels of csrc/dense_ops.cu."""
+    def forward(self, x):
+        if x.dim() != 2 or not x.is_cuda:
+            raise RuntimeError('esc_gnn_b200.ops.BatchNorm1d needs a 2-D CUDA input; there is no CPU fallback')
+        if self.training:
+            self.num_batches_tracked.add_(1)
+        if x.size(0) == 0:
+            return x
+        return _BatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                  self.momentum if self.momentum is not None else 0.1, self.training)

@@ -2,11 +2,12 @@
 /root/reference/zinc_models.py:504-611 (ELU, atom / bond type embeddings, sum-pool readout), on the sm_100a kernels."""
 import torch
 import torch.nn.functional as F
-from torch.nn import ELU, Linear
+from torch.nn import ELU
 
 from . import ops
 from .gine import GINEConv
 from .graphcount_model import _mlp, _z_embedding
+from .ops import Linear
 
 
 class NestedGIN_eff(torch.nn.Module):
@@ -24,8 +25,8 @@ class NestedGIN_eff(torch.nn.Module):
         for _ in range(num_layers - 1):
             self.convs.append(GINEConv(_mlp(hidden, hidden, dropout, ELU), train_eps=True,
                                        edge_dim=hidden + edge_attr_dim))
-        self.lin1 = torch.nn.Linear(num_layers * hidden, hidden)
-        self.bn_lin1 = torch.nn.BatchNorm1d(hidden, eps=1e-5, momentum=0.1)
+        self.lin1 = ops.Linear(num_layers * hidden, hidden)
+        self.bn_lin1 = ops.BatchNorm1d(hidden, eps=1e-5, momentum=0.1)
         self.lin2 = Linear(hidden, 1)
         self.node_type_embedding = torch.nn.Embedding(100, 32)
         self.edge_type_embedding = torch.nn.Embedding(100, 32)
