@@ -170,8 +170,12 @@ def run_own(args):
     nodes_cap = int(max(b.num_nodes for b in host_pool) * 1.04) + 64
     edges_cap = int(max(b.src.numel() for b in host_pool) * 1.04) + 128
     eng = StaticTrainEngine(model, 'zinc', fl, max_graphs=BATCH, max_nodes_per_graph=40, max_edges_per_graph=96,
-                            nodes_cap=nodes_cap, edges_cap=edges_cap, lr=LR, distributed=world > 1, use_graph=True)
+                            nodes_cap=nodes_cap, edges_cap=edges_cap, lr=LR, distributed=world > 1, use_graph=True,
+                            pipeline=bool(args.pipeline))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')     # > 126 MB L2
+
+    def read(loss):                                         # pipelined engines return the previous batch's loss (None at first)
+        return float(loss.item()) if loss is not None else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -203,7 +207,7 @@ def run_own(args):
     clocks.wait_first()
     for i in range(max(args.warmup, 3) + 2):                # W >= 3 warm-up steps (+2 eager steps before the graph capture)
         eng.step(dev_pool[i % n_pool])
-        float(eng.step(host_pool[i % n_pool]).item())
+        read(eng.step(host_pool[i % n_pool]))
     eng.check_errors()
     # ---- value: inputs resident in HBM
     launches0 = _lib.LAUNCHES['n']
@@ -213,7 +217,7 @@ def run_own(args):
     ms_value = max_over_ranks(ms_value)
     # ---- e2e: raw graphs in pinned host memory, loss read back every step
     barrier()
-    ms_e2e = timed(lambda b: float(eng.step(b).item()), host_pool, args.steps)
+    ms_e2e = timed(lambda b: read(eng.step(b)), host_pool, args.steps)
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
     clk = clocks.stop()
@@ -290,7 +294,9 @@ def run_own(args):
                warmup=max(args.warmup, 3), ms_per_step=ms_value / args.steps, higher_is_better=True, scaling='weak',
                vs_baseline=None, dtype='int64+f64 (encode), f32 (model)', data='synthetic',
                config=dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism='dp%d' % world,
-                           l2='flushed between timed iterations (256 MB write)', lr=LR),
+                           l2='flushed between timed iterations (256 MB write)', lr=LR,
+                           pipeline=('encoder of batch k overlaps training of batch k-1 (one encode + one train step per step)'
+                                     if args.pipeline else 'off')),
                clocks=clk,
                e2e=dict(value=graphs / (ms_e2e * 1e-3), unit='graphs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                         ms_per_step=ms_e2e / args.steps),
@@ -309,6 +315,7 @@ def main():
     ap.add_argument('--steps', type=int, default=300)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--pipeline', type=int, default=0, help='1: overlap the encoder of batch k with the training of batch k-1')
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

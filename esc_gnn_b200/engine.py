@@ -35,10 +35,10 @@ def _p(t):
 class _Ctx(object):
     """Allocation + launch helpers shared by the tapes."""
 
-    def __init__(self, device, caps):
+    def __init__(self, device, caps, dims):
         self.dev = device
         self.caps = dict(caps)                       # 'N', 'E', 'B', 'nnz', 'E_in'
-        self.dims = torch.zeros(4, dtype=torch.int32, device=device)      # N, E, B, nnz
+        self.dims = dims                             # int32[4] on the device: N, E, B, nnz of the batch being trained on
         self.rows = {'N': self.dims[0:1], 'E': self.dims[1:2], 'B': self.dims[2:3]}
         tile = _lib.lib().escgnn_dense_tile_rows()
         max_tiles = (max(self.caps['N'], self.caps['E'], self.caps['B']) + tile - 1) // tile
@@ -52,11 +52,47 @@ class _Ctx(object):
         return torch.zeros((self.caps[kind], cols), dtype=dtype, device=self.dev)
 
 
+class _BatchSet(object):
+    """Everything the training tapes read about ONE encoded batch, carved out of a single contiguous allocation so that a
+    whole batch moves from the encoder's staging set to the live set with one device-to-device copy (pipelined mode)."""
+
+    def __init__(self, dev, variant, G, N, E, nnz_cap):
+        i64, i32, f32 = torch.int64, torch.int32, torch.float32
+        spec = [('rec', i32, (nnz_cap, )), ('rec_off', i64, (E + 1, )), ('rec_nnz', i32, (E + 1, )), ('ei', i64, (2, E)),
+                ('batch', i64, (N, )), ('idx_buf', i32, (4 * (N + 1) + 2 * E + 2, )), ('graph_ptr', i32, (G + 1, )),
+                ('dims', i32, (4, ))]
+        if variant == 'zinc':
+            spec += [('in_x', i64, (N, )), ('in_ea', i64, (E, )), ('in_y', f32, (G, ))]
+        else:
+            spec += [('in_x', f32, (N, 10)), ('in_y', f32, (N, ))]
+        esz = {i64: 8, i32: 4, f32: 4}
+        off, offs = 0, []
+        for _, dt, shape in spec:
+            offs.append(off)
+            n = 1
+            for d in shape:
+                n *= d
+            off += (n * esz[dt] + 255) // 256 * 256
+        self.buf = torch.zeros(off, dtype=torch.uint8, device=dev)
+        for (name, dt, shape), o in zip(spec, offs):
+            n = 1
+            for d in shape:
+                n *= d
+            setattr(self, name, self.buf[o:o + n * esz[dt]].view(dt).view(shape))
+        if variant != 'zinc':
+            self.in_ea = None
+        b = self.idx_buf
+        self.dst_ptr, self.src_ptr = b[:N + 1], b[N + 1:2 * N + 2]
+        self.tmp_a, self.tmp_b = b[2 * N + 2:3 * N + 3], b[3 * N + 3:4 * N + 4]
+        self.dst_perm, self.src_perm = b[4 * N + 4:4 * N + 4 + E], b[4 * N + 4 + E:4 * N + 4 + 2 * E]
+        self.rows = {'N': self.dims[0:1], 'E': self.dims[1:2], 'B': self.dims[2:3]}
+
+
 class StaticTrainEngine(object):
     """One NestedGIN_eff variant ('zinc' or 'count') at a fixed capacity."""
 
     def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
-                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True):
+                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False):
         if variant not in ('zinc', 'count'):
             raise NotImplementedError('engine variants: zinc, count (the OGB model runs through the module path)')
         p0 = next(model.parameters())
@@ -74,22 +110,20 @@ class StaticTrainEngine(object):
         self.max_n, self.max_e = int(max_nodes_per_graph), int(max_edges_per_graph)   # per-graph maxima (after E1)
         e_in_cap = int(edges_cap)
         e_cap = e_in_cap + (int(nodes_cap) if flags['self_loop'] else 0)
-        self.c = c = _Ctx(dev, dict(N=int(nodes_cap), E=e_cap, B=self.G, nnz=e_cap * records_per_edge, E_in=e_in_cap))
+        caps = dict(N=int(nodes_cap), E=e_cap, B=self.G, nnz=e_cap * records_per_edge, E_in=e_in_cap)
+        # pipeline: step(raw_k) trains on batch k-1 while the encoder works on batch k (two branches of one graph); the encoder
+        # then writes a staging set that becomes live with one copy at the start of the next step
+        self.pipeline = bool(pipeline)
+        self.live = _BatchSet(dev, variant, self.G, caps['N'], caps['E'], caps['nnz'])
+        self.stage = _BatchSet(dev, variant, self.G, caps['N'], caps['E'], caps['nnz']) if self.pipeline else self.live
+        self.c = c = _Ctx(dev, caps, self.live.dims)
         i64 = torch.int64
-        # ---- static input buffers (the only thing the host touches per step)
+        # ---- static raw-input buffers (the only thing the host touches per step)
         self.in_src = torch.zeros(e_in_cap, dtype=i64, device=dev)
         self.in_dst = torch.zeros(e_in_cap, dtype=i64, device=dev)
         self.in_eptr = torch.zeros(self.G + 1, dtype=i64, device=dev)
         self.in_nptr = torch.zeros(self.G + 1, dtype=i64, device=dev)
-        if variant == 'zinc':
-            self.in_x = torch.zeros(c.caps['N'], dtype=i64, device=dev)
-            self.in_ea = torch.zeros(c.caps['E'], dtype=i64, device=dev)
-            self.in_y = torch.zeros(self.G, dtype=torch.float32, device=dev)
-        else:
-            self.in_x = torch.zeros((c.caps['N'], 10), dtype=torch.float32, device=dev)
-            self.in_ea = None
-            self.in_y = torch.zeros(c.caps['N'], dtype=torch.float32, device=dev)
-        # ---- encoder state
+        # ---- encoder-private state
         self.counters = torch.zeros(_lib.NUM_COUNTERS, dtype=i64, device=dev)
         if flags['self_loop']:
             self.eo = torch.zeros((2, e_cap), dtype=i64, device=dev)
@@ -100,20 +134,22 @@ class StaticTrainEngine(object):
             sb = max(sb, c.L.escgnn_encode_rd_scratch_bytes(self.max_n, self.max_e, flags['h']))
         self.scratch = torch.zeros(max(sb, 16), dtype=torch.uint8, device=dev)
         self.rdh = torch.zeros((e_cap + 1, _lib.RD_SLOTS), dtype=torch.int16, device=dev) if flags['use_rd'] else None
-        self.rec = torch.zeros(c.caps['nnz'], dtype=torch.int32, device=dev)
-        self.rec_off = torch.zeros(e_cap + 1, dtype=i64, device=dev)
-        self.rec_nnz = torch.zeros(e_cap + 1, dtype=torch.int32, device=dev)
         self.edge_graph = torch.zeros(e_cap + 1, dtype=torch.int32, device=dev)
-        # ---- collated graph + indices
-        N, E = c.caps['N'], c.caps['E']
-        self.ei = torch.zeros((2, E), dtype=i64, device=dev)
-        self.batch = torch.zeros(N, dtype=i64, device=dev)
-        self.idx_buf = torch.zeros(4 * (N + 1) + 2 * E + 2, dtype=torch.int32, device=dev)
-        b = self.idx_buf
-        self.dst_ptr, self.src_ptr = b[:N + 1], b[N + 1:2 * N + 2]
-        self.tmp_a, self.tmp_b = b[2 * N + 2:3 * N + 3], b[3 * N + 3:4 * N + 4]
-        self.dst_perm, self.src_perm = b[4 * N + 4:4 * N + 4 + E], b[4 * N + 4 + E:4 * N + 4 + 2 * E]
-        self.graph_ptr = torch.zeros(self.G + 1, dtype=torch.int32, device=dev)
+        # ---- what the tapes read: the LIVE batch set
+        lv = self.live
+        self.in_x, self.in_ea, self.in_y = lv.in_x, lv.in_ea, lv.in_y
+        self.rec, self.rec_off, self.rec_nnz = lv.rec, lv.rec_off, lv.rec_nnz
+        self.ei, self.batch, self.graph_ptr = lv.ei, lv.batch, lv.graph_ptr
+        self.dst_ptr, self.src_ptr, self.dst_perm, self.src_perm = lv.dst_ptr, lv.src_ptr, lv.dst_perm, lv.src_perm
+        self.enc_stream = torch.cuda.Stream(device=dev)
+        self._primed = False
+        if self.pipeline:
+            class _Raw(object):
+                pass
+            self.raw_feat = _Raw()
+            self.raw_feat.in_x = torch.zeros_like(lv.in_x)
+            self.raw_feat.in_y = torch.zeros_like(lv.in_y)
+            self.raw_feat.in_ea = torch.zeros_like(lv.in_ea) if lv.in_ea is not None else None
         self.idx_err = torch.zeros(1, dtype=i64, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.tensor_cores = tensor_cores
@@ -415,7 +451,9 @@ class StaticTrainEngine(object):
         self.bwd.append(back)
 
     # ------------------------------------------------------------------ one step
-    def _encode_and_index(self):
+    def _encode_and_index(self, t=None):
+        """E1 / E5 / E2-E4 on the raw-input buffers, device collation and index builds, written into batch set `t`."""
+        t = self.live if t is None else t
         c, L, fl, G = self.c, self.c.L, self.flags, self.G
         st = c.st()
         self.counters.zero_()
@@ -430,27 +468,32 @@ class StaticTrainEngine(object):
         if fl['use_rd']:
             _lib.check(L.escgnn_encode_rd(_p(es), _p(ed), _p(ep), _p(self.in_nptr), G, fl['h'], _p(self.rdh), _p(self.counters),
                                           self.max_n, self.max_e, _p(self.scratch), self.scratch.numel(), st), 'encode_rd')
-        _lib.check(L.escgnn_encode(_p(es), _p(ed), _p(ep), _p(self.in_nptr), G, fl['h'], _p(self.rdh), _p(self.rec),
-                                   self.rec.numel(), _p(self.rec_off), _p(self.rec_nnz), _p(self.edge_graph),
+        _lib.check(L.escgnn_encode(_p(es), _p(ed), _p(ep), _p(self.in_nptr), G, fl['h'], _p(self.rdh), _p(t.rec),
+                                   t.rec.numel(), _p(t.rec_off), _p(t.rec_nnz), _p(self.edge_graph),
                                    _p(self.counters), self.max_n, self.max_e, _p(self.scratch), self.scratch.numel(), st),
                    'encode')
-        _lib.check(L.escgnn_make_dims(_p(ep), _p(self.in_nptr), G, _p(self.counters), _p(c.dims), st), 'make_dims')
+        _lib.check(L.escgnn_make_dims(_p(ep), _p(self.in_nptr), G, _p(self.counters), _p(t.dims), st), 'make_dims')
         N, E = c.caps['N'], c.caps['E']
-        _lib.check(L.escgnn_collate_edges(_p(es), _p(ed), _p(self.edge_graph), _p(self.in_nptr), E, _p(self.ei[0]),
-                                          _p(self.ei[1]), _p(c.rows['E']), st), 'collate_edges')
-        _lib.check(L.escgnn_ptr_to_ids(_p(self.in_nptr), G, N, _p(self.batch), _p(c.rows['N']), st), 'ptr_to_ids')
-        _lib.check(L.escgnn_csr_build(_p(self.ei[1]), E, N, _p(self.dst_ptr), _p(self.dst_perm), _p(self.tmp_a),
-                                      _p(self.idx_err), _p(c.rows['E']), st), 'csr_build')
-        _lib.check(L.escgnn_csr_build(_p(self.ei[0]), E, N, _p(self.src_ptr), _p(self.src_perm), _p(self.tmp_b),
-                                      _p(self.idx_err), _p(c.rows['E']), st), 'csr_build')
-        _lib.check(L.escgnn_sorted_ids_to_ptr(_p(self.batch), N, G, _p(self.graph_ptr), _p(c.rows['N']), st),
+        _lib.check(L.escgnn_collate_edges(_p(es), _p(ed), _p(self.edge_graph), _p(self.in_nptr), E, _p(t.ei[0]),
+                                          _p(t.ei[1]), _p(t.rows['E']), st), 'collate_edges')
+        _lib.check(L.escgnn_ptr_to_ids(_p(self.in_nptr), G, N, _p(t.batch), _p(t.rows['N']), st), 'ptr_to_ids')
+        _lib.check(L.escgnn_csr_build(_p(t.ei[1]), E, N, _p(t.dst_ptr), _p(t.dst_perm), _p(t.tmp_a),
+                                      _p(self.idx_err), _p(t.rows['E']), st), 'csr_build')
+        _lib.check(L.escgnn_csr_build(_p(t.ei[0]), E, N, _p(t.src_ptr), _p(t.src_perm), _p(t.tmp_b),
+                                      _p(self.idx_err), _p(t.rows['E']), st), 'csr_build')
+        _lib.check(L.escgnn_sorted_ids_to_ptr(_p(t.batch), N, G, _p(t.graph_ptr), _p(t.rows['N']), st),
                    'sorted_ids_to_ptr')
 
+    def _forward_features(self, t):
+        """Pipelined mode: features / targets of the batch just loaded travel with the batch set they belong to."""
+        t.in_x.copy_(self.raw_feat.in_x)
+        t.in_y.copy_(self.raw_feat.in_y)
+        if t.in_ea is not None:
+            t.in_ea.copy_(self.raw_feat.in_ea)
+
     @torch.no_grad()
-    def _run_main(self):
-        """Everything up to the gradients as a fixed launch sequence (run eagerly, or captured once and replayed)."""
-        _lib.mark('start')
-        self._encode_and_index()
+    def _run_train(self):
+        """Forward, loss and backward on the LIVE batch set."""
         self.opt.grad.zero_()
         _lib.mark('memset')
         for f in self.fwd:
@@ -458,6 +501,32 @@ class StaticTrainEngine(object):
         for b in reversed(self.bwd):
             b()
         self._join()                                 # every weight gradient is in place before the optimiser / exchange
+
+    @torch.no_grad()
+    def _run_main(self):
+        """Everything up to the gradients as a fixed launch sequence (run eagerly, or captured once and replayed)."""
+        _lib.mark('start')
+        if self.pipeline and not self.inline_branches:
+            # batch k-1 goes live with one copy; the encoder then fills the staging set with batch k on its own branch
+            # while the main branch trains on batch k-1
+            main = torch.cuda.current_stream(self.c.dev)
+            self.live.buf.copy_(self.stage.buf)
+            moved = torch.cuda.Event()
+            moved.record(main)
+            with torch.cuda.stream(self.enc_stream):
+                self.enc_stream.wait_event(moved)
+                self._forward_features(self.stage)
+                self._encode_and_index(self.stage)
+                enc_done = torch.cuda.Event()
+                enc_done.record(self.enc_stream)
+            self._run_train()
+            main.wait_event(enc_done)
+        else:
+            if self.pipeline:                        # single-stream profile of the same work
+                self._forward_features(self.live)
+                _lib.mark('copy')
+            self._encode_and_index(self.live)
+            self._run_train()
 
     @torch.no_grad()
     def _run_opt(self):
@@ -482,13 +551,48 @@ class StaticTrainEngine(object):
         self.in_eptr.copy_(raw.edge_ptr, non_blocking=True)
         self.in_nptr.copy_(raw.node_ptr, non_blocking=True)
         n = raw.num_nodes
-        self.in_x[:n].copy_(raw.x, non_blocking=True)
-        if self.in_ea is not None:
-            self.in_ea[:raw.edge_attr.size(0)].copy_(raw.edge_attr, non_blocking=True)
-        self.in_y[:raw.y.numel()].copy_(raw.y.view(-1), non_blocking=True)
+        t = self.raw_feat if self.pipeline else self.live   # pipelined: the encoder branch forwards them into the staging set
+        t.in_x[:n].copy_(raw.x, non_blocking=True)
+        if t.in_ea is not None:
+            t.in_ea[:raw.edge_attr.size(0)].copy_(raw.edge_attr, non_blocking=True)
+        t.in_y[:raw.y.numel()].copy_(raw.y.view(-1), non_blocking=True)
+
+    @torch.no_grad()
+    def prime(self, raw):
+        """Pipelined mode: encode `raw` into the staging set without training (the first batch of a run)."""
+        self.load(raw)
+        self._forward_features(self.stage)
+        self._encode_and_index(self.stage)
+        self._primed = True
+
+    @torch.no_grad()
+    def drain(self):
+        """Pipelined mode: train on the batch still waiting in the staging set (the last batch of a run)."""
+        if not (self.pipeline and self._primed):
+            return None
+        self.opt.sync_hyper(self._world())
+        self.live.buf.copy_(self.stage.buf)
+        self._run_train()
+        if self.distributed:
+            self.opt.all_reduce_grads()
+        self._run_opt()
+        self._primed = False
+        self.steps += 1
+        return self.loss
+
+    def _world(self):
+        if self.distributed:
+            import torch.distributed as dist
+            return dist.get_world_size()
+        return 1
 
     def step(self, raw):
-        """One full step on `raw`; returns the loss as a device tensor (read it with .item() when needed)."""
+        """One full step on `raw`; returns the loss as a device tensor (read it with .item() when needed).
+        Pipelined engines encode `raw` while training on the batch handed to the PREVIOUS call and return that batch's
+        loss (None for the first call, which only encodes); drain() trains the last one."""
+        if self.pipeline and not self._primed:
+            self.prime(raw)
+            return None
         world = 1
         if self.distributed:
             import torch.distributed as dist

@@ -127,7 +127,7 @@ def test_ops_refuse_cpu_tensors():
         ops.GraphIndex(torch.tensor([[0, 1], [1, 0]]), 2)
 
 
-def _engine_for(variant, config, count, kw, use_graph):
+def _engine_for(variant, config, count, kw, use_graph, **extra):
     from esc_gnn_b200 import synth
     from esc_gnn_b200.engine import StaticTrainEngine
     from esc_gnn_b200.pipeline import RawBatch
@@ -138,8 +138,30 @@ def _engine_for(variant, config, count, kw, use_graph):
     model.train()
     fl = synth.ENCODER_FLAGS[config]
     eng = StaticTrainEngine(model, variant, fl, max_graphs=count, max_nodes_per_graph=64, max_edges_per_graph=256,
-                            nodes_cap=raw.num_nodes + 300, edges_cap=raw.src.numel() + 700, lr=1e-3, use_graph=use_graph)
+                            nodes_cap=raw.num_nodes + 300, edges_cap=raw.src.numel() + 700, lr=1e-3, use_graph=use_graph,
+                            **extra)
     return eng, model, raw
+
+
+@pytest.mark.parametrize('name', ['zinc', 'count_h64'])
+def test_pipelined_engine_matches_sequential_engine(name):
+    """pipeline=True (encoder of batch k overlapped with the training of batch k-1, staged batch set copied live at the
+    start of the next step) produces the sequential engine's loss trajectory, one call late, over eager steps, the
+    capture and graph replays, on batches of different sizes."""
+    from esc_gnn_b200.pipeline import RawBatch
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    seq, _, raw0 = _engine_for(variant, config, count, kw, True)
+    pip, _, _ = _engine_for(variant, config, count, kw, True, pipeline=True)
+    raws = [raw0] + [RawBatch.synth(config, 100 + 7 * i, count) for i in (1, 2)]
+    raws = [r for r in raws if r.num_nodes <= seq.c.caps['N'] and r.src.numel() <= seq.c.caps['E_in']]
+    assert len(raws) >= 2
+    order = [raws[i % len(raws)] for i in range(7)]
+    want = [float(seq.step(r).item()) for r in order]
+    assert pip.step(order[0]) is None
+    got = [float(pip.step(r).item()) for r in order[1:]] + [float(pip.drain().item())]
+    seq.check_errors(); pip.check_errors()
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=1e-5)
 
 
 @pytest.mark.parametrize('name,use_graph', [('zinc', False), ('zinc', True), ('count_h256', True), ('count_h64', False),
