@@ -11,7 +11,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <initializer_list>
+
 #include "../../include/escgnn_b200.h"
+#include "launch.cuh"
 
 namespace {
 
@@ -45,6 +48,7 @@ __device__ __forceinline__ void cta_reduce2(float& a, float& b, float (*s)[2][kC
 // partial[tile][0][c] = sum_r x[r][c], partial[tile][1][c] = sum_r x[r][c]^2 over the tile's valid rows
 __global__ void __launch_bounds__(256)
 colstats_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ d_rows, int C, float* __restrict__ partial) {
+    escgnn::pdl_enter();
     __shared__ float s[8][2][kCols];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
@@ -62,6 +66,7 @@ bn_act_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
                   const float* __restrict__ beta, float* running_mean, float* running_var, float* __restrict__ mean_out,
                   float* __restrict__ rstd_out, int act, float eps, float momentum, int training,
                   const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ y, int ldy) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = min(*d_rows, rows_cap);
     const int tiles = (rows + kTileRows - 1) / kTileRows;
@@ -104,6 +109,7 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ x, int ldx, const float* __re
                          const float* __restrict__ dy2, int lddy2, const float* __restrict__ mean,
                          const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                          int act, const int* __restrict__ d_rows, int C, float* __restrict__ partial) {
+    escgnn::pdl_enter();
     __shared__ float s[8][2][kCols];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
@@ -132,6 +138,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ x, int ldx, const float* __res
                         int act, int training, const float* __restrict__ partial, const int* __restrict__ d_rows,
                         int rows_cap, int C, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx,
                         int lddx) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = min(*d_rows, rows_cap);
     if (c >= C) return;
@@ -156,10 +163,261 @@ bn_act_bwd_apply_kernel(const float* __restrict__ x, int ldx, const float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// float4 variants (every operand 16-byte aligned, C and all leading dimensions multiples of 4 - the engine's case).
+// One CTA = kVRows rows x kVCols columns, a lane owns 4 adjacent columns and a warp a row, so a warp reads 512
+// contiguous bytes per row and keeps 8 independent 16-byte loads in flight per thread.  The reduction kernels write
+// per-tile partials, and the LAST tile to arrive (a ticket per column block at the head of the workspace) sums them
+// in a fixed order and finalises the statistics, so the apply kernels read two numbers per column instead of
+// re-summing every tile in every CTA.  Workspace (floats): [0,64) tickets (left zero), [64, 64+2C) final sums,
+// then [tile][2][C] partials.
+constexpr int kVRows = 64, kVCols = 128, kHdr = 64;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// Per-CTA sums of (a, b) over its 8 warps -> tile partial; returns true (uniformly) in the last CTA of the column block.
+__device__ __forceinline__ bool tile_commit(const float4& a, const float4& b, float* ws, int C, float (*s)[2][kVCols], int* s_last) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    st4(&s[warp][0][lane * 4], a);
+    st4(&s[warp][1][lane * 4], b);
+    __syncthreads();
+    const int which = threadIdx.x >> 7, col = threadIdx.x & 127, c = blockIdx.x * kVCols + col;
+    float v = 0.f;
+    #pragma unroll
+    for (int w = 0; w < 8; ++w) v += s[w][which][col];
+    if (c < C) ws[kHdr + 2 * C + ((size_t)blockIdx.y * 2 + which) * C + c] = v;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *s_last = atomicAdd(reinterpret_cast<unsigned*>(ws) + blockIdx.x, 1u) == gridDim.y - 1;
+    __syncthreads();
+    return *s_last != 0;
+}
+
+// Last CTA: ordered sum of the first `tiles` tile partials; valid in threads [0, 128) (one column each).
+__device__ __forceinline__ void final_sums(float* ws, int C, int tiles, float (*s)[2][kVCols], float& s1, float& s2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c4 = blockIdx.x * kVCols + lane * 4;
+    __threadfence();
+    float4 a = zero4(), b = zero4();
+    if (c4 < C) {
+        const float* base = ws + kHdr + 2 * C + c4;
+        #pragma unroll 4
+        for (int t = warp; t < tiles; t += 8) {
+            const float4 u = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(t * 2) * C));
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(t * 2 + 1) * C));
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+            b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+        }
+    }
+    st4(&s[warp][0][lane * 4], a);
+    st4(&s[warp][1][lane * 4], b);
+    __syncthreads();
+    s1 = 0.f; s2 = 0.f;
+    if (threadIdx.x < kVCols) {
+        #pragma unroll
+        for (int w = 0; w < 8; ++w) { s1 += s[w][0][threadIdx.x]; s2 += s[w][1][threadIdx.x]; }
+    }
+    if (threadIdx.x == 0) reinterpret_cast<unsigned*>(ws)[blockIdx.x] = 0u;      // ticket ready for the next launch
+}
+
+// mode 0: BatchNorm statistics (sum x, sum x^2 -> mean / rstd / running stats); mode 1: column sums only (-> out_sum)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colstats_v4_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ d_rows, int rows_cap, int C, float* ws,
+                   float* running_mean, float* running_var, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                   float eps, float momentum, float* __restrict__ out_sum) {
+    escgnn::pdl_enter();
+    __shared__ __align__(16) float s[8][2][kVCols];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * kVCols + lane * 4, r0 = blockIdx.y * kVRows + warp, rows = min(*d_rows, rows_cap);
+    float4 a = zero4(), b = zero4();
+    if (c4 < C) {
+        float4 v[kVRows / 8];
+        #pragma unroll
+        for (int i = 0; i < kVRows / 8; ++i) v[i] = r0 + 8 * i < rows ? ld4(x + (size_t)(r0 + 8 * i) * ldx + c4) : zero4();
+        #pragma unroll
+        for (int i = 0; i < kVRows / 8; ++i) {
+            a.x += v[i].x; a.y += v[i].y; a.z += v[i].z; a.w += v[i].w;
+            if (MODE == 0) { b.x += v[i].x * v[i].x; b.y += v[i].y * v[i].y; b.z += v[i].z * v[i].z; b.w += v[i].w * v[i].w; }
+        }
+    }
+    if (!tile_commit(a, b, ws, C, s, &s_last)) return;
+    float s1, s2;
+    final_sums(ws, C, (rows + kVRows - 1) / kVRows, s, s1, s2);
+    const int c = blockIdx.x * kVCols + threadIdx.x;
+    if (threadIdx.x >= kVCols || c >= C) return;
+    if (MODE == 1) { out_sum[c] = s1; return; }
+    const float m = (float)max(rows, 1), mean = s1 / m, var = fmaxf(s2 / m - mean * mean, 0.f);
+    mean_out[c] = mean; rstd_out[c] = rsqrtf(var + eps);
+    if (rows > 0) {
+        const float unbiased = rows > 1 ? var * m / (m - 1.f) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+}
+
+__device__ __forceinline__ float4 act_fwd4(const float4& v, int act) {
+    return make_float4(act_fwd(v.x, act), act_fwd(v.y, act), act_fwd(v.z, act), act_fwd(v.w, act));
+}
+
+// y = act((x - mean) * rstd * gamma + beta) with the statistics already final (training) or the running ones (eval)
+__global__ void __launch_bounds__(256)
+bn_act_fwd_v4_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ running_mean, const float* __restrict__ running_var, float* mean_io, float* rstd_io,
+                     int act, float eps, int training, const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ y,
+                     int ldy) {
+    escgnn::pdl_enter();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * kVCols + lane * 4, r0 = blockIdx.y * kVRows + warp, rows = min(*d_rows, rows_cap);
+    if (c4 >= C) return;
+    float4 mean, rstd;
+    if (training) { mean = ld4(mean_io + c4); rstd = ld4(rstd_io + c4); }
+    else {
+        mean = ld4(running_mean + c4);
+        const float4 rv = ld4(running_var + c4);
+        rstd = make_float4(rsqrtf(rv.x + eps), rsqrtf(rv.y + eps), rsqrtf(rv.z + eps), rsqrtf(rv.w + eps));
+        if (blockIdx.y == 0 && warp == 0) { st4(mean_io + c4, mean); st4(rstd_io + c4, rstd); }
+    }
+    const float4 g = gamma ? ld4(gamma + c4) : make_float4(1.f, 1.f, 1.f, 1.f), bt = beta ? ld4(beta + c4) : zero4();
+    const float4 sc = make_float4(rstd.x * g.x, rstd.y * g.y, rstd.z * g.z, rstd.w * g.w);
+    const float4 sh = make_float4(bt.x - mean.x * sc.x, bt.y - mean.y * sc.y, bt.z - mean.z * sc.z, bt.w - mean.w * sc.w);
+    float4 v[kVRows / 8];
+    #pragma unroll
+    for (int i = 0; i < kVRows / 8; ++i) v[i] = r0 + 8 * i < rows ? ld4(x + (size_t)(r0 + 8 * i) * ldx + c4) : zero4();
+    #pragma unroll
+    for (int i = 0; i < kVRows / 8; ++i) {
+        const int r = r0 + 8 * i;
+        if (r >= rows_cap) break;
+        float4 o = zero4();                           // rows >= actual count are zeroed (inert in the next GEMM)
+        if (r < rows) o = act_fwd4(make_float4(v[i].x * sc.x + sh.x, v[i].y * sc.y + sh.y, v[i].z * sc.z + sh.z, v[i].w * sc.w + sh.w), act);
+        st4(y + (size_t)r * ldy + c4, o);
+    }
+}
+
+struct BnCols { float4 mu, rs, g, bt; };
+__device__ __forceinline__ BnCols bn_cols(const float* mean, const float* rstd, const float* gamma, const float* beta, int c4) {
+    BnCols k;
+    k.mu = ld4(mean + c4); k.rs = ld4(rstd + c4);
+    k.g = gamma ? ld4(gamma + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+    k.bt = beta ? ld4(beta + c4) : zero4();
+    return k;
+}
+// dz = d * act'(xhat * g + bt) and xhat, per component
+__device__ __forceinline__ void bn_dz(const float4& x, const float4& d, const BnCols& k, int act, float4& dz, float4& xh) {
+    xh = make_float4((x.x - k.mu.x) * k.rs.x, (x.y - k.mu.y) * k.rs.y, (x.z - k.mu.z) * k.rs.z, (x.w - k.mu.w) * k.rs.w);
+    dz = make_float4(d.x * act_grad(xh.x * k.g.x + k.bt.x, act), d.y * act_grad(xh.y * k.g.y + k.bt.y, act),
+                     d.z * act_grad(xh.z * k.g.z + k.bt.z, act), d.w * act_grad(xh.w * k.g.w + k.bt.w, act));
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_v4_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy,
+                            const float* __restrict__ dy2, int lddy2, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            int act, const int* __restrict__ d_rows, int rows_cap, int C, float* ws, float* __restrict__ dgamma,
+                            float* __restrict__ dbeta) {
+    escgnn::pdl_enter();
+    __shared__ __align__(16) float s[8][2][kVCols];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * kVCols + lane * 4, r0 = blockIdx.y * kVRows + warp, rows = min(*d_rows, rows_cap);
+    float4 a = zero4(), b = zero4();
+    if (c4 < C) {
+        const BnCols k = bn_cols(mean, rstd, gamma, beta, c4);
+        #pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 xv[kVRows / 16], dv[kVRows / 16];
+            #pragma unroll
+            for (int i = 0; i < kVRows / 16; ++i) {
+                const int r = r0 + 8 * (h * (kVRows / 16) + i);
+                xv[i] = zero4(); dv[i] = zero4();
+                if (r < rows) {
+                    xv[i] = ld4(x + (size_t)r * ldx + c4);
+                    dv[i] = ld4(dy + (size_t)r * lddy + c4);
+                    if (dy2) { const float4 e = ld4(dy2 + (size_t)r * lddy2 + c4); dv[i].x += e.x; dv[i].y += e.y; dv[i].z += e.z; dv[i].w += e.w; }
+                }
+            }
+            #pragma unroll
+            for (int i = 0; i < kVRows / 16; ++i) {
+                const int r = r0 + 8 * (h * (kVRows / 16) + i);
+                if (r < rows) {
+                    float4 dz, xh;
+                    bn_dz(xv[i], dv[i], k, act, dz, xh);
+                    a.x += dz.x; a.y += dz.y; a.z += dz.z; a.w += dz.w;
+                    b.x += dz.x * xh.x; b.y += dz.y * xh.y; b.z += dz.z * xh.z; b.w += dz.w * xh.w;
+                }
+            }
+        }
+    }
+    if (!tile_commit(a, b, ws, C, s, &s_last)) return;
+    float s1, s2;
+    final_sums(ws, C, (rows + kVRows - 1) / kVRows, s, s1, s2);
+    const int c = blockIdx.x * kVCols + threadIdx.x;
+    if (threadIdx.x >= kVCols || c >= C) return;
+    ws[kHdr + c] = s1; ws[kHdr + C + c] = s2;
+    if (dgamma) dgamma[c] = s2;
+    if (dbeta) dbeta[c] = s1;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_v4_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy,
+                           const float* __restrict__ dy2, int lddy2, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           int act, int training, const float* __restrict__ ws, const int* __restrict__ d_rows, int rows_cap, int C,
+                           float* __restrict__ dx, int lddx) {
+    escgnn::pdl_enter();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * kVCols + lane * 4, r0 = blockIdx.y * kVRows + warp, rows = min(*d_rows, rows_cap);
+    if (c4 >= C) return;
+    const BnCols k = bn_cols(mean, rstd, gamma, beta, c4);
+    const float inv_m = training ? 1.f / (float)max(rows, 1) : 0.f;
+    const float4 s1 = ld4(ws + kHdr + c4), s2 = ld4(ws + kHdr + C + c4);
+    const float4 m1 = make_float4(s1.x * inv_m, s1.y * inv_m, s1.z * inv_m, s1.w * inv_m);
+    const float4 m2 = make_float4(s2.x * inv_m, s2.y * inv_m, s2.z * inv_m, s2.w * inv_m);
+    const float4 kk = make_float4(k.g.x * k.rs.x, k.g.y * k.rs.y, k.g.z * k.rs.z, k.g.w * k.rs.w);
+    #pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float4 xv[kVRows / 16], dv[kVRows / 16];
+        #pragma unroll
+        for (int i = 0; i < kVRows / 16; ++i) {
+            const int r = r0 + 8 * (h * (kVRows / 16) + i);
+            xv[i] = zero4(); dv[i] = zero4();
+            if (r < rows) {
+                xv[i] = ld4(x + (size_t)r * ldx + c4);
+                dv[i] = ld4(dy + (size_t)r * lddy + c4);
+                if (dy2) { const float4 e = ld4(dy2 + (size_t)r * lddy2 + c4); dv[i].x += e.x; dv[i].y += e.y; dv[i].z += e.z; dv[i].w += e.w; }
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < kVRows / 16; ++i) {
+            const int r = r0 + 8 * (h * (kVRows / 16) + i);
+            if (r >= rows_cap) break;
+            float4 o = zero4();
+            if (r < rows) {
+                float4 dz, xh;
+                bn_dz(xv[i], dv[i], k, act, dz, xh);
+                o = make_float4(kk.x * (dz.x - m1.x - xh.x * m2.x), kk.y * (dz.y - m1.y - xh.y * m2.y),
+                                kk.z * (dz.z - m1.z - xh.z * m2.z), kk.w * (dz.w - m1.w - xh.w * m2.w));
+            }
+            st4(dx + (size_t)r * lddx + c4, o);
+        }
+    }
+}
+
+inline bool vec_ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds) {
+    if (C % 4) return false;
+    for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+    for (int l : lds) if (l % 4) return false;
+    return true;
+}
+inline dim3 vec_grid(int rows_cap, int C) { return dim3((unsigned)((C + kVCols - 1) / kVCols), (unsigned)((rows_cap + kVRows - 1) / kVRows)); }
+
 // activation only (no BatchNorm): y = act(x), rows beyond the count zeroed; backward: dx = dy * act'(x)
 __global__ void __launch_bounds__(256)
 act_fwd_kernel(const float* __restrict__ x, int ldx, int act, const int* __restrict__ d_rows, int rows_cap, int C,
                float* __restrict__ y, int ldy) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = min(*d_rows, rows_cap);
     if (c >= C) return;
@@ -168,6 +426,7 @@ act_fwd_kernel(const float* __restrict__ x, int ldx, int act, const int* __restr
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy, int act,
                const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ dx, int lddx) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = min(*d_rows, rows_cap);
     if (c >= C) return;
@@ -178,6 +437,7 @@ act_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ d
 // column sums (bias gradients): partial per tile, then an ordered final sum
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ d_rows, int C, float* __restrict__ partial) {
+    escgnn::pdl_enter();
     __shared__ float s[8][2][kCols];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
@@ -187,6 +447,7 @@ colsum_partial_kernel(const float* __restrict__ x, int ldx, const int* __restric
     if (warp == 0 && c < C) partial[(size_t)blockIdx.y * C + c] = a;
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, const int* __restrict__ d_rows, int C, float* __restrict__ out) {
+    escgnn::pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int tiles = (*d_rows + kTileRows - 1) / kTileRows;
@@ -199,6 +460,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, const int
 __global__ void embedding_fwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int n_cols_idx,
                                      const int64_t* __restrict__ col_offsets, const int* __restrict__ d_rows, int rows_cap,
                                      int C, float* __restrict__ y, int ldy) {
+    escgnn::pdl_enter();
     const int rows = *d_rows;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)rows_cap * C; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / C), c = (int)(i % C);
@@ -212,6 +474,7 @@ __global__ void embedding_fwd_kernel(const float* __restrict__ table, const int6
 __global__ void embedding_bwd_kernel(const float* __restrict__ dy, int lddy, const int64_t* __restrict__ idx, int n_cols_idx,
                                      const int64_t* __restrict__ col_offsets, const int* __restrict__ d_rows, int C,
                                      float* __restrict__ dtable) {
+    escgnn::pdl_enter();
     const int rows = *d_rows;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)rows * C; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / C), c = (int)(i % C);
@@ -226,6 +489,7 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ dy, int lddy, con
 __global__ void __launch_bounds__(1024)
 loss_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ target, int kind, const int* __restrict__ d_rows,
             int T, float* __restrict__ loss, float* __restrict__ dpred, int lddp, int rows_cap) {
+    escgnn::pdl_enter();
     __shared__ float s_sum[32], s_cnt[32];
     const int rows = *d_rows;
     float acc = 0.f, cnt = 0.f;
@@ -262,14 +526,35 @@ extern "C" {
 
 int escgnn_dense_tile_rows(void) { return kTileRows; }
 
+int escgnn_set_pdl(int on) {
+    const int was = escgnn::pdl_enabled();
+    escgnn::pdl_enabled() = on ? 1 : 0;
+    return was;
+}
+
+int64_t escgnn_dense_partial_floats(int rows_cap, int channels) {
+    const int64_t c = (channels + 3) / 4 * 4;
+    return kHdr + 2 * c + ((int64_t)(rows_cap + kVRows - 1) / kVRows + 1) * 2 * c;
+}
+
 int escgnn_bn_act_fwd(const float* d_x, int ldx, const float* d_gamma, const float* d_beta, float* d_running_mean,
                       float* d_running_var, float* d_mean, float* d_rstd, float* d_partial, int act, float eps,
                       float momentum, int training, const int* d_rows, int rows_cap, int channels, float* d_y, int ldy,
                       void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (vec_ok(channels, {d_x, d_y, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, d_partial}, {ldx, ldy})) {
+        const dim3 g = vec_grid(rows_cap, channels);
+        if (training)
+            escgnn::launch_pdl(colstats_v4_kernel<0>, g, 256, 0, st, d_x, ldx, d_rows, rows_cap, channels, d_partial, d_running_mean, d_running_var,
+                                                     d_mean, d_rstd, eps, momentum, nullptr);
+        escgnn::launch_pdl(bn_act_fwd_v4_kernel, g, 256, 0, st, d_x, ldx, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, act, eps,
+                                                training, d_rows, rows_cap, channels, d_y, ldy);
+        return (int)cudaGetLastError();
+    }
+    d_partial += kHdr;                                       // scalar fallback: plain [tile][2][C] partials behind the tickets
     const dim3 g = tile_grid(rows_cap, channels);
-    if (training) colstats_kernel<<<g, 256, 0, st>>>(d_x, ldx, d_rows, channels, d_partial);
-    bn_act_fwd_kernel<<<g, 256, 0, st>>>(d_x, ldx, d_partial, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd,
+    if (training) escgnn::launch_pdl(colstats_kernel, g, 256, 0, st, d_x, ldx, d_rows, channels, d_partial);
+    escgnn::launch_pdl(bn_act_fwd_kernel, g, 256, 0, st, d_x, ldx, d_partial, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd,
                                          act, eps, momentum, training, d_rows, rows_cap, channels, d_y, ldy);
     return (int)cudaGetLastError();
 }
@@ -279,31 +564,46 @@ int escgnn_bn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, co
                       int training, float* d_partial, const int* d_rows, int rows_cap, int channels, float* d_dgamma,
                       float* d_dbeta, float* d_dx, int lddx, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (vec_ok(channels, {d_x, d_dy, d_dy2, d_mean, d_rstd, d_gamma, d_beta, d_partial, d_dx}, {ldx, lddy, d_dy2 ? lddy2 : 0, lddx})) {
+        const dim3 g = vec_grid(rows_cap, channels);
+        escgnn::launch_pdl(bn_act_bwd_reduce_v4_kernel, g, 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
+                                                       d_rows, rows_cap, channels, d_partial, d_dgamma, d_dbeta);
+        escgnn::launch_pdl(bn_act_bwd_apply_v4_kernel, g, 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
+                                                      training, d_partial, d_rows, rows_cap, channels, d_dx, lddx);
+        return (int)cudaGetLastError();
+    }
+    d_partial += kHdr;
     const dim3 g = tile_grid(rows_cap, channels);
-    bn_act_bwd_reduce_kernel<<<g, 256, 0, st>>>(d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
+    escgnn::launch_pdl(bn_act_bwd_reduce_kernel, g, 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
                                                 d_rows, channels, d_partial);
-    bn_act_bwd_apply_kernel<<<g, 256, 0, st>>>(d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
+    escgnn::launch_pdl(bn_act_bwd_apply_kernel, g, 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
                                                training, d_partial, d_rows, rows_cap, channels, d_dgamma, d_dbeta, d_dx, lddx);
     return (int)cudaGetLastError();
 }
 
 int escgnn_act_fwd(const float* d_x, int ldx, int act, const int* d_rows, int rows_cap, int channels, float* d_y, int ldy,
                    void* stream) {
-    act_fwd_kernel<<<tile_grid(rows_cap, channels), 256, 0, (cudaStream_t)stream>>>(d_x, ldx, act, d_rows, rows_cap, channels, d_y, ldy);
+    escgnn::launch_pdl(act_fwd_kernel, tile_grid(rows_cap, channels), 256, 0, (cudaStream_t)stream, d_x, ldx, act, d_rows, rows_cap, channels, d_y, ldy);
     return (int)cudaGetLastError();
 }
 
 int escgnn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, int act, const int* d_rows, int rows_cap,
                    int channels, float* d_dx, int lddx, void* stream) {
-    act_bwd_kernel<<<tile_grid(rows_cap, channels), 256, 0, (cudaStream_t)stream>>>(d_x, ldx, d_dy, lddy, act, d_rows, rows_cap, channels, d_dx, lddx);
+    escgnn::launch_pdl(act_bwd_kernel, tile_grid(rows_cap, channels), 256, 0, (cudaStream_t)stream, d_x, ldx, d_dy, lddy, act, d_rows, rows_cap, channels, d_dx, lddx);
     return (int)cudaGetLastError();
 }
 
 int escgnn_colsum(const float* d_x, int ldx, const int* d_rows, int rows_cap, int channels, float* d_partial, float* d_out,
                   void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    colsum_partial_kernel<<<tile_grid(rows_cap, channels), 256, 0, st>>>(d_x, ldx, d_rows, channels, d_partial);
-    colsum_final_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(d_partial, d_rows, channels, d_out);
+    if (vec_ok(channels, {d_x, d_partial}, {ldx})) {         // one launch: the last tile to arrive writes the sums
+        escgnn::launch_pdl(colstats_v4_kernel<1>, vec_grid(rows_cap, channels), 256, 0, st, d_x, ldx, d_rows, rows_cap, channels, d_partial, nullptr,
+                                                                           nullptr, nullptr, nullptr, 0.f, 0.f, d_out);
+        return (int)cudaGetLastError();
+    }
+    d_partial += kHdr;
+    escgnn::launch_pdl(colsum_partial_kernel, tile_grid(rows_cap, channels), 256, 0, st, d_x, ldx, d_rows, channels, d_partial);
+    escgnn::launch_pdl(colsum_final_kernel, (unsigned)((channels + 127) / 128), 128, 0, st, d_partial, d_rows, channels, d_out);
     return (int)cudaGetLastError();
 }
 
@@ -311,7 +611,7 @@ int escgnn_embedding_fwd(const float* d_table, const int64_t* d_idx, int idx_col
                          const int* d_rows, int rows_cap, int channels, float* d_y, int ldy, void* stream) {
     int64_t total = (int64_t)rows_cap * channels;
     unsigned b = (unsigned)((total + 255) / 256); if (b > 1184) b = 1184; if (b < 1) b = 1;
-    embedding_fwd_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_table, d_idx, idx_cols, d_col_offsets, d_rows, rows_cap, channels, d_y, ldy);
+    escgnn::launch_pdl(embedding_fwd_kernel, b, 256, 0, (cudaStream_t)stream, d_table, d_idx, idx_cols, d_col_offsets, d_rows, rows_cap, channels, d_y, ldy);
     return (int)cudaGetLastError();
 }
 
@@ -319,13 +619,13 @@ int escgnn_embedding_bwd(const float* d_dy, int lddy, const int64_t* d_idx, int 
                          const int* d_rows, int rows_cap, int channels, float* d_dtable, void* stream) {
     int64_t total = (int64_t)rows_cap * channels;
     unsigned b = (unsigned)((total + 255) / 256); if (b > 1184) b = 1184; if (b < 1) b = 1;
-    embedding_bwd_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_dy, lddy, d_idx, idx_cols, d_col_offsets, d_rows, channels, d_dtable);
+    escgnn::launch_pdl(embedding_bwd_kernel, b, 256, 0, (cudaStream_t)stream, d_dy, lddy, d_idx, idx_cols, d_col_offsets, d_rows, channels, d_dtable);
     return (int)cudaGetLastError();
 }
 
 int escgnn_loss_fwd_bwd(const float* d_pred, int ldp, const float* d_target, int kind, const int* d_rows, int rows_cap,
                         int n_targets, float* d_loss, float* d_dpred, int lddp, void* stream) {
-    loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_pred, ldp, d_target, kind, d_rows, n_targets, d_loss, d_dpred, lddp, rows_cap);
+    escgnn::launch_pdl(loss_kernel, 1, 1024, 0, (cudaStream_t)stream, d_pred, ldp, d_target, kind, d_rows, n_targets, d_loss, d_dpred, lddp, rows_cap);
     return (int)cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "../../include/escgnn_b200.h"
+#include "launch.cuh"
 
 namespace {
 
@@ -110,8 +111,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int num_kb = max(kb_end - kb_begin, 0);
     constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : 128;
 
-    for (int i = threadIdx.x; i < BLOCK_N; i += kThreads)
-        s_bias[i] = (p.bias && !p.partial && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+    // ---- prologue without global-memory traffic: overlaps the tail of the preceding kernel (launch.cuh)
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < LO_BUFS; ++b) { mbar_init(&split_bar[b], 128); mbar_init(&lo_free_bar[b], 1); }
@@ -126,6 +126,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
+    escgnn::pdl_wait();                              // operands (and the buffers written below) belong to earlier kernels until here
+    escgnn::pdl_trigger();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -183,6 +185,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else {
         // ===== splitters (main loop), then epilogue: 4 warps, TMEM lane quarter = warp % 4 =====
         const int t = threadIdx.x - 64;                 // 0..127
+        for (int i = t; i < BLOCK_N; i += 128)          // bias tile for the epilogue (these four warps are its only readers)
+            s_bias[i] = (p.bias && !p.partial && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
         for (int i = 0; i < num_kb; ++i) {
             const int s = i % STAGES, lb = i % LO_BUFS;
             mbar_wait(&full_bar[s], (i / STAGES) & 1);
@@ -203,6 +207,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_arrive(&split_bar[lb]);
         }
         const int q = warp & 3;
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_bias complete
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + q * 32 + lane;
@@ -265,6 +270,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // split-K reduction: C = (accumulate ? C : 0) + bias + sum_s partial[s]   (fixed order -> deterministic)
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C, int ldc,
                                      const float* __restrict__ bias, int accumulate) {
+    escgnn::pdl_enter();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)M * N; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / N), c = (int)(i % N);
         float s = accumulate ? C[(size_t)r * ldc + c] : 0.f;
@@ -276,6 +282,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 
 // lo plane of the 3xTF32 split: x - trunc_tf32(x), exact in fp32
 __global__ void tf32_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t rows, int cols, int ldx, int ldlo) {
+    escgnn::pdl_enter();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows * cols; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / cols; const int c = (int)(i % cols);
         const float v = x[r * ldx + c];
@@ -287,6 +294,7 @@ __global__ void tf32_lo_kernel(const float* __restrict__ x, float* __restrict__ 
 __global__ void __launch_bounds__(256)
 gemm_simple_kernel(const float* __restrict__ A, int lda, int a_mn, const float* __restrict__ B, int ldb, int b_mn,
                    float* __restrict__ C, int ldc, const float* __restrict__ bias, int M, int N, int K, int accumulate) {
+    escgnn::pdl_enter();
     __shared__ float sA[16][65], sB[16][65];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
@@ -367,7 +375,7 @@ int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    kern<<<grid, kThreads, smem, st>>>(a, b, p);
+    escgnn::launch_pdl(kern, grid, kThreads, smem, st, a, b, p);
     return (int)cudaGetLastError();
 }
 
@@ -414,7 +422,7 @@ int escgnn_tf32_split_lo(const float* d_x, int ldx, float* d_lo, int ldlo, int64
     if (total <= 0) return 0;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    tf32_lo_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_x, d_lo, rows, cols, ldx, ldlo);
+    escgnn::launch_pdl(tf32_lo_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, d_x, d_lo, rows, cols, ldx, ldlo);
     return (int)cudaGetLastError();
 }
 
@@ -422,7 +430,7 @@ int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d
                        const float* d_bias, int M, int N, int K, int accumulate, void* stream) {
     if (M <= 0 || N <= 0) return 0;
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
-    gemm_simple_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, lda, a_mn_major, d_b, ldb, b_mn_major, d_c, ldc, d_bias, M, N, K, accumulate);
+    escgnn::launch_pdl(gemm_simple_kernel, grid, 256, 0, (cudaStream_t)stream, d_a, lda, a_mn_major, d_b, ldb, b_mn_major, d_c, ldc, d_bias, M, N, K, accumulate);
     return (int)cudaGetLastError();
 }
 
@@ -470,7 +478,7 @@ int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d
     if (splits > 1) {
         int64_t blocks = ((int64_t)M * N + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_workspace, splits, M, N, d_c, ldc, d_bias, accumulate);
+        escgnn::launch_pdl(splitk_reduce_kernel, (unsigned)blocks, 256, 0, st, d_workspace, splits, M, N, d_c, ldc, d_bias, accumulate);
         rc = (int)cudaGetLastError();
     }
     return rc;

@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "../../include/escgnn_b200.h"
+#include "launch.cuh"
 
 namespace escgnn {
 
@@ -29,6 +30,7 @@ __device__ __forceinline__ int64_t dyn(int64_t host_n, const int* d_count) {
 
 __global__ void count_keys_kernel(const int64_t* __restrict__ keys, int64_t e, int n, int* __restrict__ ptr,
                                   unsigned long long* err, const int* d_count) {
+    escgnn::pdl_enter();
     e = dyn(e, d_count);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = keys[i];
@@ -39,6 +41,7 @@ __global__ void count_keys_kernel(const int64_t* __restrict__ keys, int64_t e, i
 
 // single block, in place: inclusive scan of ptr[0..n]
 __global__ void scan_ptr_kernel(int* ptr, int n1) {
+    escgnn::pdl_enter();
     __shared__ int s_warp[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int carry = 0;
@@ -65,6 +68,7 @@ __global__ void scan_ptr_kernel(int* ptr, int n1) {
 
 __global__ void fill_perm_kernel(const int64_t* __restrict__ keys, int64_t e, int n, const int* __restrict__ ptr,
                                  int* __restrict__ cursor, int* __restrict__ perm, const int* d_count) {
+    escgnn::pdl_enter();
     e = dyn(e, d_count);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = keys[i];
@@ -75,6 +79,7 @@ __global__ void fill_perm_kernel(const int64_t* __restrict__ keys, int64_t e, in
 
 // order every segment by edge id so the segmented float sums are run-to-run deterministic
 __global__ void sort_segments_kernel(const int* __restrict__ ptr, int n, int* __restrict__ perm) {
+    escgnn::pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int a = ptr[i], b = ptr[i + 1];
@@ -88,6 +93,7 @@ __global__ void sort_segments_kernel(const int* __restrict__ ptr, int n, int* __
 
 __global__ void sorted_to_ptr_kernel(const int64_t* __restrict__ ids, int64_t n, int segs, int* __restrict__ ptr,
                                      const int* d_count) {
+    escgnn::pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s > segs) return;
     n = dyn(n, d_count);
@@ -105,6 +111,7 @@ bag_embed_fwd_kernel(const float* __restrict__ W, int H, const int64_t* __restri
                      const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off,
                      const int32_t* __restrict__ rec_nnz, int64_t n_edges, float* __restrict__ out,
                      const int* d_count) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= n_edges) return;
@@ -136,6 +143,7 @@ bag_embed_bwd_kernel(const float* __restrict__ g, int H, const int64_t* __restri
                      const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off,
                      const int32_t* __restrict__ rec_nnz, int64_t n_edges, float* __restrict__ dW,
                      const int* d_count) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= dyn(n_edges, d_count)) return;
@@ -165,6 +173,7 @@ constexpr int kBagChunk = 64;          // sorted records per warp in the reducti
 __global__ void __launch_bounds__(256)
 bag_count_kernel(const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off, const int32_t* __restrict__ rec_nnz,
                  int64_t n_edges, const int* d_count, int* __restrict__ counts) {
+    escgnn::pdl_enter();
     __shared__ int hist[kBagRows];
     for (int i = threadIdx.x; i < kBagRows; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -182,6 +191,7 @@ bag_count_kernel(const uint32_t* __restrict__ rec, const int64_t* __restrict__ r
 // single block: ptr = exclusive scan of counts (ptr[1800] = total records); cursors zeroed
 __global__ void __launch_bounds__(1024)
 bag_scan_kernel(const int* __restrict__ counts, int* __restrict__ ptr, int* __restrict__ cursor) {
+    escgnn::pdl_enter();
     __shared__ int s_warp[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int carry = 0;
@@ -212,6 +222,7 @@ __global__ void __launch_bounds__(256)
 bag_fill_kernel(const uint32_t* __restrict__ rec, const int64_t* __restrict__ rec_off, const int32_t* __restrict__ rec_nnz,
                 int64_t n_edges, const int* d_count, const int* __restrict__ ptr, int* __restrict__ cursor,
                 int* __restrict__ sorted_edge, float* __restrict__ sorted_cnt) {
+    escgnn::pdl_enter();
     __shared__ int hist[kBagRows], base[kBagRows];
     for (int i = threadIdx.x; i < kBagRows; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -245,6 +256,7 @@ bag_fill_kernel(const uint32_t* __restrict__ rec, const int64_t* __restrict__ re
 __global__ void __launch_bounds__(256)
 bag_reduce_kernel(const float* __restrict__ g, int H, const int* __restrict__ ptr, const int* __restrict__ sorted_edge,
                   const float* __restrict__ sorted_cnt, float* __restrict__ dW) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int total = ptr[kBagRows];
@@ -284,6 +296,7 @@ __global__ void __launch_bounds__(256)
 gine_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ee, const int64_t* __restrict__ src,
                 const int* __restrict__ dst_ptr, const int* __restrict__ dst_perm, const float* __restrict__ eps,
                 int n, int C, float* __restrict__ out, const int* d_count, int ldx, int lde, int ldo) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -325,6 +338,7 @@ gine_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ x, co
                 const int64_t* __restrict__ dst, const int* __restrict__ src_ptr, const int* __restrict__ src_perm,
                 const float* __restrict__ eps, int n, int C, float* __restrict__ g_x, float* __restrict__ g_e,
                 float* __restrict__ dots, const int* d_count, int ldx, int lde, int ldg, int ldgx) {
+    escgnn::pdl_enter();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -377,6 +391,7 @@ gine_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ x, co
 
 // deterministic single-block sum of a float vector into out[0] (optionally accumulating)
 __global__ void reduce_sum_kernel(const float* __restrict__ v, int64_t n, float* out, int accumulate) {
+    escgnn::pdl_enter();
     __shared__ float s[32];
     float t = 0.f;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) t += v[i];
@@ -396,6 +411,7 @@ __global__ void reduce_sum_kernel(const float* __restrict__ v, int64_t n, float*
 __global__ void __launch_bounds__(256)
 segment_pool_fwd_kernel(const float* __restrict__ x, const int* __restrict__ ptr, int segs, int C, int mean,
                         float* __restrict__ out) {
+    escgnn::pdl_enter();
     const int s = blockIdx.x;
     const int a = ptr[s], b = ptr[s + 1];
     const float inv = mean ? 1.f / (float)max(b - a, 1) : 1.f;
@@ -409,6 +425,7 @@ segment_pool_fwd_kernel(const float* __restrict__ x, const int* __restrict__ ptr
 __global__ void __launch_bounds__(256)
 segment_pool_bwd_kernel(const float* __restrict__ g, const int* __restrict__ ptr, int segs, int C, int mean,
                         float* __restrict__ gx) {
+    escgnn::pdl_enter();
     const int s = blockIdx.x;
     const int a = ptr[s], b = ptr[s + 1];
     const float inv = mean ? 1.f / (float)max(b - a, 1) : 1.f;
@@ -423,6 +440,7 @@ __global__ void collate_edges_kernel(const int64_t* __restrict__ src, const int6
                                      const int32_t* __restrict__ edge_graph, const int64_t* __restrict__ node_ptr,
                                      int64_t e, int64_t* __restrict__ out_src, int64_t* __restrict__ out_dst,
                                      const int* d_count) {
+    escgnn::pdl_enter();
     e = dyn(e, d_count);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t off = node_ptr[edge_graph[i]];       // edge_index += cumulative num_nodes (Data.__inc__)
@@ -433,6 +451,7 @@ __global__ void collate_edges_kernel(const int64_t* __restrict__ src, const int6
 
 __global__ void ptr_to_ids_kernel(const int64_t* __restrict__ ptr, int64_t segs, int64_t n, int64_t* __restrict__ ids,
                                   const int* d_count) {
+    escgnn::pdl_enter();
     n = dyn(n, d_count);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t lo = 0, hi = segs;                           // last segment with ptr[s] <= i
@@ -443,6 +462,7 @@ __global__ void ptr_to_ids_kernel(const int64_t* __restrict__ ptr, int64_t segs,
 
 __global__ void make_dims_kernel(const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int64_t g,
                                  const unsigned long long* __restrict__ counters, int* __restrict__ dims) {
+    escgnn::pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         dims[0] = (int)node_ptr[g]; dims[1] = (int)eo_ptr[g]; dims[2] = (int)g;
         dims[3] = counters ? (int)counters[ESCGNN_CTR_NNZ] : 0;
@@ -465,10 +485,10 @@ int escgnn_csr_build(const int64_t* d_keys, int64_t n_edges, int64_t n_nodes, in
     cudaMemsetAsync(d_tmp, 0, (size_t)(n_nodes + 1) * 4, st);
     if (n_edges > 0) {
         const unsigned gb = blocks_for(n_edges, 256) > 1184 ? 1184 : blocks_for(n_edges, 256);
-        count_keys_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_err, d_count);
-        scan_ptr_kernel<<<1, 1024, 0, st>>>(d_ptr, (int)n_nodes + 1);
-        fill_perm_kernel<<<gb, 256, 0, st>>>(d_keys, n_edges, (int)n_nodes, d_ptr, d_tmp, d_perm, d_count);
-        sort_segments_kernel<<<blocks_for(n_nodes, 128), 128, 0, st>>>(d_ptr, (int)n_nodes, d_perm);
+        escgnn::launch_pdl(count_keys_kernel, gb, 256, 0, st, d_keys, n_edges, (int)n_nodes, d_ptr, d_err, d_count);
+        escgnn::launch_pdl(scan_ptr_kernel, 1, 1024, 0, st, d_ptr, (int)n_nodes + 1);
+        escgnn::launch_pdl(fill_perm_kernel, gb, 256, 0, st, d_keys, n_edges, (int)n_nodes, d_ptr, d_tmp, d_perm, d_count);
+        escgnn::launch_pdl(sort_segments_kernel, blocks_for(n_nodes, 128), 128, 0, st, d_ptr, (int)n_nodes, d_perm);
     }
     return (int)cudaGetLastError();
 }
@@ -478,13 +498,13 @@ int escgnn_collate_edges(const int64_t* d_src, const int64_t* d_dst, const int32
                          const int* d_count, void* stream) {
     if (n_edges <= 0) return 0;
     unsigned b = blocks_for(n_edges, 256); if (b > 2368) b = 2368;
-    collate_edges_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, d_edge_graph, d_node_ptr, n_edges, d_out_src, d_out_dst, d_count);
+    escgnn::launch_pdl(collate_edges_kernel, b, 256, 0, (cudaStream_t)stream, d_src, d_dst, d_edge_graph, d_node_ptr, n_edges, d_out_src, d_out_dst, d_count);
     return (int)cudaGetLastError();
 }
 
 int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t n_graphs,
                      const unsigned long long* d_counters, int* d_dims, void* stream) {
-    make_dims_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_eo_ptr, d_node_ptr, n_graphs, d_counters, d_dims);
+    escgnn::launch_pdl(make_dims_kernel, 1, 32, 0, (cudaStream_t)stream, d_eo_ptr, d_node_ptr, n_graphs, d_counters, d_dims);
     return (int)cudaGetLastError();
 }
 
@@ -492,14 +512,14 @@ int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64
                       void* stream) {
     if (n <= 0) return 0;
     unsigned b = blocks_for(n, 256); if (b > 2368) b = 2368;
-    ptr_to_ids_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(d_ptr, n_segments, n, d_ids, d_count);
+    escgnn::launch_pdl(ptr_to_ids_kernel, b, 256, 0, (cudaStream_t)stream, d_ptr, n_segments, n, d_ids, d_count);
     return (int)cudaGetLastError();
 }
 
 int escgnn_sorted_ids_to_ptr(const int64_t* d_ids, int64_t n, int64_t n_segments, int32_t* d_ptr, const int* d_count,
                              void* stream) {
     if (n_segments < 0 || n > 0x7ffffff0) return ESCGNN_ERR_BAD_ARG;
-    sorted_to_ptr_kernel<<<blocks_for(n_segments + 1, 256), 256, 0, (cudaStream_t)stream>>>(d_ids, n, (int)n_segments,
+    escgnn::launch_pdl(sorted_to_ptr_kernel, blocks_for(n_segments + 1, 256), 256, 0, (cudaStream_t)stream, d_ids, n, (int)n_segments,
                                                                                             d_ptr, d_count);
     return (int)cudaGetLastError();
 }
@@ -510,8 +530,8 @@ int escgnn_bag_embed_fwd(const float* d_weight, int hidden, const int64_t* d_pos
     if (hidden % 4 != 0) return ESCGNN_ERR_BAD_ARG;
     if (n_edges <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d_rec) bag_embed_fwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_weight, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_out, d_count);
-    else bag_embed_fwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_weight, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_out, d_count);
+    if (d_rec) escgnn::launch_pdl(bag_embed_fwd_kernel<true>, blocks_for(n_edges, 8), 256, 0, st, d_weight, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_out, d_count);
+    else escgnn::launch_pdl(bag_embed_fwd_kernel<false>, blocks_for(n_edges, 8), 256, 0, st, d_weight, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_out, d_count);
     return (int)cudaGetLastError();
 }
 
@@ -522,8 +542,8 @@ int escgnn_bag_embed_bwd(const float* d_grad, int hidden, const int64_t* d_pos_i
     if (hidden % 4 != 0) return ESCGNN_ERR_BAD_ARG;
     if (n_edges <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d_rec) bag_embed_bwd_kernel<true><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_grad_weight, d_count);
-    else bag_embed_bwd_kernel<false><<<blocks_for(n_edges, 8), 256, 0, st>>>(d_grad, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_grad_weight, d_count);
+    if (d_rec) escgnn::launch_pdl(bag_embed_bwd_kernel<true>, blocks_for(n_edges, 8), 256, 0, st, d_grad, hidden, nullptr, nullptr, nullptr, d_rec, d_rec_off, d_rec_nnz, n_edges, d_grad_weight, d_count);
+    else escgnn::launch_pdl(bag_embed_bwd_kernel<false>, blocks_for(n_edges, 8), 256, 0, st, d_grad, hidden, d_pos_index, d_pos_enc, d_ptr, nullptr, nullptr, nullptr, n_edges, d_grad_weight, d_count);
     return (int)cudaGetLastError();
 }
 
@@ -537,11 +557,11 @@ int escgnn_bag_embed_bwd_sorted(const float* d_grad, int hidden, const uint32_t*
     int* counts = d_work; int* ptr = d_work + kBagRows; int* cursor = d_work + 2 * kBagRows + 1;
     cudaMemsetAsync(counts, 0, kBagRows * sizeof(int), st);
     unsigned gb = blocks_for(n_edges, 8 * 16); if (gb > 296) gb = 296; if (gb < 1) gb = 1;
-    bag_count_kernel<<<gb, 256, 0, st>>>(d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, counts);
-    bag_scan_kernel<<<1, 1024, 0, st>>>(counts, ptr, cursor);
-    bag_fill_kernel<<<gb, 256, 0, st>>>(d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, ptr, cursor, d_sorted_edge, d_sorted_cnt);
+    escgnn::launch_pdl(bag_count_kernel, gb, 256, 0, st, d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, counts);
+    escgnn::launch_pdl(bag_scan_kernel, 1, 1024, 0, st, counts, ptr, cursor);
+    escgnn::launch_pdl(bag_fill_kernel, gb, 256, 0, st, d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, ptr, cursor, d_sorted_edge, d_sorted_cnt);
     const int64_t chunks = (rec_cap + kBagChunk - 1) / kBagChunk;
-    bag_reduce_kernel<<<blocks_for(chunks, 8), 256, 0, st>>>(d_grad, hidden, ptr, d_sorted_edge, d_sorted_cnt, d_grad_weight);
+    escgnn::launch_pdl(bag_reduce_kernel, blocks_for(chunks, 8), 256, 0, st, d_grad, hidden, ptr, d_sorted_edge, d_sorted_cnt, d_grad_weight);
     return (int)cudaGetLastError();
 }
 
@@ -567,8 +587,8 @@ int escgnn_gine_aggregate_fwd_ld(const float* d_x, int ldx, const float* d_edge_
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = channels % 4 == 0 && ldx % 4 == 0 && lde % 4 == 0 && ldo % 4 == 0 &&
                      (((uintptr_t)d_x | (uintptr_t)d_edge_feat | (uintptr_t)d_out) & 15) == 0;
-    if (vec) gine_fwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count, ldx, lde, ldo);
-    else gine_fwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count, ldx, lde, ldo);
+    if (vec) escgnn::launch_pdl(gine_fwd_kernel<true>, blocks_for(n_nodes, 8), 256, 0, st, d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count, ldx, lde, ldo);
+    else escgnn::launch_pdl(gine_fwd_kernel<false>, blocks_for(n_nodes, 8), 256, 0, st, d_x, d_edge_feat, d_src, d_dst_ptr, d_dst_perm, d_eps, (int)n_nodes, channels, d_out, d_count, ldx, lde, ldo);
     return (int)cudaGetLastError();
 }
 
@@ -590,23 +610,23 @@ int escgnn_gine_aggregate_bwd_ld(const float* d_grad_out, int ldg, const float* 
     const bool vec = channels % 4 == 0 && ldx % 4 == 0 && lde % 4 == 0 && ldg % 4 == 0 && ldgx % 4 == 0 &&
                      (((uintptr_t)d_x | (uintptr_t)d_edge_feat | (uintptr_t)d_grad_out | (uintptr_t)d_grad_x |
                        (uintptr_t)d_grad_edge_feat) & 15) == 0;
-    if (vec) gine_bwd_kernel<true><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count, ldx, lde, ldg, ldgx);
-    else gine_bwd_kernel<false><<<blocks_for(n_nodes, 8), 256, 0, st>>>(d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count, ldx, lde, ldg, ldgx);
-    if (d_grad_eps) reduce_sum_kernel<<<1, 1024, 0, st>>>(d_node_dots, n_nodes, d_grad_eps, 0);
+    if (vec) escgnn::launch_pdl(gine_bwd_kernel<true>, blocks_for(n_nodes, 8), 256, 0, st, d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count, ldx, lde, ldg, ldgx);
+    else escgnn::launch_pdl(gine_bwd_kernel<false>, blocks_for(n_nodes, 8), 256, 0, st, d_grad_out, d_x, d_edge_feat, d_dst, d_src_ptr, d_src_perm, d_eps, (int)n_nodes, channels, d_grad_x, d_grad_edge_feat, d_node_dots, d_count, ldx, lde, ldg, ldgx);
+    if (d_grad_eps) escgnn::launch_pdl(reduce_sum_kernel, 1, 1024, 0, st, d_node_dots, n_nodes, d_grad_eps, 0);
     return (int)cudaGetLastError();
 }
 
 int escgnn_segment_pool_fwd(const float* d_x, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
                             float* d_out, void* stream) {
     if (n_segments <= 0) return 0;
-    segment_pool_fwd_kernel<<<(unsigned)n_segments, 256, 0, (cudaStream_t)stream>>>(d_x, d_ptr, (int)n_segments, channels, mean, d_out);
+    escgnn::launch_pdl(segment_pool_fwd_kernel, (unsigned)n_segments, 256, 0, (cudaStream_t)stream, d_x, d_ptr, (int)n_segments, channels, mean, d_out);
     return (int)cudaGetLastError();
 }
 
 int escgnn_segment_pool_bwd(const float* d_grad, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
                             float* d_grad_x, void* stream) {
     if (n_segments <= 0) return 0;
-    segment_pool_bwd_kernel<<<(unsigned)n_segments, 256, 0, (cudaStream_t)stream>>>(d_grad, d_ptr, (int)n_segments, channels, mean, d_grad_x);
+    escgnn::launch_pdl(segment_pool_bwd_kernel, (unsigned)n_segments, 256, 0, (cudaStream_t)stream, d_grad, d_ptr, (int)n_segments, channels, mean, d_grad_x);
     return (int)cudaGetLastError();
 }
 

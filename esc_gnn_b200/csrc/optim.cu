@@ -6,12 +6,14 @@
 #include <stdint.h>
 
 #include "../../include/escgnn_b200.h"
+#include "launch.cuh"
 
 namespace {
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+    escgnn::pdl_enter();
     const int64_t n4 = n >> 2;
     const float step = lr / bc1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -39,6 +41,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // device-side step counter + bias corrections, so a captured CUDA graph stays valid from step to step
 // hyper: [0] lr, [1] beta1, [2] beta2, [3] eps, [4] grad_scale, [5] bc1 (out), [6] sqrt(bc2) (out); state: [0] step
 __global__ void adam_tick_kernel(float* hyper, long long* state) {
+    escgnn::pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const long long t = ++state[0];
         hyper[5] = (float)(1.0 - pow((double)hyper[1], (double)t));
@@ -49,6 +52,7 @@ __global__ void adam_tick_kernel(float* hyper, long long* state) {
 __global__ void __launch_bounds__(256)
 adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 int64_t n, const float* __restrict__ hyper) {
+    escgnn::pdl_enter();
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], gs = hyper[4], bc1 = hyper[5], bc2s = hyper[6];
     const float step = lr / bc1;
     const int64_t n4 = n >> 2;                      // n is padded to a multiple of 4 by FlatAdam
@@ -74,8 +78,8 @@ extern "C" int escgnn_adam_step_device(float* d_param, const float* d_grad, floa
     if (n <= 0 || (n & 3)) return ESCGNN_ERR_BAD_ARG;
     int64_t blocks = ((n >> 2) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    adam_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_hyper, d_state);
-    adam_dev_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, d_hyper);
+    escgnn::launch_pdl(adam_tick_kernel, 1, 32, 0, (cudaStream_t)stream, d_hyper, d_state);
+    escgnn::launch_pdl(adam_dev_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, d_hyper);
     return (int)cudaGetLastError();
 }
 
@@ -87,7 +91,7 @@ extern "C" int escgnn_adam_step(float* d_param, const float* d_grad, float* d_ex
     int64_t blocks = ((n >> 2) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, lr, beta1,
+    escgnn::launch_pdl(adam_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, lr, beta1,
                                                                     beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
     return (int)cudaGetLastError();
 }

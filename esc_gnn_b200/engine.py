@@ -40,9 +40,8 @@ class _Ctx(object):
         self.caps = dict(caps)                       # 'N', 'E', 'B', 'nnz', 'E_in'
         self.dims = dims                             # int32[4] on the device: N, E, B, nnz of the batch being trained on
         self.rows = {'N': self.dims[0:1], 'E': self.dims[1:2], 'B': self.dims[2:3]}
-        tile = _lib.lib().escgnn_dense_tile_rows()
-        max_tiles = (max(self.caps['N'], self.caps['E'], self.caps['B']) + tile - 1) // tile
-        self.partial = torch.zeros(max_tiles * 2 * 2048, dtype=torch.float32, device=device)
+        self.partial = torch.zeros(_lib.lib().escgnn_dense_partial_floats(max(self.caps['N'], self.caps['E'], self.caps['B']), 2048),
+                                   dtype=torch.float32, device=device)
         self.L = _lib.lib()
 
     def st(self):

@@ -315,8 +315,7 @@ class _BatchNormFn(torch.autograd.Function):
         rows, C = x.shape
         L = _lib.lib()
         d_rows = torch.tensor([rows], dtype=torch.int32, device=x.device)
-        tile = L.escgnn_dense_tile_rows()
-        partial = torch.empty(((rows + tile - 1) // tile + 1) * 2 * C, dtype=torch.float32, device=x.device)
+        partial = torch.zeros(L.escgnn_dense_partial_floats(rows, C), dtype=torch.float32, device=x.device)   # tickets start at 0
         mean, rstd = torch.empty(C, device=x.device), torch.empty(C, device=x.device)
         y = torch.empty_like(x)
         _lib.check(L.escgnn_bn_act_fwd(_p(x), C, _p(weight), _p(bias), _p(running_mean), _p(running_var), _p(mean), _p(rstd),

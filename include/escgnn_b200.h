@@ -211,7 +211,14 @@ int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t
 
 /* ---- dense row-wise kernels of the static-shape engine (M2, M4, M5); `d_rows` = actual row count on the device,
  * rows_cap = capacity; ld* = leading dimensions (outputs can be column slices of a wider buffer = free concat) ---- */
-int escgnn_dense_tile_rows(void);     /* rows per reduction tile: d_partial needs ceil(rows_cap/tile) * 2 * channels floats */
+/* Programmatic dependent launch for the model-side kernels (csrc/launch.cuh): on by default; 0 launches them with plain
+ * stream ordering (same results, used for A/B timing). Returns the previous setting. */
+int escgnn_set_pdl(int on);
+int escgnn_dense_tile_rows(void);     /* rows per reduction tile of the scalar fallback kernels */
+/* floats the reduction workspace `d_partial` of bn_act_fwd / bn_act_bwd / colsum needs. It must be zero before its
+ * first use (its first 64 words are arrival tickets, which every launch leaves at zero again), and two launches that
+ * may run concurrently (different streams) need different workspaces. */
+int64_t escgnn_dense_partial_floats(int rows_cap, int channels);
 /* training-mode BatchNorm1d + activation (act: 0 none, 1 ReLU, 2 ELU). Replaces the BN,act pairs of
  * nn.Sequential(Linear,Dropout,BN,act,...) (run_graphcount.py:54-61,78-87; zinc_models.py:513-522). Updates the
  * running statistics like torch (momentum, unbiased variance); saves mean / rstd for the backward. */

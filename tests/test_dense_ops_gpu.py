@@ -31,8 +31,7 @@ def test_bn_act_forward_backward_match_torch(rows, cap, C, act):
         bn.weight.copy_(1 + 0.1 * torch.randn(C, device='cuda', generator=g)); bn.bias.copy_(0.1 * torch.randn(C, device='cuda', generator=g))
     ref_bn = torch.nn.BatchNorm1d(C).cuda(); ref_bn.load_state_dict(bn.state_dict())
     d_rows = torch.tensor([rows], dtype=torch.int32, device='cuda')
-    tile = L.escgnn_dense_tile_rows()
-    partial = torch.zeros(((cap + tile - 1) // tile) * 2 * C, device='cuda')
+    partial = torch.zeros(L.escgnn_dense_partial_floats(cap, C), device='cuda')
     mean, rstd = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
     ybuf = torch.full((cap + 200, ld), 7.0, device='cuda'); y = ybuf[:cap, 4:4 + C]     # 200 guard rows past the capacity
     _lib.check(L.escgnn_bn_act_fwd(_p(x), ld, _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(mean),
@@ -66,8 +65,7 @@ def test_colsum_matches_torch(rows, cap, C):
     L = _lib.lib()
     x = torch.randn(cap, C, device='cuda')
     d_rows = torch.tensor([rows], dtype=torch.int32, device='cuda')
-    tile = L.escgnn_dense_tile_rows()
-    partial = torch.zeros(((cap + tile - 1) // tile) * 2 * max(C, 32), device='cuda')
+    partial = torch.zeros(L.escgnn_dense_partial_floats(cap, C), device='cuda')
     out = torch.zeros(C, device='cuda')
     _lib.check(L.escgnn_colsum(_p(x), C, _p(d_rows), cap, C, _p(partial), _p(out), _st()), 'colsum')
     torch.testing.assert_close(out, x[:rows].sum(0), rtol=1e-5, atol=1e-5)
