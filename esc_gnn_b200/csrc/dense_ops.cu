@@ -231,21 +231,23 @@ colstats_v4_kernel(const float* __restrict__ x, int ldx, const int* __restrict__
     __shared__ __align__(16) float s[8][2][kVCols];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c4 = blockIdx.x * kVCols + lane * 4, r0 = blockIdx.y * kVRows + warp, rows = min(*d_rows, rows_cap);
+    const int c4 = blockIdx.x * kVCols + lane * 4, rows = min(*d_rows, rows_cap);
     float4 a = zero4(), b = zero4();
     if (c4 < C) {
-        float4 v[kVRows / 8];
-        #pragma unroll
-        for (int i = 0; i < kVRows / 8; ++i) v[i] = r0 + 8 * i < rows ? ld4(x + (size_t)(r0 + 8 * i) * ldx + c4) : zero4();
-        #pragma unroll
-        for (int i = 0; i < kVRows / 8; ++i) {
-            a.x += v[i].x; a.y += v[i].y; a.z += v[i].z; a.w += v[i].w;
-            if (MODE == 0) { b.x += v[i].x * v[i].x; b.y += v[i].y * v[i].y; b.z += v[i].z * v[i].z; b.w += v[i].w * v[i].w; }
+        for (int r0 = blockIdx.y * kVRows + warp; r0 < rows; r0 += gridDim.y * kVRows) {      // row chunks of this tile
+            float4 v[kVRows / 8];
+            #pragma unroll
+            for (int i = 0; i < kVRows / 8; ++i) v[i] = r0 + 8 * i < rows ? ld4(x + (size_t)(r0 + 8 * i) * ldx + c4) : zero4();
+            #pragma unroll
+            for (int i = 0; i < kVRows / 8; ++i) {
+                a.x += v[i].x; a.y += v[i].y; a.z += v[i].z; a.w += v[i].w;
+                if (MODE == 0) { b.x += v[i].x * v[i].x; b.y += v[i].y * v[i].y; b.z += v[i].z * v[i].z; b.w += v[i].w * v[i].w; }
+            }
         }
     }
     if (!tile_commit(a, b, ws, C, s, &s_last)) return;
     float s1, s2;
-    final_sums(ws, C, (rows + kVRows - 1) / kVRows, s, s1, s2);
+    final_sums(ws, C, min((int)gridDim.y, (rows + kVRows - 1) / kVRows), s, s1, s2);
     const int c = blockIdx.x * kVCols + threadIdx.x;
     if (threadIdx.x >= kVCols || c >= C) return;
     if (MODE == 1) { out_sum[c] = s1; return; }
@@ -321,10 +323,11 @@ bn_act_bwd_reduce_v4_kernel(const float* __restrict__ x, int ldx, const float* _
     __shared__ __align__(16) float s[8][2][kVCols];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c4 = blockIdx.x * kVCols + lane * 4, r0 = blockIdx.y * kVRows + warp, rows = min(*d_rows, rows_cap);
+    const int c4 = blockIdx.x * kVCols + lane * 4, rows = min(*d_rows, rows_cap);
     float4 a = zero4(), b = zero4();
     if (c4 < C) {
         const BnCols k = bn_cols(mean, rstd, gamma, beta, c4);
+        for (int r0 = blockIdx.y * kVRows + warp; r0 < rows; r0 += gridDim.y * kVRows)       // row chunks of this tile
         #pragma unroll
         for (int h = 0; h < 2; ++h) {
             float4 xv[kVRows / 16], dv[kVRows / 16];
@@ -352,7 +355,7 @@ bn_act_bwd_reduce_v4_kernel(const float* __restrict__ x, int ldx, const float* _
     }
     if (!tile_commit(a, b, ws, C, s, &s_last)) return;
     float s1, s2;
-    final_sums(ws, C, (rows + kVRows - 1) / kVRows, s, s1, s2);
+    final_sums(ws, C, min((int)gridDim.y, (rows + kVRows - 1) / kVRows), s, s1, s2);
     const int c = blockIdx.x * kVCols + threadIdx.x;
     if (threadIdx.x >= kVCols || c >= C) return;
     ws[kHdr + c] = s1; ws[kHdr + C + c] = s2;
@@ -410,6 +413,11 @@ inline bool vec_ok(int C, std::initializer_list<const void*> ptrs, std::initiali
     for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
     for (int l : lds) if (l % 4) return false;
     return true;
+}
+constexpr int kMaxTiles = 1024;   // reduction tiles per column block (more rows -> several 64-row chunks per CTA): bounds the last tile's sum
+inline dim3 reduce_grid(int rows_cap, int C) {
+    const int t = (rows_cap + kVRows - 1) / kVRows;
+    return dim3((unsigned)((C + kVCols - 1) / kVCols), (unsigned)(t < kMaxTiles ? (t < 1 ? 1 : t) : kMaxTiles));
 }
 inline dim3 vec_grid(int rows_cap, int C) { return dim3((unsigned)((C + kVCols - 1) / kVCols), (unsigned)((rows_cap + kVRows - 1) / kVRows)); }
 
@@ -545,7 +553,7 @@ int escgnn_bn_act_fwd(const float* d_x, int ldx, const float* d_gamma, const flo
     if (vec_ok(channels, {d_x, d_y, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, d_partial}, {ldx, ldy})) {
         const dim3 g = vec_grid(rows_cap, channels);
         if (training)
-            escgnn::launch_pdl(colstats_v4_kernel<0>, g, 256, 0, st, d_x, ldx, d_rows, rows_cap, channels, d_partial, d_running_mean, d_running_var,
+            escgnn::launch_pdl(colstats_v4_kernel<0>, reduce_grid(rows_cap, channels), 256, 0, st, d_x, ldx, d_rows, rows_cap, channels, d_partial, d_running_mean, d_running_var,
                                                      d_mean, d_rstd, eps, momentum, nullptr);
         escgnn::launch_pdl(bn_act_fwd_v4_kernel, g, 256, 0, st, d_x, ldx, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, act, eps,
                                                 training, d_rows, rows_cap, channels, d_y, ldy);
@@ -566,7 +574,7 @@ int escgnn_bn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, co
     cudaStream_t st = (cudaStream_t)stream;
     if (vec_ok(channels, {d_x, d_dy, d_dy2, d_mean, d_rstd, d_gamma, d_beta, d_partial, d_dx}, {ldx, lddy, d_dy2 ? lddy2 : 0, lddx})) {
         const dim3 g = vec_grid(rows_cap, channels);
-        escgnn::launch_pdl(bn_act_bwd_reduce_v4_kernel, g, 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
+        escgnn::launch_pdl(bn_act_bwd_reduce_v4_kernel, reduce_grid(rows_cap, channels), 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
                                                        d_rows, rows_cap, channels, d_partial, d_dgamma, d_dbeta);
         escgnn::launch_pdl(bn_act_bwd_apply_v4_kernel, g, 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
                                                       training, d_partial, d_rows, rows_cap, channels, d_dx, lddx);
@@ -597,7 +605,7 @@ int escgnn_colsum(const float* d_x, int ldx, const int* d_rows, int rows_cap, in
                   void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (vec_ok(channels, {d_x, d_partial}, {ldx})) {         // one launch: the last tile to arrive writes the sums
-        escgnn::launch_pdl(colstats_v4_kernel<1>, vec_grid(rows_cap, channels), 256, 0, st, d_x, ldx, d_rows, rows_cap, channels, d_partial, nullptr,
+        escgnn::launch_pdl(colstats_v4_kernel<1>, reduce_grid(rows_cap, channels), 256, 0, st, d_x, ldx, d_rows, rows_cap, channels, d_partial, nullptr,
                                                                            nullptr, nullptr, nullptr, 0.f, 0.f, d_out);
         return (int)cudaGetLastError();
     }

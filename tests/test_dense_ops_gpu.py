@@ -17,7 +17,7 @@ def _st():
 
 
 @pytest.mark.parametrize('rows,cap,C,act', [(300, 384, 256, 'elu'), (48, 48, 256, 'relu'), (1000, 1500, 10, 'relu'),
-                                            (257, 400, 300, 'none'), (5, 130, 32, 'elu')])
+                                            (257, 400, 300, 'none'), (5, 130, 32, 'elu'), (70000, 70100, 64, 'relu')])
 def test_bn_act_forward_backward_match_torch(rows, cap, C, act):
     from esc_gnn_b200 import _lib
     from esc_gnn_b200.engine import ACT
@@ -59,7 +59,7 @@ def test_bn_act_forward_backward_match_torch(rows, cap, C, act):
     assert float(dxbuf[cap:].min()) == 3.0 and float(dxbuf[cap:].max()) == 3.0, 'wrote past rows_cap'
 
 
-@pytest.mark.parametrize('rows,cap,C', [(48, 48, 1), (48, 48, 256), (300, 1000, 288), (1, 200, 7)])
+@pytest.mark.parametrize('rows,cap,C', [(48, 48, 1), (48, 48, 256), (300, 1000, 288), (1, 200, 7), (70000, 70100, 64)])
 def test_colsum_matches_torch(rows, cap, C):
     from esc_gnn_b200 import _lib
     L = _lib.lib()
@@ -68,7 +68,7 @@ def test_colsum_matches_torch(rows, cap, C):
     partial = torch.zeros(L.escgnn_dense_partial_floats(cap, C), device='cuda')
     out = torch.zeros(C, device='cuda')
     _lib.check(L.escgnn_colsum(_p(x), C, _p(d_rows), cap, C, _p(partial), _p(out), _st()), 'colsum')
-    torch.testing.assert_close(out, x[:rows].sum(0), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out, x[:rows].sum(0), rtol=1e-5, atol=1e-5 * max(1.0, rows ** 0.5))
 
 
 def test_embedding_loss_and_adam_match_torch():
