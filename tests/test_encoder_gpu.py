@@ -203,3 +203,33 @@ def test_pre_transform_batched_equals_per_graph_calls():
             for k in ('edge_index', 'pos_enc', 'pos_index', 'pos_batch'):
                 assert torch.equal(o[k], w[k]), k
             assert (o.edge_attr is None) == (w.edge_attr is None) and (o.edge_attr is None or torch.equal(o.edge_attr, w.edge_attr))
+
+
+def test_encoded_dataset_processes_once_and_serves_from_cache(tmp_path):
+    """N1: EncodedDataset.process() (batched encoder -> collate -> torch.save) then a second open from the cache alone;
+    every served graph equals the oracle's per-graph encoding, and the loader batches it like any Data list."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.dataloader import DataLoader
+    from esc_gnn_b200.dataset import EncodedDataset
+    from tests import model_util as MU
+    raw = []
+    for i in range(300, 323):
+        g = synth.make_graph(2, i)
+        raw.append(Data(x=torch.as_tensor(g['x']), edge_index=torch.as_tensor(g['edge_index']),
+                        edge_attr=torch.as_tensor(g['edge_attr']), y=torch.as_tensor(g['y']).view(1)))
+    ds = EncodedDataset(str(tmp_path), raw, h=3, use_rd=True, self_loop=False, chunk=10, name='zincish')
+
+    def boom():
+        raise AssertionError('cache ignored')
+    ds2 = EncodedDataset(str(tmp_path), boom, h=3, use_rd=True, self_loop=False, name='zincish')
+    assert len(ds) == len(ds2) == 23
+    want = MU.graph_dicts(2, 300, 23)
+    for i in (0, 7, 22):
+        for k in ('edge_index', 'pos_enc', 'pos_index', 'pos_batch', 'x', 'edge_attr'):
+            assert torch.equal(ds2[i][k], want[i][k]), (i, k)
+        assert ds2[i].num_nodes == want[i]['num_nodes']
+    sub = ds2.shuffle(torch.Generator().manual_seed(0))[:8]
+    assert len(sub) == 8
+    b = next(iter(DataLoader(list(sub), batch_size=8)))
+    assert b.num_graphs == 8 and int(b.pos_batch[-1]) + 1 == b.edge_index.size(1)
