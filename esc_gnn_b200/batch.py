@@ -53,11 +53,11 @@ class Batch(Data):
                 if first.dtype != torch.bool:
                     if k == 'pos_batch':
                         off = torch.tensor([0] + pb_counts[:-1], dtype=torch.long).cumsum(0)
-                        cat = cat + torch.repeat_interleave(off, sizes)
+                        cat = cat + torch.repeat_interleave(off, sizes).to(cat.device)
                     elif k in ('pos_enc', 'pos_index', 'edge_pos'):
                         pass
                     elif 'index' in k:
-                        cat = cat + torch.repeat_interleave(node_off, sizes).to(cat.dtype)
+                        cat = cat + torch.repeat_interleave(node_off, sizes).to(device=cat.device, dtype=cat.dtype)
                 out[k] = cat
             elif isinstance(first, (int, float)):
                 out[k] = torch.tensor(items)

@@ -20,7 +20,9 @@ ENCODER_FLAGS = {
     3: dict(h=4, use_rd=True, self_loop=True),     # count_graphlet
     4: dict(h=4, use_rd=True, self_loop=True),     # run_ogb_mol.py:329-332
     5: dict(h=3, use_rd=False, self_loop=False),   # sweep: h in 1..4, rd off
+    6: dict(h=3, use_rd=True, self_loop=True),     # run_qm9.py:203-205 (QM9 variant)
 }
+QM9_FEATURES = 11                                  # dataset.num_features of the reference's QM9 (run_qm9.py:216-231)
 
 
 def random_graph(rng, n, m, max_degree=199):
@@ -74,7 +76,7 @@ def symmetrise(und):
 
 
 def make_graph(config, i):
-    """One synthetic graph of `config` (1..5) as a dict of numpy arrays: edge_index, num_nodes, x, y[, edge_attr]."""
+    """One synthetic graph of `config` (1..6) as a dict of numpy arrays: edge_index, num_nodes, x, y[, edge_attr]."""
     rng = np.random.Generator(np.random.PCG64(1000 * config + i))
     if config in (1, 3):
         n = int(rng.integers(10, 31))
@@ -97,6 +99,13 @@ def make_graph(config, i):
         ea = np.stack([rng.integers(0, d, size=und.shape[0]) for d in BOND_DIMS], axis=1).astype(np.int64)
         return dict(edge_index=ei, num_nodes=n, x=x, edge_attr=np.concatenate([ea, ea], axis=0),
                     y=np.float32(rng.random() < 0.03))
+    if config == 6:      # QM9-shaped: small 3-D molecules, continuous node features, one-hot bond types, per-graph target
+        n = int(rng.integers(4, 30))
+        und = random_graph(rng, n, n - 1 + int(rng.integers(0, 3)), max_degree=4)
+        bond = np.eye(4, dtype=np.float32)[rng.integers(0, 4, size=und.shape[0])]
+        return dict(edge_index=symmetrise(und), num_nodes=n, x=rng.random((n, QM9_FEATURES)).astype(np.float32),
+                    pos=(1.5 * rng.normal(size=(n, 3))).astype(np.float32), node_type=rng.integers(0, 5, size=n).astype(np.int64),
+                    edge_attr=np.concatenate([bond, bond], axis=0), y=np.float32(rng.normal()))
     if config == 5:
         n = int(rng.integers(25, 501))
         und = random_graph(rng, n, int(1.25 * n))

@@ -7,6 +7,8 @@ this oracle and the product modules.
 Follows (paths under /root/reference):
   * count  : run_graphcount.py:39-194          (NestedGIN_eff, node-level, ReLU, x_embedding JK)
   * ZINC   : zinc_models.py:504-611            (NestedGIN_eff, ELU, type embeddings, global_add_pool readout)
+  * QM9    : qm9_models.py:25-139              (NestedGIN_eff, continuous edge attributes, global_mean_pool readout)
+             with distance.py:25-65 as the load-time edge transform
   * OGB    : ogb_mol_gnn.py:66-117,252-261 (GNN), :264-282 (AtomEncoder), :323-358 (GINConv_eff),
              :614-792 (GNN_node_efficient: virtual node, residual, BN + dropout)
   * GINEConv semantics (PyG 2.0.4; third-party, not under /root/reference): restated from the in-tree twin
@@ -137,6 +139,56 @@ class NestedGINEffZinc(torch.nn.Module):
         return self.lin2(x)
 
 
+class NestedGINEffQM9(torch.nn.Module):
+    """qm9_models.py:25-139 (hidden 256, dropout 0 hard-coded there): continuous node features + 3-D positions, a
+    node-type embedding ADDED to them, bond one-hot + distance as continuous edge attributes, mean-pool readout."""
+    def __init__(self, num_layers, num_features, edge_attr_dim=5, hidden=256, dropout=0.0):
+        super().__init__()
+        self.dropout = dropout
+        self.z_initial = torch.nn.Embedding(1800, hidden)
+        self.z_embedding = _z_embedding(hidden, dropout, ReLU)
+        input_dim = num_features + 3
+        self.conv1 = GINEConv(_mlp(input_dim, hidden, dropout, ReLU), train_eps=True, edge_dim=hidden + edge_attr_dim)
+        self.convs = torch.nn.ModuleList(
+            [GINEConv(_mlp(hidden, hidden, dropout, ReLU), train_eps=True, edge_dim=hidden + edge_attr_dim)
+             for _ in range(num_layers - 1)])
+        self.lin1 = Linear(num_layers * hidden, hidden)
+        self.bn_lin1 = BN(hidden, eps=1e-5, momentum=0.1)
+        self.lin2 = Linear(hidden, 1)
+        self.node_type_embedding = torch.nn.Embedding(5, input_dim)
+
+    def forward(self, data):
+        x, edge_index, batch = torch.cat([data.x, data.pos], 1), data.edge_index, data.batch
+        x = x + self.node_type_embedding(data.node_type)
+        z = self.z_embedding(bag_embed(self.z_initial.weight, data.pos_index, data.pos_enc, data.pos_batch))
+        z = torch.cat((z, data.edge_attr), dim=-1)
+        x = self.conv1(x, edge_index, z)
+        xs = [x]
+        for conv in self.convs:
+            x = conv(x, edge_index, z)
+            xs += [x]
+        x = global_mean_pool(torch.cat(xs, dim=1), batch)
+        x = self.lin1(x)
+        if x.size(0) > 1:
+            x = self.bn_lin1(x)
+        x = F.relu(F.dropout(x, p=self.dropout, training=self.training))
+        return self.lin2(x).view(-1)
+
+
+def distance_transform(edge_index, pos, edge_attr, norm=True, max_value=None, squared=False):
+    """distance.py:28-42: Euclidean length of every edge (loops -> 0), divided by the graph's maximum, appended as
+    the last edge-attribute column."""
+    row, col = edge_index
+    d = pos[col] - pos[row]
+    dist = (d ** 2).sum(1).view(-1, 1) if squared else torch.norm(d, p=2, dim=-1).view(-1, 1)
+    if norm and dist.numel() > 0:
+        dist = dist / (dist.max() if max_value is None else max_value)
+    if edge_attr is None:
+        return dist
+    pseudo = edge_attr.view(-1, 1) if edge_attr.dim() == 1 else edge_attr
+    return torch.cat([pseudo, dist.type_as(pseudo)], dim=-1)
+
+
 class _SumEmbedding(torch.nn.Module):
     def __init__(self, dims, emb_dim, list_name):
         super().__init__()
@@ -237,7 +289,8 @@ def collate(graphs):
     pos_enc / pos_index concatenated unchanged (:72-73), batch vector (:120-123)."""
     b = RefBatch()
     node_off, pb_off = 0, 0
-    cols = {k: [] for k in ('x', 'edge_index', 'edge_attr', 'y', 'pos_enc', 'pos_index', 'pos_batch', 'batch')}
+    cols = {k: [] for k in ('x', 'edge_index', 'edge_attr', 'y', 'pos_enc', 'pos_index', 'pos_batch', 'batch', 'pos',
+                            'node_type')}
     for i, g in enumerate(graphs):
         n = g['x'].size(0)
         cols['x'].append(g['x'])
@@ -249,6 +302,9 @@ def collate(graphs):
         cols['pos_index'].append(g['pos_index'])
         cols['pos_batch'].append(g['pos_batch'] + pb_off)
         cols['batch'].append(torch.full((n, ), i, dtype=torch.long))
+        for k in ('pos', 'node_type'):            # QM9 extras: plain concatenation (batch.py default rule)
+            if g.get(k) is not None:
+                cols[k].append(g[k])
         node_off += n
         pb_off += int(g['pos_batch'].max()) + 1
     b.x = torch.cat(cols['x'], 0)
@@ -257,5 +313,8 @@ def collate(graphs):
     b.y = torch.cat(cols['y'], 0)
     b.pos_enc, b.pos_index, b.pos_batch = (torch.cat(cols[k], 0) for k in ('pos_enc', 'pos_index', 'pos_batch'))
     b.batch = torch.cat(cols['batch'], 0)
+    for k in ('pos', 'node_type'):
+        if cols[k]:
+            setattr(b, k, torch.cat(cols[k], 0))
     b.num_graphs = len(graphs)
     return b

@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 from torch_geometric.nn import GINEConv, MessagePassing, global_add_pool, global_mean_pool  # noqa: E402 (stand-ins)
 
+from esc_gnn_b200 import synth  # noqa: E402
 from tests import model_util as MU  # noqa: E402
 from oracle import model_ref  # noqa: E402
 
@@ -71,6 +72,12 @@ def build_reference_model(variant, kw):
     if variant == 'zinc':
         ns = extract('/root/reference/zinc_models.py', {'NestedGIN_eff'})
         return ns['NestedGIN_eff'](_DS(), kw['num_layers'])                  # run_zinc.py:241-257
+    if variant == 'qm9':
+        ns = extract('/root/reference/qm9_models.py', {'NestedGIN_eff'})
+
+        class _QM9(object):
+            num_features = synth.QM9_FEATURES
+        return ns['NestedGIN_eff'](_QM9(), kw['num_layers'])                 # run_qm9.py:262-270
     ns = extract('/root/reference/ogb_mol_gnn.py', {'GNN', 'AtomEncoder', 'GINConv_eff', 'GNN_node_efficient',
                                                       'center_pool', 'center_pool_virtual'})
     return ns['GNN']('ogbg-molhiv', kw['num_tasks'], num_layer=kw['num_layer'], emb_dim=kw['emb_dim'],
@@ -91,8 +98,14 @@ class _Batch(object):                           # what batch.py hands the model:
 
 def main():
     torch.set_num_threads(4)
+    path = os.path.join(HERE, 'model.npz')
     store = {}
+    if os.path.exists(path) and '--all' not in sys.argv:       # default: keep the committed cases, add the missing ones
+        with np.load(path) as old:
+            store = {k: old[k] for k in old.files}
     for name, (variant, config, count, kw) in MU.MODEL_CASES.items():
+        if name + '/loss' in store:
+            continue
         torch.manual_seed(0)
         model = build_reference_model(variant, kw)
         sd = MU.det_state(model.state_dict(), seed=1234)
@@ -137,7 +150,6 @@ def main():
         print('%-12s params %8d  N %5d  E %6d  nnz %7d  loss %.6f  adam %s' % (
             name, nparam, batch.x.shape[0], batch.edge_index.shape[1], batch.pos_enc.numel(), loss.item(),
             ['%.5f' % t for t in traj]))
-    path = os.path.join(HERE, 'model.npz')
     np.savez_compressed(path, **store)
     print('model.npz %.1f KB' % (os.path.getsize(path) / 1024))
 

@@ -53,6 +53,9 @@ def graph_dicts(config, start, count, h=None, use_rd=None, self_loop=None):
             if fl['self_loop']:      # E1 on attributes: (no loops in synth graphs) append N rows of ones
                 ea = torch.cat([ea, ea.new_full((g['num_nodes'], ) + tuple(ea.shape[1:]), 1)], 0)
             d['edge_attr'] = ea
+        if 'pos' in g:       # QM9 flow: Distance(norm=True) runs as a load-time transform AFTER the pre_transform
+            d['pos'], d['node_type'] = torch.as_tensor(g['pos']), torch.as_tensor(g['node_type'])
+            d['edge_attr'] = model_ref.distance_transform(d['edge_index'], d['pos'], d['edge_attr'])
         out.append(d)
     return out
 
@@ -74,6 +77,7 @@ MODEL_CASES = {
     'zinc': ('zinc', 2, 48, dict(num_layers=5)),
     'zinc_l2': ('zinc', 2, 3, dict(num_layers=2)),
     'ogb': ('ogb', 4, 12, dict(num_tasks=1, num_layer=3, emb_dim=64, drop_ratio=0.0, virtual_node=True, residual=True)),
+    'qm9': ('qm9', 6, 20, dict(num_layers=3)),
     'ogb_full': ('ogb', 4, 8, dict(num_tasks=1, num_layer=6, emb_dim=300, drop_ratio=0.0, virtual_node=True, residual=False)),
 }
 
@@ -83,6 +87,8 @@ def loss_fn(variant, pred, y):
         y = y.to(torch.float32).view(pred.shape)
         lab = y == y
         return torch.nn.BCEWithLogitsLoss()(pred.to(torch.float32)[lab], y[lab])      # run_ogb_mol.py:58-74
+    if variant == 'qm9':
+        return torch.nn.functional.mse_loss(pred, y.view(-1))                          # run_qm9.py:348
     return torch.nn.L1Loss()(pred, y.view(-1, 1))                                      # run_graphcount.py:494-500
 
 
@@ -91,5 +97,7 @@ def build_oracle_model(variant, kw):
         return model_ref.NestedGINEffCount(kw['num_layers'], kw['hidden'])
     if variant == 'zinc':
         return model_ref.NestedGINEffZinc(kw['num_layers'])
+    if variant == 'qm9':
+        return model_ref.NestedGINEffQM9(kw['num_layers'], synth.QM9_FEATURES)
     return model_ref.GNNOgbEff(kw['num_tasks'], kw['num_layer'], kw['emb_dim'], kw['virtual_node'], kw['residual'],
                                kw['drop_ratio'])

@@ -19,8 +19,32 @@ def product_batch(config, start, count):
     return Batch.from_data_list([to_data(g) for g in MU.graph_dicts(config, start, count)]).to('cuda')
 
 
+def qm9_product_batch(start, count):
+    """The reference's QM9 flow end to end on the product side (run_qm9.py:200-231): raw molecule -> create_subgraphs
+    (h=3, rd, self-loops; a Data with `name` keeps pos / node_type, utils_edge_efficient.py:150-151) -> Distance ->
+    collation."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.batch import Batch
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.distance import Distance
+    from esc_gnn_b200.transform import create_subgraphs
+    out = []
+    for i in range(start, start + count):
+        g = synth.make_graph(6, i)
+        d = Data(x=torch.as_tensor(g['x']), edge_index=torch.as_tensor(g['edge_index']), edge_attr=torch.as_tensor(g['edge_attr']),
+                 y=torch.as_tensor(g['y']).view(1), pos=torch.as_tensor(g['pos']), name='gdb_%d' % i,
+                 node_type=torch.as_tensor(g['node_type']))
+        d = create_subgraphs(d, 3, node_label='hop', use_rd=True, subgraph_pretransform=None, self_loop=True)
+        out.append(Distance(norm=True, relative_pos=False, squared=False)(d.to('cuda')))
+    return Batch.from_data_list(out).to('cuda')
+
+
 def build_product_model(variant, kw):
-    from esc_gnn_b200 import graphcount_model, ogb_model, zinc_model
+    from esc_gnn_b200 import graphcount_model, ogb_model, qm9_model, synth, zinc_model
+    if variant == 'qm9':
+        class _QM9(object):
+            num_features = synth.QM9_FEATURES
+        return qm9_model.NestedGIN_eff(_QM9(), kw['num_layers'])
     if variant == 'count':
         return graphcount_model.NestedGIN_eff(None, kw['num_layers'], kw['hidden'], use_rd=True, graph_pred=False,
                                               dropout=0, edge_nest=True, use_cycle=True)
@@ -37,7 +61,7 @@ def test_models_match_reference_class_fixtures(name):
     torch.manual_seed(0)
     torch.backends.cuda.matmul.allow_tf32 = False
     model = build_product_model(variant, kw).cuda()
-    batch = product_batch(config, 100, count)
+    batch = qm9_product_batch(100, count) if variant == 'qm9' else product_batch(config, 100, count)
     run_case(model, variant, batch, name, rtol=RTOL, atol=1e-5)
 
 
