@@ -69,6 +69,8 @@ SIGNATURES = {
     'escgnn_adam_step_device': (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'escgnn_make_dims': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     'escgnn_adam_step': (_i32, [_vp, _vp, _vp, _vp, _i64] + [ctypes.c_float] * 4 + [_i64, ctypes.c_float, _vp]),
+    'escgnn_all_pairs_spd_smem_bytes': (_i64, [_i64, _i64]),
+    'escgnn_all_pairs_spd': (_i32, [_vp] * 4 + [_i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'escgnn_edge_distance': (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i32, ctypes.c_float, _vp, _vp, _vp, _vp]),
 }
 
@@ -94,7 +96,7 @@ def lib():
 KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'encode_subset': 1, 'scan': 3, 'expand_records': 1,
                     'csr_build': 4, 'sorted_ids_to_ptr': 1, 'bag_embed_fwd': 1, 'bag_embed_bwd': 1,
                     'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'gine_aggregate_fwd_ld': 1, 'gine_aggregate_bwd_ld': 2, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
-                    'edge_distance': 2, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 2, 'bn_act_bwd': 2,
+                    'edge_distance': 2, 'all_pairs_spd': 1, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 2, 'bn_act_bwd': 2,
                     'act_fwd': 1, 'act_bwd': 1, 'colsum': 1, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
                     'make_dims': 1, 'adam_step_device': 2, 'bag_embed_bwd_sorted': 4, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1}
 LAUNCHES = {'n': 0}

@@ -263,3 +263,56 @@ def create_subgraphs(data, h=1, sample_ratio=1.0, max_nodes_per_hop=None, node_l
         return data.__class__(data.x, r.edge_index, edge_attr, data.y, None, **kw)
     return data.__class__(data.x, r.edge_index, edge_attr, data.y, pos=data.pos, name=data.name,
                           node_type=data.node_type, **kw)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GraphGPS twin of the transform: the same encodings plus `attn_bias`, the flattened
+# all-pairs shortest-path matrix the transformer layers use as an attention bias.
+def all_pairs_spd_batch(src, dst, edge_ptr, node_ptr, unreachable=100, device=None):
+    """Shortest-path lengths between all node pairs of every graph (undirected, unreachable -> `unreachable`).
+    src/dst: int64 graph-local node ids, edge_ptr/node_ptr: int64 [G+1] (host or device).  Returns
+    (flat int64 tensor on the device, out_ptr int64 [G+1] on the host) -- graph g's [n, n] block is
+    flat[out_ptr[g]:out_ptr[g+1]].view(n, n).  Reference: GraphGPS/graphgps/loader/utils_escgnn.py:29-38."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('esc_gnn_b200: no CUDA device -- the transform has no CPU fallback')
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    ep = torch.as_tensor(edge_ptr, dtype=torch.int64).cpu()
+    npt = torch.as_tensor(node_ptr, dtype=torch.int64).cpu()
+    n = npt[1:] - npt[:-1]
+    out_ptr = torch.zeros(npt.numel(), dtype=torch.int64)
+    out_ptr[1:] = torch.cumsum(n * n, 0)
+    G = int(n.numel())
+    max_n = int(n.max()) if G else 0
+    max_e = int((ep[1:] - ep[:-1]).max()) if G else 0
+    L = _lib.lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    s, d = torch.as_tensor(src).to(dev, torch.int64).contiguous(), torch.as_tensor(dst).to(dev, torch.int64).contiguous()
+    out = torch.empty(int(out_ptr[-1]), dtype=torch.int64, device=dev)
+    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
+    if G:
+        ep_d, np_d, op_d = ep.to(dev), npt.to(dev), out_ptr.to(dev)       # named: they must outlive the launch
+        _lib.check(L.escgnn_all_pairs_spd(P(s), P(d), P(ep_d), P(np_d), G, P(op_d), P(out), max_n, max_e,
+                                          int(unreachable), P(counters),
+                                          ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), 'all_pairs_spd')
+        _lib.raise_data_errors(int(counters[1]))
+    return out, out_ptr
+
+
+def all_pairs_spd(edge_index, num_nodes, unreachable=100):
+    """`attn_bias` of ONE graph: int64 [num_nodes * num_nodes], on the device of `edge_index`."""
+    ei = edge_index.to(torch.int64)
+    out, _ = all_pairs_spd_batch(ei[0], ei[1], [0, ei.size(1)], [0, int(num_nodes)], unreachable,
+                                 device=ei.device if ei.is_cuda else None)
+    return out.to(edge_index.device)
+
+
+def create_subgraphs_gps(data, h=1, sample_ratio=1.0, max_nodes_per_hop=None, node_label='hop', use_rd=False,
+                         subgraph_pretransform=None, data_name=None, self_loop=False):
+    """`create_subgraphs` of the GraphGPS loader (GraphGPS/graphgps/loader/utils_escgnn.py:22-154): the encodings of
+    `create_subgraphs` plus `attn_bias` computed on the INPUT graph (before self-loops are appended, :29-38)."""
+    num_nodes = data.num_nodes
+    num_nodes = int(num_nodes.item()) if torch.is_tensor(num_nodes) else int(num_nodes)
+    out = create_subgraphs(data, h, sample_ratio, max_nodes_per_hop, node_label, use_rd, subgraph_pretransform, data_name,
+                           self_loop)
+    out.attn_bias = all_pairs_spd(data.edge_index, num_nodes)
+    return out

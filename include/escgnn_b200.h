@@ -187,6 +187,15 @@ int escgnn_edge_distance(const float* d_pos, int dim, const int64_t* d_row, cons
                          int squared, int norm, float max_value, float* d_dist, float* d_rel, unsigned* d_max_scratch,
                          void* stream);
 
+/* All-pairs shortest-path lengths per graph on the UNDIRECTED edge set, unreachable pairs = `unreachable` (100 in the
+ * reference). Replaces the networkx loop that fills `attn_bias` in the GraphGPS twin of the transform
+ * (GraphGPS/graphgps/loader/utils_escgnn.py:29-38). d_out_ptr[g] = sum_{g'<g} n_g'^2; graph g's [n_g, n_g] block is
+ * written row-major at d_out + d_out_ptr[g]. max_nodes / max_edges: per-graph maxima (shared-memory sizing). */
+int64_t escgnn_all_pairs_spd_smem_bytes(int64_t max_nodes, int64_t max_edges);
+int escgnn_all_pairs_spd(const int64_t* d_src, const int64_t* d_dst, const int64_t* d_edge_ptr, const int64_t* d_node_ptr,
+                         int64_t n_graphs, const int64_t* d_out_ptr, int64_t* d_out, int64_t max_nodes, int64_t max_edges,
+                         int64_t unreachable, unsigned long long* d_counters, void* stream);
+
 /* M5 Adam over one flat fp32 buffer (torch.optim.Adam rule, no amsgrad / weight decay; reference call sites
  * run_graphcount.py:478,505, run_zinc.py:263, run_ogb_mol.py:436). `step` counts from 1; grad_scale multiplies
  * the gradient first (1/world_size after a sum all-reduce). */

@@ -151,3 +151,30 @@ def encode_graph(edge_index, num_nodes, h, use_rd=False, self_loop=False, rd_mod
         pos_batch.append(np.full(idx.size, e, dtype=np.int64))
     cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, dtype=np.int64)
     return ei, cat(pos_enc), cat(pos_index), cat(pos_batch)
+
+
+def all_pairs_spd(edge_index, num_nodes, unreachable=100):
+    """`attn_bias` of the GraphGPS twin (GraphGPS/graphgps/loader/utils_escgnn.py:29-38): shortest-path length between
+    every pair of nodes of the UNDIRECTED graph (`to_networkx(data, to_undirected=True)` then networkx
+    `all_pairs_shortest_path_length`, a third-party routine: plain BFS per source), `unreachable` (100) where no path
+    exists, flattened row-major to int64 [n*n].  Pinned against networkx itself by tests/golden/make_golden_spd.py."""
+    n = int(num_nodes)
+    ei = np.asarray(edge_index, dtype=np.int64).reshape(2, -1)
+    nbr = [set() for _ in range(n)]
+    for s, t in zip(ei[0].tolist(), ei[1].tolist()):
+        if s != t:
+            nbr[s].add(t); nbr[t].add(s)
+    out = np.full((n, n), unreachable, dtype=np.int64)
+    for r in range(n):
+        out[r, r] = 0
+        frontier, d = [r], 0
+        seen = {r}
+        while frontier:
+            d += 1
+            nxt = []
+            for w in frontier:
+                for s in nbr[w]:
+                    if s not in seen:
+                        seen.add(s); out[r, s] = d; nxt.append(s)
+            frontier = nxt
+    return out.reshape(-1)

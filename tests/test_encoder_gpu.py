@@ -233,3 +233,39 @@ def test_encoded_dataset_processes_once_and_serves_from_cache(tmp_path):
     assert len(sub) == 8
     b = next(iter(DataLoader(list(sub), batch_size=8)))
     assert b.num_graphs == 8 and int(b.pos_batch[-1]) + 1 == b.edge_index.size(1)
+
+
+def test_all_pairs_spd_matches_fixture_and_oracle():
+    """N4: `attn_bias` (GraphGPS/graphgps/loader/utils_escgnn.py:29-38) -- bit-exact against the networkx fixture, and
+    against the oracle on a batch of config-5 graphs (up to 500 nodes) through the batched entry point."""
+    import os
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.transform import all_pairs_spd, all_pairs_spd_batch
+    from oracle import encode_ref
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'spd.npz'))
+    for nm in sorted({k.split('/')[0] for k in fix.files}):
+        got = all_pairs_spd(torch.as_tensor(fix[nm + '/edge_index']), int(fix[nm + '/n'][0]))
+        assert got.dtype == torch.int64 and np.array_equal(got.numpy(), fix[nm + '/attn_bias']), nm
+    src, dst, eptr, nptr = synth.make_batch_arrays(5, 40, 12)
+    flat, optr = all_pairs_spd_batch(src, dst, eptr, nptr)
+    flat = flat.cpu().numpy()
+    for g in range(12):
+        ei = np.stack([src[eptr[g]:eptr[g + 1]], dst[eptr[g]:eptr[g + 1]]])
+        want = encode_ref.all_pairs_spd(ei, int(nptr[g + 1] - nptr[g]))
+        assert np.array_equal(flat[optr[g]:optr[g + 1]], want), g
+    with pytest.raises(RuntimeError):
+        all_pairs_spd(torch.tensor([[0, 5], [1, 0]]), 3)          # node id outside [0, n)
+
+
+def test_create_subgraphs_gps_adds_attn_bias():
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.transform import create_subgraphs, create_subgraphs_gps
+    from oracle import encode_ref
+    g = synth.make_graph(2, 77)
+    d = Data(x=torch.as_tensor(g['x']), edge_index=torch.as_tensor(g['edge_index']), edge_attr=torch.as_tensor(g['edge_attr']),
+             y=torch.as_tensor(g['y']).view(1))
+    a, b = create_subgraphs(d, 2, use_rd=True, self_loop=True), create_subgraphs_gps(d, 2, use_rd=True, self_loop=True)
+    for k in ('edge_index', 'pos_enc', 'pos_index', 'pos_batch', 'edge_attr'):
+        assert torch.equal(a[k], b[k])
+    assert np.array_equal(b.attn_bias.numpy(), encode_ref.all_pairs_spd(g['edge_index'], g['num_nodes']))

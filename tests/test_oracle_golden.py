@@ -93,3 +93,17 @@ def test_oracle_error_behaviour():
         c_oracle.encode_graph(hub[:, :4], 211, 5)    # h >= 5
     with pytest.raises(ValueError):
         c_oracle.encode_graph(np.array([[0, 1], [1, 2]]), 3, 2, use_rd=True)   # rd on a directed multiset
+
+
+def test_all_pairs_spd_oracle_matches_networkx_fixture():
+    """N4: the attn_bias restatement against vectors produced by networkx (the routine the reference calls,
+    GraphGPS/graphgps/loader/utils_escgnn.py:29-38): connected, disconnected, self-loop, one-directional edge, long path."""
+    import os
+    import numpy as np
+    from oracle import encode_ref
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'spd.npz'))
+    names = sorted({k.split('/')[0] for k in fix.files})
+    assert len(names) == 8
+    for nm in names:
+        got = encode_ref.all_pairs_spd(fix[nm + '/edge_index'], int(fix[nm + '/n'][0]))
+        assert np.array_equal(got, fix[nm + '/attn_bias']), nm
