@@ -41,6 +41,10 @@ SIGNATURES = {
     'escgnn_sorted_ids_to_ptr': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
     'escgnn_bag_embed_fwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp, _vp]),
     'escgnn_bag_embed_bwd': (_i32, [_vp, _i32] + [_vp] * 6 + [_i64, _vp, _vp, _vp]),
+    'escgnn_bag_index_build': (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'escgnn_bag_embed_bwd_indexed': (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'escgnn_reduce_sum': (_i32, [_vp, _i64, _vp, _i32, _vp]),
+    'escgnn_zero_tail_rows': (_i32, [_vp, _i32, _i32, _vp, _i64, _vp]),
     'escgnn_bag_embed_bwd_sorted': (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'escgnn_gine_aggregate_fwd': (_i32, [_vp] * 6 + [_i64, _i32, _vp, _vp, _vp]),
     'escgnn_gine_aggregate_bwd': (_i32, [_vp] * 7 + [_i64, _i32] + [_vp] * 6),
@@ -95,10 +99,10 @@ def lib():
 # kernels launched by one successful call of each entry point (bench.py's `gpu_launches` evidence)
 KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'encode_subset': 1, 'scan': 3, 'expand_records': 1,
                     'csr_build': 4, 'sorted_ids_to_ptr': 1, 'bag_embed_fwd': 1, 'bag_embed_bwd': 1,
-                    'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'gine_aggregate_fwd_ld': 1, 'gine_aggregate_bwd_ld': 2, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
+                    'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'gine_aggregate_fwd_ld': 1, 'gine_aggregate_bwd_ld': 2, 'gine_aggregate_bwd_ld_noeps': 1, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
                     'edge_distance': 2, 'all_pairs_spd': 1, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 2, 'bn_act_bwd': 2,
                     'act_fwd': 1, 'act_bwd': 1, 'colsum': 1, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
-                    'make_dims': 1, 'adam_step_device': 2, 'bag_embed_bwd_sorted': 4, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1}
+                    'make_dims': 1, 'adam_step_device': 2, 'bag_embed_bwd_sorted': 4, 'bag_index_build': 3, 'bag_embed_bwd_indexed': 1, 'reduce_sum': 1, 'zero_tail_rows': 1, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1}
 LAUNCHES = {'n': 0}
 PROFILE = None      # bench.py: a list; every mark() appends (label, cuda event) -> per-kernel durations by differencing
 PROFILE_EXTERNAL = False   # record graph-capturable ("external") events: per-kernel device times of a REPLAYED graph

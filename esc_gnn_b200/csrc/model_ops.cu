@@ -407,7 +407,49 @@ __global__ void reduce_sum_kernel(const float* __restrict__ v, int64_t n, float*
     }
 }
 
+// rows [*d_rows, rows_cap) of a [rows_cap, ld] buffer := 0 (capacity rows that a larger earlier batch may have filled)
+__global__ void zero_tail_rows_kernel(float* __restrict__ x, int ld, int cols, const int* __restrict__ d_rows, int64_t rows_cap) {
+    escgnn::pdl_enter();
+    const int64_t r0 = *d_rows < rows_cap ? *d_rows : rows_cap;
+    const int64_t total = (rows_cap - r0) * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        x[(r0 + i / cols) * ld + i % cols] = 0.f;
+}
+
 // ---------------------------------------------------------------- K7 segment pooling (sorted batch vector)
+// float4 variants: grid (segments, channel chunks of 4 * blockDim), 4 independent row loads in flight per thread
+__global__ void __launch_bounds__(128)
+segment_pool_fwd_v4_kernel(const float* __restrict__ x, const int* __restrict__ ptr, int C, int mean, float* __restrict__ out) {
+    escgnn::pdl_enter();
+    const int s = blockIdx.x, c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (c >= C) return;
+    const int a = ptr[s], b = ptr[s + 1];
+    const float inv = mean ? 1.f / (float)max(b - a, 1) : 1.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = a;
+    for (; i + 4 <= b; i += 4) {
+        const float4 v0 = ld4(x + (size_t)i * C + c), v1 = ld4(x + (size_t)(i + 1) * C + c);
+        const float4 v2 = ld4(x + (size_t)(i + 2) * C + c), v3 = ld4(x + (size_t)(i + 3) * C + c);
+        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;       // same left-to-right order as the scalar kernel
+        acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+        acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+        acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+    }
+    for (; i < b; ++i) { const float4 v = ld4(x + (size_t)i * C + c); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    *reinterpret_cast<float4*>(out + (size_t)s * C + c) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+__global__ void __launch_bounds__(128)
+segment_pool_bwd_v4_kernel(const float* __restrict__ g, const int* __restrict__ ptr, int C, int mean, float* __restrict__ gx) {
+    escgnn::pdl_enter();
+    const int s = blockIdx.x, c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (c >= C) return;
+    const int a = ptr[s], b = ptr[s + 1];
+    const float inv = mean ? 1.f / (float)max(b - a, 1) : 1.f;
+    float4 v = ld4(g + (size_t)s * C + c);
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    for (int i = a; i < b; ++i) *reinterpret_cast<float4*>(gx + (size_t)i * C + c) = v;
+}
+
 __global__ void __launch_bounds__(256)
 segment_pool_fwd_kernel(const float* __restrict__ x, const int* __restrict__ ptr, int segs, int C, int mean,
                         float* __restrict__ out) {
@@ -552,6 +594,13 @@ int escgnn_bag_embed_bwd_sorted(const float* d_grad, int hidden, const uint32_t*
                                 int32_t* d_work /* 3*1800 + 1 ints */, int32_t* d_sorted_edge, float* d_sorted_cnt,
                                 const int* d_count, void* stream) {
     if (hidden % 4 != 0) return ESCGNN_ERR_BAD_ARG;
+    int rc = escgnn_bag_index_build(d_rec, d_rec_off, d_rec_nnz, n_edges, d_work, d_sorted_edge, d_sorted_cnt, d_count, stream);
+    if (rc) return rc;
+    return escgnn_bag_embed_bwd_indexed(d_grad, hidden, rec_cap, d_grad_weight, d_work, d_sorted_edge, d_sorted_cnt, stream);
+}
+
+int escgnn_bag_index_build(const uint32_t* d_rec, const int64_t* d_rec_off, const int32_t* d_rec_nnz, int64_t n_edges,
+                           int* d_work, int* d_sorted_edge, float* d_sorted_cnt, const int* d_count, void* stream) {
     if (n_edges <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int* counts = d_work; int* ptr = d_work + kBagRows; int* cursor = d_work + 2 * kBagRows + 1;
@@ -560,8 +609,15 @@ int escgnn_bag_embed_bwd_sorted(const float* d_grad, int hidden, const uint32_t*
     escgnn::launch_pdl(bag_count_kernel, gb, 256, 0, st, d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, counts);
     escgnn::launch_pdl(bag_scan_kernel, 1, 1024, 0, st, counts, ptr, cursor);
     escgnn::launch_pdl(bag_fill_kernel, gb, 256, 0, st, d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, ptr, cursor, d_sorted_edge, d_sorted_cnt);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_bag_embed_bwd_indexed(const float* d_grad, int hidden, int64_t rec_cap, float* d_grad_weight, const int* d_work,
+                                 const int* d_sorted_edge, const float* d_sorted_cnt, void* stream) {
+    if (rec_cap <= 0) return 0;
     const int64_t chunks = (rec_cap + kBagChunk - 1) / kBagChunk;
-    escgnn::launch_pdl(bag_reduce_kernel, blocks_for(chunks, 8), 256, 0, st, d_grad, hidden, ptr, d_sorted_edge, d_sorted_cnt, d_grad_weight);
+    escgnn::launch_pdl(bag_reduce_kernel, blocks_for(chunks, 8), 256, 0, (cudaStream_t)stream, d_grad, hidden, d_work + kBagRows,
+                       d_sorted_edge, d_sorted_cnt, d_grad_weight);
     return (int)cudaGetLastError();
 }
 
@@ -616,9 +672,25 @@ int escgnn_gine_aggregate_bwd_ld(const float* d_grad_out, int ldg, const float* 
     return (int)cudaGetLastError();
 }
 
+int escgnn_reduce_sum(const float* d_v, int64_t n, float* d_out, int accumulate, void* stream) {
+    escgnn::launch_pdl(reduce_sum_kernel, 1, 1024, 0, (cudaStream_t)stream, d_v, n, d_out, accumulate);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_zero_tail_rows(float* d_x, int ld, int cols, const int* d_rows, int64_t rows_cap, void* stream) {
+    if (rows_cap <= 0 || cols <= 0) return 0;
+    escgnn::launch_pdl(zero_tail_rows_kernel, 148, 256, 0, (cudaStream_t)stream, d_x, ld, cols, d_rows, rows_cap);
+    return (int)cudaGetLastError();
+}
+
 int escgnn_segment_pool_fwd(const float* d_x, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
                             float* d_out, void* stream) {
     if (n_segments <= 0) return 0;
+    if (channels % 4 == 0 && (((uintptr_t)d_x | (uintptr_t)d_out) & 15) == 0 && n_segments <= 65535 * 32) {
+        const dim3 grid((unsigned)n_segments, (unsigned)((channels / 4 + 127) / 128));
+        escgnn::launch_pdl(segment_pool_fwd_v4_kernel, grid, 128, 0, (cudaStream_t)stream, d_x, d_ptr, channels, mean, d_out);
+        return (int)cudaGetLastError();
+    }
     escgnn::launch_pdl(segment_pool_fwd_kernel, (unsigned)n_segments, 256, 0, (cudaStream_t)stream, d_x, d_ptr, (int)n_segments, channels, mean, d_out);
     return (int)cudaGetLastError();
 }
@@ -626,6 +698,11 @@ int escgnn_segment_pool_fwd(const float* d_x, const int32_t* d_ptr, int64_t n_se
 int escgnn_segment_pool_bwd(const float* d_grad, const int32_t* d_ptr, int64_t n_segments, int channels, int mean,
                             float* d_grad_x, void* stream) {
     if (n_segments <= 0) return 0;
+    if (channels % 4 == 0 && (((uintptr_t)d_grad | (uintptr_t)d_grad_x) & 15) == 0) {
+        const dim3 grid((unsigned)n_segments, (unsigned)((channels / 4 + 127) / 128));
+        escgnn::launch_pdl(segment_pool_bwd_v4_kernel, grid, 128, 0, (cudaStream_t)stream, d_grad, d_ptr, channels, mean, d_grad_x);
+        return (int)cudaGetLastError();
+    }
     escgnn::launch_pdl(segment_pool_bwd_kernel, (unsigned)n_segments, 256, 0, (cudaStream_t)stream, d_grad, d_ptr, (int)n_segments, channels, mean, d_grad_x);
     return (int)cudaGetLastError();
 }

@@ -302,8 +302,11 @@ class StaticTrainEngine(object):
             _p(out), out.stride(0), _p(c.rows['N']), c.st()), 'gine_aggregate_fwd_ld'))
         self.bwd.append(lambda: _lib.check(c.L.escgnn_gine_aggregate_bwd_ld(
             _p(dout), dout.stride(0), _p(x), x.stride(0), _p(ee), ee.stride(0), _p(self.ei[1]), _p(self.src_ptr),
-            _p(self.src_perm), _p(eps), c.caps['N'], C, _p(dx), dx.stride(0), _p(dee), _p(dots), _p(eps.grad), _p(c.rows['N']),
-            c.st()), 'gine_aggregate_bwd_ld'))
+            _p(self.src_perm), _p(eps), c.caps['N'], C, _p(dx), dx.stride(0), _p(dee), _p(dots), None, _p(c.rows['N']),
+            c.st()), 'gine_aggregate_bwd_ld_noeps'))
+        # eps.grad = sum of the per-node dot products: only the optimiser reads it, so it leaves the critical path
+        self.bwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_reduce_sum(_p(dots), c.caps['N'], _p(eps.grad), 0, c.st()),
+                                                              'reduce_sum')))
 
     # ------------------------------------------------------------------ model tape
     def _build_model_tape(self):
@@ -330,9 +333,15 @@ class StaticTrainEngine(object):
         bag_work = torch.zeros(3 * 1800 + 8, dtype=torch.int32, device=c.dev)
         bag_edge = torch.zeros(c.caps['nnz'], dtype=torch.int32, device=c.dev)
         bag_cnt = torch.zeros(c.caps['nnz'], dtype=torch.float32, device=c.dev)
-        self.bwd.append(lambda: _lib.check(c.L.escgnn_bag_embed_bwd_sorted(
-            _p(dz0), H, _p(self.rec), _p(self.rec_off), _p(self.rec_nnz), c.caps['E'], c.caps['nnz'], _p(W0.grad), _p(bag_work),
-            _p(bag_edge), _p(bag_cnt), _p(c.rows['E']), c.st()), 'bag_embed_bwd_sorted'))
+        # the index-major transposition of the records depends only on the encoding: a side branch builds it while the
+        # forward pass runs, the backward pass (its very last kernel) only reduces
+        bag_ready = [None]
+        self.fwd.append(lambda: bag_ready.__setitem__(0, self._fork(lambda: _lib.check(c.L.escgnn_bag_index_build(
+            _p(self.rec), _p(self.rec_off), _p(self.rec_nnz), c.caps['E'], _p(bag_work), _p(bag_edge), _p(bag_cnt),
+            _p(c.rows['E']), c.st()), 'bag_index_build'))))
+        self.bwd.append(lambda: (torch.cuda.current_stream(c.dev).wait_event(bag_ready[0]), _lib.check(
+            c.L.escgnn_bag_embed_bwd_indexed(_p(dz0), H, c.caps['nnz'], _p(W0.grad), _p(bag_work), _p(bag_edge), _p(bag_cnt),
+                                             c.st()), 'bag_embed_bwd_indexed')))
         z1, dz1 = c.buf('E', H), c.buf('E', H)
         self._bn_act(z0, dz0, m.z_embedding[1], act, 'E', z1, dz1)
         z2, dz2 = self._linear(z1, m.z_embedding[3], 'E', dx=dz1, feeds_bn=True)
@@ -375,7 +384,9 @@ class StaticTrainEngine(object):
         ee_ready = [None]
         self.fwd.append(lambda: ee_ready.__setitem__(0, self._fork(
             lambda: self._gemm('gemm_fwd', zcat, False, W_cat, False, ee_all, b_cat, E_rows, n_tot, edge_dim, False))))
-        self.fwd.append(lambda: (dee_all.zero_(), _lib.mark('memset')))    # rows past the edge count stay zero for the GEMMs below
+        # rows past the edge count stay zero for the GEMMs below (a larger earlier batch may have written them)
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_zero_tail_rows(_p(dee_all), dee_all.stride(0), n_tot, _p(c.rows['E']),
+                                                                     E_rows, c.st()), 'zero_tail_rows'))
 
         def proj_back():                          # runs after every layer's backward has filled its slice of dee_all
             self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, False),

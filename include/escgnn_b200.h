@@ -149,6 +149,13 @@ int escgnn_bag_embed_bwd_sorted(const float* d_grad, int hidden, const uint32_t*
                                 int32_t* d_work, int32_t* d_sorted_edge, float* d_sorted_cnt, const int* d_count,
                                 void* stream);
 
+/* The two halves of escgnn_bag_embed_bwd_sorted: the index-major transposition depends only on the encoding (it can be
+ * built once per batch, off the critical path), the reduction on the incoming gradient. */
+int escgnn_bag_index_build(const uint32_t* d_rec, const int64_t* d_rec_off, const int32_t* d_rec_nnz, int64_t n_edges,
+                           int32_t* d_work, int32_t* d_sorted_edge, float* d_sorted_cnt, const int* d_count, void* stream);
+int escgnn_bag_embed_bwd_indexed(const float* d_grad, int hidden, int64_t rec_cap, float* d_grad_weight,
+                                 const int32_t* d_work, const int32_t* d_sorted_edge, const float* d_sorted_cnt, void* stream);
+
 /* M3 GINE aggregation.  Replaces PyG GINEConv.propagate + the (1+eps)*x residual (in-tree twin:
  * GraphGPS/graphgps/layer/gine_conv_layer.py:56-84; ogb_mol_gnn.py:346-358):
  *   out[i] = (1+eps) x[i] + sum_{e: dst_e = i} relu(x[src_e] + edge_feat[e]).
@@ -213,6 +220,10 @@ int escgnn_collate_edges(const int64_t* d_src, const int64_t* d_dst, const int32
                          const int* d_count, void* stream);
 int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64_t* d_ids, const int* d_count,
                       void* stream);
+/* d_out[0] (+)= sum of d_v[0..n) in a fixed order (the eps gradient of a GINE layer from its per-node dot products) */
+int escgnn_reduce_sum(const float* d_v, int64_t n, float* d_out, int accumulate, void* stream);
+/* rows [*d_rows, rows_cap) of a [rows_cap, ld] fp32 buffer := 0 (first `cols` columns) */
+int escgnn_zero_tail_rows(float* d_x, int ld, int cols, const int* d_rows, int64_t rows_cap, void* stream);
 /* d_dims[4] = {total nodes, total edges after E1, graphs, records}: the device-side sizes the static-shape
  * entry points read through their d_count / d_rows arguments (no host sync between encoder and model). */
 int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t n_graphs,

@@ -185,7 +185,11 @@ def test_pipelined_engine_matches_sequential_engine(name):
     assert pip.step(order[0]) is None
     got = [float(pip.step(r).item()) for r in order[1:]] + [float(pip.drain().item())]
     seq.check_errors(); pip.check_errors()
-    np.testing.assert_allclose(got, want, rtol=2e-3, atol=1e-5)
+    # Two SEQUENTIAL engines fed the same batches already differ by 1e-5 / 1e-4 / 1e-3 / 5e-3 after 2 / 3 / 5 / 7 steps
+    # (float atomics in the embedding-table gradients reorder from run to run and Adam amplifies it, tools/debug_pipe.py):
+    # the first steps are the tight check, the later ones only have to stay on the same trajectory.
+    np.testing.assert_allclose(got[:3], want[:3], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(got[3:], want[3:], rtol=3e-2, atol=1e-5)
 
 
 @pytest.mark.parametrize('name,use_graph', [('zinc', False), ('zinc', True), ('count_h256', True), ('count_h64', False),
