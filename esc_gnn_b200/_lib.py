@@ -56,6 +56,7 @@ SIGNATURES = {
     'escgnn_ptr_to_ids': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
     'escgnn_dense_tile_rows': (_i32, []),
     'escgnn_set_pdl': (_i32, [_i32]),
+    'escgnn_set_cluster_bn': (_i32, [_i32]),
     'escgnn_dense_partial_floats': (_i64, [_i32, _i32]),
     'escgnn_bn_act_fwd': (_i32, [_vp, _i32] + [_vp] * 7 + [_i32, ctypes.c_float, ctypes.c_float, _i32, _vp, _i32, _i32, _vp, _i32, _vp]),
     'escgnn_bn_act_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _i32] + [_vp] * 4 + [_i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
@@ -90,6 +91,8 @@ def lib():
             fn = getattr(L, name)          # AttributeError = header and library disagree: fail loudly
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get('ESCGNN_CLUSTER_BN', '1') == '0':
+            L.escgnn_set_cluster_bn(0)
         if os.environ.get('ESCGNN_PDL', '1') == '0':      # A/B switch: plain stream-ordered launches
             L.escgnn_set_pdl(0)
         _lib = L
@@ -100,7 +103,7 @@ def lib():
 KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'encode_subset': 1, 'scan': 3, 'expand_records': 1,
                     'csr_build': 4, 'sorted_ids_to_ptr': 1, 'bag_embed_fwd': 1, 'bag_embed_bwd': 1,
                     'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'gine_aggregate_fwd_ld': 1, 'gine_aggregate_bwd_ld': 2, 'gine_aggregate_bwd_ld_noeps': 1, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
-                    'edge_distance': 2, 'all_pairs_spd': 1, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 2, 'bn_act_bwd': 2,
+                    'edge_distance': 2, 'all_pairs_spd': 1, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 1, 'bn_act_bwd': 1,
                     'act_fwd': 1, 'act_bwd': 1, 'colsum': 1, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
                     'make_dims': 1, 'adam_step_device': 2, 'bag_embed_bwd_sorted': 4, 'bag_index_build': 3, 'bag_embed_bwd_indexed': 1, 'reduce_sum': 1, 'zero_tail_rows': 1, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1}
 LAUNCHES = {'n': 0}

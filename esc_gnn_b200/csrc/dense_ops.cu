@@ -11,10 +11,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cooperative_groups.h>
+
 #include <initializer_list>
 
 #include "../../include/escgnn_b200.h"
 #include "launch.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -408,6 +412,204 @@ bn_act_bwd_apply_v4_kernel(const float* __restrict__ x, int ldx, const float* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One-launch BatchNorm (+activation) for the row counts of a reference-sized batch: a thread-block CLUSTER of 8 CTAs
+// owns 4*LANES columns and splits the rows; per-CTA partial sums meet through distributed shared memory, every CTA
+// then holds the final statistics and normalises its rows (second read of x hits L2).  Replaces the statistics kernel
+// + apply kernel pair, i.e. one launch and one dependent-launch gap per BatchNorm, forward and backward.
+constexpr int kClRanks = 8;
+constexpr int kClMaxRows = 1 << 16;          // above this the two-kernel path (all SMs busy) wins
+constexpr int kClFwdUnroll = 8, kClBwdUnroll = 4;    // independent row loads in flight per thread
+
+template <int LANES>
+struct ClusterTile {
+    static constexpr int kCols = 4 * LANES, kSlots = 256 / LANES, kSweep = kClRanks * kSlots;
+    float (*s_w)[2][kCols];
+    float (*s_part)[kCols];
+    float (*s_tot)[kCols];
+    // (a, b): this thread's partial sums for its 4 columns -> s_tot[0..1][cols] = cluster-wide sums (all threads may read)
+    __device__ __forceinline__ void reduce(float4 a, float4 b, cg::cluster_group& cluster) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cl = threadIdx.x % LANES;
+        #pragma unroll
+        for (int d = LANES; d < 32; d <<= 1) {
+            a.x += __shfl_xor_sync(kFull, a.x, d); a.y += __shfl_xor_sync(kFull, a.y, d);
+            a.z += __shfl_xor_sync(kFull, a.z, d); a.w += __shfl_xor_sync(kFull, a.w, d);
+            b.x += __shfl_xor_sync(kFull, b.x, d); b.y += __shfl_xor_sync(kFull, b.y, d);
+            b.z += __shfl_xor_sync(kFull, b.z, d); b.w += __shfl_xor_sync(kFull, b.w, d);
+        }
+        if (lane < LANES) { st4(&s_w[warp][0][4 * cl], a); st4(&s_w[warp][1][4 * cl], b); }
+        __syncthreads();
+        const int which = threadIdx.x / kCols, col = threadIdx.x % kCols;
+        if (threadIdx.x < 2 * kCols) {
+            float v = 0.f;
+            #pragma unroll
+            for (int w = 0; w < 8; ++w) v += s_w[w][which][col];
+            s_part[which][col] = v;
+        }
+        cluster.sync();
+        if (threadIdx.x < 2 * kCols) {
+            float v = 0.f;
+            #pragma unroll
+            for (int r = 0; r < kClRanks; ++r) v += *cluster.map_shared_rank(&s_part[which][col], r);     // fixed order: deterministic
+            s_tot[which][col] = v;
+        }
+        __syncthreads();
+    }
+};
+
+template <int LANES>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_cluster_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float* running_mean, float* running_var, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                          int act, float eps, float momentum, const int* __restrict__ d_rows, int rows_cap, int C,
+                          float* __restrict__ y, int ldy) {
+    escgnn::pdl_enter();
+    using T = ClusterTile<LANES>;
+    __shared__ __align__(16) float s_w[8][2][T::kCols];
+    __shared__ __align__(16) float s_part[2][T::kCols];
+    __shared__ __align__(16) float s_tot[2][T::kCols];
+    cg::cluster_group cluster = cg::this_cluster();
+    T t{s_w, s_part, s_tot};
+    const int cl = threadIdx.x % LANES, rs = threadIdx.x / LANES, rank = (int)cluster.block_rank();
+    const int c4 = blockIdx.x * T::kCols + 4 * cl, rows = min(*d_rows, rows_cap);
+    const bool col_ok = c4 < C;
+    float4 a = zero4(), b = zero4();
+    if (col_ok)
+        for (int r0 = rank * T::kSlots + rs; r0 < rows; r0 += kClFwdUnroll * T::kSweep) {
+            float4 v[kClFwdUnroll];
+            #pragma unroll
+            for (int k = 0; k < kClFwdUnroll; ++k) v[k] = r0 + k * T::kSweep < rows ? ld4(x + (size_t)(r0 + k * T::kSweep) * ldx + c4) : zero4();
+            #pragma unroll
+            for (int k = 0; k < kClFwdUnroll; ++k) {
+                a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
+                b.x += v[k].x * v[k].x; b.y += v[k].y * v[k].y; b.z += v[k].z * v[k].z; b.w += v[k].w * v[k].w;
+            }
+        }
+    t.reduce(a, b, cluster);
+    if (col_ok) {
+        const float m = (float)max(rows, 1);
+        const float4 s1 = ld4(&s_tot[0][4 * cl]), s2 = ld4(&s_tot[1][4 * cl]);
+        const float4 mean = make_float4(s1.x / m, s1.y / m, s1.z / m, s1.w / m);
+        const float4 var = make_float4(fmaxf(s2.x / m - mean.x * mean.x, 0.f), fmaxf(s2.y / m - mean.y * mean.y, 0.f),
+                                       fmaxf(s2.z / m - mean.z * mean.z, 0.f), fmaxf(s2.w / m - mean.w * mean.w, 0.f));
+        const float4 rstd = make_float4(rsqrtf(var.x + eps), rsqrtf(var.y + eps), rsqrtf(var.z + eps), rsqrtf(var.w + eps));
+        if (rank == 0 && rs == 0) {
+            st4(mean_out + c4, mean); st4(rstd_out + c4, rstd);
+            if (rows > 0) {
+                const float ub = rows > 1 ? m / (m - 1.f) : 1.f, k0 = 1.f - momentum;
+                const float4 rm = ld4(running_mean + c4), rv = ld4(running_var + c4);
+                st4(running_mean + c4, make_float4(k0 * rm.x + momentum * mean.x, k0 * rm.y + momentum * mean.y,
+                                                   k0 * rm.z + momentum * mean.z, k0 * rm.w + momentum * mean.w));
+                st4(running_var + c4, make_float4(k0 * rv.x + momentum * var.x * ub, k0 * rv.y + momentum * var.y * ub,
+                                                  k0 * rv.z + momentum * var.z * ub, k0 * rv.w + momentum * var.w * ub));
+            }
+        }
+        const float4 g = gamma ? ld4(gamma + c4) : make_float4(1.f, 1.f, 1.f, 1.f), bt = beta ? ld4(beta + c4) : zero4();
+        const float4 sc = make_float4(rstd.x * g.x, rstd.y * g.y, rstd.z * g.z, rstd.w * g.w);
+        const float4 sh = make_float4(bt.x - mean.x * sc.x, bt.y - mean.y * sc.y, bt.z - mean.z * sc.z, bt.w - mean.w * sc.w);
+        for (int r0 = rank * T::kSlots + rs; r0 < rows_cap; r0 += kClFwdUnroll * T::kSweep) {
+            float4 v[kClFwdUnroll];
+            #pragma unroll
+            for (int k = 0; k < kClFwdUnroll; ++k) v[k] = r0 + k * T::kSweep < rows ? ld4(x + (size_t)(r0 + k * T::kSweep) * ldx + c4) : zero4();
+            #pragma unroll
+            for (int k = 0; k < kClFwdUnroll; ++k) {
+                const int r = r0 + k * T::kSweep;
+                if (r >= rows_cap) break;
+                float4 o = zero4();                   // rows >= actual count are zeroed (inert in the next GEMM)
+                if (r < rows) o = act_fwd4(make_float4(v[k].x * sc.x + sh.x, v[k].y * sc.y + sh.y, v[k].z * sc.z + sh.z, v[k].w * sc.w + sh.w), act);
+                st4(y + (size_t)r * ldy + c4, o);
+            }
+        }
+    }
+    cluster.sync();                                   // nobody leaves while a peer may still read its partial sums
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_cluster_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy,
+                          const float* __restrict__ dy2, int lddy2, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          int act, const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, float* __restrict__ dx, int lddx) {
+    escgnn::pdl_enter();
+    using T = ClusterTile<LANES>;
+    __shared__ __align__(16) float s_w[8][2][T::kCols];
+    __shared__ __align__(16) float s_part[2][T::kCols];
+    __shared__ __align__(16) float s_tot[2][T::kCols];
+    cg::cluster_group cluster = cg::this_cluster();
+    T t{s_w, s_part, s_tot};
+    const int cl = threadIdx.x % LANES, rs = threadIdx.x / LANES, rank = (int)cluster.block_rank();
+    const int c4 = blockIdx.x * T::kCols + 4 * cl, rows = min(*d_rows, rows_cap);
+    const bool col_ok = c4 < C;
+    BnCols k;
+    k.mu = k.rs = k.g = k.bt = zero4();
+    float4 a = zero4(), b = zero4();
+    if (col_ok) {
+        k = bn_cols(mean, rstd, gamma, beta, c4);
+        for (int r0 = rank * T::kSlots + rs; r0 < rows; r0 += kClBwdUnroll * T::kSweep) {
+            float4 xv[kClBwdUnroll], dv[kClBwdUnroll];
+            #pragma unroll
+            for (int i = 0; i < kClBwdUnroll; ++i) {
+                const int r = r0 + i * T::kSweep;
+                xv[i] = zero4(); dv[i] = zero4();
+                if (r < rows) {
+                    xv[i] = ld4(x + (size_t)r * ldx + c4);
+                    dv[i] = ld4(dy + (size_t)r * lddy + c4);
+                    if (dy2) { const float4 e = ld4(dy2 + (size_t)r * lddy2 + c4); dv[i].x += e.x; dv[i].y += e.y; dv[i].z += e.z; dv[i].w += e.w; }
+                }
+            }
+            #pragma unroll
+            for (int i = 0; i < kClBwdUnroll; ++i)
+                if (r0 + i * T::kSweep < rows) {
+                    float4 dz, xh;
+                    bn_dz(xv[i], dv[i], k, act, dz, xh);
+                    a.x += dz.x; a.y += dz.y; a.z += dz.z; a.w += dz.w;
+                    b.x += dz.x * xh.x; b.y += dz.y * xh.y; b.z += dz.z * xh.z; b.w += dz.w * xh.w;
+                }
+        }
+    }
+    t.reduce(a, b, cluster);
+    if (col_ok) {
+        const float4 s1 = ld4(&s_tot[0][4 * cl]), s2 = ld4(&s_tot[1][4 * cl]);
+        if (rank == 0 && rs == 0) { if (dgamma) st4(dgamma + c4, s2); if (dbeta) st4(dbeta + c4, s1); }
+        const float inv_m = 1.f / (float)max(rows, 1);
+        const float4 m1 = make_float4(s1.x * inv_m, s1.y * inv_m, s1.z * inv_m, s1.w * inv_m);
+        const float4 m2 = make_float4(s2.x * inv_m, s2.y * inv_m, s2.z * inv_m, s2.w * inv_m);
+        const float4 kk = make_float4(k.g.x * k.rs.x, k.g.y * k.rs.y, k.g.z * k.rs.z, k.g.w * k.rs.w);
+        for (int r0 = rank * T::kSlots + rs; r0 < rows_cap; r0 += kClBwdUnroll * T::kSweep) {
+            float4 xv[kClBwdUnroll], dv[kClBwdUnroll];
+            #pragma unroll
+            for (int i = 0; i < kClBwdUnroll; ++i) {
+                const int r = r0 + i * T::kSweep;
+                xv[i] = zero4(); dv[i] = zero4();
+                if (r < rows) {
+                    xv[i] = ld4(x + (size_t)r * ldx + c4);
+                    dv[i] = ld4(dy + (size_t)r * lddy + c4);
+                    if (dy2) { const float4 e = ld4(dy2 + (size_t)r * lddy2 + c4); dv[i].x += e.x; dv[i].y += e.y; dv[i].z += e.z; dv[i].w += e.w; }
+                }
+            }
+            #pragma unroll
+            for (int i = 0; i < kClBwdUnroll; ++i) {
+                const int r = r0 + i * T::kSweep;
+                if (r >= rows_cap) break;
+                float4 o = zero4();
+                if (r < rows) {
+                    float4 dz, xh;
+                    bn_dz(xv[i], dv[i], k, act, dz, xh);
+                    o = make_float4(kk.x * (dz.x - m1.x - xh.x * m2.x), kk.y * (dz.y - m1.y - xh.y * m2.y),
+                                    kk.z * (dz.z - m1.z - xh.z * m2.z), kk.w * (dz.w - m1.w - xh.w * m2.w));
+                }
+                st4(dx + (size_t)r * lddx + c4, o);
+            }
+        }
+    }
+    cluster.sync();
+}
+
+inline int& cluster_bn_enabled() {
+    static int on = 1;
+    return on;
+}
 inline bool vec_ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds) {
     if (C % 4) return false;
     for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
@@ -534,6 +736,12 @@ extern "C" {
 
 int escgnn_dense_tile_rows(void) { return kTileRows; }
 
+int escgnn_set_cluster_bn(int on) {
+    const int was = cluster_bn_enabled();
+    cluster_bn_enabled() = on ? 1 : 0;
+    return was;
+}
+
 int escgnn_set_pdl(int on) {
     const int was = escgnn::pdl_enabled();
     escgnn::pdl_enabled() = on ? 1 : 0;
@@ -551,6 +759,14 @@ int escgnn_bn_act_fwd(const float* d_x, int ldx, const float* d_gamma, const flo
                       void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (vec_ok(channels, {d_x, d_y, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, d_partial}, {ldx, ldy})) {
+        if (training && rows_cap <= kClMaxRows && cluster_bn_enabled()) {       // one launch: cluster-wide statistics
+            const int lanes = channels <= 512 ? 2 : channels <= 1024 ? 4 : 8;
+            const dim3 grid((unsigned)((channels + 4 * lanes - 1) / (4 * lanes)), kClRanks);
+            auto kern = lanes == 2 ? bn_act_fwd_cluster_kernel<2> : lanes == 4 ? bn_act_fwd_cluster_kernel<4> : bn_act_fwd_cluster_kernel<8>;
+            escgnn::launch_pdl_cluster(kern, grid, 256, 0, st, kClRanks, d_x, ldx, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, act, eps, momentum,
+                                       d_rows, rows_cap, channels, d_y, ldy);
+            return (int)cudaGetLastError();
+        }
         const dim3 g = vec_grid(rows_cap, channels);
         if (training)
             escgnn::launch_pdl(colstats_v4_kernel<0>, reduce_grid(rows_cap, channels), 256, 0, st, d_x, ldx, d_rows, rows_cap, channels, d_partial, d_running_mean, d_running_var,
@@ -573,6 +789,14 @@ int escgnn_bn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, co
                       float* d_dbeta, float* d_dx, int lddx, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (vec_ok(channels, {d_x, d_dy, d_dy2, d_mean, d_rstd, d_gamma, d_beta, d_partial, d_dx}, {ldx, lddy, d_dy2 ? lddy2 : 0, lddx})) {
+        if (training && rows_cap <= kClMaxRows && cluster_bn_enabled()) {
+            const int lanes = channels <= 512 ? 2 : channels <= 1024 ? 4 : 8;
+            const dim3 grid((unsigned)((channels + 4 * lanes - 1) / (4 * lanes)), kClRanks);
+            auto kern = lanes == 2 ? bn_act_bwd_cluster_kernel<2> : lanes == 4 ? bn_act_bwd_cluster_kernel<4> : bn_act_bwd_cluster_kernel<8>;
+            escgnn::launch_pdl_cluster(kern, grid, 256, 0, st, kClRanks, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act, d_rows, rows_cap,
+                                       channels, d_dgamma, d_dbeta, d_dx, lddx);
+            return (int)cudaGetLastError();
+        }
         const dim3 g = vec_grid(rows_cap, channels);
         escgnn::launch_pdl(bn_act_bwd_reduce_v4_kernel, reduce_grid(rows_cap, channels), 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
                                                        d_rows, rows_cap, channels, d_partial, d_dgamma, d_dbeta);

@@ -300,13 +300,14 @@ class StaticTrainEngine(object):
         self.fwd.append(lambda: _lib.check(c.L.escgnn_gine_aggregate_fwd_ld(
             _p(x), x.stride(0), _p(ee), ee.stride(0), _p(self.ei[0]), _p(self.dst_ptr), _p(self.dst_perm), _p(eps), c.caps['N'], C,
             _p(out), out.stride(0), _p(c.rows['N']), c.st()), 'gine_aggregate_fwd_ld'))
+        # (the backward tape runs in REVERSE order of registration: the aggregation's backward first, then the fork)
+        # eps.grad = sum of the per-node dot products: only the optimiser reads it, so it leaves the critical path
+        self.bwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_reduce_sum(_p(dots), c.caps['N'], _p(eps.grad), 0, c.st()),
+                                                              'reduce_sum')))
         self.bwd.append(lambda: _lib.check(c.L.escgnn_gine_aggregate_bwd_ld(
             _p(dout), dout.stride(0), _p(x), x.stride(0), _p(ee), ee.stride(0), _p(self.ei[1]), _p(self.src_ptr),
             _p(self.src_perm), _p(eps), c.caps['N'], C, _p(dx), dx.stride(0), _p(dee), _p(dots), None, _p(c.rows['N']),
             c.st()), 'gine_aggregate_bwd_ld_noeps'))
-        # eps.grad = sum of the per-node dot products: only the optimiser reads it, so it leaves the critical path
-        self.bwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_reduce_sum(_p(dots), c.caps['N'], _p(eps.grad), 0, c.st()),
-                                                              'reduce_sum')))
 
     # ------------------------------------------------------------------ model tape
     def _build_model_tape(self):

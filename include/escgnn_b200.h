@@ -234,6 +234,9 @@ int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t
 /* Programmatic dependent launch for the model-side kernels (csrc/launch.cuh): on by default; 0 launches them with plain
  * stream ordering (same results, used for A/B timing). Returns the previous setting. */
 int escgnn_set_pdl(int on);
+/* One-launch cluster BatchNorm kernels (rows_cap <= 65536, training mode): on by default; 0 = statistics + apply kernel pair
+ * (same results up to summation order). Returns the previous setting. */
+int escgnn_set_cluster_bn(int on);
 int escgnn_dense_tile_rows(void);     /* rows per reduction tile of the scalar fallback kernels */
 /* floats the reduction workspace `d_partial` of bn_act_fwd / bn_act_bwd / colsum needs. It must be zero before its
  * first use (its first 64 words are arrival tickets, which every launch leaves at zero again), and two launches that
