@@ -263,7 +263,7 @@ def test_static_engine_handles_varying_batches_under_one_graph():
     eng_g.model.eval(); eng_e.model.eval()
     with torch.no_grad():
         pg, pe = eng_g.model(b), eng_e.model(b)
-    assert (pg - pe).abs().max().item() <= 2e-3 * max(1.0, pe.abs().max().item())
+    assert (pg - pe).abs().max().item() <= 5e-3 * max(1.0, pe.abs().max().item())
 
 
 def test_bag_embed_backward_index_major_matches_atomic_version():
