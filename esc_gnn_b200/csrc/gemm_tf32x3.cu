@@ -267,6 +267,212 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// "TS" variant for K-major A (forward and dgrad): A never returns to shared memory.  The four splitter warps own one
+// row of the 128 x 32 A tile each (TMEM lane = row), read it from the swizzled stage, and store BOTH planes -- hi (raw
+// fp32) and lo = x - trunc_tf32(x) -- into tensor memory with tcgen05.st; the MMA then takes A from TMEM
+// (tcgen05.mma [d], [a], b_desc) for all three passes.  Only B's lo plane is still written to shared memory.  Per k-block
+// that removes the A_lo write and three A reads from the shared-memory pipe (192 KB -> 128 KB of traffic for
+// BLOCK_N = 128), which is what bounds the "SS" kernel above, and the freed space holds a second lo buffer.
+// TMEM columns: [0, 128) accumulator, [128 + 64 b, 128 + 64 b + 32) A_hi and the next 32 A_lo of buffer b.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+template <int BLOCK_N, bool B_MN, int STAGES, int LO_BUFS>
+__global__ void __launch_bounds__(kThreads, STAGES == 2 ? 2 : 1)
+gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int kABytes = kBlockM * 128;           // 16 KB
+    constexpr int kBBytes = BLOCK_N * 128;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* lo_buf = smem + (size_t)STAGES * kStageBytes;          // LO_BUFS x B_lo
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[LO_BUFS], lo_free_bar[LO_BUFS], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_bias[BLOCK_N];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+    const int num_kb = max(kb_end - kb_begin, 0);
+    constexpr uint32_t kTmemCols = 256, kTmemA = 128;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < LO_BUFS; ++b) { mbar_init(&split_bar[b], 128); mbar_init(&lo_free_bar[b], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+    escgnn::pdl_wait();
+    escgnn::pdl_trigger();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
+                uint8_t* st = smem + (size_t)s * kStageBytes;
+                mbar_expect_tx(&full_bar[s], kStageBytes);
+                const int k0 = (kb_begin + i) * kBlockK;
+                tma_load_2d(st, &tmA, &full_bar[s], k0, m0);
+                uint8_t* sb = st + kABytes;
+                if (!B_MN) tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+                else {
+                    #pragma unroll
+                    for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * kSlabBytes, &tmB, &full_bar[s], n0 + 32 * j, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES, lb = i % LO_BUFS;
+                mbar_wait(&split_bar[lb], (i / LO_BUFS) & 1);    // A planes in TMEM, B_lo in shared memory (implies the stage landed)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_hi = smem_u32(smem + (size_t)s * kStageBytes) + kABytes;
+                const uint32_t b_lo = smem_u32(lo_buf + (size_t)lb * kBBytes);
+                const uint32_t a_hi = tmem_d + kTmemA + (uint32_t)lb * 64u, a_lo = a_hi + 32u;
+                #pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t at = pass == 2 ? a_lo : a_hi, bb = pass == 1 ? b_lo : b_hi;
+                    #pragma unroll
+                    for (int k = 0; k < kBlockK / 8; ++k) {
+                        const uint64_t bd = B_MN ? make_desc(bb + k * 1024, kSlabBytes, 512, 1) : make_desc(bb + k * 32, 0, 1024, 2);
+                        mma_tf32_ts(tmem_d, at + (uint32_t)(k * 8), bd, idesc, (i | pass | k) ? 1u : 0u);
+                    }
+                }
+                tcgen05_commit(&empty_bar[s]);
+                tcgen05_commit(&lo_free_bar[lb]);
+            }
+            tcgen05_commit(&tmem_full_bar);
+        }
+    } else {
+        const int t = threadIdx.x - 64, q = warp & 3, r = q * 32 + lane;       // r: this thread's row of the A tile = its TMEM lane
+        for (int i = t; i < BLOCK_N; i += 128)
+            s_bias[i] = (p.bias && !p.partial && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES, lb = i % LO_BUFS;
+            mbar_wait(&full_bar[s], (i / STAGES) & 1);
+            mbar_wait(&lo_free_bar[lb], ((i / LO_BUFS) & 1) ^ 1);     // MMAs that read TMEM A buffer / B_lo buffer `lb` are done
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint8_t* stage = smem + (size_t)s * kStageBytes;
+            uint32_t hi[32], lo[32];
+            #pragma unroll
+            for (int c = 0; c < 8; ++c) {                  // 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+                const float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
+                hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+                hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+                lo[4 * c + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+                lo[4 * c + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+                lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+                lo[4 * c + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+            }
+            const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + kTmemA + (uint32_t)lb * 64u;
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32u, lo);
+            const float4* src = reinterpret_cast<const float4*>(stage + kABytes);
+            float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kBBytes);
+            #pragma unroll 4
+            for (int e = t; e < kBBytes / 16; e += 128) {
+                const float4 v = src[e];
+                float4 w;
+                w.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                w.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                w.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                w.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                dst[e] = w;
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&split_bar[lb]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + r;
+        const bool row_ok = row < p.M;
+        float* out = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
+        #pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+            if (num_kb > 0) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (row_ok) {
+                const int nb = n0 + c;
+                const bool acc = p.accumulate && !p.partial;
+                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(out + nb) & 15) == 0)) {
+                    #pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 w = make_float4(__uint_as_float(v[j]) + s_bias[c + j], __uint_as_float(v[j + 1]) + s_bias[c + j + 1],
+                                               __uint_as_float(v[j + 2]) + s_bias[c + j + 2], __uint_as_float(v[j + 3]) + s_bias[c + j + 3]);
+                        float4* dst = reinterpret_cast<float4*>(out + nb + j);
+                        if (acc) { const float4 o = *dst; w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+                        *dst = w;
+                    }
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nb + j;
+                        if (n < p.N) {
+                            float w = __uint_as_float(v[j]) + s_bias[c + j];
+                            if (acc) w += out[n];
+                            out[n] = w;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+    }
+}
+
 // split-K reduction: C = (accumulate ? C : 0) + bias + sum_s partial[s]   (fixed order -> deterministic)
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C, int ldc,
                                      const float* __restrict__ bias, int accumulate) {
@@ -379,12 +585,31 @@ int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3
     return (int)cudaGetLastError();
 }
 
-int g_gemm_plan = -1;      // -1 auto, 0 dual, 1 deep (escgnn_gemm_set_plan; experiments / tests)
+int g_gemm_plan = -1;      // -1 auto, 0 dual, 1 deep (escgnn_gemm_set_plan; experiments / tests); +2: force the "SS" kernel for K-major A
+
+template <int BLOCK_N, bool B_MN, int STAGES, int LO_BUFS>
+int launch_cfg_ts(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+    const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + LO_BUFS * BLOCK_N * 128 + 1024;
+    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, B_MN, STAGES, LO_BUFS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    escgnn::launch_pdl(kern, grid, kThreads, smem, st, a, b, p);
+    return (int)cudaGetLastError();
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
     const int ctas = (int)(grid.x * grid.y * grid.z);
-    const bool deep = g_gemm_plan >= 0 ? g_gemm_plan == 1 : (ctas <= 148 && grid.z == 1);   // one wave at 1 CTA/SM: deeper ring
+    const int plan = g_gemm_plan >= 0 ? (g_gemm_plan & 1) : -1;
+    const bool deep = plan >= 0 ? plan == 1 : (ctas <= 148 && grid.z == 1);   // one wave at 1 CTA/SM: deeper ring
+    if constexpr (!A_MN) {
+        if (!(g_gemm_plan >= 2))       // K-major A: planes of A in tensor memory (2 stages + 2 lo buffers still fit two CTAs per SM)
+            return deep ? launch_cfg_ts<BLOCK_N, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg_ts<BLOCK_N, B_MN, 2, 2>(a, b, p, grid, st);
+    }
     return deep ? launch_cfg<BLOCK_N, A_MN, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg<BLOCK_N, A_MN, B_MN, 2, 1>(a, b, p, grid, st);
 }
 
