@@ -268,7 +268,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// "TS" variant for K-major A (forward and dgrad): A never returns to shared memory.  The four splitter warps own one
+// "TS" variant (default): A never returns to shared memory.  The four splitter warps own one
 // row of the 128 x 32 A tile each (TMEM lane = row), read it from the swizzled stage, and store BOTH planes -- hi (raw
 // fp32) and lo = x - trunc_tf32(x) -- into tensor memory with tcgen05.st; the MMA then takes A from TMEM
 // (tcgen05.mma [d], [a], b_desc) for all three passes.  Only B's lo plane is still written to shared memory.  Per k-block
@@ -294,7 +294,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         : "memory");
 }
 
-template <int BLOCK_N, bool B_MN, int STAGES, int LO_BUFS>
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS>
 __global__ void __launch_bounds__(kThreads, STAGES == 2 ? 2 : 1)
 gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -338,7 +338,11 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 uint8_t* st = smem + (size_t)s * kStageBytes;
                 mbar_expect_tx(&full_bar[s], kStageBytes);
                 const int k0 = (kb_begin + i) * kBlockK;
-                tma_load_2d(st, &tmA, &full_bar[s], k0, m0);
+                if (!A_MN) tma_load_2d(st, &tmA, &full_bar[s], k0, m0);
+                else {
+                    #pragma unroll
+                    for (int j = 0; j < kBlockM / 32; ++j) tma_load_2d(st + j * kSlabBytes, &tmA, &full_bar[s], m0 + 32 * j, k0);
+                }
                 uint8_t* sb = st + kABytes;
                 if (!B_MN) tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
                 else {
@@ -349,6 +353,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
     } else if (warp == 1) {
         if (lane == 0) {
+            // A comes from tensor memory, where it is K-major by construction (the splitter transposes an MN-major tile on the fly)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
             for (int i = 0; i < num_kb; ++i) {
@@ -383,15 +388,25 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint8_t* stage = smem + (size_t)s * kStageBytes;
             uint32_t hi[32], lo[32];
+            if (!A_MN) {
+                #pragma unroll
+                for (int c = 0; c < 8; ++c) {              // 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+                    const float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
+                    hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+                    hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+                }
+            } else {
+                // MN-major tile: slab q holds rows 32q..32q+31 as [k][32 m] lines of 128 B whose 32-byte units are XOR-ed with
+                // (k & 3) (SWIZZLE_128B_ATOM_32B); a warp reads one permuted line per k -- conflict-free, and transposed for free
+                const uint8_t* slab = stage + q * kSlabBytes + (lane & 7) * 4;
+                #pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    hi[k] = *reinterpret_cast<const uint32_t*>(slab + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+            }
             #pragma unroll
-            for (int c = 0; c < 8; ++c) {                  // 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
-                const float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
-                hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
-                hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
-                lo[4 * c + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
-                lo[4 * c + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
-                lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
-                lo[4 * c + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+            for (int k = 0; k < 32; ++k) {
+                const float x = __uint_as_float(hi[k]);
+                lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
             }
             const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + kTmemA + (uint32_t)lb * 64u;
             tmem_st32(ta, hi);
@@ -587,10 +602,10 @@ int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3
 
 int g_gemm_plan = -1;      // -1 auto, 0 dual, 1 deep (escgnn_gemm_set_plan; experiments / tests); +2: force the "SS" kernel for K-major A
 
-template <int BLOCK_N, bool B_MN, int STAGES, int LO_BUFS>
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS>
 int launch_cfg_ts(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
     const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + LO_BUFS * BLOCK_N * 128 + 1024;
-    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, B_MN, STAGES, LO_BUFS>;
+    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -606,10 +621,8 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 gri
     const int ctas = (int)(grid.x * grid.y * grid.z);
     const int plan = g_gemm_plan >= 0 ? (g_gemm_plan & 1) : -1;
     const bool deep = plan >= 0 ? plan == 1 : (ctas <= 148 && grid.z == 1);   // one wave at 1 CTA/SM: deeper ring
-    if constexpr (!A_MN) {
-        if (!(g_gemm_plan >= 2))       // K-major A: planes of A in tensor memory (2 stages + 2 lo buffers still fit two CTAs per SM)
-            return deep ? launch_cfg_ts<BLOCK_N, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg_ts<BLOCK_N, B_MN, 2, 2>(a, b, p, grid, st);
-    }
+    if (!(g_gemm_plan >= 2))           // planes of A in tensor memory (2 stages + 2 lo buffers still fit two CTAs per SM)
+        return deep ? launch_cfg_ts<BLOCK_N, A_MN, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg_ts<BLOCK_N, A_MN, B_MN, 2, 2>(a, b, p, grid, st);
     return deep ? launch_cfg<BLOCK_N, A_MN, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg<BLOCK_N, A_MN, B_MN, 2, 1>(a, b, p, grid, st);
 }
 
