@@ -80,10 +80,14 @@ struct Params {
     float* C; int ldc; const float* bias;
     int M, N, K;                  // problem (M = row capacity; TMA zero-fills beyond the tensor extents)
     int kb_per_split, kb_total;   // k-blocks of 32
-    float* partial;               // split-K partial tiles [splits][M][N] (nullptr when splits == 1)
+    float* partial;               // split-K partial tiles [splits][M][N] (nullptr when splits == 1 or atomic)
     int accumulate;
+    int atomic;                   // split-K slices add their tile into C with fp32 vector reductions (C holds the initial value)
 };
 
+__device__ __forceinline__ void red_add4(float4* dst, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -186,7 +190,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ===== splitters (main loop), then epilogue: 4 warps, TMEM lane quarter = warp % 4 =====
         const int t = threadIdx.x - 64;                 // 0..127
         for (int i = t; i < BLOCK_N; i += 128)          // bias tile for the epilogue (these four warps are its only readers)
-            s_bias[i] = (p.bias && !p.partial && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+            s_bias[i] = (p.bias && !p.partial && (!p.atomic || blockIdx.z == 0) && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
         for (int i = 0; i < num_kb; ++i) {
             const int s = i % STAGES, lb = i % LO_BUFS;
             mbar_wait(&full_bar[s], (i / STAGES) & 1);
@@ -241,6 +245,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         float4 r = make_float4(__uint_as_float(v[j]) + s_bias[c + j], __uint_as_float(v[j + 1]) + s_bias[c + j + 1],
                                                __uint_as_float(v[j + 2]) + s_bias[c + j + 2], __uint_as_float(v[j + 3]) + s_bias[c + j + 3]);
                         float4* dst = reinterpret_cast<float4*>(out + nb + j);
+                        if (p.atomic) { red_add4(dst, r); continue; }
                         if (acc) { const float4 o = *dst; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
                         *dst = r;
                     }
@@ -250,6 +255,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const int n = nb + j;
                         if (n < p.N) {
                             float r = __uint_as_float(v[j]) + s_bias[c + j];
+                            if (p.atomic) { atomicAdd(out + n, r); continue; }
                             if (acc) r += out[n];
                             out[n] = r;
                         }
@@ -380,7 +386,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else {
         const int t = threadIdx.x - 64, q = warp & 3, r = q * 32 + lane;       // r: this thread's row of the A tile = its TMEM lane
         for (int i = t; i < BLOCK_N; i += 128)
-            s_bias[i] = (p.bias && !p.partial && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+            s_bias[i] = (p.bias && !p.partial && (!p.atomic || blockIdx.z == 0) && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
         for (int i = 0; i < num_kb; ++i) {
             const int s = i % STAGES, lb = i % LO_BUFS;
             mbar_wait(&full_bar[s], (i / STAGES) & 1);
@@ -462,6 +468,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         float4 w = make_float4(__uint_as_float(v[j]) + s_bias[c + j], __uint_as_float(v[j + 1]) + s_bias[c + j + 1],
                                                __uint_as_float(v[j + 2]) + s_bias[c + j + 2], __uint_as_float(v[j + 3]) + s_bias[c + j + 3]);
                         float4* dst = reinterpret_cast<float4*>(out + nb + j);
+                        if (p.atomic) { red_add4(dst, w); continue; }
                         if (acc) { const float4 o = *dst; w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
                         *dst = w;
                     }
@@ -471,6 +478,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         const int n = nb + j;
                         if (n < p.N) {
                             float w = __uint_as_float(v[j]) + s_bias[c + j];
+                            if (p.atomic) { atomicAdd(out + n, w); continue; }
                             if (acc) w += out[n];
                             out[n] = w;
                         }
@@ -693,13 +701,16 @@ int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d
     const int block_n = pick_block_n(N);
     const int tiles_m = (M + kBlockM - 1) / kBlockM, n_tiles = (N + block_n - 1) / block_n;
     const int kb_total = (K + kBlockK - 1) / kBlockK;
-    int splits = d_workspace ? pick_splits(tiles_m * n_tiles, kb_total, M, N, workspace_floats) : 1;
+    const bool atomic = accumulate == 2;       // C += A B^T with the K-slices added by fp32 reductions (order not fixed)
+    int splits = atomic ? pick_splits(tiles_m * n_tiles, kb_total, M, N, (int64_t)1 << 40)
+                        : d_workspace ? pick_splits(tiles_m * n_tiles, kb_total, M, N, workspace_floats) : 1;
     Params p;
     p.C = d_c; p.ldc = ldc; p.bias = d_bias; p.M = M; p.N = N; p.K = K;
     p.kb_total = kb_total; p.kb_per_split = (kb_total + splits - 1) / splits;
     splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
-    p.partial = splits > 1 ? d_workspace : nullptr;
+    p.partial = (splits > 1 && !atomic) ? d_workspace : nullptr;
     p.accumulate = accumulate;
+    p.atomic = atomic ? 1 : 0;
     CUtensorMap a, b;
     int rc = 0;
     if (!a_mn_major) rc |= make_map(&a, d_a, K, M, lda, kBlockK, kBlockM);          // [M, K] row-major: inner = K
@@ -713,7 +724,7 @@ int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d
     else if (a_mn_major && !b_mn_major) rc = dispatch_n<true, false>(block_n, a, b, p, grid, st);
     else rc = dispatch_n<true, true>(block_n, a, b, p, grid, st);
     if (rc) return rc;
-    if (splits > 1) {
+    if (splits > 1 && !atomic) {
         int64_t blocks = ((int64_t)M * N + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
         escgnn::launch_pdl(splitk_reduce_kernel, (unsigned)blocks, 256, 0, st, d_workspace, splits, M, N, d_c, ldc, d_bias, accumulate);

@@ -91,7 +91,7 @@ class StaticTrainEngine(object):
     """One NestedGIN_eff variant ('zinc' or 'count') at a fixed capacity."""
 
     def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
-                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False):
+                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True):
         if variant not in ('zinc', 'count'):
             raise NotImplementedError('engine variants: zinc, count (the OGB model runs through the module path)')
         p0 = next(model.parameters())
@@ -152,6 +152,9 @@ class StaticTrainEngine(object):
         self.idx_err = torch.zeros(1, dtype=i64, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.tensor_cores = tensor_cores
+        # weight gradients land in the flat gradient buffer, which every step zeroes first: their split-K slices can be added
+        # in place with vector reductions (2) instead of going through partial tiles and a reduction launch (0)
+        self.wgrad_mode = 2 if atomic_wgrad else 0
         self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
         # weight / bias gradients are off the critical path (only Adam consumes them): they run on a side stream that
         # forks from the backward chain wherever a dY becomes available and joins before the optimiser
@@ -230,7 +233,7 @@ class StaticTrainEngine(object):
 
         def grads():
             # wgrad: dW[n_out, k_in] = dY^T X   (A = dY stored [rows, n_out] = MN-major, B = X stored [rows, k_in] = MN-major)
-            self._gemm('gemm_wgrad', dy, True, x, True, W.grad, None, n_out, k_in, rows, False)
+            self._gemm('gemm_wgrad', dy, True, x, True, W.grad, None, n_out, k_in, rows, self.wgrad_mode)
             if not feeds_bn:
                 _lib.check(c.L.escgnn_colsum(_p(dy), dy.stride(0), _p(c.rows[kind]), c.caps[kind], dy.size(1),
                                              _p(self.side_partial), _p(bvec.grad), c.st()), 'colsum')
@@ -390,7 +393,7 @@ class StaticTrainEngine(object):
                                                                      E_rows, c.st()), 'zero_tail_rows'))
 
         def proj_back():                          # runs after every layer's backward has filled its slice of dee_all
-            self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, False),
+            self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, self.wgrad_mode),
                                 _lib.check(c.L.escgnn_colsum(_p(dee_all), dee_all.stride(0), _p(c.rows['E']), E_rows, n_tot,
                                                              _p(self.side_partial), _p(db_cat), c.st()), 'colsum')))
             self._gemm('gemm_dgrad', dee_all, False, W_cat, True, dzcat, None, E_rows, edge_dim, n_tot, False)

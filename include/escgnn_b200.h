@@ -279,12 +279,15 @@ int escgnn_loss_fwd_bwd(const float* d_pred, int ldp, const float* d_target, int
  *   b_mn_major == 0: B is [N,K] row-major (ldb);  != 0: B is stored [K,N] row-major
  * Operands are plain fp32; the low tf32 planes are produced on chip. lda / ldb multiples of 4 and 16-byte aligned bases
  * (TMA). Rows beyond the tensor extents read as zero. Split-K (small output, long K: wgrad) uses d_workspace
- * (escgnn_gemm_workspace_floats(M,N,K) floats; NULL disables it) with an ordered reduction. */
+ * (escgnn_gemm_workspace_floats(M,N,K) floats; NULL disables it) with an ordered reduction.
+ * accumulate: 0 C = ..., 1 C += ... (ordered), 2 C += ... with the K-slices added by fp32 vector reductions
+ * (red.global.add.v4.f32): no workspace, no reduction launch, summation order not fixed. */
 int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,
                        const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats,
                        void* stream);
 int64_t escgnn_gemm_workspace_floats(int M, int N, int K);
-/* shared-memory plan of the GEMM: -1 auto, 0 = 2 stages + 1 lo buffer (2 CTAs/SM), 1 = 4 stages + 2 lo buffers (1 CTA/SM) */
+/* shared-memory plan of the GEMM: -1 auto, 0 = 2 stages (2 CTAs/SM), 1 = 4 stages (1 CTA/SM); +2 = the variant that keeps
+ * both planes of A in shared memory instead of tensor memory (experiments / tests) */
 int escgnn_gemm_set_plan(int plan);
 /* x - tf32_trunc(x): the low plane of the 3xTF32 split (diagnostics; the GEMM computes it on chip) */
 int escgnn_tf32_split_lo(const float* d_x, int ldx, float* d_lo, int ldlo, int64_t rows, int cols, void* stream);

@@ -100,3 +100,24 @@ def test_gemm_precision_beats_single_pass_tf32():
     torch.backends.cuda.matmul.allow_tf32 = False
     rel_fp32 = (((A @ B.t()).double() - ref).norm() / ref.norm()).item()
     assert rel < 5e-6 and rel < rel_tf32 / 20, (rel, rel_tf32, rel_fp32)
+
+
+@pytest.mark.parametrize('M,N,K,a_mn,b_mn', [(256, 288, 12800, True, True), (800, 288, 6000, True, True), (256, 256, 5000, False, False),
+                                             (128, 40, 4096, True, True)])
+def test_gemm_atomic_split_k_accumulates_in_place(M, N, K, a_mn, b_mn):
+    """accumulate = 2: the K-slices of a weight-gradient-shaped product are added into C with vector reductions (no
+    workspace, no reduction launch); C keeps its initial value plus the product, bias added exactly once."""
+    from esc_gnn_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    A = torch.randn(M, K, device='cuda', generator=g); B = torch.randn(N, K, device='cuda', generator=g)
+    bias = torch.randn(N, device='cuda', generator=g)
+    C0 = torch.randn(M, N, device='cuda', generator=g)
+    As = A.t().contiguous() if a_mn else A.contiguous()
+    Bs = B.t().contiguous() if b_mn else B.contiguous()
+    C = C0.clone()
+    _lib.check(L.escgnn_gemm_tf32x3(_p(As), As.stride(0), int(a_mn), _p(Bs), Bs.stride(0), int(b_mn), _p(C), N, _p(bias), M, N, K, 2,
+                                    None, 0, _st()), 'gemm_tf32x3')
+    ref = A.double() @ B.double().t() + bias.double() + C0.double()
+    scale = (A.double().abs() @ B.double().abs().t()).max().item()
+    assert (C.double() - ref).abs().max().item() <= 4e-6 * scale
