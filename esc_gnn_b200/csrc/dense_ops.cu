@@ -606,6 +606,153 @@ bn_act_bwd_cluster_kernel(const float* __restrict__ x, int ldx, const float* __r
     cluster.sync();
 }
 
+// Register-resident variants: when the rows a thread owns fit in R float4 registers (rows_cap <= R * kSweep) the tile is
+// read ONCE -- statistics and normalisation both come from registers -- and the kernel is one L2 round trip, one
+// cluster exchange and the stores.
+template <int LANES, int R>
+__global__ void __launch_bounds__(256, 2)
+bn_act_fwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* running_mean, float* running_var, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                              int act, float eps, float momentum, const int* __restrict__ d_rows, int rows_cap, int C,
+                              float* __restrict__ y, int ldy) {
+    escgnn::pdl_enter();
+    using T = ClusterTile<LANES>;
+    __shared__ __align__(16) float s_w[8][2][T::kCols];
+    __shared__ __align__(16) float s_part[2][T::kCols];
+    __shared__ __align__(16) float s_tot[2][T::kCols];
+    cg::cluster_group cluster = cg::this_cluster();
+    T t{s_w, s_part, s_tot};
+    const int cl = threadIdx.x % LANES, rs = threadIdx.x / LANES, rank = (int)cluster.block_rank();
+    const int c4 = blockIdx.x * T::kCols + 4 * cl, rows = min(*d_rows, rows_cap);
+    const bool col_ok = c4 < C;
+    const int r_first = rank * T::kSlots + rs;
+    float4 v[R];
+    float4 a = zero4(), b = zero4();
+    #pragma unroll
+    for (int k = 0; k < R; ++k) v[k] = (col_ok && r_first + k * T::kSweep < rows) ? ld4(x + (size_t)(r_first + k * T::kSweep) * ldx + c4) : zero4();
+    #pragma unroll
+    for (int k = 0; k < R; ++k) {
+        a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
+        b.x += v[k].x * v[k].x; b.y += v[k].y * v[k].y; b.z += v[k].z * v[k].z; b.w += v[k].w * v[k].w;
+    }
+    t.reduce(a, b, cluster);
+    cluster.barrier_arrive();                         // this CTA is done reading its peers' shared memory ...
+    if (col_ok) {
+        const float m = (float)max(rows, 1);
+        const float4 s1 = ld4(&s_tot[0][4 * cl]), s2 = ld4(&s_tot[1][4 * cl]);
+        const float4 mean = make_float4(s1.x / m, s1.y / m, s1.z / m, s1.w / m);
+        const float4 var = make_float4(fmaxf(s2.x / m - mean.x * mean.x, 0.f), fmaxf(s2.y / m - mean.y * mean.y, 0.f),
+                                       fmaxf(s2.z / m - mean.z * mean.z, 0.f), fmaxf(s2.w / m - mean.w * mean.w, 0.f));
+        const float4 rstd = make_float4(rsqrtf(var.x + eps), rsqrtf(var.y + eps), rsqrtf(var.z + eps), rsqrtf(var.w + eps));
+        if (rank == 0 && rs == 0) {
+            st4(mean_out + c4, mean); st4(rstd_out + c4, rstd);
+            if (rows > 0) {
+                const float ub = rows > 1 ? m / (m - 1.f) : 1.f, k0 = 1.f - momentum;
+                const float4 rm = ld4(running_mean + c4), rv = ld4(running_var + c4);
+                st4(running_mean + c4, make_float4(k0 * rm.x + momentum * mean.x, k0 * rm.y + momentum * mean.y,
+                                                   k0 * rm.z + momentum * mean.z, k0 * rm.w + momentum * mean.w));
+                st4(running_var + c4, make_float4(k0 * rv.x + momentum * var.x * ub, k0 * rv.y + momentum * var.y * ub,
+                                                  k0 * rv.z + momentum * var.z * ub, k0 * rv.w + momentum * var.w * ub));
+            }
+        }
+        const float4 g = gamma ? ld4(gamma + c4) : make_float4(1.f, 1.f, 1.f, 1.f), bt = beta ? ld4(beta + c4) : zero4();
+        const float4 sc = make_float4(rstd.x * g.x, rstd.y * g.y, rstd.z * g.z, rstd.w * g.w);
+        const float4 sh = make_float4(bt.x - mean.x * sc.x, bt.y - mean.y * sc.y, bt.z - mean.z * sc.z, bt.w - mean.w * sc.w);
+        #pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int r = r_first + k * T::kSweep;
+            if (r < rows_cap) {
+                float4 o = zero4();                   // rows >= actual count are zeroed (inert in the next GEMM)
+                if (r < rows) o = act_fwd4(make_float4(v[k].x * sc.x + sh.x, v[k].y * sc.y + sh.y, v[k].z * sc.z + sh.z, v[k].w * sc.w + sh.w), act);
+                st4(y + (size_t)r * ldy + c4, o);
+            }
+        }
+    }
+    cluster.barrier_wait();                           // ... and leaves only when every peer is done reading its own
+}
+
+template <int LANES, int R>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy,
+                              const float* __restrict__ dy2, int lddy2, const float* __restrict__ mean,
+                              const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              int act, const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, float* __restrict__ dx, int lddx) {
+    escgnn::pdl_enter();
+    using T = ClusterTile<LANES>;
+    __shared__ __align__(16) float s_w[8][2][T::kCols];
+    __shared__ __align__(16) float s_part[2][T::kCols];
+    __shared__ __align__(16) float s_tot[2][T::kCols];
+    cg::cluster_group cluster = cg::this_cluster();
+    T t{s_w, s_part, s_tot};
+    const int cl = threadIdx.x % LANES, rs = threadIdx.x / LANES, rank = (int)cluster.block_rank();
+    const int c4 = blockIdx.x * T::kCols + 4 * cl, rows = min(*d_rows, rows_cap);
+    const bool col_ok = c4 < C;
+    const int r_first = rank * T::kSlots + rs;
+    BnCols k;
+    k.mu = k.rs = k.g = k.bt = zero4();
+    if (col_ok) k = bn_cols(mean, rstd, gamma, beta, c4);
+    float4 dz[R], xh[R];                              // after the loads: dz and xhat of this thread's rows
+    #pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int r = r_first + i * T::kSweep;
+        dz[i] = zero4(); xh[i] = zero4();
+        if (col_ok && r < rows) {
+            xh[i] = ld4(x + (size_t)r * ldx + c4);
+            dz[i] = ld4(dy + (size_t)r * lddy + c4);
+            if (dy2) { const float4 e = ld4(dy2 + (size_t)r * lddy2 + c4); dz[i].x += e.x; dz[i].y += e.y; dz[i].z += e.z; dz[i].w += e.w; }
+        }
+    }
+    float4 a = zero4(), b = zero4();
+    #pragma unroll
+    for (int i = 0; i < R; ++i)
+        if (col_ok && r_first + i * T::kSweep < rows) {
+            float4 z, h;
+            bn_dz(xh[i], dz[i], k, act, z, h);
+            dz[i] = z; xh[i] = h;
+            a.x += z.x; a.y += z.y; a.z += z.z; a.w += z.w;
+            b.x += z.x * h.x; b.y += z.y * h.y; b.z += z.z * h.z; b.w += z.w * h.w;
+        }
+    t.reduce(a, b, cluster);
+    cluster.barrier_arrive();
+    if (col_ok) {
+        const float4 s1 = ld4(&s_tot[0][4 * cl]), s2 = ld4(&s_tot[1][4 * cl]);
+        if (rank == 0 && rs == 0) { if (dgamma) st4(dgamma + c4, s2); if (dbeta) st4(dbeta + c4, s1); }
+        const float inv_m = 1.f / (float)max(rows, 1);
+        const float4 m1 = make_float4(s1.x * inv_m, s1.y * inv_m, s1.z * inv_m, s1.w * inv_m);
+        const float4 m2 = make_float4(s2.x * inv_m, s2.y * inv_m, s2.z * inv_m, s2.w * inv_m);
+        const float4 kk = make_float4(k.g.x * k.rs.x, k.g.y * k.rs.y, k.g.z * k.rs.z, k.g.w * k.rs.w);
+        #pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int r = r_first + i * T::kSweep;
+            if (r < rows_cap) {
+                float4 o = zero4();
+                if (r < rows)
+                    o = make_float4(kk.x * (dz[i].x - m1.x - xh[i].x * m2.x), kk.y * (dz[i].y - m1.y - xh[i].y * m2.y),
+                                    kk.z * (dz[i].z - m1.z - xh[i].z * m2.z), kk.w * (dz[i].w - m1.w - xh[i].w * m2.w));
+                st4(dx + (size_t)r * lddx + c4, o);
+            }
+        }
+    }
+    cluster.barrier_wait();
+}
+
+// (lanes, registers) plan of the one-launch BatchNorm: as many clusters as the column count allows, rows in registers when they fit
+template <class K2_8, class K2_16, class KS2, class KS4, class KS8, class... Args>
+inline void launch_cluster_bn(bool backward, int rows_cap, int channels, cudaStream_t st, K2_8 k2_8, K2_16 k2_16, KS2 ks2,
+                              KS4 ks4, KS8 ks8, Args... args) {
+    auto go = [&](auto kern, int lanes) {
+        escgnn::launch_pdl_cluster(kern, dim3((unsigned)((channels + 4 * lanes - 1) / (4 * lanes)), kClRanks), 256, 0, st, kClRanks, args...);
+    };
+    if (channels <= 512) {
+        if (rows_cap <= 8 * 1024) return go(k2_8, 2);                       // lanes 2: 1024 rows per sweep
+        if (!backward && rows_cap <= 16 * 1024) return go(k2_16, 2);
+        return go(ks2, 2);
+    }
+    if (channels <= 1024) return go(ks4, 4);
+    return go(ks8, 8);
+}
+
 inline int& cluster_bn_enabled() {
     static int on = 1;
     return on;
@@ -760,11 +907,10 @@ int escgnn_bn_act_fwd(const float* d_x, int ldx, const float* d_gamma, const flo
     cudaStream_t st = (cudaStream_t)stream;
     if (vec_ok(channels, {d_x, d_y, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, d_partial}, {ldx, ldy})) {
         if (training && rows_cap <= kClMaxRows && cluster_bn_enabled()) {       // one launch: cluster-wide statistics
-            const int lanes = channels <= 512 ? 2 : channels <= 1024 ? 4 : 8;
-            const dim3 grid((unsigned)((channels + 4 * lanes - 1) / (4 * lanes)), kClRanks);
-            auto kern = lanes == 2 ? bn_act_fwd_cluster_kernel<2> : lanes == 4 ? bn_act_fwd_cluster_kernel<4> : bn_act_fwd_cluster_kernel<8>;
-            escgnn::launch_pdl_cluster(kern, grid, 256, 0, st, kClRanks, d_x, ldx, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, act, eps, momentum,
-                                       d_rows, rows_cap, channels, d_y, ldy);
+            launch_cluster_bn(false, rows_cap, channels, st, bn_act_fwd_cluster_reg_kernel<2, 8>, bn_act_fwd_cluster_reg_kernel<2, 16>,
+                              bn_act_fwd_cluster_kernel<2>, bn_act_fwd_cluster_kernel<4>,
+                              bn_act_fwd_cluster_kernel<8>, d_x, ldx, d_gamma, d_beta, d_running_mean, d_running_var, d_mean, d_rstd, act,
+                              eps, momentum, d_rows, rows_cap, channels, d_y, ldy);
             return (int)cudaGetLastError();
         }
         const dim3 g = vec_grid(rows_cap, channels);
@@ -790,11 +936,10 @@ int escgnn_bn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, co
     cudaStream_t st = (cudaStream_t)stream;
     if (vec_ok(channels, {d_x, d_dy, d_dy2, d_mean, d_rstd, d_gamma, d_beta, d_partial, d_dx}, {ldx, lddy, d_dy2 ? lddy2 : 0, lddx})) {
         if (training && rows_cap <= kClMaxRows && cluster_bn_enabled()) {
-            const int lanes = channels <= 512 ? 2 : channels <= 1024 ? 4 : 8;
-            const dim3 grid((unsigned)((channels + 4 * lanes - 1) / (4 * lanes)), kClRanks);
-            auto kern = lanes == 2 ? bn_act_bwd_cluster_kernel<2> : lanes == 4 ? bn_act_bwd_cluster_kernel<4> : bn_act_bwd_cluster_kernel<8>;
-            escgnn::launch_pdl_cluster(kern, grid, 256, 0, st, kClRanks, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act, d_rows, rows_cap,
-                                       channels, d_dgamma, d_dbeta, d_dx, lddx);
+            launch_cluster_bn(true, rows_cap, channels, st, bn_act_bwd_cluster_reg_kernel<2, 8>, bn_act_bwd_cluster_reg_kernel<2, 8>,
+                              bn_act_bwd_cluster_kernel<2>, bn_act_bwd_cluster_kernel<4>,
+                              bn_act_bwd_cluster_kernel<8>, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act, d_rows,
+                              rows_cap, channels, d_dgamma, d_dbeta, d_dx, lddx);
             return (int)cudaGetLastError();
         }
         const dim3 g = vec_grid(rows_cap, channels);

@@ -39,6 +39,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// plain stream order (no programmatic edge): for a kernel whose predecessor on the stream is NOT a kernel (a memset / copy
+// node) -- griddepcontrol.wait only covers prerequisite GRIDS
+template <class... KArgs, class... Args>
+inline cudaError_t launch_ordered(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // same, as thread-block clusters of (1, cluster_y, 1) CTAs (gridDim.y must be a multiple of cluster_y)
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_y,

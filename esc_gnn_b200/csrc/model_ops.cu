@@ -527,7 +527,7 @@ int escgnn_csr_build(const int64_t* d_keys, int64_t n_edges, int64_t n_nodes, in
     cudaMemsetAsync(d_tmp, 0, (size_t)(n_nodes + 1) * 4, st);
     if (n_edges > 0) {
         const unsigned gb = blocks_for(n_edges, 256) > 1184 ? 1184 : blocks_for(n_edges, 256);
-        escgnn::launch_pdl(count_keys_kernel, gb, 256, 0, st, d_keys, n_edges, (int)n_nodes, d_ptr, d_err, d_count);
+        escgnn::launch_ordered(count_keys_kernel, gb, 256, 0, st, d_keys, n_edges, (int)n_nodes, d_ptr, d_err, d_count);
         escgnn::launch_pdl(scan_ptr_kernel, 1, 1024, 0, st, d_ptr, (int)n_nodes + 1);
         escgnn::launch_pdl(fill_perm_kernel, gb, 256, 0, st, d_keys, n_edges, (int)n_nodes, d_ptr, d_tmp, d_perm, d_count);
         escgnn::launch_pdl(sort_segments_kernel, blocks_for(n_nodes, 128), 128, 0, st, d_ptr, (int)n_nodes, d_perm);
@@ -606,7 +606,7 @@ int escgnn_bag_index_build(const uint32_t* d_rec, const int64_t* d_rec_off, cons
     int* counts = d_work; int* ptr = d_work + kBagRows; int* cursor = d_work + 2 * kBagRows + 1;
     cudaMemsetAsync(counts, 0, kBagRows * sizeof(int), st);
     unsigned gb = blocks_for(n_edges, 8 * 16); if (gb > 296) gb = 296; if (gb < 1) gb = 1;
-    escgnn::launch_pdl(bag_count_kernel, gb, 256, 0, st, d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, counts);
+    escgnn::launch_ordered(bag_count_kernel, gb, 256, 0, st, d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, counts);
     escgnn::launch_pdl(bag_scan_kernel, 1, 1024, 0, st, counts, ptr, cursor);
     escgnn::launch_pdl(bag_fill_kernel, gb, 256, 0, st, d_rec, d_rec_off, d_rec_nnz, n_edges, d_count, ptr, cursor, d_sorted_edge, d_sorted_cnt);
     return (int)cudaGetLastError();
