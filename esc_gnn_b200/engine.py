@@ -277,22 +277,25 @@ class StaticTrainEngine(object):
             _p(rstd), _p(bn.weight), _p(bn.bias), ACT[act], 1, _p(c.partial), _p(c.rows[kind]), c.caps[kind], C,
             _p(bn.weight.grad), _p(bn.bias.grad), _p(dx), dx.stride(0), c.st()), 'bn_act_bwd'))
 
-    def _embedding(self, table, idx, kind, out):
+    def _embedding(self, table, idx, kind, out, side=False):
+        """side: the first consumer is ordered behind a LATER fork of the side branch (the grouped projection GEMM, whose
+        completion the first GINE layer waits for), so the lookup leaves the critical path."""
         c = self.c
         C = table.weight.size(1)
         cols = 1 if idx.dim() == 1 else idx.size(1)
-        self.fwd.append(lambda: _lib.check(c.L.escgnn_embedding_fwd(_p(table.weight), _p(idx), cols, None, _p(c.rows[kind]),
-                                                                    c.caps[kind], C, _p(out), out.stride(0), c.st()),
-                                           'embedding_fwd'))
+        run = lambda: _lib.check(c.L.escgnn_embedding_fwd(_p(table.weight), _p(idx), cols, None, _p(c.rows[kind]),
+                                                          c.caps[kind], C, _p(out), out.stride(0), c.st()), 'embedding_fwd')
+        self.fwd.append((lambda: self._fork(run)) if side else run)
         return C
 
     def _embedding_bwd(self, table, idx, kind, dout):
+        """Table gradients are read by the optimiser only: side branch."""
         c = self.c
         C = table.weight.size(1)
         cols = 1 if idx.dim() == 1 else idx.size(1)
-        self.bwd.append(lambda: _lib.check(c.L.escgnn_embedding_bwd(_p(dout), dout.stride(0), _p(idx), cols, None,
-                                                                    _p(c.rows[kind]), c.caps[kind], C, _p(table.weight.grad),
-                                                                    c.st()), 'embedding_bwd'))
+        self.bwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_embedding_bwd(
+            _p(dout), dout.stride(0), _p(idx), cols, None, _p(c.rows[kind]), c.caps[kind], C, _p(table.weight.grad), c.st()),
+            'embedding_bwd')))
 
     def _gine(self, x, dx, ee, dee, eps, out, dout):
         """out = (1+eps) x + sum relu(x_src + ee).  x / ee / dee may be column slices (leading dimensions are passed).
@@ -322,7 +325,7 @@ class StaticTrainEngine(object):
         # node input
         if self.variant == 'zinc':
             x0 = c.buf('N', 32)
-            self._embedding(m.node_type_embedding, self.in_x, 'N', x0)
+            self._embedding(m.node_type_embedding, self.in_x, 'N', x0, side=True)
             dx0 = c.buf('N', 32)
             self._embedding_bwd(m.node_type_embedding, self.in_x, 'N', dx0)
             edge_dim = H + 32
@@ -352,7 +355,7 @@ class StaticTrainEngine(object):
         zcat, dzcat = c.buf('E', edge_dim), c.buf('E', edge_dim)
         self._bn_act(z2, dz2, m.z_embedding[5], act, 'E', zcat[:, :H], dzcat[:, :H])
         if self.variant == 'zinc':
-            self._embedding(m.edge_type_embedding, self.in_ea, 'E', zcat[:, H:])
+            self._embedding(m.edge_type_embedding, self.in_ea, 'E', zcat[:, H:], side=True)
             self._embedding_bwd(m.edge_type_embedding, self.in_ea, 'E', dzcat[:, H:])
         # JK buffer: [x_embedding(x) | x1 .. xL] for count, [x1 .. xL] for zinc
         jk_slots = Lh + (1 if self.variant == 'count' else 0)
@@ -386,11 +389,12 @@ class StaticTrainEngine(object):
         ee_all, dee_all = c.buf('E', ld_all), c.buf('E', ld_all)
         E_rows = c.caps['E']
         ee_ready = [None]
+        # rows past the edge count stay zero for the GEMMs of the backward pass (a larger earlier batch may have written them);
+        # side branch, ahead of the projection GEMM whose completion the first GINE layer waits for
+        self.fwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_zero_tail_rows(
+            _p(dee_all), dee_all.stride(0), n_tot, _p(c.rows['E']), E_rows, c.st()), 'zero_tail_rows')))
         self.fwd.append(lambda: ee_ready.__setitem__(0, self._fork(
             lambda: self._gemm('gemm_fwd', zcat, False, W_cat, False, ee_all, b_cat, E_rows, n_tot, edge_dim, False))))
-        # rows past the edge count stay zero for the GEMMs below (a larger earlier batch may have written them)
-        self.fwd.append(lambda: _lib.check(c.L.escgnn_zero_tail_rows(_p(dee_all), dee_all.stride(0), n_tot, _p(c.rows['E']),
-                                                                     E_rows, c.st()), 'zero_tail_rows'))
 
         def proj_back():                          # runs after every layer's backward has filled its slice of dee_all
             self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, self.wgrad_mode),

@@ -286,4 +286,8 @@ def test_bag_embed_backward_index_major_matches_atomic_version():
                                                       P(sc), P(d_count), st), 'bag_embed_bwd_sorted')
     ref = torch.zeros(1800, H, device='cuda', dtype=torch.float64)
     ref.index_add_(0, r.pos_index, g[r.pos_batch].double() * r.pos_enc.view(-1, 1).double())
-    torch.testing.assert_close(dW.double(), ref, rtol=1e-5, atol=1e-4)
+    # fp32 accumulation (float atomics across chunks, order varies) of terms far larger than their sum: the absolute error
+    # scales with sum |terms| (entries reach ~1e3 here; 1.4e-4 observed on one entry in one of six runs)
+    mag = torch.zeros(1800, H, device='cuda', dtype=torch.float64)
+    mag.index_add_(0, r.pos_index, g[r.pos_batch].double().abs() * r.pos_enc.view(-1, 1).double())
+    assert ((dW.double() - ref).abs() <= 1e-5 * ref.abs() + 2e-6 * mag + 1e-6).all()
