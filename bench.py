@@ -240,10 +240,29 @@ def run_own(args):
         del seq, model_s
     # ---- large batch ("report both reference-batch and large-batch (8 192 graphs) numbers"): the same engine
     # at 32x the reference batch, where the kernels stop being launch-latency bound; explains the roofline, not the headline
-    large = None
+    large, extraction = None, None
+    LG = 8192
+    if not args.no_large:
+        # ---- extraction alone (the encoder shards by graph with no collective): every rank encodes its own 8192
+        # graphs through the reference contract (int64 pos_enc / pos_index / pos_batch + rewritten edge_index); whole-job graphs/s
+        from esc_gnn_b200.transform import encode_batch
+        raw_l = RawBatch.synth(CONFIG, 5_000_000 + rank * LG, LG).cuda(non_blocking=False)
+        ep_h, np_h = raw_l.edge_ptr_host, raw_l.node_ptr_host
+        enc = lambda: encode_batch(raw_l.src, raw_l.dst, ep_h, np_h, fl['h'], fl['use_rd'], fl['self_loop'], expand=True)
+        for _ in range(3):
+            r_enc = enc()
+        barrier()
+        k_x = 10
+        ms_x = timed(lambda _b: enc(), [None], k_x)
+        barrier()
+        ms_x = max_over_ranks(ms_x)
+        b_enc = 16 * raw_l.src.numel() + 16 * r_enc.num_edges + 24 * r_enc.nnz
+        extraction = dict(value=LG * world * k_x / (ms_x * 1e-3), unit='graphs/s', graphs_per_rank=LG, ms_per_call=ms_x / k_x,
+                          contract_bytes_per_call=b_enc, contract_GBps_per_gpu=b_enc / (ms_x / k_x * 1e-3) / 1e9,
+                          what='encode_batch (h=3, rd on): E1 + E5 + E2-E4 kernels + expansion to the int64 triple, one device->host '
+                               'read of two counters per call')
+        del r_enc
     if world == 1 and not args.no_large:
-        LG = 8192
-        raw_l = RawBatch.synth(CONFIG, 5_000_000, LG).cuda(non_blocking=False)
         torch.manual_seed(0)
         model_l = zinc_model.NestedGIN_eff(None, LAYERS).cuda()
         model_l.train()
@@ -309,6 +328,9 @@ def run_own(args):
                         unit='TFLOP/s', frac=achieved / pk, traffic=None, peak_source=peak_src + ' dense bf16, sustained',
                         share_of_step=g_ms / sum_ms, algorithmic_flops_per_step=flops, launches_per_step=g_calls,
                         launch_ms=g_ms / max(g_calls, 1), frac_of_3xtf32_ceiling=achieved / (pk / 6.0),
+                        traffic_ncu=dict(launch='gemm_tf32x3_ts_kernel<128,0,0,2,2>, forward 12800x288 -> 256', dram_read_bytes=15102464,
+                                         dram_write_bytes=24064, algorithmic_operand_bytes=4 * (12800 * 288 + 256 * 288),
+                                         source='profiles/r01_prof_dense_r1d_metrics.txt (ncu --set full); output tile stays in L2'),
                         note='useful fp32-equivalent flops; the kernel issues 3 tf32 MMA passes per product and tf32 runs at half '
                              'the bf16 rate, so 1/6 of this peak is the ceiling of a 3xTF32 scheme')
     else:
@@ -353,7 +375,7 @@ def run_own(args):
                e2e=dict(value=graphs / (ms_e2e * 1e-3), unit='graphs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                         ms_per_step=ms_e2e / args.steps),
                gpu_launches=launches, kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
-               roofline=roofline, cpu_baseline=cpu, sequential=sequential, large_batch=large,
+               roofline=roofline, cpu_baseline=cpu, sequential=sequential, large_batch=large, extraction=extraction,
                shape=dict(graphs=BATCH, nodes=n_nodes, edges=e_out, nnz=nnz, nodes_cap=nodes_cap, edges_cap=edges_cap),
                engine='one CUDA graph per step (encode+collate+fwd+bwd+Adam), programmatic dependent launches; every GEMM on the hand-written '
                       'tcgen05 3xTF32 kernel')

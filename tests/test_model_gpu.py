@@ -167,6 +167,22 @@ def _engine_for(variant, config, count, kw, use_graph, **extra):
     return eng, model, raw
 
 
+def test_engine_ordered_and_atomic_weight_gradients_agree():
+    """atomic_wgrad=False (split-K partial tiles + ordered reduction) and the default (vector reductions into the zeroed
+    gradient buffer) compute the same gradients."""
+    variant, config, count, kw = MU.MODEL_CASES['zinc']
+    torch.backends.cuda.matmul.allow_tf32 = False
+    grads = []
+    for atomic in (False, True):
+        eng, model, raw = _engine_for(variant, config, count, kw, use_graph=False, atomic_wgrad=atomic)
+        eng.opt.hyper[0] = 0.0
+        eng.opt._hyper_host = (0.0, 1.0); eng.opt.param_groups[0]['lr'] = 0.0
+        eng.step(raw)
+        grads.append(eng.opt.grad.clone())
+    scale = grads[0].abs().max().item()
+    assert (grads[0] - grads[1]).abs().max().item() <= 2e-4 * scale
+
+
 @pytest.mark.parametrize('name', ['zinc', 'count_h64'])
 def test_pipelined_engine_matches_sequential_engine(name):
     """pipeline=True (encoder of batch k overlapped with the training of batch k-1, staged batch set copied live at the
