@@ -67,6 +67,7 @@ SIGNATURES = {
     'escgnn_embedding_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     'escgnn_loss_fwd_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     'escgnn_gemm_tf32x3': (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    'escgnn_gemm_tf32x3_bounded': (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
     'escgnn_gemm_set_plan': (_i32, [_i32]),
     'escgnn_gemm_workspace_floats': (_i64, [_i32, _i32, _i32]),
     'escgnn_tf32_split_lo': (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp]),

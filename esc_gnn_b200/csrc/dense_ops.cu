@@ -623,13 +623,18 @@ bn_act_fwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
     cg::cluster_group cluster = cg::this_cluster();
     T t{s_w, s_part, s_tot};
     const int cl = threadIdx.x % LANES, rs = threadIdx.x / LANES, rank = (int)cluster.block_rank();
-    const int c4 = blockIdx.x * T::kCols + 4 * cl, rows = min(*d_rows, rows_cap);
+    const int c4 = blockIdx.x * T::kCols + 4 * cl;
     const bool col_ok = c4 < C;
     const int r_first = rank * T::kSlots + rs;
     float4 v[R];
     float4 a = zero4(), b = zero4();
+    // every row below the CAPACITY is valid memory: issue the tile loads together with the load of the row count instead of
+    // behind it (one L2 round trip less on the critical path), then mask
     #pragma unroll
-    for (int k = 0; k < R; ++k) v[k] = (col_ok && r_first + k * T::kSweep < rows) ? ld4(x + (size_t)(r_first + k * T::kSweep) * ldx + c4) : zero4();
+    for (int k = 0; k < R; ++k) v[k] = (col_ok && r_first + k * T::kSweep < rows_cap) ? ld4(x + (size_t)(r_first + k * T::kSweep) * ldx + c4) : zero4();
+    const int rows = min(*d_rows, rows_cap);
+    #pragma unroll
+    for (int k = 0; k < R; ++k) if (r_first + k * T::kSweep >= rows) v[k] = zero4();
     #pragma unroll
     for (int k = 0; k < R; ++k) {
         a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
@@ -686,7 +691,7 @@ bn_act_bwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
     cg::cluster_group cluster = cg::this_cluster();
     T t{s_w, s_part, s_tot};
     const int cl = threadIdx.x % LANES, rs = threadIdx.x / LANES, rank = (int)cluster.block_rank();
-    const int c4 = blockIdx.x * T::kCols + 4 * cl, rows = min(*d_rows, rows_cap);
+    const int c4 = blockIdx.x * T::kCols + 4 * cl;
     const bool col_ok = c4 < C;
     const int r_first = rank * T::kSlots + rs;
     BnCols k;
@@ -694,15 +699,16 @@ bn_act_bwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
     if (col_ok) k = bn_cols(mean, rstd, gamma, beta, c4);
     float4 dz[R], xh[R];                              // after the loads: dz and xhat of this thread's rows
     #pragma unroll
-    for (int i = 0; i < R; ++i) {
+    for (int i = 0; i < R; ++i) {                     // loads bounded by the capacity, issued alongside the row count (see forward)
         const int r = r_first + i * T::kSweep;
         dz[i] = zero4(); xh[i] = zero4();
-        if (col_ok && r < rows) {
+        if (col_ok && r < rows_cap) {
             xh[i] = ld4(x + (size_t)r * ldx + c4);
             dz[i] = ld4(dy + (size_t)r * lddy + c4);
             if (dy2) { const float4 e = ld4(dy2 + (size_t)r * lddy2 + c4); dz[i].x += e.x; dz[i].y += e.y; dz[i].z += e.z; dz[i].w += e.w; }
         }
     }
+    const int rows = min(*d_rows, rows_cap);
     float4 a = zero4(), b = zero4();
     #pragma unroll
     for (int i = 0; i < R; ++i)

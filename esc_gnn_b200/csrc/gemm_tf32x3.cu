@@ -83,6 +83,8 @@ struct Params {
     float* partial;               // split-K partial tiles [splits][M][N] (nullptr when splits == 1 or atomic)
     int accumulate;
     int atomic;                   // split-K slices add their tile into C with fp32 vector reductions (C holds the initial value)
+    const int* rows_ptr;          // optional device-side row count (static-shape engine): rows_dim 1 = bounds M (tiles past it
+    int rows_dim;                 // leave without touching C), 2 = bounds K (k-blocks past it are skipped)
 };
 
 __device__ __forceinline__ void red_add4(float4* dst, const float4& v) {
@@ -111,8 +113,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
     const int kb_begin = blockIdx.z * p.kb_per_split;
-    const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
-    const int num_kb = max(kb_end - kb_begin, 0);
     constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : 128;
 
     // ---- prologue without global-memory traffic: overlaps the tail of the preceding kernel (launch.cuh)
@@ -132,6 +132,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t tmem_d = tmem_base_slot;
     escgnn::pdl_wait();                              // operands (and the buffers written below) belong to earlier kernels until here
     escgnn::pdl_trigger();
+    const int rows_now = p.rows_ptr ? *p.rows_ptr : 0;
+    const bool skip = p.rows_dim == 1 && m0 >= rows_now;                      // tile past the actual row count: nothing to do
+    const int kb_total = p.rows_dim == 2 ? min(p.kb_total, (rows_now + kBlockK - 1) / kBlockK) : p.kb_total;
+    const int num_kb = skip ? 0 : max(min(kb_begin + p.kb_per_split, kb_total) - kb_begin, 0);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -215,7 +219,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < p.M;
+        const bool row_ok = row < p.M && !skip;
         float* out = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
         #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
@@ -315,8 +319,6 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
     const int kb_begin = blockIdx.z * p.kb_per_split;
-    const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
-    const int num_kb = max(kb_end - kb_begin, 0);
     constexpr uint32_t kTmemCols = 256, kTmemA = 128;
 
     if (threadIdx.x == 0) {
@@ -335,6 +337,10 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tmem_d = tmem_base_slot;
     escgnn::pdl_wait();
     escgnn::pdl_trigger();
+    const int rows_now = p.rows_ptr ? *p.rows_ptr : 0;
+    const bool skip = p.rows_dim == 1 && m0 >= rows_now;
+    const int kb_total = p.rows_dim == 2 ? min(p.kb_total, (rows_now + kBlockK - 1) / kBlockK) : p.kb_total;
+    const int num_kb = skip ? 0 : max(min(kb_begin + p.kb_per_split, kb_total) - kb_begin, 0);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -438,7 +444,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + r;
-        const bool row_ok = row < p.M;
+        const bool row_ok = row < p.M && !skip;
         float* out = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
         #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
@@ -694,6 +700,13 @@ int64_t escgnn_gemm_workspace_floats(int M, int N, int K) {
 int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,
                        const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats,
                        void* stream) {
+    return escgnn_gemm_tf32x3_bounded(d_a, lda, a_mn_major, d_b, ldb, b_mn_major, d_c, ldc, d_bias, M, N, K, accumulate, d_workspace,
+                                      workspace_floats, nullptr, 0, stream);
+}
+
+int escgnn_gemm_tf32x3_bounded(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,
+                               const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats,
+                               const int* d_rows, int rows_dim, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     if ((lda & 3) || (ldb & 3) || ((uintptr_t)d_a & 15) || ((uintptr_t)d_b & 15))
         return ESCGNN_ERR_BAD_ARG;            // TMA needs 16-byte aligned bases and row pitches
@@ -711,6 +724,7 @@ int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d
     p.partial = (splits > 1 && !atomic) ? d_workspace : nullptr;
     p.accumulate = accumulate;
     p.atomic = atomic ? 1 : 0;
+    p.rows_ptr = d_rows; p.rows_dim = d_rows ? rows_dim : 0;
     CUtensorMap a, b;
     int rc = 0;
     if (!a_mn_major) rc |= make_map(&a, d_a, K, M, lda, kBlockK, kBlockM);          // [M, K] row-major: inner = K

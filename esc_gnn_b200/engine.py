@@ -155,6 +155,7 @@ class StaticTrainEngine(object):
         # weight gradients land in the flat gradient buffer, which every step zeroes first: their split-K slices can be added
         # in place with vector reductions (2) instead of going through partial tiles and a reduction launch (0)
         self.wgrad_mode = 2 if atomic_wgrad else 0
+        self.bounded_gemm = True
         self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
         # weight / bias gradients are off the critical path (only Adam consumes them): they run on a side stream that
         # forks from the backward chain wherever a dY becomes available and joins before the optimiser
@@ -171,14 +172,18 @@ class StaticTrainEngine(object):
 
     # ------------------------------------------------------------------ primitive ops (append to the tapes)
     # ---- dense contractions: tcgen05 3xTF32 GEMM (csrc/gemm_tf32x3.cu); CUDA-core kernel for 10-wide odd shapes
-    def _gemm(self, tag, A, a_mn, B, b_mn, C, bias, M, N, K, accumulate):
+    def _gemm(self, tag, A, a_mn, B, b_mn, C, bias, M, N, K, accumulate, rows=None):
+        """rows: the capacity dimension of this product (M for forward / dgrad, K for wgrad) as a row kind 'N' / 'E' / 'B':
+        the kernel then follows the batch's actual row count (read on the device) instead of the capacity."""
         c = self.c
         ok = all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (A, B)) and self.tensor_cores
         if ok:
             # split-K partials: one workspace per stream (GEMMs of the two graph branches may run concurrently)
             ws = self.gemm_ws_side if torch.cuda.current_stream(c.dev) == self.side else self.gemm_ws
-            _lib.check(c.L.escgnn_gemm_tf32x3(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
-                                              _p(bias), M, N, K, int(accumulate), _p(ws), ws.numel(), c.st()), tag)
+            d_rows = _p(c.rows[rows]) if (rows is not None and self.bounded_gemm) else None
+            _lib.check(c.L.escgnn_gemm_tf32x3_bounded(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C),
+                                                      C.stride(0), _p(bias), M, N, K, int(accumulate), _p(ws), ws.numel(), d_rows,
+                                                      2 if tag == 'gemm_wgrad' else 1, c.st()), tag)
         else:
             _lib.check(c.L.escgnn_gemm_simple(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
                                               _p(bias), M, N, K, int(accumulate), c.st()), tag + '_simple')
@@ -224,7 +229,7 @@ class StaticTrainEngine(object):
         y = out if out is not None else c.buf(kind, n_out)
         dy = c.buf(kind, n_out)
         # forward: Y[rows, n_out] = X[rows, k_in] W[n_out, k_in]^T + b          (A, B K-major)
-        fwd_gemm = lambda: self._gemm('gemm_fwd', x, False, W, False, y, bvec, rows, n_out, k_in, False)
+        fwd_gemm = lambda: self._gemm('gemm_fwd', x, False, W, False, y, bvec, rows, n_out, k_in, False, rows=kind)
         fwd_event = [None]
         if branch:
             self.fwd.append(lambda: fwd_event.__setitem__(0, self._fork(fwd_gemm)))
@@ -233,14 +238,14 @@ class StaticTrainEngine(object):
 
         def grads():
             # wgrad: dW[n_out, k_in] = dY^T X   (A = dY stored [rows, n_out] = MN-major, B = X stored [rows, k_in] = MN-major)
-            self._gemm('gemm_wgrad', dy, True, x, True, W.grad, None, n_out, k_in, rows, self.wgrad_mode)
+            self._gemm('gemm_wgrad', dy, True, x, True, W.grad, None, n_out, k_in, rows, self.wgrad_mode, rows=kind)
             if not feeds_bn:
                 _lib.check(c.L.escgnn_colsum(_p(dy), dy.stride(0), _p(c.rows[kind]), c.caps[kind], dy.size(1),
                                              _p(self.side_partial), _p(bvec.grad), c.st()), 'colsum')
 
         def dgrad():
             # dgrad: dX[rows, k_in] = dY W      (A = dY K-major, B = W stored [n_out, k_in] = MN-major for this product)
-            self._gemm('gemm_dgrad', dy, False, W, True, dx, None, rows, k_in, n_out, dx_accumulate)
+            self._gemm('gemm_dgrad', dy, False, W, True, dx, None, rows, k_in, n_out, dx_accumulate, rows=kind)
 
         def back():
             if branch:
@@ -394,13 +399,13 @@ class StaticTrainEngine(object):
         self.fwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_zero_tail_rows(
             _p(dee_all), dee_all.stride(0), n_tot, _p(c.rows['E']), E_rows, c.st()), 'zero_tail_rows')))
         self.fwd.append(lambda: ee_ready.__setitem__(0, self._fork(
-            lambda: self._gemm('gemm_fwd', zcat, False, W_cat, False, ee_all, b_cat, E_rows, n_tot, edge_dim, False))))
+            lambda: self._gemm('gemm_fwd', zcat, False, W_cat, False, ee_all, b_cat, E_rows, n_tot, edge_dim, False, rows='E'))))
 
         def proj_back():                          # runs after every layer's backward has filled its slice of dee_all
-            self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, self.wgrad_mode),
+            self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, self.wgrad_mode, rows='E'),
                                 _lib.check(c.L.escgnn_colsum(_p(dee_all), dee_all.stride(0), _p(c.rows['E']), E_rows, n_tot,
                                                              _p(self.side_partial), _p(db_cat), c.st()), 'colsum')))
-            self._gemm('gemm_dgrad', dee_all, False, W_cat, True, dzcat, None, E_rows, edge_dim, n_tot, False)
+            self._gemm('gemm_dgrad', dee_all, False, W_cat, True, dzcat, None, E_rows, edge_dim, n_tot, False, rows='E')
         self.bwd.append(proj_back)
         layer_dx_from_next = [None] * Lh          # gradient flowing into layer l's output from layer l+1's aggregation
         for l, conv in enumerate(convs):

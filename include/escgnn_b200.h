@@ -285,6 +285,13 @@ int escgnn_loss_fwd_bwd(const float* d_pred, int ldp, const float* d_target, int
 int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,
                        const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace, int64_t workspace_floats,
                        void* stream);
+/* Same product for the static-shape engine, where M (forward / dgrad) or K (wgrad) is a row CAPACITY and the actual row
+ * count lives in device memory: rows_dim = 1 -> output tiles that start at or past *d_rows leave without touching C (their
+ * rows of C keep their previous contents); rows_dim = 2 -> k-blocks past *d_rows are skipped. Keeps the launch shape static
+ * (CUDA-graph capturable) while the work follows the batch; d_rows = NULL: identical to escgnn_gemm_tf32x3. */
+int escgnn_gemm_tf32x3_bounded(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c,
+                               int ldc, const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace,
+                               int64_t workspace_floats, const int* d_rows, int rows_dim, void* stream);
 int64_t escgnn_gemm_workspace_floats(int M, int N, int K);
 /* shared-memory plan of the GEMM: -1 auto, 0 = 2 stages (2 CTAs/SM), 1 = 4 stages (1 CTA/SM); +2 = the variant that keeps
  * both planes of A in shared memory instead of tensor memory (experiments / tests) */

@@ -121,3 +121,35 @@ def test_gemm_atomic_split_k_accumulates_in_place(M, N, K, a_mn, b_mn):
     ref = A.double() @ B.double().t() + bias.double() + C0.double()
     scale = (A.double().abs() @ B.double().abs().t()).max().item()
     assert (C.double() - ref).abs().max().item() <= 4e-6 * scale
+
+
+def test_gemm_bounded_follows_device_row_count():
+    """escgnn_gemm_tf32x3_bounded: with a device-side row count, output tiles past it are left untouched (rows_dim 1) and
+    k-blocks past it are skipped (rows_dim 2); everything before the bound equals the unbounded product."""
+    from esc_gnn_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device='cuda').manual_seed(7)
+    M, N, K, rows = 1000, 288, 256, 530
+    A = torch.randn(M, K, device='cuda', generator=g); B = torch.randn(N, K, device='cuda', generator=g)
+    d_rows = torch.tensor([rows], dtype=torch.int32, device='cuda')
+    C = torch.full((M, N), 5.0, device='cuda')
+    _lib.check(L.escgnn_gemm_tf32x3_bounded(_p(A), K, 0, _p(B), K, 0, _p(C), N, None, M, N, K, 0, None, 0, _p(d_rows), 1, _st()), 'gemm_tf32x3')
+    ref = (A.double() @ B.double().t())
+    scale = (A.double().abs() @ B.double().abs().t()).max().item()
+    assert (C[:rows].double() - ref[:rows]).abs().max().item() <= 4e-6 * scale
+    first_skipped = (rows + 127) // 128 * 128
+    assert float(C[first_skipped:].min()) == 5.0 and float(C[first_skipped:].max()) == 5.0      # tiles past the bound: untouched
+    # rows_dim 2: wgrad shape, K = row capacity, rows beyond the count hold garbage that must not contribute
+    R, cap, n_out, n_in = 700, 1024, 256, 288
+    dY = torch.randn(cap, n_out, device='cuda', generator=g); X = torch.randn(cap, n_in, device='cuda', generator=g)
+    d_rows2 = torch.tensor([R], dtype=torch.int32, device='cuda')
+    dY[((R + 31) // 32) * 32:] = float('nan')                # whole k-blocks past the bound may hold anything
+    dY[R:((R + 31) // 32) * 32] = 0.0                        # inside the last k-block the engine keeps tail rows zero
+    for mode in (0, 2):
+        dW = torch.zeros(n_out, n_in, device='cuda')
+        ws = torch.empty(max(L.escgnn_gemm_workspace_floats(n_out, n_in, cap), 1), device='cuda')
+        _lib.check(L.escgnn_gemm_tf32x3_bounded(_p(dY), n_out, 1, _p(X), n_in, 1, _p(dW), n_in, None, n_out, n_in, cap, mode, _p(ws),
+                                                ws.numel(), _p(d_rows2), 2, _st()), 'gemm_tf32x3')
+        ref2 = dY[:R].double().t() @ X[:R].double()
+        sc2 = (dY[:R].double().abs().t() @ X[:R].double().abs()).max().item()
+        assert torch.isfinite(dW).all() and (dW.double() - ref2).abs().max().item() <= 4e-6 * sc2, mode

@@ -30,3 +30,23 @@ for rows, tag in ((E, 'E'), (Nn, 'N')):
         run('fwd   %s x %d -> %d' % (tag, cin, cout), X, 0, W, 0, rows, cout, cin)
         run('dgrad %s x %d -> %d' % (tag, cout, cin), dY, 0, W, 1, rows, cin, cout)
         run('wgrad %s rows, %d x %d' % (tag, cout, cin), dY, 1, X, 1, cout, cin, rows)
+# grouped edge-projection shapes of the engine (all layers' conv.lin in one product)
+Z = torch.randn(E, 288, device='cuda'); Wc = torch.randn(800, 288, device='cuda'); dEE = torch.randn(E, 800, device='cuda')
+run('grouped fwd   E x 288 -> 800', Z, 0, Wc, 0, E, 800, 288)
+run('grouped dgrad E x 800 -> 288', dEE, 0, Wc, 1, E, 288, 800)
+run('grouped wgrad E rows, 800 x 288', dEE, 1, Z, 1, 800, 288, E)
+def run_atomic(name, A, B, M, N, K, reps=30):
+    C = torch.zeros(M, N, device='cuda')
+    f = lambda: _lib.check(L.escgnn_gemm_tf32x3(P(A), A.stride(0), 1, P(B), B.stride(0), 1, P(C), N, None, M, N, K, 2, None, 0, st()), 'g')
+    for _ in range(3): f()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps): f()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 1e3 / reps
+    print('%-34s M=%6d N=%4d K=%6d  %7.1f us  %6.1f useful TFLOP/s  (atomic split-K)' % (name, M, N, K, us, 2.0 * M * N * K / us / 1e6))
+run_atomic('grouped wgrad E rows, 800 x 288', dEE, Z, 800, 288, E)
+dYn = torch.randn(Nn, 256, device='cuda'); Xn = torch.randn(Nn, 256, device='cuda')
+run_atomic('wgrad N rows, 256 x 256', dYn, Xn, 256, 256, Nn)
