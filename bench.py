@@ -171,7 +171,7 @@ def run_own(args):
     edges_cap = int(max(b.src.numel() for b in host_pool) * 1.04) + 128
     eng = StaticTrainEngine(model, 'zinc', fl, max_graphs=BATCH, max_nodes_per_graph=40, max_edges_per_graph=96,
                             nodes_cap=nodes_cap, edges_cap=edges_cap, lr=LR, distributed=world > 1, use_graph=True,
-                            pipeline=bool(args.pipeline))
+                            pipeline=bool(args.pipeline), encoder_ctas=args.encoder_ctas)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')     # > 126 MB L2
 
     def read(loss):                                         # pipelined engines return the previous batch's loss (None at first)
@@ -369,8 +369,8 @@ def run_own(args):
                vs_baseline=None, dtype='int64+f64 (encode), f32 (model)', data='synthetic',
                config=dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism='dp%d' % world,
                            l2='flushed between timed iterations (256 MB write)', lr=LR,
-                           pipeline=('encoder of batch k overlaps training of batch k-1 (one encode + one train step per step)'
-                                     if args.pipeline else 'off')),
+                           pipeline=('encoder of batch k overlaps training of batch k-1 (one encode + one train step per step); '
+                                     'encoder grids capped at %d CTAs' % args.encoder_ctas if args.pipeline else 'off')),
                clocks=clk,
                e2e=dict(value=graphs / (ms_e2e * 1e-3), unit='graphs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                         ms_per_step=ms_e2e / args.steps),
@@ -394,6 +394,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-large', action='store_true', help='skip the 8192-graph section')
+    ap.add_argument('--encoder-ctas', type=int, default=74, help='pipelined engine: cap of the encoder grids (0 = fill the machine)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

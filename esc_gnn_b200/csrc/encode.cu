@@ -322,6 +322,7 @@ static int launch_encode_t(const int64_t* eo_src, const int64_t* eo_dst, const i
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)sms * occ;
     if (grid > n_graphs) grid = n_graphs;
+    if (encoder_grid_cap() > 0 && grid > encoder_grid_cap()) grid = encoder_grid_cap();
     if (grid < 1) grid = 1;
     int64_t slab = 0;
     if (need > graph_bytes) {
@@ -364,6 +365,12 @@ int escgnn_encode_subset(const int64_t* d_eo_src, const int64_t* d_eo_dst, const
                          int64_t scratch_bytes, void* stream);
 
 int escgnn_version(void) { return 100; }
+
+int escgnn_set_encoder_grid_cap(int ctas) {
+    const int was = encoder_grid_cap();
+    encoder_grid_cap() = ctas > 0 ? ctas : 0;
+    return was;
+}
 
 int64_t escgnn_encode_scratch_bytes(int64_t max_nodes, int64_t max_edges, int h) {
     (void)h;

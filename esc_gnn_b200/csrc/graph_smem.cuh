@@ -58,6 +58,13 @@ __device__ __forceinline__ uint32_t nibbles_equal(uint32_t word, uint32_t v) {
 // bit 4k set where nibble k != 15 (node within h hops)
 __device__ __forceinline__ uint32_t nibbles_near(uint32_t word) { return ~nibbles_equal(word, kFar) & 0x11111111u; }
 
+// upper bound on the persistent encoder grids (0 = fill the machine): a pipelined training step confines the encoder of
+// the NEXT batch to a few SMs so that it does not evict the latency-critical kernels of the current one
+inline int& encoder_grid_cap() {
+    static int cap = 0;
+    return cap;
+}
+
 constexpr int kWideNodes = 64;      // graphs above this size scan 8 nodes per lane (one distance word) instead of 1
 
 // Build both CSRs and run the N bounded BFS.  All threads of the CTA call this; `base` points at the graph's

@@ -388,6 +388,7 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)sms * occ;
     if (grid > n_graphs) grid = n_graphs;
+    if (encoder_grid_cap() > 0 && grid > encoder_grid_cap()) grid = encoder_grid_cap();
     if (p.slab) {
         if (scratch == nullptr || scratch_bytes < p.slab) return ESCGNN_ERR_BAD_ARG;
         const int64_t fit = scratch_bytes / p.slab;

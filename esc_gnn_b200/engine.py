@@ -91,7 +91,7 @@ class StaticTrainEngine(object):
     """One NestedGIN_eff variant ('zinc' or 'count') at a fixed capacity."""
 
     def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
-                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True):
+                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True, encoder_ctas=None):
         if variant not in ('zinc', 'count'):
             raise NotImplementedError('engine variants: zinc, count (the OGB model runs through the module path)')
         p0 = next(model.parameters())
@@ -156,6 +156,7 @@ class StaticTrainEngine(object):
         # in place with vector reductions (2) instead of going through partial tiles and a reduction launch (0)
         self.wgrad_mode = 2 if atomic_wgrad else 0
         self.bounded_gemm = True
+        self.encoder_ctas = int(encoder_ctas) if encoder_ctas else None
         self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
         # weight / bias gradients are off the critical path (only Adam consumes them): they run on a side stream that
         # forks from the backward chain wherever a dY becomes available and joins before the optimiser
@@ -539,7 +540,12 @@ class StaticTrainEngine(object):
             with torch.cuda.stream(self.enc_stream):
                 self.enc_stream.wait_event(moved)
                 self._forward_features(self.stage)
+                # the next batch's encoder has a whole step of slack: confined to a few SMs it stops competing with the
+                # latency-critical chain of the current batch for registers and shared memory
+                prev = self.c.L.escgnn_set_encoder_grid_cap(self.encoder_ctas) if self.encoder_ctas else None
                 self._encode_and_index(self.stage)
+                if prev is not None:
+                    self.c.L.escgnn_set_encoder_grid_cap(prev)
                 enc_done = torch.cuda.Event()
                 enc_done.record(self.enc_stream)
             self._run_train()

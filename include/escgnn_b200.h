@@ -234,6 +234,10 @@ int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t
 /* Programmatic dependent launch for the model-side kernels (csrc/launch.cuh): on by default; 0 launches them with plain
  * stream ordering (same results, used for A/B timing). Returns the previous setting. */
 int escgnn_set_pdl(int on);
+/* Cap the persistent encoder grids (ego_encode / ego_rd) at `ctas` CTAs (0 = fill the machine, the default): used by the
+ * pipelined training step, where the encoder of the next batch has a whole step of slack and should leave most SMs to the
+ * latency-critical kernels of the current batch. Returns the previous cap. */
+int escgnn_set_encoder_grid_cap(int ctas);
 /* One-launch cluster BatchNorm kernels (rows_cap <= 65536, training mode): on by default; 0 = statistics + apply kernel pair
  * (same results up to summation order). Returns the previous setting. */
 int escgnn_set_cluster_bn(int on);

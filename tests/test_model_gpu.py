@@ -192,7 +192,7 @@ def test_pipelined_engine_matches_sequential_engine(name):
     variant, config, count, kw = MU.MODEL_CASES[name]
     torch.backends.cuda.matmul.allow_tf32 = False
     seq, _, raw0 = _engine_for(variant, config, count, kw, True)
-    pip, _, _ = _engine_for(variant, config, count, kw, True, pipeline=True)
+    pip, _, _ = _engine_for(variant, config, count, kw, True, pipeline=True, encoder_ctas=8)      # encoder confined to 8 CTAs
     raws = [raw0] + [RawBatch.synth(config, 100 + 7 * i, count) for i in (1, 2)]
     raws = [r for r in raws if r.num_nodes <= seq.c.caps['N'] and r.src.numel() <= seq.c.caps['E_in']]
     assert len(raws) >= 2
