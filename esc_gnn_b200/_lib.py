@@ -69,6 +69,7 @@ SIGNATURES = {
     'escgnn_loss_fwd_bwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     'escgnn_gemm_tf32x3': (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     'escgnn_gemm_tf32x3_bounded': (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
+    'escgnn_gemm_set_split_target': (_i32, [_i32]),
     'escgnn_gemm_set_plan': (_i32, [_i32]),
     'escgnn_gemm_workspace_floats': (_i64, [_i32, _i32, _i32]),
     'escgnn_tf32_split_lo': (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp]),
@@ -93,6 +94,8 @@ def lib():
             fn = getattr(L, name)          # AttributeError = header and library disagree: fail loudly
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get('ESCGNN_SPLIT_TARGET'):
+            L.escgnn_gemm_set_split_target(int(os.environ['ESCGNN_SPLIT_TARGET']))
         if os.environ.get('ESCGNN_CLUSTER_BN', '1') == '0':
             L.escgnn_set_cluster_bn(0)
         if os.environ.get('ESCGNN_PDL', '1') == '0':      # A/B switch: plain stream-ordered launches

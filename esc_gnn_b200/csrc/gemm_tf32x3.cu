@@ -657,9 +657,11 @@ int pick_block_n(int N) {
     return bn > 128 ? 128 : bn;
 }
 
+int g_split_target = 296;   // CTAs a split-K product aims for (escgnn_gemm_set_split_target)
+
 int pick_splits(int tiles, int kb_total, int M, int N, int64_t workspace_floats) {
     if (tiles >= 96 || kb_total < 16) return 1;
-    int splits = 296 / tiles;
+    int splits = g_split_target / tiles;
     if (splits > kb_total / 4) splits = kb_total / 4;
     if ((int64_t)splits * M * N > workspace_floats) splits = (int)(workspace_floats / ((int64_t)M * N));
     return splits < 1 ? 1 : splits;
@@ -684,6 +686,12 @@ int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
     escgnn::launch_pdl(gemm_simple_kernel, grid, 256, 0, (cudaStream_t)stream, d_a, lda, a_mn_major, d_b, ldb, b_mn_major, d_c, ldc, d_bias, M, N, K, accumulate);
     return (int)cudaGetLastError();
+}
+
+int escgnn_gemm_set_split_target(int ctas) {
+    const int was = g_split_target;
+    if (ctas > 0) g_split_target = ctas;
+    return was;
 }
 
 int escgnn_gemm_set_plan(int plan) { g_gemm_plan = plan; return 0; }

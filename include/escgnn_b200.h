@@ -300,6 +300,9 @@ int64_t escgnn_gemm_workspace_floats(int M, int N, int K);
 /* shared-memory plan of the GEMM: -1 auto, 0 = 2 stages (2 CTAs/SM), 1 = 4 stages (1 CTA/SM); +2 = the variant that keeps
  * both planes of A in shared memory instead of tensor memory (experiments / tests) */
 int escgnn_gemm_set_plan(int plan);
+/* number of CTAs a split-K product (weight gradients) spreads over; default 296 = two per SM. Fewer, longer slices leave
+ * room for kernels running concurrently on other streams. Returns the previous value. */
+int escgnn_gemm_set_split_target(int ctas);
 /* x - tf32_trunc(x): the low plane of the 3xTF32 split (diagnostics; the GEMM computes it on chip) */
 int escgnn_tf32_split_lo(const float* d_x, int ldx, float* d_lo, int ldlo, int64_t rows, int cols, void* stream);
 /* CUDA-core GEMM with the same contract (any strides): odd shapes (K or N = 10, 1) and the test reference */

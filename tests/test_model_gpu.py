@@ -167,6 +167,33 @@ def _engine_for(variant, config, count, kw, use_graph, **extra):
     return eng, model, raw
 
 
+@pytest.mark.parametrize('name', ['zinc', 'count_h64'])
+def test_engine_small_batch_after_large_batch_has_no_stale_rows(name):
+    """Capacity rows past the batch's row count must stay inert: a small batch run right after a large one (whose rows filled
+    the buffers further) gives the same loss and gradients as the same small batch on a fresh engine (lr = 0)."""
+    from esc_gnn_b200.pipeline import RawBatch
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    raw0 = RawBatch.synth(config, 100, count)                       # _engine_for sizes the capacities from this batch
+    raws = [RawBatch.synth(config, 500 + 31 * i, count) for i in range(10)]
+    raws = [r for r in raws if r.num_nodes <= raw0.num_nodes + 300 and r.src.numel() <= raw0.src.numel() + 700]
+    big, small = max(raws, key=lambda r: r.num_nodes), min(raws, key=lambda r: r.num_nodes)
+    assert big.num_nodes >= small.num_nodes + 16 and big.src.numel() > small.src.numel()
+    out = []
+    for history in ([big, big, small], [small]):
+        eng, _, raw0 = _engine_for(variant, config, count, kw, use_graph=False)
+        assert big.num_nodes <= eng.c.caps['N'] and big.src.numel() <= eng.c.caps['E_in']
+        eng.opt.hyper[0] = 0.0
+        eng.opt._hyper_host = (0.0, 1.0); eng.opt.param_groups[0]['lr'] = 0.0
+        for r in history:
+            loss = float(eng.step(r).item())
+        eng.check_errors()
+        out.append((loss, eng.opt.grad.clone()))
+    (la, ga), (lb, gb) = out
+    assert abs(la - lb) <= 1e-6 * max(1.0, abs(lb))
+    assert (ga - gb).abs().max().item() <= 2e-5 * gb.abs().max().item()
+
+
 def test_engine_ordered_and_atomic_weight_gradients_agree():
     """atomic_wgrad=False (split-K partial tiles + ordered reduction) and the default (vector reductions into the zeroed
     gradient buffer) compute the same gradients."""
