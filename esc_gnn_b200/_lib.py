@@ -55,6 +55,7 @@ SIGNATURES = {
     'escgnn_collate_edges': (_i32, [_vp] * 4 + [_i64, _vp, _vp, _vp, _vp]),
     'escgnn_ptr_to_ids': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
     'escgnn_dense_tile_rows': (_i32, []),
+    'escgnn_head_bn_linear_l1': (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     'escgnn_set_pdl': (_i32, [_i32]),
     'escgnn_set_encoder_grid_cap': (_i32, [_i32]),
     'escgnn_set_cluster_bn': (_i32, [_i32]),

@@ -881,6 +881,134 @@ loss_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ t
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Graph-level readout tail in ONE launch (zinc_models.py:604-609 and the loss / its backward, run_zinc.py:276-281):
+//   p2 = act(BN(x));  pred = p2 w2 + b2;  loss = mean |pred - y|;  and straight away the backward of all of it:
+//   d pred, d w2, d b2, d p2, BatchNorm backward -> dx, d gamma, d beta.
+// A few hundred rows x <= 256 columns: five dependent launches (BN, GEMV, loss, GEMV^T, BN backward) of ~6 us each for
+// microseconds of work.  One 8-CTA cluster: a thread owns one column of RPC rows (registers), the two column reductions
+// (statistics; dz sums + d w2) cross the cluster through distributed shared memory, the row dot products stay inside a CTA.
+template <int RPC>
+__global__ void __launch_bounds__(256)
+head_bn_linear_l1_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* running_mean, float* running_var, int act, float eps, float momentum,
+                         const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ target,
+                         const int* __restrict__ d_rows, int rows_cap, int H, float* __restrict__ pred, float* __restrict__ loss,
+                         float* __restrict__ dx, int lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         float* __restrict__ dw2, float* __restrict__ db2) {
+    escgnn::pdl_enter();
+    __shared__ float s_stat[2][256], s_back[3][256], s_row[8][RPC], s_dpred[RPC], s_scal[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5, rank = (int)cluster.block_rank(), r_base = rank * RPC;
+    const bool col_ok = c < H;
+    float xv[RPC];
+    #pragma unroll
+    for (int i = 0; i < RPC; ++i) xv[i] = (col_ok && r_base + i < rows_cap) ? x[(size_t)(r_base + i) * ldx + c] : 0.f;
+    const int rows = min(*d_rows, rows_cap);
+    const float m = (float)max(rows, 1);
+    float s1 = 0.f, s2 = 0.f;
+    #pragma unroll
+    for (int i = 0; i < RPC; ++i) {
+        if (r_base + i >= rows) xv[i] = 0.f;
+        s1 += xv[i]; s2 += xv[i] * xv[i];
+    }
+    s_stat[0][c] = s1; s_stat[1][c] = s2;
+    cluster.sync();
+    float t1 = 0.f, t2 = 0.f;
+    #pragma unroll
+    for (int r = 0; r < kClRanks; ++r) { t1 += *cluster.map_shared_rank(&s_stat[0][c], r); t2 += *cluster.map_shared_rank(&s_stat[1][c], r); }
+    const float mean = t1 / m, var = fmaxf(t2 / m - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+    if (rank == 0 && col_ok && rows > 0) {
+        const float ub = rows > 1 ? m / (m - 1.f) : 1.f;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * ub;
+    }
+    const float g = col_ok ? (gamma ? gamma[c] : 1.f) : 0.f, bt = col_ok ? (beta ? beta[c] : 0.f) : 0.f, w = col_ok ? w2[c] : 0.f;
+    // forward: xv becomes xhat, pv the activation (ONE transcendental per element: act' follows from the activation value);
+    // row dot products pred[r] = sum_c p2[r][c] w2[c]
+    float pv[RPC];
+    #pragma unroll
+    for (int i = 0; i < RPC; ++i) {
+        xv[i] = (xv[i] - mean) * rstd;
+        pv[i] = (col_ok && r_base + i < rows) ? act_fwd(xv[i] * g + bt, act) : 0.f;
+    }
+    #pragma unroll
+    for (int i = 0; i < RPC; ++i) {
+        float v = pv[i] * w;
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+        if (lane == 0) s_row[warp][i] = v;
+    }
+    __syncthreads();
+    if (c < RPC) {
+        const int r = r_base + c;
+        float p = b2[0];
+        #pragma unroll
+        for (int wv = 0; wv < 8; ++wv) p += s_row[wv][c];
+        float dp = 0.f, l = 0.f;
+        if (r < rows) {
+            const float diff = p - target[r];
+            l = fabsf(diff);
+            dp = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) / m;
+        }
+        if (r < rows_cap) pred[r] = r < rows ? p : 0.f;
+        s_dpred[c] = dp;
+        s_row[0][c] = l;                                        // this thread's own slot: reused for the loss terms
+    }
+    __syncthreads();
+    if (c == 0) {
+        float ls = 0.f, ds = 0.f;
+        for (int i = 0; i < RPC; ++i) { ls += s_row[0][i]; ds += s_dpred[i]; }
+        s_scal[0] = ls; s_scal[1] = ds;
+    }
+    // backward: dz = d p2 * act'(z), d p2 = d pred (x) w2
+    // act'(z) from the activation value: ReLU / ELU are positive exactly where z is, and elu'(z) = elu(z) + 1 for z <= 0
+    auto slope = [act](float pval) { return act == 0 ? 1.f : (pval > 0.f ? 1.f : (act == 2 ? pval + 1.f : 0.f)); };
+    float a = 0.f, b = 0.f, dw = 0.f;
+    #pragma unroll
+    for (int i = 0; i < RPC; ++i) {
+        if (col_ok && r_base + i < rows) {
+            const float dp = s_dpred[i];
+            dw += dp * pv[i];
+            const float dz = dp * w * slope(pv[i]);
+            a += dz; b += dz * xv[i];
+        }
+    }
+    s_back[0][c] = a; s_back[1][c] = b; s_back[2][c] = dw;
+    cluster.sync();
+    float A = 0.f, B = 0.f, DW = 0.f;
+    #pragma unroll
+    for (int r = 0; r < kClRanks; ++r) {
+        A += *cluster.map_shared_rank(&s_back[0][c], r); B += *cluster.map_shared_rank(&s_back[1][c], r);
+        DW += *cluster.map_shared_rank(&s_back[2][c], r);
+    }
+    if (rank == 0) {
+        if (col_ok) { if (dgamma) dgamma[c] = B; if (dbeta) dbeta[c] = A; dw2[c] = DW; }
+        if (c == 0) {
+            float ls = 0.f, ds = 0.f;
+            for (int r = 0; r < kClRanks; ++r) { ls += *cluster.map_shared_rank(&s_scal[0], r); ds += *cluster.map_shared_rank(&s_scal[1], r); }
+            loss[0] = ls / m; db2[0] = ds;
+        }
+    }
+    cluster.barrier_arrive();
+    if (col_ok) {
+        const float k = g * rstd, m1 = A / m, m2 = B / m;
+        #pragma unroll
+        for (int i = 0; i < RPC; ++i) {
+            const int r = r_base + i;
+            if (r < rows_cap) {
+                float o = 0.f;
+                if (r < rows) {
+                    const float dz = s_dpred[i] * w * slope(pv[i]);
+                    o = k * (dz - m1 - xv[i] * m2);
+                }
+                dx[(size_t)r * lddx + c] = o;
+            }
+        }
+    }
+    cluster.barrier_wait();
+}
+
 inline dim3 tile_grid(int rows_cap, int C) { return dim3((unsigned)((C + kCols - 1) / kCols), (unsigned)((rows_cap + kTileRows - 1) / kTileRows)); }
 
 }  // namespace
@@ -888,6 +1016,23 @@ inline dim3 tile_grid(int rows_cap, int C) { return dim3((unsigned)((C + kCols -
 extern "C" {
 
 int escgnn_dense_tile_rows(void) { return kTileRows; }
+
+int escgnn_head_bn_linear_l1(const float* d_x, int ldx, const float* d_gamma, const float* d_beta, float* d_running_mean,
+                             float* d_running_var, int act, float eps, float momentum, const float* d_w2, const float* d_b2,
+                             const float* d_target, const int* d_rows, int rows_cap, int channels, float* d_pred, float* d_loss,
+                             float* d_dx, int lddx, float* d_dgamma, float* d_dbeta, float* d_dw2, float* d_db2, void* stream) {
+    if (channels > 256 || rows_cap > kClRanks * 64 || rows_cap < 1) return ESCGNN_ERR_TOO_LARGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows_cap <= kClRanks * 32)
+        escgnn::launch_pdl_cluster(head_bn_linear_l1_kernel<32>, dim3(1, kClRanks), 256, 0, st, kClRanks, d_x, ldx, d_gamma, d_beta,
+                                   d_running_mean, d_running_var, act, eps, momentum, d_w2, d_b2, d_target, d_rows, rows_cap, channels,
+                                   d_pred, d_loss, d_dx, lddx, d_dgamma, d_dbeta, d_dw2, d_db2);
+    else
+        escgnn::launch_pdl_cluster(head_bn_linear_l1_kernel<64>, dim3(1, kClRanks), 256, 0, st, kClRanks, d_x, ldx, d_gamma, d_beta,
+                                   d_running_mean, d_running_var, act, eps, momentum, d_w2, d_b2, d_target, d_rows, rows_cap, channels,
+                                   d_pred, d_loss, d_dx, lddx, d_dgamma, d_dbeta, d_dw2, d_db2);
+    return (int)cudaGetLastError();
+}
 
 int escgnn_set_cluster_bn(int on) {
     const int was = cluster_bn_enabled();

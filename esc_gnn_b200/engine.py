@@ -91,7 +91,7 @@ class StaticTrainEngine(object):
     """One NestedGIN_eff variant ('zinc' or 'count') at a fixed capacity."""
 
     def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
-                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True, encoder_ctas=None):
+                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True, encoder_ctas=None, fused_head=True):
         if variant not in ('zinc', 'count'):
             raise NotImplementedError('engine variants: zinc, count (the OGB model runs through the module path)')
         p0 = next(model.parameters())
@@ -156,6 +156,7 @@ class StaticTrainEngine(object):
         # in place with vector reductions (2) instead of going through partial tiles and a reduction launch (0)
         self.wgrad_mode = 2 if atomic_wgrad else 0
         self.bounded_gemm = True
+        self.fused_head = fused_head
         self.encoder_ctas = int(encoder_ctas) if encoder_ctas else None
         self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
         # weight / bias gradients are off the critical path (only Adam consumes them): they run on a side stream that
@@ -444,6 +445,21 @@ class StaticTrainEngine(object):
             head_in, dhead_in, kind = xs, dxs, 'N'
         head_bn = self.G > 1 or kind == 'N'
         p1, dp1 = self._linear(head_in, m.lin1, kind, dx=dhead_in, feeds_bn=head_bn)
+        if self.fused_head and self.variant == 'zinc' and head_bn and H <= 256 and self.G <= 512:
+            # BatchNorm + activation + lin2 + L1 loss AND their backward in one launch (five dependent launches otherwise);
+            # dp1 is ready when the backward tape starts, so the head registers no backward entries of its own
+            bn, lin2 = m.bn_lin1, m.lin2
+            pred = c.buf(kind, 1)
+            self.pred = pred
+            self._bns.append(bn)
+            self.debug_buffers = dict(head_in=head_in, dhead_in=dhead_in, p1=p1, dp1=dp1, pred=pred, xs=xs, dxs=dxs, zcat=zcat,
+                                      dzcat=dzcat)
+            self.fwd.append(lambda: _lib.check(c.L.escgnn_head_bn_linear_l1(
+                _p(p1), p1.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), ACT[act], bn.eps,
+                bn.momentum, _p(lin2.weight), _p(lin2.bias), _p(self.in_y), _p(c.rows[kind]), c.caps[kind], H, _p(pred),
+                _p(self.loss), _p(dp1), dp1.stride(0), _p(bn.weight.grad), _p(bn.bias.grad), _p(lin2.weight.grad),
+                _p(lin2.bias.grad), c.st()), 'head_bn_linear_l1'))
+            return
         p2, dp2 = c.buf(kind, H), c.buf(kind, H)
         self._bn_act(p1, dp1, m.bn_lin1, act, kind, p2, dp2, use_bn=head_bn)
         pred, dpred = self._linear(p2, m.lin2, kind, dx=dp2)

@@ -259,6 +259,14 @@ int escgnn_bn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, co
                       const float* d_mean, const float* d_rstd, const float* d_gamma, const float* d_beta, int act,
                       int training, float* d_partial, const int* d_rows, int rows_cap, int channels, float* d_dgamma,
                       float* d_dbeta, float* d_dx, int lddx, void* stream);
+/* Graph-level readout tail of the ZINC model in one launch (zinc_models.py:604-609 + L1 loss, run_zinc.py:276-281), forward
+ * AND backward: p2 = act(BN(x)), pred = p2 w2 + b2, loss = mean |pred - target|, then d_dx (gradient wrt x), d_dgamma,
+ * d_dbeta, d_dw2 [channels], d_db2 [1]. channels <= 256, rows_cap <= 512 (ESCGNN_ERR_TOO_LARGE otherwise: use the separate
+ * entry points). Training-mode statistics; running statistics updated like torch. */
+int escgnn_head_bn_linear_l1(const float* d_x, int ldx, const float* d_gamma, const float* d_beta, float* d_running_mean,
+                             float* d_running_var, int act, float eps, float momentum, const float* d_w2, const float* d_b2,
+                             const float* d_target, const int* d_rows, int rows_cap, int channels, float* d_pred, float* d_loss,
+                             float* d_dx, int lddx, float* d_dgamma, float* d_dbeta, float* d_dw2, float* d_db2, void* stream);
 int escgnn_act_fwd(const float* d_x, int ldx, int act, const int* d_rows, int rows_cap, int channels, float* d_y, int ldy,
                    void* stream);
 int escgnn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, int act, const int* d_rows, int rows_cap,

@@ -199,15 +199,17 @@ def test_engine_ordered_and_atomic_weight_gradients_agree():
     gradient buffer) compute the same gradients."""
     variant, config, count, kw = MU.MODEL_CASES['zinc']
     torch.backends.cuda.matmul.allow_tf32 = False
-    grads = []
-    for atomic in (False, True):
-        eng, model, raw = _engine_for(variant, config, count, kw, use_graph=False, atomic_wgrad=atomic)
+    grads, losses = [], []
+    for atomic, fused in ((False, False), (True, False), (True, True)):      # last: the one-launch readout tail as well
+        eng, model, raw = _engine_for(variant, config, count, kw, use_graph=False, atomic_wgrad=atomic, fused_head=fused)
         eng.opt.hyper[0] = 0.0
         eng.opt._hyper_host = (0.0, 1.0); eng.opt.param_groups[0]['lr'] = 0.0
-        eng.step(raw)
+        losses.append(float(eng.step(raw).item()))
         grads.append(eng.opt.grad.clone())
     scale = grads[0].abs().max().item()
-    assert (grads[0] - grads[1]).abs().max().item() <= 2e-4 * scale
+    for g, l in zip(grads[1:], losses[1:]):
+        assert (grads[0] - g).abs().max().item() <= 2e-4 * scale
+        assert abs(l - losses[0]) <= 1e-6 * max(1.0, abs(losses[0]))
 
 
 @pytest.mark.parametrize('name', ['zinc', 'count_h64'])
