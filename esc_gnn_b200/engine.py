@@ -166,7 +166,7 @@ class StaticTrainEngine(object):
         self.side_partial = torch.zeros_like(c.partial)
         self._side_used = False
         self.inline_branches = False
-        self.fwd, self.bwd, self._bns = [], [], []
+        self.fwd, self.bwd, self._bns, self._emb_ready = [], [], [], []
         self._build_model_tape()
         self._bn_synced = 0
         self.graph = None
@@ -292,7 +292,12 @@ class StaticTrainEngine(object):
         cols = 1 if idx.dim() == 1 else idx.size(1)
         run = lambda: _lib.check(c.L.escgnn_embedding_fwd(_p(table.weight), _p(idx), cols, None, _p(c.rows[kind]),
                                                           c.caps[kind], C, _p(out), out.stride(0), c.st()), 'embedding_fwd')
-        self.fwd.append((lambda: self._fork(run)) if side else run)
+        if side:
+            ready = [None]
+            self._emb_ready.append(ready)             # the first consumer on the main branch waits for these
+            self.fwd.append(lambda: ready.__setitem__(0, self._fork(run)))
+        else:
+            self.fwd.append(run)
         return C
 
     def _embedding_bwd(self, table, idx, kind, dout):
@@ -339,6 +344,9 @@ class StaticTrainEngine(object):
         else:
             x0, dx0, edge_dim = self.in_x, c.buf('N', 10), H
         # M1 bag-embed + M2 z_embedding
+        zcat, dzcat = c.buf('E', edge_dim), c.buf('E', edge_dim)
+        if self.variant == 'zinc':                  # lookups first: their side-branch forks queue ahead of the record transposition
+            self._embedding(m.edge_type_embedding, self.in_ea, 'E', zcat[:, H:], side=True)
         z0, dz0 = c.buf('E', H), c.buf('E', H)
         W0 = m.z_initial.weight
         self.fwd.append(lambda: _lib.check(c.L.escgnn_bag_embed_fwd(_p(W0), H, None, None, None, _p(self.rec), _p(self.rec_off),
@@ -359,10 +367,8 @@ class StaticTrainEngine(object):
         z1, dz1 = c.buf('E', H), c.buf('E', H)
         self._bn_act(z0, dz0, m.z_embedding[1], act, 'E', z1, dz1)
         z2, dz2 = self._linear(z1, m.z_embedding[3], 'E', dx=dz1, feeds_bn=True)
-        zcat, dzcat = c.buf('E', edge_dim), c.buf('E', edge_dim)
         self._bn_act(z2, dz2, m.z_embedding[5], act, 'E', zcat[:, :H], dzcat[:, :H])
         if self.variant == 'zinc':
-            self._embedding(m.edge_type_embedding, self.in_ea, 'E', zcat[:, H:], side=True)
             self._embedding_bwd(m.edge_type_embedding, self.in_ea, 'E', dzcat[:, H:])
         # JK buffer: [x_embedding(x) | x1 .. xL] for count, [x1 .. xL] for zinc
         jk_slots = Lh + (1 if self.variant == 'count' else 0)
@@ -400,8 +406,22 @@ class StaticTrainEngine(object):
         # side branch, ahead of the projection GEMM whose completion the first GINE layer waits for
         self.fwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_zero_tail_rows(
             _p(dee_all), dee_all.stride(0), n_tot, _p(c.rows['E']), E_rows, c.st()), 'zero_tail_rows')))
-        self.fwd.append(lambda: ee_ready.__setitem__(0, self._fork(
-            lambda: self._gemm('gemm_fwd', zcat, False, W_cat, False, ee_all, b_cat, E_rows, n_tot, edge_dim, False, rows='E'))))
+        # forward projections: the first layer's narrow block (the LAST rows of W_cat) on the main branch, right where it is
+        # needed; the wide blocks of layers 2..L on the side branch -- the second GINE layer is the first to wait for them
+        c1 = col[id(self.lin_convs[-1])]
+        n_rest = c1                                   # columns of layers 2..L
+        if n_rest > 0:
+            self.fwd.append(lambda: ee_ready.__setitem__(0, self._fork(
+                lambda: self._gemm('gemm_fwd', zcat, False, W_cat[:n_rest], False, ee_all[:, :n_rest], b_cat[:n_rest], E_rows, n_rest,
+                                   edge_dim, False, rows='E'))))
+
+        def first_projection():
+            main = torch.cuda.current_stream(c.dev)
+            for ready in self._emb_ready:             # x0 and the edge-type columns of zcat come from the side branch
+                main.wait_event(ready[0])
+            self._gemm('gemm_fwd', zcat, False, W_cat[c1:], False, ee_all[:, c1:n_tot], b_cat[c1:], E_rows, n_tot - c1, edge_dim,
+                       False, rows='E')
+        self.fwd.append(first_projection)
 
         def proj_back():                          # runs after every layer's backward has filled its slice of dee_all
             self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, self.wgrad_mode, rows='E'),
@@ -417,8 +437,9 @@ class StaticTrainEngine(object):
             agg, dagg = c.buf('N', cin), c.buf('N', cin)
             if l == 0:
                 xin, dxin_buf = x_prev, dx_prev
-                self.fwd.append(lambda: torch.cuda.current_stream(c.dev).wait_event(ee_ready[0]))
             else:                                  # the previous layer's output is a column slice of the JK buffer
+                if l == 1:
+                    self.fwd.append(lambda: torch.cuda.current_stream(c.dev).wait_event(ee_ready[0]))
                 xin = xs[:, (slot0 + l - 1) * H:(slot0 + l) * H]
                 dxin_buf = c.buf('N', H)
                 layer_dx_from_next[l - 1] = dxin_buf
