@@ -534,12 +534,15 @@ gemm_simple_kernel(const float* __restrict__ A, int lda, int a_mn, const float* 
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
+    // gridDim.z > 1: split-K, every slice adds its tile with atomics (accumulate == 2: C holds the initial value)
+    const int k_per = ((K + (int)gridDim.z - 1) / (int)gridDim.z + 15) / 16 * 16;
+    const int k_lo = blockIdx.z * k_per, k_hi = min(K, k_lo + k_per);
+    for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
         for (int i = threadIdx.x; i < 64 * 16; i += 256) {
             const int kk = i & 15, mm = i >> 4;
             const int m = m0 + mm, n = n0 + mm, k = k0 + kk;
-            sA[kk][mm] = (m < M && k < K) ? (a_mn ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
-            sB[kk][mm] = (n < N && k < K) ? (b_mn ? B[(size_t)k * ldb + n] : B[(size_t)n * ldb + k]) : 0.f;
+            sA[kk][mm] = (m < M && k < k_hi) ? (a_mn ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
+            sB[kk][mm] = (n < N && k < k_hi) ? (b_mn ? B[(size_t)k * ldb + n] : B[(size_t)n * ldb + k]) : 0.f;
         }
         __syncthreads();
         #pragma unroll
@@ -558,7 +561,8 @@ gemm_simple_kernel(const float* __restrict__ A, int lda, int a_mn, const float* 
         for (int j = 0; j < 4; ++j) {
             const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
             if (m < M && n < N) {
-                float r = acc[i][j] + (bias ? bias[n] : 0.f);
+                float r = acc[i][j] + ((bias && blockIdx.z == 0) ? bias[n] : 0.f);
+                if (gridDim.z > 1) { atomicAdd(&C[(size_t)m * ldc + n], r); continue; }
                 if (accumulate) r += C[(size_t)m * ldc + n];
                 C[(size_t)m * ldc + n] = r;
             }
@@ -684,6 +688,12 @@ int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d
                        const float* d_bias, int M, int N, int K, int accumulate, void* stream) {
     if (M <= 0 || N <= 0) return 0;
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+    if (accumulate == 2) {               // long-K, small-output products (weight gradients): spread K over up to 64 slices
+        int splits = K / 128;
+        const int tiles = (int)(grid.x * grid.y);
+        if (splits * tiles > 296) splits = 296 / tiles;
+        grid.z = (unsigned)(splits < 1 ? 1 : splits > 64 ? 64 : splits);
+    }
     escgnn::launch_pdl(gemm_simple_kernel, grid, 256, 0, (cudaStream_t)stream, d_a, lda, a_mn_major, d_b, ldb, b_mn_major, d_c, ldc, d_bias, M, N, K, accumulate);
     return (int)cudaGetLastError();
 }

@@ -313,7 +313,8 @@ int escgnn_gemm_set_plan(int plan);
 int escgnn_gemm_set_split_target(int ctas);
 /* x - tf32_trunc(x): the low plane of the 3xTF32 split (diagnostics; the GEMM computes it on chip) */
 int escgnn_tf32_split_lo(const float* d_x, int ldx, float* d_lo, int ldlo, int64_t rows, int cols, void* stream);
-/* CUDA-core GEMM with the same contract (any strides): odd shapes (K or N = 10, 1) and the test reference */
+/* CUDA-core GEMM with the same contract (any strides): odd shapes (K or N = 10, 1) and the test reference; accumulate = 2
+ * spreads a long K over up to 64 slices that add into C with atomics (weight gradients of the odd-shaped layers) */
 int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,
                        const float* d_bias, int M, int N, int K, int accumulate, void* stream);
 

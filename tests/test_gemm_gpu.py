@@ -153,3 +153,20 @@ def test_gemm_bounded_follows_device_row_count():
         ref2 = dY[:R].double().t() @ X[:R].double()
         sc2 = (dY[:R].double().abs().t() @ X[:R].double().abs()).max().item()
         assert torch.isfinite(dW).all() and (dW.double() - ref2).abs().max().item() <= 4e-6 * sc2, mode
+
+
+@pytest.mark.parametrize('M,N,K', [(256, 10, 2500), (1, 256, 2557), (10, 256, 11063)])
+def test_gemm_simple_atomic_split_k(M, N, K):
+    """escgnn_gemm_simple with accumulate = 2 (odd-shaped weight gradients of the count variant): K spread over slices that add
+    into C atomically; equals C0 + A B^T."""
+    from esc_gnn_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device='cuda').manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device='cuda', generator=g); B = torch.randn(N, K, device='cuda', generator=g)
+    As, Bs = A.t().contiguous(), B.t().contiguous()              # both MN-major, as in wgrad
+    C0 = torch.randn(M, N, device='cuda', generator=g)
+    C = C0.clone()
+    _lib.check(L.escgnn_gemm_simple(_p(As), As.stride(0), 1, _p(Bs), Bs.stride(0), 1, _p(C), N, None, M, N, K, 2, _st()), 'gemm_simple')
+    ref = A.double() @ B.double().t() + C0.double()
+    scale = (A.double().abs() @ B.double().abs().t()).max().item()
+    assert (C.double() - ref).abs().max().item() <= 2e-6 * scale

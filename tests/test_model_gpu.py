@@ -191,7 +191,7 @@ def test_engine_small_batch_after_large_batch_has_no_stale_rows(name):
         out.append((loss, eng.opt.grad.clone()))
     (la, ga), (lb, gb) = out
     assert abs(la - lb) <= 1e-6 * max(1.0, abs(lb))
-    assert (ga - gb).abs().max().item() <= 2e-5 * gb.abs().max().item()
+    assert (ga - gb).abs().max().item() <= 1e-4 * gb.abs().max().item()       # float atomics reorder sums run to run (~3e-5); a stale row is O(1)
 
 
 def test_engine_ordered_and_atomic_weight_gradients_agree():
