@@ -234,7 +234,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
               const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int n_graphs,
               uint16_t* __restrict__ rdh, unsigned long long* counters, long long graph_smem_bytes,
               long long mat_region_doubles, int sub_stride, unsigned char* scratch, long long slab_bytes,
-              long long slab_graph_bytes) {
+              long long slab_graph_bytes, int parts) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     __shared__ int s_misc[2];
@@ -252,7 +252,9 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
         __syncthreads();
         if (tid == 0) { s_ticket = (int)atomicAdd(&counters[ESCGNN_CTR_TICKET_RD], 1ull); s_err = 0; }
         __syncthreads();
-        const int gi = s_ticket;
+        // small batches: `parts` CTAs share a graph (each rebuilds the cheap per-graph state and solves every parts-th pair
+        // system), because a graph's pair systems are the only parallelism there is when the batch does not fill the machine
+        const int gi = s_ticket / parts, part = s_ticket % parts;
         if (gi >= n_graphs) break;
         const long long e0 = eo_ptr[gi];
         const int e = (int)(eo_ptr[gi + 1] - e0);
@@ -291,7 +293,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
             // warp per edge
             double* M = mat_region + (size_t)warp * warp_cap;
             uint16_t* sub = sub_region + (size_t)warp * sub_stride;
-            for (int ed = warp; ed < e; ed += nw) {
+            for (int ed = warp + nw * part; ed < e; ed += nw * parts) {
                 const int u = (int)eo_src[e0 + ed], v = (int)eo_dst[e0 + ed];
                 if (u > v) continue;                                   // handled together with its reverse edge (v, u)
                 // the first occurrence of (u, v) does the work for every copy of (u, v) and (v, u) in the edge list
@@ -321,7 +323,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
                                                    : reinterpret_cast<double*>(slab + slab_graph_bytes);
             uint16_t* sub = (n <= nw * sub_stride) ? sub_region
                                                    : reinterpret_cast<uint16_t*>(slab + slab_graph_bytes + align16(need * 8));
-            for (int ed = 0; ed < e; ++ed) {
+            for (int ed = part; ed < e; ed += parts) {
                 const int u = (int)eo_src[e0 + ed], v = (int)eo_dst[e0 + ed];
                 if (u > v) continue;
                 bool first = true;
@@ -387,8 +389,10 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, (size_t)p.smem);
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)sms * occ;
-    if (grid > n_graphs) grid = n_graphs;
     if (encoder_grid_cap() > 0 && grid > encoder_grid_cap()) grid = encoder_grid_cap();
+    int parts = (int)(grid / n_graphs);                      // CTAs left over by a small batch share its graphs
+    parts = parts < 1 ? 1 : parts > 8 ? 8 : parts;
+    if (grid > n_graphs * parts) grid = n_graphs * parts;
     if (p.slab) {
         if (scratch == nullptr || scratch_bytes < p.slab) return ESCGNN_ERR_BAD_ARG;
         const int64_t fit = scratch_bytes / p.slab;
@@ -399,7 +403,7 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
                                                             counters, (long long)p.graph_bytes,
                                                             (long long)p.mat_doubles, p.sub_stride,
                                                             (unsigned char*)scratch, (long long)p.slab,
-                                                            (long long)p.slab_graph);
+                                                            (long long)p.slab_graph, parts);
     return (int)cudaGetLastError();
 }
 

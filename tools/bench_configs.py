@@ -46,7 +46,7 @@ def run(tag, variant, config, batch, layers=5, hidden=256, steps=200, encoder_ct
         tag, batch, d[0], d[1], d[3], ms, batch / ms * 1e3, losses[0], losses[-1]), flush=True)
 
 
-for cap in (74, ):
+for cap in (74, 0):
     run('cfg1 count_cycle-shaped h=3 (encoder cap %d)' % cap, 'count', 1, 128, encoder_ctas=cap)
     run('cfg3 count_graphlet-shaped h=4 (cap %d)' % cap, 'count', 3, 32, encoder_ctas=cap)
 for bsz in (64, 256, 1024):
