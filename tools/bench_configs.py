@@ -51,3 +51,32 @@ for cap in (74, 0):
     run('cfg3 count_graphlet-shaped h=4 (cap %d)' % cap, 'count', 3, 32, encoder_ctas=cap)
 for bsz in (64, 256, 1024):
     run('cfg2 ZINC-shaped h=3', 'zinc', 2, bsz)
+
+
+def run_module_path(tag, config, batch, steps=60):
+    """Config 4 (ogbg-molhiv-shaped, h=4): GNN(gin_eff, virtual node) through the drop-in module path (torch autograd around the
+    sm_100a kernels) -- the static engine has no OGB variant yet."""
+    from esc_gnn_b200 import ogb_model
+    from esc_gnn_b200.pipeline import TrainPipeline
+    from tests.model_util import loss_fn
+    fl = synth.ENCODER_FLAGS[config]
+    pool = [RawBatch.synth(config, 9000 + i * batch, batch).cuda(non_blocking=False) for i in range(6)]
+    torch.manual_seed(0)
+    model = ogb_model.GNN('ogbg-molhiv', 1, num_layer=6, emb_dim=300, gnn_type='gin_eff', virtual_node=True, residual=False,
+                          drop_ratio=0.5).cuda()
+    model.train()
+    pipe = TrainPipeline(model, lambda p, y: loss_fn('ogb', p, y), fl['h'], fl['use_rd'], fl['self_loop'], lr=1e-3)
+    for i in range(5):
+        l0 = float(pipe.step_device(pool[i % 6]).item())
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        l = pipe.step_device(pool[i % 6])
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    print('%-48s batch %5d  %.3f ms/step  %9.0f graphs/s   loss %.4f -> %.4f (module path)' % (tag, batch, ms, batch / ms * 1e3, l0,
+                                                                                              float(l.item())), flush=True)
+
+
+run_module_path('cfg4 ogbg-molhiv-shaped h=4, 6 layers emb 300', 4, 32)
