@@ -290,8 +290,8 @@ class _LinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         M, K = x.shape
         N = weight.size(0)
-        dx = torch.zeros_like(x)
-        dw = torch.zeros_like(weight)
+        dx = torch.empty_like(x) if M else torch.zeros_like(x)
+        dw = torch.empty_like(weight) if M else torch.zeros_like(weight)
         if M:
             _gemm(dy, False, weight, True, dx, None, M, K, N)        # dX = dY W        (W read as an MN-major operand)
             _gemm(dy, True, x, True, dw, None, N, K, M)              # dW = dY^T X      (both operands MN-major, split-K)
@@ -307,6 +307,31 @@ class Linear(torch.nn.Linear):
         return _LinearFn.apply(x, self.weight, self.bias)
 
 
+_ROWS, _PARTIAL = {}, {}
+
+
+def _device_rows(rows, dev):
+    """The row count as a 1-element device tensor, cached: building it per call is a pageable host-to-device copy that
+    stalls the launching thread."""
+    key = (dev, int(rows))
+    t = _ROWS.get(key)
+    if t is None:
+        if len(_ROWS) > 4096:
+            _ROWS.clear()
+        t = _ROWS[key] = torch.tensor([rows], dtype=torch.int32, device=dev)
+    return t
+
+
+def _reduction_workspace(rows, C, dev):
+    """One zero-initialised reduction workspace per device, grown on demand (the kernels leave its ticket words at zero and
+    calls on one stream are serialised)."""
+    need = _lib.lib().escgnn_dense_partial_floats(rows, C)
+    ws = _PARTIAL.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = _PARTIAL[dev] = torch.zeros(max(need, 1 << 20), dtype=torch.float32, device=dev)
+    return ws
+
+
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, training):
@@ -314,8 +339,8 @@ class _BatchNormFn(torch.autograd.Function):
         x = x.contiguous()
         rows, C = x.shape
         L = _lib.lib()
-        d_rows = torch.tensor([rows], dtype=torch.int32, device=x.device)
-        partial = torch.zeros(L.escgnn_dense_partial_floats(rows, C), dtype=torch.float32, device=x.device)   # tickets start at 0
+        d_rows = _device_rows(rows, x.device)
+        partial = _reduction_workspace(rows, C, x.device)
         mean, rstd = torch.empty(C, device=x.device), torch.empty(C, device=x.device)
         y = torch.empty_like(x)
         _lib.check(L.escgnn_bn_act_fwd(_p(x), C, _p(weight), _p(bias), _p(running_mean), _p(running_var), _p(mean), _p(rstd),
