@@ -797,6 +797,30 @@ act_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ d
         dx[(size_t)r * lddx + c] = r < rows ? dy[(size_t)r * lddy + c] * act_grad(x[(size_t)r * ldx + c], act) : 0.f;
 }
 
+// inverted dropout with a counter-based mask: keep(r, c) = hash(salt, step, r * C + c) >= p, y = keep ? x / (1 - p) : 0.  The mask
+// is a pure function of (salt, step counter, position), so the backward pass applies the SAME kernel to the gradient and nothing
+// is stored; `step` lives in device memory (the optimiser's counter), which keeps the captured graph valid from step to step.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
+}
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float* __restrict__ x, int ldx, float p, uint32_t salt, const long long* __restrict__ d_step,
+               const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ y, int ldy) {
+    escgnn::pdl_enter();
+    const int rows = min(*d_rows, rows_cap);
+    const uint32_t step = d_step ? (uint32_t)*d_step : 0u;
+    const uint32_t key = mix32(salt * 0x9e3779b9u + step);
+    const uint32_t thresh = p >= 1.f ? 0xffffffffu : (uint32_t)((double)p * 4294967296.0);
+    const float scale = p >= 1.f ? 0.f : 1.f / (1.f - p);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)rows_cap * C; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / C), c = (int)(i % C);
+        float o = 0.f;
+        if (r < rows && mix32((uint32_t)i ^ key) >= thresh) o = x[(size_t)r * ldx + c] * scale;
+        y[(size_t)r * ldy + c] = o;
+    }
+}
+
 // column sums (bias gradients): partial per tile, then an ordered final sum
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ d_rows, int C, float* __restrict__ partial) {
@@ -1106,6 +1130,15 @@ int escgnn_bn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, co
                                                 d_rows, channels, d_partial);
     escgnn::launch_pdl(bn_act_bwd_apply_kernel, g, 256, 0, st, d_x, ldx, d_dy, lddy, d_dy2, lddy2, d_mean, d_rstd, d_gamma, d_beta, act,
                                                training, d_partial, d_rows, rows_cap, channels, d_dgamma, d_dbeta, d_dx, lddx);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_dropout(const float* d_x, int ldx, float p, uint32_t salt, const long long* d_step, const int* d_rows, int rows_cap,
+                   int channels, float* d_y, int ldy, void* stream) {
+    int64_t total = (int64_t)rows_cap * channels;
+    if (total <= 0) return 0;
+    unsigned b = (unsigned)((total + 255) / 256); if (b > 148 * 16) b = 148 * 16;
+    escgnn::launch_pdl(dropout_kernel, b, 256, 0, (cudaStream_t)stream, d_x, ldx, p, salt, d_step, d_rows, rows_cap, channels, d_y, ldy);
     return (int)cudaGetLastError();
 }
 

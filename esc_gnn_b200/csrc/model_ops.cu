@@ -416,6 +416,47 @@ __global__ void zero_tail_rows_kernel(float* __restrict__ x, int ld, int cols, c
         x[(r0 + i / cols) * ld + i % cols] = 0.f;
 }
 
+// ---------------------------------------------------------------- per-graph rows broadcast to nodes (virtual node, ogb_mol_gnn.py:737)
+// out[i, :] = x[i, :] + v[seg(i), :] for the nodes of every segment (x == out: in place).  The backward of the broadcast is a
+// segment sum (segment_pool_fwd), the backward of a segment sum is this kernel applied to the gradient.
+__global__ void __launch_bounds__(256)
+add_segment_rows_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ v, int ldv, const int* __restrict__ ptr, int C,
+                        float* __restrict__ out, int ldo) {
+    escgnn::pdl_enter();
+    const int s = blockIdx.x;
+    const int a = ptr[s], b = ptr[s + 1];
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {
+        const float add = v[(size_t)s * ldv + c];
+        for (int i = a; i < b; ++i) out[(size_t)i * ldo + c] = x[(size_t)i * ldx + c] + add;
+    }
+}
+
+// E1 on integer edge attributes (utils_edge_efficient.py:35-36): rows of removed loops dropped, order kept, then one row of
+// `fill` per node for the appended loops -- the same permutation rewrite_kernel applies to the edge list.
+__global__ void rewrite_edge_attr_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                         const int64_t* __restrict__ edge_ptr, const int64_t* __restrict__ node_ptr, int64_t n_graphs,
+                                         const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ attr, int C, int64_t fill,
+                                         int64_t* __restrict__ out) {
+    escgnn::pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int64_t gi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gi >= n_graphs) return;
+    const int64_t a = edge_ptr[gi], b = edge_ptr[gi + 1];
+    int64_t o = eo_ptr[gi];
+    for (int64_t i0 = a; i0 < b; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const bool keep = i < b && src[i] != dst[i];
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int p = __popc(m & ((1u << lane) - 1));
+            for (int c = 0; c < C; ++c) out[(o + p) * C + c] = attr[i * C + c];
+        }
+        o += __popc(m);
+    }
+    const int64_t n = node_ptr[gi + 1] - node_ptr[gi];
+    for (int64_t i = lane; i < n * C; i += 32) out[o * C + i] = fill;
+}
+
 // ---------------------------------------------------------------- K7 segment pooling (sorted batch vector)
 // float4 variants: grid (segments, channel chunks of 4 * blockDim), 4 independent row loads in flight per thread
 __global__ void __launch_bounds__(128)
@@ -680,6 +721,25 @@ int escgnn_reduce_sum(const float* d_v, int64_t n, float* d_out, int accumulate,
 int escgnn_zero_tail_rows(float* d_x, int ld, int cols, const int* d_rows, int64_t rows_cap, void* stream) {
     if (rows_cap <= 0 || cols <= 0) return 0;
     escgnn::launch_pdl(zero_tail_rows_kernel, 148, 256, 0, (cudaStream_t)stream, d_x, ld, cols, d_rows, rows_cap);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_add_segment_rows(const float* d_x, int ldx, const float* d_v, int ldv, const int32_t* d_ptr, int64_t n_segments,
+                            int channels, float* d_out, int ldo, void* stream) {
+    if (n_segments <= 0) return 0;
+    const dim3 grid((unsigned)n_segments, (unsigned)((channels + 255) / 256));
+    escgnn::launch_pdl(add_segment_rows_kernel, grid, 256, 0, (cudaStream_t)stream, d_x, ldx, d_v, ldv, d_ptr, channels, d_out, ldo);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_rewrite_edge_attr(const int64_t* d_src, const int64_t* d_dst, const int64_t* d_edge_ptr, const int64_t* d_node_ptr,
+                             int64_t n_graphs, const int64_t* d_eo_ptr, const int64_t* d_attr, int attr_cols, int64_t fill,
+                             int64_t* d_out, void* stream) {
+    if (n_graphs <= 0) return 0;
+    const int wpb = 8;
+    const unsigned blocks = (unsigned)((n_graphs + wpb - 1) / wpb);
+    escgnn::launch_pdl(rewrite_edge_attr_kernel, blocks, wpb * 32, 0, (cudaStream_t)stream, d_src, d_dst, d_edge_ptr, d_node_ptr, n_graphs,
+                       d_eo_ptr, d_attr, attr_cols, fill, d_out);
     return (int)cudaGetLastError();
 }
 

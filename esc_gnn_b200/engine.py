@@ -62,6 +62,8 @@ class _BatchSet(object):
                 ('dims', i32, (4, ))]
         if variant == 'zinc':
             spec += [('in_x', i64, (N, )), ('in_ea', i64, (E, )), ('in_y', f32, (G, ))]
+        elif variant == 'ogb':          # 9 atom columns, 3 bond columns (after E1), one target per graph (NaN = unlabelled)
+            spec += [('in_x', i64, (N, 9)), ('in_ea', i64, (E, 3)), ('in_y', f32, (G, ))]
         else:
             spec += [('in_x', f32, (N, 10)), ('in_y', f32, (N, ))]
         esz = {i64: 8, i32: 4, f32: 4}
@@ -78,7 +80,7 @@ class _BatchSet(object):
             for d in shape:
                 n *= d
             setattr(self, name, self.buf[o:o + n * esz[dt]].view(dt).view(shape))
-        if variant != 'zinc':
+        if variant == 'count':
             self.in_ea = None
         b = self.idx_buf
         self.dst_ptr, self.src_ptr = b[:N + 1], b[N + 1:2 * N + 2]
@@ -88,21 +90,33 @@ class _BatchSet(object):
 
 
 class StaticTrainEngine(object):
-    """One NestedGIN_eff variant ('zinc' or 'count') at a fixed capacity."""
+    """One model variant at a fixed capacity: NestedGIN_eff 'zinc' / 'count', or 'ogb' = GNN(gnn_type='gin_eff')."""
 
     def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
                  lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True, encoder_ctas=None, fused_head=True):
-        if variant not in ('zinc', 'count'):
-            raise NotImplementedError('engine variants: zinc, count (the OGB model runs through the module path)')
+        if variant not in ('zinc', 'count', 'ogb'):
+            raise NotImplementedError('engine variants: zinc, count, ogb')
         p0 = next(model.parameters())
         if not p0.is_cuda:
             raise RuntimeError('StaticTrainEngine needs a CUDA model; there is no CPU fallback')
         self.model, self.variant, self.flags = model, variant, dict(flags)
         # the edge projections `conv.lin` of ALL layers read the same z, so they are one GEMM against the row-concatenation
         # of their weights: lay those tensors out adjacently (256-wide layers first, the narrow first layer last)
-        self.lin_convs = list(model.convs) + [model.conv1]
-        self.opt = FlatAdam(model.parameters(), lr=lr, first=[cv.lin.weight for cv in self.lin_convs] +
-                            [cv.lin.bias for cv in self.lin_convs])
+        if variant == 'ogb':
+            gn = model.gnn_node
+            if gn.JK != 'last' or model.num_tasks != 1 or not atomic_wgrad:
+                raise NotImplementedError('ogb engine variant: JK="last", one task, atomic_wgrad=True')
+            # adjacent in the flat buffer: the per-layer projections of z (one grouped GEMM), the 9 atom tables (one lookup with
+            # row offsets), and every layer's 3 bond tables
+            first = [cv.edge_encoder_pos.weight for cv in gn.convs] + [cv.edge_encoder_pos.bias for cv in gn.convs]
+            first += [e.weight for e in gn.node_encoder.atom_embedding_list]
+            for cv in gn.convs:
+                first += [e.weight for e in cv.edge_encoder.bond_embedding_list]
+            self.opt = FlatAdam(model.parameters(), lr=lr, first=first)
+        else:
+            self.lin_convs = list(model.convs) + [model.conv1]
+            self.opt = FlatAdam(model.parameters(), lr=lr, first=[cv.lin.weight for cv in self.lin_convs] +
+                                [cv.lin.bias for cv in self.lin_convs])
         self.distributed, self.use_graph = distributed, use_graph
         dev = p0.device
         self.G = int(max_graphs)
@@ -167,7 +181,11 @@ class StaticTrainEngine(object):
         self._side_used = False
         self.inline_branches = False
         self.fwd, self.bwd, self._bns, self._emb_ready = [], [], [], []
-        self._build_model_tape()
+        if variant == 'ogb':
+            self.in_ea_raw = torch.zeros((e_in_cap, 3), dtype=torch.int64, device=dev)     # bond columns before E1
+            self._build_ogb_tape()
+        else:
+            self._build_model_tape()
         self._bn_synced = 0
         self.graph = None
         self.steps = 0
@@ -491,6 +509,213 @@ class StaticTrainEngine(object):
                                                                    c.caps[kind], 1, _p(self.loss), _p(dpred), dpred.stride(0),
                                                                    c.st()), 'loss_fwd_bwd'))
 
+    # ------------------------------------------------------------------ OGB variant (ogb_mol_gnn.py:66-117,614-792)
+    def _dropout(self, x, dx, kind, p):
+        """(out, dout) with out = dropout(x) in training mode; the backward applies the same counter-based mask to dout.
+        p == 0: no kernels, the buffers are passed through."""
+        if p <= 0.0:
+            return x, dx
+        c = self.c
+        C = x.size(1)
+        out, dout = c.buf(kind, C), c.buf(kind, C)
+        self._salt += 1
+        salt = self._salt
+        step = self.opt.state
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_dropout(_p(x), x.stride(0), p, salt, _p(step), _p(c.rows[kind]), c.caps[kind], C,
+                                                              _p(out), out.stride(0), c.st()), 'dropout'))
+        self.bwd.append(lambda: _lib.check(c.L.escgnn_dropout(_p(dout), dout.stride(0), p, salt, _p(step), _p(c.rows[kind]),
+                                                              c.caps[kind], C, _p(dx), dx.stride(0), c.st()), 'dropout'))
+        return out, dout
+
+    def _build_ogb_tape(self):
+        """GNN(gnn_type='gin_eff'): AtomEncoder, z path, L x [virtual-node broadcast, GINConv_eff, BN(+ReLU), dropout, virtual-node
+        update], mean / sum pooling, Linear head, BCE-with-logits over labelled targets.  Registration order = a topological order
+        of the forward pass; the backward tape is its reverse, so for every buffer with several consumers the LAST registered
+        consumer's backward writes the gradient and the earlier ones accumulate."""
+        m, c = self.model, self.c
+        gn = m.gnn_node
+        H, Lh, p = m.emb_dim, gn.num_layer, float(gn.drop_ratio)
+        G = self.G
+        self._salt = 0
+        i64 = torch.int64
+        dev = c.dev
+        # ---- node input: sum of the 9 atom tables (adjacent in the flat buffer -> one lookup with row offsets)
+        atom = list(gn.node_encoder.atom_embedding_list)
+        atom_off = torch.tensor([0] + list(torch.tensor([e.weight.size(0) for e in atom]).cumsum(0)[:-1]), dtype=i64, device=dev)
+        h = [c.buf('N', H) for _ in range(Lh + 1)]
+        dh = [c.buf('N', H) for _ in range(Lh + 1)]
+        a0, ga0 = atom[0].weight, atom[0].weight.grad
+        assert atom[-1].weight.data_ptr() == a0.data_ptr() + 4 * H * int(atom_off[-1]), 'atom tables not adjacent'
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_embedding_fwd(_p(a0), _p(self.in_x), 9, _p(atom_off), _p(c.rows['N']), c.caps['N'],
+                                                                    H, _p(h[0]), H, c.st()), 'embedding_fwd'))
+        self.bwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_embedding_bwd(
+            _p(dh[0]), H, _p(self.in_x), 9, _p(atom_off), _p(c.rows['N']), c.caps['N'], H, _p(ga0), c.st()), 'embedding_bwd')))
+        # ---- z path: bag-embed -> Dropout, BN, ReLU, Linear, Dropout, BN, ReLU
+        z0, dz0 = c.buf('E', H), c.buf('E', H)
+        W0 = gn.z_initial.weight
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_bag_embed_fwd(_p(W0), H, None, None, None, _p(self.rec), _p(self.rec_off),
+                                                                    _p(self.rec_nnz), c.caps['E'], _p(z0), _p(c.rows['E']),
+                                                                    c.st()), 'bag_embed_fwd'))
+        bag_work = torch.zeros(3 * 1800 + 8, dtype=torch.int32, device=dev)
+        bag_edge = torch.zeros(c.caps['nnz'], dtype=torch.int32, device=dev)
+        bag_cnt = torch.zeros(c.caps['nnz'], dtype=torch.float32, device=dev)
+        bag_ready = [None]
+        self.fwd.append(lambda: bag_ready.__setitem__(0, self._fork(lambda: _lib.check(c.L.escgnn_bag_index_build(
+            _p(self.rec), _p(self.rec_off), _p(self.rec_nnz), c.caps['E'], _p(bag_work), _p(bag_edge), _p(bag_cnt),
+            _p(c.rows['E']), c.st()), 'bag_index_build'))))
+        self.bwd.append(lambda: (torch.cuda.current_stream(dev).wait_event(bag_ready[0]), _lib.check(
+            c.L.escgnn_bag_embed_bwd_indexed(_p(dz0), H, c.caps['nnz'], _p(W0.grad), _p(bag_work), _p(bag_edge), _p(bag_cnt),
+                                             c.st()), 'bag_embed_bwd_indexed')))
+        ze = gn.z_embedding
+        z0d, dz0d = self._dropout(z0, dz0, 'E', p)
+        z1, dz1 = c.buf('E', H), c.buf('E', H)
+        self._bn_act(z0d, dz0d, ze[1], 'relu', 'E', z1, dz1)
+        z2, dz2 = self._linear(z1, ze[3], 'E', dx=dz1, feeds_bn=(p <= 0.0))
+        z2d, dz2d = self._dropout(z2, dz2, 'E', p)
+        zemb, dzemb = c.buf('E', H), c.buf('E', H)
+        self._bn_act(z2d, dz2d, ze[5], 'relu', 'E', zemb, dzemb)
+        # ---- edge features of every layer: e_l = BondEncoder_l(edge_attr) + Linear_l(z): the lookups write the slices of one
+        # [E, L*H] buffer, then ONE grouped GEMM accumulates all projections on top (C += zemb W_cat^T + b_cat)
+        convs = list(gn.convs)
+        flat, gflat = self.opt.flat, self.opt.grad
+        w0 = (convs[0].edge_encoder_pos.weight.data_ptr() - flat.data_ptr()) // 4
+        b0 = (convs[0].edge_encoder_pos.bias.data_ptr() - flat.data_ptr()) // 4
+        n_tot = Lh * H
+        W_cat, dW_cat = flat[w0:w0 + n_tot * H].view(n_tot, H), gflat[w0:w0 + n_tot * H].view(n_tot, H)
+        b_cat, db_cat = flat[b0:b0 + n_tot], gflat[b0:b0 + n_tot]
+        assert convs[-1].edge_encoder_pos.weight.data_ptr() == W_cat[(Lh - 1) * H].data_ptr(), 'projection weights not adjacent'
+        assert convs[-1].edge_encoder_pos.bias.data_ptr() == b_cat[(Lh - 1) * H:].data_ptr(), 'projection biases not adjacent'
+        ld_all = (n_tot + 3) // 4 * 4
+        e_all, de_all = c.buf('E', ld_all), c.buf('E', ld_all)
+        E_rows = c.caps['E']
+        bond_off = []
+        for l, cv in enumerate(convs):
+            tabs = list(cv.edge_encoder.bond_embedding_list)
+            off = torch.tensor([0] + list(torch.tensor([e.weight.size(0) for e in tabs]).cumsum(0)[:-1]), dtype=i64, device=dev)
+            assert tabs[-1].weight.data_ptr() == tabs[0].weight.data_ptr() + 4 * H * int(off[-1]), 'bond tables not adjacent'
+            bond_off.append(off)
+            t0, e_l, de_l = tabs[0].weight, e_all[:, l * H:(l + 1) * H], de_all[:, l * H:(l + 1) * H]
+            self.fwd.append(lambda t0=t0, off=off, e_l=e_l: _lib.check(c.L.escgnn_embedding_fwd(
+                _p(t0), _p(self.in_ea), 3, _p(off), _p(c.rows['E']), E_rows, H, _p(e_l), e_l.stride(0), c.st()), 'embedding_fwd'))
+            self.bwd.append(lambda t0=t0, off=off, de_l=de_l: self._fork(lambda: _lib.check(c.L.escgnn_embedding_bwd(
+                _p(de_l), de_l.stride(0), _p(self.in_ea), 3, _p(off), _p(c.rows['E']), E_rows, H, _p(t0.grad), c.st()),
+                'embedding_bwd')))
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_zero_tail_rows(_p(de_all), de_all.stride(0), n_tot, _p(c.rows['E']), E_rows,
+                                                                     c.st()), 'zero_tail_rows'))
+        self.fwd.append(lambda: self._gemm('gemm_fwd', zemb, False, W_cat, False, e_all, b_cat, E_rows, n_tot, H, True, rows='E'))
+
+        def proj_back():                          # after every layer's backward: d zemb, d W_cat, d b_cat from de_all
+            self._fork(lambda: (self._gemm('gemm_wgrad', de_all, True, zemb, True, dW_cat, None, n_tot, H, E_rows, self.wgrad_mode,
+                                           rows='E'),
+                                _lib.check(c.L.escgnn_colsum(_p(de_all), de_all.stride(0), _p(c.rows['E']), E_rows, n_tot,
+                                                             _p(self.side_partial), _p(db_cat), c.st()), 'colsum')))
+            self._gemm('gemm_dgrad', de_all, False, W_cat, True, dzemb, None, E_rows, H, n_tot, False, rows='E')
+        self.bwd.append(proj_back)
+        # ---- virtual node
+        vnode = gn.virtual_node
+        if vnode:
+            vn = [c.buf('B', H) for _ in range(Lh)]
+            dvn = [c.buf('B', H) for _ in range(Lh)]
+            zeros_idx = torch.zeros(G, dtype=i64, device=dev)
+            vw = gn.virtualnode_embedding.weight
+            self.fwd.append(lambda: _lib.check(c.L.escgnn_embedding_fwd(_p(vw), _p(zeros_idx), 1, None, _p(c.rows['B']), G, H,
+                                                                        _p(vn[0]), H, c.st()), 'embedding_fwd'))
+            self.bwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_colsum(
+                _p(dvn[0]), H, _p(c.rows['B']), G, H, _p(self.side_partial), _p(vw.grad), c.st()), 'colsum')))
+        gptr = self.graph_ptr
+        for l, cv in enumerate(convs):
+            last = l == Lh - 1
+            e_l, de_l = e_all[:, l * H:(l + 1) * H], de_all[:, l * H:(l + 1) * H]
+            if vnode:
+                # F1: h_l += vn_l[batch] (in place); backward: d vn_l (+)= segment sums of d h_l.  Registered first, so it runs
+                # LAST of this layer's backward entries, when d h_l is complete.
+                self.fwd.append(lambda l=l: _lib.check(c.L.escgnn_add_segment_rows(_p(h[l]), H, _p(vn[l]), H, _p(gptr), G, H, _p(h[l]), H,
+                                                                                   c.st()), 'add_segment_rows'))
+                if last:
+                    self.bwd.append(lambda l=l: _lib.check(c.L.escgnn_segment_pool_fwd(_p(dh[l]), _p(gptr), G, H, 0, _p(dvn[l]), c.st()),
+                                                           'segment_pool_fwd'))
+                else:
+                    seg_tmp = c.buf('B', H)
+
+                    def vn_grad(l=l, seg_tmp=seg_tmp):       # d vn_l = (dgrad of the update MLP, already there) + segment sums
+                        _lib.check(c.L.escgnn_segment_pool_fwd(_p(dh[l]), _p(gptr), G, H, 0, _p(seg_tmp), c.st()), 'segment_pool_fwd')
+                        dvn[l].add_(seg_tmp)
+                        _lib.mark('misc')
+                    self.bwd.append(vn_grad)
+                    if gn.residual:                  # vn_{l+1} = vn_l + update: d vn_l += d vn_{l+1} (after the dgrad below has written)
+                        self.bwd.append(lambda l=l: (dvn[l].add_(dvn[l + 1]), _lib.mark('misc')))
+                    # F4: vn_{l+1} = dropout(MLP(add_pool(h_l) + vn_l)); the sum goes through the first Linear as two products
+                    seq = gn.mlp_virtualnode_list[l]
+                    pooled, dpooled = c.buf('B', H), c.buf('B', H)
+                    self.fwd.append(lambda l=l, pooled=pooled: _lib.check(c.L.escgnn_segment_pool_fwd(
+                        _p(h[l]), _p(gptr), G, H, 0, _p(pooled), c.st()), 'segment_pool_fwd'))
+                    # backward of the pooling: d h_l += d pooled[batch]  (runs after the aggregation's backward has written d h_l)
+                    self.bwd.append(lambda l=l, dpooled=dpooled: _lib.check(c.L.escgnn_add_segment_rows(
+                        _p(dh[l]), H, _p(dpooled), H, _p(gptr), G, H, _p(dh[l]), H, c.st()), 'add_segment_rows'))
+                    lin_a = seq[0]
+                    t1, dt1 = self._linear(pooled, lin_a, 'B', dx=dpooled, feeds_bn=True)
+                    # second product of the same Linear: t1 += vn_l W^T; backward: d vn_l = d t1 W (writes), d W += d t1^T vn_l
+                    self.fwd.append(lambda l=l, t1=t1, lin_a=lin_a: self._gemm('gemm_fwd', vn[l], False, lin_a.weight, False, t1, None,
+                                                                              G, 2 * H, H, True, rows='B'))
+
+                    def vn_lin_back(l=l, dt1=dt1, lin_a=lin_a):
+                        self._fork(lambda: self._gemm('gemm_wgrad', dt1, True, vn[l], True, lin_a.weight.grad, None, 2 * H, H, G,
+                                                      2 if self.wgrad_mode == 2 else 1, rows='B'))
+                        self._gemm('gemm_dgrad', dt1, False, lin_a.weight, True, dvn[l], None, G, H, 2 * H, False, rows='B')
+                    self.bwd.append(vn_lin_back)
+                    t2, dt2 = c.buf('B', 2 * H), c.buf('B', 2 * H)
+                    self._bn_act(t1, dt1, seq[1], 'relu', 'B', t2, dt2)
+                    t3, dt3 = self._linear(t2, seq[3], 'B', dx=dt2, feeds_bn=True)
+                    t4, dt4 = c.buf('B', H), c.buf('B', H)
+                    self._bn_act(t3, dt3, seq[4], 'relu', 'B', t4, dt4)
+                    if p > 0.0:
+                        self._salt += 1
+                        salt, step = self._salt, self.opt.state
+                        self.fwd.append(lambda l=l, t4=t4, salt=salt: _lib.check(c.L.escgnn_dropout(
+                            _p(t4), H, p, salt, _p(step), _p(c.rows['B']), G, H, _p(vn[l + 1]), H, c.st()), 'dropout'))
+                        self.bwd.append(lambda l=l, dt4=dt4, salt=salt: _lib.check(c.L.escgnn_dropout(
+                            _p(dvn[l + 1]), H, p, salt, _p(step), _p(c.rows['B']), G, H, _p(dt4), H, c.st()), 'dropout'))
+                    else:
+                        self.fwd.append(lambda l=l, t4=t4: (vn[l + 1].copy_(t4), _lib.mark('copy')))
+                        self.bwd.append(lambda l=l, dt4=dt4: (dt4.copy_(dvn[l + 1]), _lib.mark('copy')))
+                    if gn.residual:
+                        self.fwd.append(lambda l=l: (vn[l + 1].add_(vn[l]), _lib.mark('misc')))
+            if gn.residual:      # h_{l+1} = layer(h_l) + h_l: d h_l += d h_{l+1}; registered here so that it runs AFTER the aggregation's
+                self.bwd.append(lambda l=l: (dh[l].add_(dh[l + 1]), _lib.mark('misc')))      # backward has written d h_l
+            # F2: GINConv_eff aggregation, F3: its MLP, the layer's BatchNorm (+ReLU except after the last layer), dropout
+            agg, dagg = c.buf('N', H), c.buf('N', H)
+            self._gine(h[l], dh[l], e_l, de_l, cv.eps, agg, dagg)
+            m1, dm1 = self._linear(agg, cv.mlp[0], 'N', dx=dagg, feeds_bn=True)
+            m2, dm2 = c.buf('N', 2 * H), c.buf('N', 2 * H)
+            self._bn_act(m1, dm1, cv.mlp[1], 'relu', 'N', m2, dm2)
+            m3, dm3 = self._linear(m2, cv.mlp[3], 'N', dx=dm2, feeds_bn=True)
+            if p > 0.0:
+                m4, dm4 = c.buf('N', H), c.buf('N', H)
+                self._bn_act(m3, dm3, gn.batch_norms[l], 'none' if last else 'relu', 'N', m4, dm4)
+                self._salt += 1
+                salt, step = self._salt, self.opt.state
+                self.fwd.append(lambda l=l, m4=m4, salt=salt: _lib.check(c.L.escgnn_dropout(
+                    _p(m4), H, p, salt, _p(step), _p(c.rows['N']), c.caps['N'], H, _p(h[l + 1]), H, c.st()), 'dropout'))
+                self.bwd.append(lambda l=l, dm4=dm4, salt=salt: _lib.check(c.L.escgnn_dropout(
+                    _p(dh[l + 1]), H, p, salt, _p(step), _p(c.rows['N']), c.caps['N'], H, _p(dm4), H, c.st()), 'dropout'))
+            else:
+                self._bn_act(m3, dm3, gn.batch_norms[l], 'none' if last else 'relu', 'N', h[l + 1], dh[l + 1])
+            if gn.residual:
+                self.fwd.append(lambda l=l: (h[l + 1].add_(h[l]), _lib.mark('misc')))
+        # ---- readout: pooling, Linear head, BCE-with-logits over labelled targets (run_ogb_mol.py:58-74)
+        mean = 1 if m.graph_pooling == 'mean' else 0
+        hg, dhg = c.buf('B', H), c.buf('B', H)
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_segment_pool_fwd(_p(h[Lh]), _p(gptr), G, H, mean, _p(hg), c.st()),
+                                           'segment_pool_fwd'))
+        self.bwd.append(lambda: _lib.check(c.L.escgnn_segment_pool_bwd(_p(dhg), _p(gptr), G, H, mean, _p(dh[Lh]), c.st()),
+                                           'segment_pool_bwd'))
+        pred, dpred = self._linear(hg, m.graph_pred_linear, 'B', dx=dhg)
+        self.pred = pred
+        self.debug_buffers = dict(h=h, dh=dh, pred=pred, dpred=dpred, zemb=zemb, dzemb=dzemb, e_all=e_all, de_all=de_all)
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_loss_fwd_bwd(_p(pred), pred.stride(0), _p(self.in_y), 1, _p(c.rows['B']), G, 1,
+                                                                   _p(self.loss), _p(dpred), dpred.stride(0), c.st()),
+                                           'loss_fwd_bwd'))
+
     def _bn_act_late(self, x, dx, bn, act, out, dout, dx_from_next, l):
         """Like _bn_act, but the second gradient source (next layer's aggregation) is resolved when the tape runs."""
         c = self.c
@@ -524,8 +749,13 @@ class StaticTrainEngine(object):
                                                    _p(self.eo_ptr), _p(self.eo[0]), _p(self.eo[1]), _p(self.rw_tmp), st),
                        'rewrite_self_loops')
             es, ed, ep = self.eo[0], self.eo[1], self.eo_ptr
+            if self.variant == 'ogb':
+                _lib.check(L.escgnn_rewrite_edge_attr(_p(self.in_src), _p(self.in_dst), _p(self.in_eptr), _p(self.in_nptr), G,
+                                                      _p(self.eo_ptr), _p(self.in_ea_raw), 3, 1, _p(t.in_ea), st), 'rewrite_edge_attr')
         else:
             es, ed, ep = self.in_src, self.in_dst, self.in_eptr
+            if self.variant == 'ogb':
+                t.in_ea[:self.in_ea_raw.size(0)].copy_(self.in_ea_raw)
         if fl['use_rd']:
             _lib.check(L.escgnn_encode_rd(_p(es), _p(ed), _p(ep), _p(self.in_nptr), G, fl['h'], _p(self.rdh), _p(self.counters),
                                           self.max_n, self.max_e, _p(self.scratch), self.scratch.numel(), st), 'encode_rd')
@@ -549,7 +779,7 @@ class StaticTrainEngine(object):
         """Pipelined mode: features / targets of the batch just loaded travel with the batch set they belong to."""
         t.in_x.copy_(self.raw_feat.in_x)
         t.in_y.copy_(self.raw_feat.in_y)
-        if t.in_ea is not None:
+        if t.in_ea is not None and self.variant != 'ogb':
             t.in_ea.copy_(self.raw_feat.in_ea)
 
     @torch.no_grad()
@@ -619,7 +849,9 @@ class StaticTrainEngine(object):
         n = raw.num_nodes
         t = self.raw_feat if self.pipeline else self.live   # pipelined: the encoder branch forwards them into the staging set
         t.in_x[:n].copy_(raw.x, non_blocking=True)
-        if t.in_ea is not None:
+        if self.variant == 'ogb':                    # the encoder applies E1 to the bond columns (loop rows = 1)
+            self.in_ea_raw[:raw.edge_attr.size(0)].copy_(raw.edge_attr, non_blocking=True)
+        elif t.in_ea is not None:
             t.in_ea[:raw.edge_attr.size(0)].copy_(raw.edge_attr, non_blocking=True)
         t.in_y[:raw.y.numel()].copy_(raw.y.view(-1), non_blocking=True)
 

@@ -220,6 +220,14 @@ int escgnn_collate_edges(const int64_t* d_src, const int64_t* d_dst, const int32
                          const int* d_count, void* stream);
 int escgnn_ptr_to_ids(const int64_t* d_ptr, int64_t n_segments, int64_t n, int64_t* d_ids, const int* d_count,
                       void* stream);
+/* out[i] = x[i] + v[segment of i] (virtual-node broadcast, ogb_mol_gnn.py:737; x == out allowed); d_ptr int32 [n_segments+1] */
+int escgnn_add_segment_rows(const float* d_x, int ldx, const float* d_v, int ldv, const int32_t* d_ptr, int64_t n_segments,
+                            int channels, float* d_out, int ldo, void* stream);
+/* E1 on int64 edge attributes [E_in, attr_cols]: the permutation of escgnn_rewrite_self_loops (loop rows dropped, order kept,
+ * `fill` rows appended per node; utils_edge_efficient.py:35-36 -> add_self_loops fills 1) */
+int escgnn_rewrite_edge_attr(const int64_t* d_src, const int64_t* d_dst, const int64_t* d_edge_ptr, const int64_t* d_node_ptr,
+                             int64_t n_graphs, const int64_t* d_eo_ptr, const int64_t* d_attr, int attr_cols, int64_t fill,
+                             int64_t* d_out, void* stream);
 /* d_out[0] (+)= sum of d_v[0..n) in a fixed order (the eps gradient of a GINE layer from its per-node dot products) */
 int escgnn_reduce_sum(const float* d_v, int64_t n, float* d_out, int accumulate, void* stream);
 /* rows [*d_rows, rows_cap) of a [rows_cap, ld] fp32 buffer := 0 (first `cols` columns) */
@@ -267,6 +275,11 @@ int escgnn_head_bn_linear_l1(const float* d_x, int ldx, const float* d_gamma, co
                              float* d_running_var, int act, float eps, float momentum, const float* d_w2, const float* d_b2,
                              const float* d_target, const int* d_rows, int rows_cap, int channels, float* d_pred, float* d_loss,
                              float* d_dx, int lddx, float* d_dgamma, float* d_dbeta, float* d_dw2, float* d_db2, void* stream);
+/* inverted dropout (F.dropout, ogb_mol_gnn.py:756-758,774; run_graphcount.py:54-61): y = keep ? x / (1 - p) : 0 with a
+ * counter-based mask keep = hash(salt, *d_step, position) >= p. The same call on the gradient is the backward pass (nothing
+ * is stored); d_step (may be NULL) is a device-side step counter, so a captured graph draws a fresh mask every replay. */
+int escgnn_dropout(const float* d_x, int ldx, float p, uint32_t salt, const long long* d_step, const int* d_rows, int rows_cap,
+                   int channels, float* d_y, int ldy, void* stream);
 int escgnn_act_fwd(const float* d_x, int ldx, int act, const int* d_rows, int rows_cap, int channels, float* d_y, int ldy,
                    void* stream);
 int escgnn_act_bwd(const float* d_x, int ldx, const float* d_dy, int lddy, int act, const int* d_rows, int rows_cap,

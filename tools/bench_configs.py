@@ -80,3 +80,40 @@ def run_module_path(tag, config, batch, steps=60):
 
 
 run_module_path('cfg4 ogbg-molhiv-shaped h=4, 6 layers emb 300', 4, 32)
+
+
+def run_ogb_engine(tag, batch, steps=200, drop_ratio=0.5):
+    """Config 4 through the static engine (GNN gin_eff, 6 layers, emb 300, virtual node, dropout)."""
+    from esc_gnn_b200 import ogb_model
+    config = 4
+    fl = synth.ENCODER_FLAGS[config]
+    pool = [RawBatch.synth(config, 9000 + i * batch, batch).cuda(non_blocking=False) for i in range(6)]
+    ncap = int(max(b.num_nodes for b in pool) * 1.04) + 64
+    ecap = int(max(b.src.numel() for b in pool) * 1.04) + 128
+    torch.manual_seed(0)
+    model = ogb_model.GNN('ogbg-molhiv', 1, num_layer=6, emb_dim=300, gnn_type='gin_eff', virtual_node=True, residual=False,
+                          drop_ratio=drop_ratio).cuda()
+    model.train()
+    eng = StaticTrainEngine(model, 'ogb', fl, max_graphs=batch, max_nodes_per_graph=max(b.max_nodes for b in pool),
+                            max_edges_per_graph=max(b.max_loop_edges for b in pool), nodes_cap=ncap, edges_cap=ecap, lr=1e-3,
+                            pipeline=True)
+    losses = []
+    for i in range(10):
+        l = eng.step(pool[i % 6])
+        if l is not None:
+            losses.append(float(l.item()))
+    eng.check_errors()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        l = eng.step(pool[i % 6])
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    eng.check_errors()
+    print('%-48s batch %5d  %.3f ms/step  %9.0f graphs/s   loss %.4f -> %.4f (engine, dropout %.1f)' % (
+        tag, batch, ms, batch / ms * 1e3, losses[0], float(l.item()), drop_ratio), flush=True)
+
+
+run_ogb_engine('cfg4 ogbg-molhiv-shaped h=4, 6 layers emb 300', 32)
+run_ogb_engine('cfg4 ogbg-molhiv-shaped h=4, 6 layers emb 300', 256)
