@@ -46,6 +46,7 @@ SIGNATURES = {
     'escgnn_dropout': (_i32, [_vp, _i32, ctypes.c_float, ctypes.c_uint32, _vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     'escgnn_add_segment_rows': (_i32, [_vp, _i32, _vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),
     'escgnn_rewrite_edge_attr': (_i32, [_vp] * 4 + [_i64, _vp, _vp, _i32, _i64, _vp, _vp]),
+    'escgnn_embedding_bwd_small': (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     'escgnn_reduce_sum': (_i32, [_vp, _i64, _vp, _i32, _vp]),
     'escgnn_zero_tail_rows': (_i32, [_vp, _i32, _i32, _vp, _i64, _vp]),
     'escgnn_bag_embed_bwd_sorted': (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

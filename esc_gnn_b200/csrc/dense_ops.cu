@@ -871,6 +871,33 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ dy, int lddy, con
     }
 }
 
+// small tables (BondEncoder: 13 rows, the type embeddings: 100): thousands of rows hammer a handful of addresses, so every CTA
+// accumulates into a private copy of the table in shared memory and adds it to the global gradient once
+__global__ void __launch_bounds__(256)
+embedding_bwd_small_kernel(const float* __restrict__ dy, int lddy, const int64_t* __restrict__ idx, int n_cols_idx,
+                           const int64_t* __restrict__ col_offsets, const int* __restrict__ d_rows, int C, int table_rows,
+                           float* __restrict__ dtable) {
+    escgnn::pdl_enter();
+    extern __shared__ float s_tab[];
+    const int total = table_rows * C;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) s_tab[i] = 0.f;
+    __syncthreads();
+    const int rows = *d_rows;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)rows * C; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / C), c = (int)(i % C);
+        const float g = dy[(size_t)r * lddy + c];
+        for (int k = 0; k < n_cols_idx; ++k) {
+            const int64_t t = idx[(size_t)r * n_cols_idx + k] + (col_offsets ? col_offsets[k] : 0);
+            if (t >= 0 && t < table_rows) atomicAdd(&s_tab[(int)t * C + c], g);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const float v = s_tab[i];
+        if (v != 0.f) atomicAdd(&dtable[i], v);
+    }
+}
+
 // losses over `rows` predictions [rows, T]: kind 0 = L1 mean (run_graphcount.py:498, run_zinc.py:283),
 // kind 1 = BCE-with-logits mean over labelled entries y == y (run_ogb_mol.py:58-74). Single CTA, ordered sum.
 __global__ void __launch_bounds__(1024)
@@ -1181,6 +1208,18 @@ int escgnn_embedding_bwd(const float* d_dy, int lddy, const int64_t* d_idx, int 
     int64_t total = (int64_t)rows_cap * channels;
     unsigned b = (unsigned)((total + 255) / 256); if (b > 1184) b = 1184; if (b < 1) b = 1;
     escgnn::launch_pdl(embedding_bwd_kernel, b, 256, 0, (cudaStream_t)stream, d_dy, lddy, d_idx, idx_cols, d_col_offsets, d_rows, channels, d_dtable);
+    return (int)cudaGetLastError();
+}
+
+int escgnn_embedding_bwd_small(const float* d_dy, int lddy, const int64_t* d_idx, int idx_cols, const int64_t* d_col_offsets,
+                               const int* d_rows, int rows_cap, int channels, int table_rows, float* d_dtable, void* stream) {
+    const size_t smem = (size_t)table_rows * channels * sizeof(float);
+    if (smem > 48 * 1024)
+        return escgnn_embedding_bwd(d_dy, lddy, d_idx, idx_cols, d_col_offsets, d_rows, rows_cap, channels, d_dtable, stream);
+    int64_t total = (int64_t)rows_cap * channels;
+    unsigned b = (unsigned)((total + 256 * 16 - 1) / (256 * 16)); if (b > 296) b = 296; if (b < 1) b = 1;
+    escgnn::launch_pdl(embedding_bwd_small_kernel, b, 256, smem, (cudaStream_t)stream, d_dy, lddy, d_idx, idx_cols, d_col_offsets, d_rows,
+                       channels, table_rows, d_dtable);
     return (int)cudaGetLastError();
 }
 

@@ -323,9 +323,9 @@ class StaticTrainEngine(object):
         c = self.c
         C = table.weight.size(1)
         cols = 1 if idx.dim() == 1 else idx.size(1)
-        self.bwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_embedding_bwd(
-            _p(dout), dout.stride(0), _p(idx), cols, None, _p(c.rows[kind]), c.caps[kind], C, _p(table.weight.grad), c.st()),
-            'embedding_bwd')))
+        self.bwd.append(lambda: self._fork(lambda: _lib.check(c.L.escgnn_embedding_bwd_small(
+            _p(dout), dout.stride(0), _p(idx), cols, None, _p(c.rows[kind]), c.caps[kind], C, table.weight.size(0),
+            _p(table.weight.grad), c.st()), 'embedding_bwd')))
 
     def _gine(self, x, dx, ee, dee, eps, out, dout):
         """out = (1+eps) x + sum relu(x_src + ee).  x / ee / dee may be column slices (leading dimensions are passed).
@@ -597,9 +597,10 @@ class StaticTrainEngine(object):
             t0, e_l, de_l = tabs[0].weight, e_all[:, l * H:(l + 1) * H], de_all[:, l * H:(l + 1) * H]
             self.fwd.append(lambda t0=t0, off=off, e_l=e_l: _lib.check(c.L.escgnn_embedding_fwd(
                 _p(t0), _p(self.in_ea), 3, _p(off), _p(c.rows['E']), E_rows, H, _p(e_l), e_l.stride(0), c.st()), 'embedding_fwd'))
-            self.bwd.append(lambda t0=t0, off=off, de_l=de_l: self._fork(lambda: _lib.check(c.L.escgnn_embedding_bwd(
-                _p(de_l), de_l.stride(0), _p(self.in_ea), 3, _p(off), _p(c.rows['E']), E_rows, H, _p(t0.grad), c.st()),
-                'embedding_bwd')))
+            n_bond = sum(e.weight.size(0) for e in tabs)
+            self.bwd.append(lambda t0=t0, off=off, de_l=de_l, n_bond=n_bond: self._fork(lambda: _lib.check(
+                c.L.escgnn_embedding_bwd_small(_p(de_l), de_l.stride(0), _p(self.in_ea), 3, _p(off), _p(c.rows['E']), E_rows, H, n_bond,
+                                               _p(t0.grad), c.st()), 'embedding_bwd')))
         self.fwd.append(lambda: _lib.check(c.L.escgnn_zero_tail_rows(_p(de_all), de_all.stride(0), n_tot, _p(c.rows['E']), E_rows,
                                                                      c.st()), 'zero_tail_rows'))
         self.fwd.append(lambda: self._gemm('gemm_fwd', zemb, False, W_cat, False, e_all, b_cat, E_rows, n_tot, H, True, rows='E'))

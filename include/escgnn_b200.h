@@ -293,6 +293,10 @@ int escgnn_embedding_fwd(const float* d_table, const int64_t* d_idx, int idx_col
                          const int* d_rows, int rows_cap, int channels, float* d_y, int ldy, void* stream);
 int escgnn_embedding_bwd(const float* d_dy, int lddy, const int64_t* d_idx, int idx_cols, const int64_t* d_col_offsets,
                          const int* d_rows, int rows_cap, int channels, float* d_dtable, void* stream);
+/* same gradient for a SMALL table (table_rows * channels * 4 <= 48 KB, e.g. BondEncoder's 13 rows): per-CTA accumulation in
+ * shared memory, one global add per CTA and entry; larger tables fall through to escgnn_embedding_bwd */
+int escgnn_embedding_bwd_small(const float* d_dy, int lddy, const int64_t* d_idx, int idx_cols, const int64_t* d_col_offsets,
+                               const int* d_rows, int rows_cap, int channels, int table_rows, float* d_dtable, void* stream);
 /* loss + its gradient: kind 0 = L1Loss mean (run_graphcount.py:498, run_zinc.py:283); kind 1 = BCEWithLogitsLoss
  * over labelled targets y == y (run_ogb_mol.py:58-74) */
 int escgnn_loss_fwd_bwd(const float* d_pred, int ldp, const float* d_target, int kind, const int* d_rows, int rows_cap,

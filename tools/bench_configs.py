@@ -113,6 +113,9 @@ def run_ogb_engine(tag, batch, steps=200, drop_ratio=0.5):
     eng.check_errors()
     print('%-48s batch %5d  %.3f ms/step  %9.0f graphs/s   loss %.4f -> %.4f (engine, dropout %.1f)' % (
         tag, batch, ms, batch / ms * 1e3, losses[0], float(l.item()), drop_ratio), flush=True)
+    if os.environ.get('ESC_PROFILE'):
+        km, _ = eng.profile(pool[0], reps=5)
+        print('   ', {k: round(v, 4) for k, v in sorted(km.items(), key=lambda kv: -kv[1])[:16]})
 
 
 run_ogb_engine('cfg4 ogbg-molhiv-shaped h=4, 6 layers emb 300', 32)
