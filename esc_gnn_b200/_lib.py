@@ -14,6 +14,7 @@ ERR_BITS = {1: 'sub_degree >= 200 (reference: F.one_hot(sub_degree, 200) raises)
             4: 'resistance-distance bin outside the supported range / singular system',
             8: 'use_rd on a non-symmetric edge multiset is not supported'}
 NUM_COUNTERS = 8
+CTR_PER_CALL, CTR_STICKY_ERROR, CTR_MAX_NNZ = 4, 4, 5
 RD_SLOTS = 12
 REC_IDX_BITS = 11
 

@@ -126,13 +126,12 @@ ego_encode_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict_
             if (__any_sync(kFull, deg_err) && lane == 0)
                 atomicOr(&counters[ESCGNN_CTR_ERROR], (unsigned long long)ESCGNN_DATA_DEG);
             long long off = 0;
-            if (lane == 0) {
-                off = (long long)atomicAdd(&counters[ESCGNN_CTR_NNZ], (unsigned long long)fresh);
-                rec_off[e0 + ed] = off;
-                rec_nnz[e0 + ed] = fresh;
-            }
+            if (lane == 0) off = (long long)atomicAdd(&counters[ESCGNN_CTR_NNZ], (unsigned long long)fresh);
             off = __shfl_sync(kFull, off, 0);
             const bool room = off + fresh <= rec_cap;
+            // an edge without room owns NO records (offset 0, count 0): consumers of the compact form never index past the
+            // capacity; the overflow itself is visible in counters[NNZ] > rec_cap (and in the sticky slots, escgnn_make_dims)
+            if (lane == 0) { rec_off[e0 + ed] = room ? off : 0; rec_nnz[e0 + ed] = room ? fresh : 0; }
             __syncwarp();
             // ---- ascending emission; each lane owns one word = two consecutive bins; table is zeroed on the way
             int pos = 0;

@@ -544,11 +544,20 @@ __global__ void ptr_to_ids_kernel(const int64_t* __restrict__ ptr, int64_t segs,
 }
 
 __global__ void make_dims_kernel(const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int64_t g,
-                                 const unsigned long long* __restrict__ counters, int* __restrict__ dims) {
+                                 unsigned long long* __restrict__ counters, int* __restrict__ dims) {
     escgnn::pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        dims[0] = (int)node_ptr[g]; dims[1] = (int)eo_ptr[g]; dims[2] = (int)g;
+        // a partial batch pads the pointer arrays with empty trailing graphs: the graph count is the first position whose
+        // node offset already equals the total (graphs have at least one node)
+        const int64_t total = node_ptr[g];
+        int64_t lo = 0, hi = g;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (node_ptr[mid] < total) lo = mid + 1; else hi = mid; }
+        dims[0] = (int)total; dims[1] = (int)eo_ptr[g]; dims[2] = (int)lo;
         dims[3] = counters ? (int)counters[ESCGNN_CTR_NNZ] : 0;
+        if (counters) {                                   // sticky: survives the per-step zeroing of slots [0, PER_CALL)
+            counters[ESCGNN_CTR_STICKY_ERROR] |= counters[ESCGNN_CTR_ERROR];
+            if (counters[ESCGNN_CTR_NNZ] > counters[ESCGNN_CTR_MAX_NNZ]) counters[ESCGNN_CTR_MAX_NNZ] = counters[ESCGNN_CTR_NNZ];
+        }
     }
 }
 
@@ -586,7 +595,7 @@ int escgnn_collate_edges(const int64_t* d_src, const int64_t* d_dst, const int32
 }
 
 int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t n_graphs,
-                     const unsigned long long* d_counters, int* d_dims, void* stream) {
+                     unsigned long long* d_counters, int* d_dims, void* stream) {
     escgnn::launch_pdl(make_dims_kernel, 1, 32, 0, (cudaStream_t)stream, d_eo_ptr, d_node_ptr, n_graphs, d_counters, d_dims);
     return (int)cudaGetLastError();
 }

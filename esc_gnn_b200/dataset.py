@@ -23,9 +23,11 @@ def pre_transform_batched(data_list, h=1, use_rd=False, self_loop=False, chunk=4
         dst = torch.cat([d.edge_index[1] for d in part]).to(torch.int64)
         eptr = np.concatenate([[0], np.cumsum(ee)]).astype(np.int64)
         nptr = np.concatenate([[0], np.cumsum(nn)]).astype(np.int64)
-        r = encode_batch_host(src, dst, eptr, nptr, h, use_rd, self_loop, local_ordinals=True, device=device)
+        # pos_batch comes back as the BATCH-wide edge ordinal (ascending), so the records of graph g are exactly those with
+        # edge_ptr[g] <= pos_batch < edge_ptr[g+1]; the graph-local ordinal the per-graph transform returns is pos_batch - edge_ptr[g]
+        r = encode_batch_host(src, dst, eptr, nptr, h, use_rd, self_loop, local_ordinals=False, device=device)
         ep = r.edge_ptr.numpy()
-        rec_ptr = np.searchsorted(_global_ordinal(r.pos_batch.numpy(), ep), ep)      # records of graph g: [rec_ptr[g], rec_ptr[g+1])
+        rec_ptr = np.searchsorted(r.pos_batch.numpy(), ep)      # records of graph g: [rec_ptr[g], rec_ptr[g+1])
         for g, d in enumerate(part):
             a, b, ra, rb = ep[g], ep[g + 1], rec_ptr[g], rec_ptr[g + 1]
             edge_attr = d.edge_attr
@@ -34,30 +36,15 @@ def pre_transform_batched(data_list, h=1, use_rd=False, self_loop=False, chunk=4
                 edge_attr = edge_attr[keep]
                 edge_attr = torch.cat([edge_attr, edge_attr.new_full((nn[g], ) + tuple(edge_attr.size()[1:]), 1.)], dim=0)
             out.append(d.__class__(d.x, r.edge_index[:, a:b].clone(), edge_attr, d.y, None, pos_enc=r.pos_enc[ra:rb].clone(),
-                                   pos_index=r.pos_index[ra:rb].clone(), pos_batch=r.pos_batch[ra:rb].clone()))
+                                   pos_index=r.pos_index[ra:rb].clone(), pos_batch=r.pos_batch[ra:rb] - int(a)))
     return out
-
-
-def _global_ordinal(pos_batch_local, edge_ptr):
-    """pos_batch comes back graph-local (local_ordinals); rebuild the batch-wide edge ordinal to split records by graph.
-    Records are grouped by graph and ascending inside a graph, so a graph boundary is where the local ordinal drops."""
-    if pos_batch_local.size == 0:
-        return pos_batch_local
-    drops = np.nonzero(np.diff(pos_batch_local) < 0)[0] + 1
-    # a graph whose first edge ordinal is not smaller than the previous graph's last one cannot happen: every graph
-    # starts at local ordinal 0 and every edge has at least three records
-    starts = np.concatenate([[0], drops])
-    graph_of = np.zeros(pos_batch_local.size, dtype=np.int64)
-    graph_of[starts[1:]] = 1
-    graph_of = np.cumsum(graph_of)
-    nonempty = np.nonzero(np.diff(edge_ptr) > 0)[0]
-    return pos_batch_local + edge_ptr[nonempty[graph_of]]
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # Processed-dataset cache: the `(data, slices)` layout of `InMemoryDataset.collate` that the reference's `process()`
-# methods write with `torch.save` (GraphCountDataset.py:118-119, dataset_zinc.py:87-88, dataset_pyg.py:183-186), so a
-# dataset processed here is laid out on disk like one processed by the reference.
+# methods write with `torch.save` (GraphCountDataset.py:118-119, dataset_zinc.py:87-88, dataset_pyg.py:183-186).  On disk the
+# first element is a plain {key: tensor} dict rather than a pickled PyG `Data` (loadable with torch.load's weights-only
+# default and without torch_geometric); `Data(**store)` rebuilds the reference's object, the slices dict is identical.
 def collate(data_list):
     """All graphs concatenated key by key (along `Data.__cat_dim__`) + per-key boundary offsets.  No index increments
     (those belong to batching, batch.py), no `batch` vector."""

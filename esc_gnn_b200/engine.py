@@ -181,8 +181,14 @@ class StaticTrainEngine(object):
         self._side_used = False
         self.inline_branches = False
         self.fwd, self.bwd, self._bns, self._emb_ready = [], [], [], []
+        # bond attributes go through E1 on the device whenever the edge list does (dropped loops, appended loop rows = 1:
+        # utils_edge_efficient.py:35-36 / PyG add_self_loops fill value) -- always for 'ogb', for 'zinc' with self_loop
+        self.ea_cols = 3 if variant == 'ogb' else 1
+        self.ea_via_raw = variant == 'ogb' or (variant == 'zinc' and bool(flags['self_loop']))
+        if self.ea_via_raw:
+            shape = (e_in_cap, 3) if variant == 'ogb' else (e_in_cap, )
+            self.in_ea_raw = torch.zeros(shape, dtype=torch.int64, device=dev)     # bond columns before E1
         if variant == 'ogb':
-            self.in_ea_raw = torch.zeros((e_in_cap, 3), dtype=torch.int64, device=dev)     # bond columns before E1
             self._build_ogb_tape()
         else:
             self._build_model_tape()
@@ -743,19 +749,20 @@ class StaticTrainEngine(object):
         t = self.live if t is None else t
         c, L, fl, G = self.c, self.c.L, self.flags, self.G
         st = c.st()
-        self.counters.zero_()
+        self.counters[:_lib.CTR_PER_CALL].zero_()    # the sticky error / max-nnz slots survive (check_errors reads them)
         _lib.mark('memset')
         if fl['self_loop']:
             _lib.check(L.escgnn_rewrite_self_loops(_p(self.in_src), _p(self.in_dst), _p(self.in_eptr), _p(self.in_nptr), G,
                                                    _p(self.eo_ptr), _p(self.eo[0]), _p(self.eo[1]), _p(self.rw_tmp), st),
                        'rewrite_self_loops')
             es, ed, ep = self.eo[0], self.eo[1], self.eo_ptr
-            if self.variant == 'ogb':
+            if self.ea_via_raw:
                 _lib.check(L.escgnn_rewrite_edge_attr(_p(self.in_src), _p(self.in_dst), _p(self.in_eptr), _p(self.in_nptr), G,
-                                                      _p(self.eo_ptr), _p(self.in_ea_raw), 3, 1, _p(t.in_ea), st), 'rewrite_edge_attr')
+                                                      _p(self.eo_ptr), _p(self.in_ea_raw), self.ea_cols, 1, _p(t.in_ea), st),
+                           'rewrite_edge_attr')
         else:
             es, ed, ep = self.in_src, self.in_dst, self.in_eptr
-            if self.variant == 'ogb':
+            if self.ea_via_raw:
                 t.in_ea[:self.in_ea_raw.size(0)].copy_(self.in_ea_raw)
         if fl['use_rd']:
             _lib.check(L.escgnn_encode_rd(_p(es), _p(ed), _p(ep), _p(self.in_nptr), G, fl['h'], _p(self.rdh), _p(self.counters),
@@ -780,7 +787,7 @@ class StaticTrainEngine(object):
         """Pipelined mode: features / targets of the batch just loaded travel with the batch set they belong to."""
         t.in_x.copy_(self.raw_feat.in_x)
         t.in_y.copy_(self.raw_feat.in_y)
-        if t.in_ea is not None and self.variant != 'ogb':
+        if t.in_ea is not None and not self.ea_via_raw:
             t.in_ea.copy_(self.raw_feat.in_ea)
 
     @torch.no_grad()
@@ -838,19 +845,26 @@ class StaticTrainEngine(object):
     def load(self, raw):
         """Copy one RawBatch (pinned host or device) into the static input buffers (async on the current stream)."""
         e, g = raw.src.numel(), raw.num_graphs
-        if g != self.G:
-            raise ValueError('engine built for %d graphs per step, got %d' % (self.G, g))
+        if g > self.G or g < 1:
+            raise ValueError('engine built for at most %d graphs per step, got %d' % (self.G, g))
+        if g == 1 and self.G > 1 and self.variant != 'ogb':
+            # the reference skips bn_lin1 when the batch has a single row (zinc_models.py:605-606); the engine's readout tail is
+            # built once from the capacity
+            raise NotImplementedError('a one-graph batch needs an engine built with max_graphs=1')
         if e > self.c.caps['E_in'] or raw.num_nodes > self.c.caps['N'] or raw.max_nodes > self.max_n or \
                 (raw.max_loop_edges if self.flags['self_loop'] else raw.max_in_edges) > self.max_e:
             raise ValueError('batch exceeds the engine capacity')
         self.in_src[:e].copy_(raw.src, non_blocking=True)
         self.in_dst[:e].copy_(raw.dst, non_blocking=True)
-        self.in_eptr.copy_(raw.edge_ptr, non_blocking=True)
-        self.in_nptr.copy_(raw.node_ptr, non_blocking=True)
+        self.in_eptr[:g + 1].copy_(raw.edge_ptr, non_blocking=True)
+        self.in_nptr[:g + 1].copy_(raw.node_ptr, non_blocking=True)
         n = raw.num_nodes
+        if g < self.G:        # the last, partial batch of an epoch (the reference trains on it): empty trailing graphs; every
+            self.in_eptr[g + 1:].fill_(e)     # kernel reads the actual node / edge / graph counts from the device (make_dims)
+            self.in_nptr[g + 1:].fill_(n)
         t = self.raw_feat if self.pipeline else self.live   # pipelined: the encoder branch forwards them into the staging set
         t.in_x[:n].copy_(raw.x, non_blocking=True)
-        if self.variant == 'ogb':                    # the encoder applies E1 to the bond columns (loop rows = 1)
+        if self.ea_via_raw:                          # the encoder applies E1 to the bond columns (loop rows = 1)
             self.in_ea_raw[:raw.edge_attr.size(0)].copy_(raw.edge_attr, non_blocking=True)
         elif t.in_ea is not None:
             t.in_ea[:raw.edge_attr.size(0)].copy_(raw.edge_attr, non_blocking=True)
@@ -959,10 +973,14 @@ class StaticTrainEngine(object):
             self._bn_synced = self.steps
 
     def check_errors(self):
-        """Lazy data-error check (degree >= 200, bad ids, capacity): one sync, call it once per epoch."""
+        """Lazy data-error check (degree >= 200, bad ids, capacity) over EVERY batch since the last call: one sync, call it
+        once per epoch.  The encoder's per-call counters are zeroed each step, the sticky slots are not."""
         cnt = self.counters.cpu()
-        _lib.raise_data_errors(int(cnt[1]))
-        if int(cnt[0]) > self.rec.numel():
-            raise RuntimeError('engine record capacity exceeded: %d > %d' % (int(cnt[0]), self.rec.numel()))
+        self.counters[_lib.CTR_STICKY_ERROR:_lib.CTR_MAX_NNZ + 1].zero_()
+        _lib.raise_data_errors(int(cnt[_lib.CTR_STICKY_ERROR]) | int(cnt[1]))
+        worst = max(int(cnt[_lib.CTR_MAX_NNZ]), int(cnt[0]))
+        if worst > self.rec.numel():
+            raise RuntimeError('engine record capacity exceeded: %d > %d (the edges without room were trained on as empty bags; '
+                               'raise records_per_edge)' % (worst, self.rec.numel()))
         if int(self.idx_err.cpu()[0]):
             raise RuntimeError('edge_index out of range after collation')

@@ -34,6 +34,9 @@ extern "C" {
 #define ESCGNN_CTR_ERROR 1            /* OR of ESCGNN_DATA_* */
 #define ESCGNN_CTR_TICKET 2           /* persistent-CTA work ticket */
 #define ESCGNN_CTR_TICKET_RD 3
+#define ESCGNN_CTR_STICKY_ERROR 4     /* OR of every ERROR word seen by escgnn_make_dims since the caller last cleared it */
+#define ESCGNN_CTR_MAX_NNZ 5          /* max of every NNZ seen by escgnn_make_dims (record-capacity overflow detection) */
+#define ESCGNN_CTR_PER_CALL 4         /* slots [0, 4) are per-call state: a caller that keeps the sticky slots zeroes only these */
 #define ESCGNN_NUM_COUNTERS 8
 
 #define ESCGNN_RD_SLOTS 12            /* rd histogram slots kept per edge (bins 0..11; R(u,w) <= 2h+1 <= 9) */
@@ -233,9 +236,12 @@ int escgnn_reduce_sum(const float* d_v, int64_t n, float* d_out, int accumulate,
 /* rows [*d_rows, rows_cap) of a [rows_cap, ld] fp32 buffer := 0 (first `cols` columns) */
 int escgnn_zero_tail_rows(float* d_x, int ld, int cols, const int* d_rows, int64_t rows_cap, void* stream);
 /* d_dims[4] = {total nodes, total edges after E1, graphs, records}: the device-side sizes the static-shape
- * entry points read through their d_count / d_rows arguments (no host sync between encoder and model). */
+ * entry points read through their d_count / d_rows arguments (no host sync between encoder and model).
+ * Also folds this call's ERROR / NNZ words into the sticky slots ESCGNN_CTR_STICKY_ERROR / ESCGNN_CTR_MAX_NNZ of
+ * d_counters, so a caller that zeroes only the per-call slots [0, ESCGNN_CTR_PER_CALL) every step can check ONCE per
+ * epoch whether ANY batch had a data error or exceeded its record capacity. */
 int escgnn_make_dims(const int64_t* d_eo_ptr, const int64_t* d_node_ptr, int64_t n_graphs,
-                     const unsigned long long* d_counters, int* d_dims, void* stream);
+                     unsigned long long* d_counters, int* d_dims, void* stream);
 
 /* ---- dense row-wise kernels of the static-shape engine (M2, M4, M5); `d_rows` = actual row count on the device,
  * rows_cap = capacity; ld* = leading dimensions (outputs can be column slices of a wider buffer = free concat) ---- */

@@ -146,6 +146,35 @@ def main():
         model.eval()
         with torch.no_grad():
             store[name + '/pred_after_adam'] = model(batch).numpy().astype(np.float32)
+        if name in MU.FP64_CASES:
+            # fp64 truth of the SAME reference class: per-tensor ||g32 - g64||_2 is the yardstick the product's gradients are
+            # measured with (tests: ||g_product - g64|| <= 3 * ||g32_reference - g64|| + floor)
+            model.load_state_dict(sd)
+            model.train()
+            g32 = {}
+            model.zero_grad()
+            MU.loss_fn(variant, model(batch), batch.y).backward()
+            for k, p in model.named_parameters():
+                if p.grad is not None:
+                    g32[k] = p.grad.detach().double().clone()
+            model64 = build_reference_model(variant, kw).double()
+            model64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()})
+            model64.train()
+            b64 = _Batch(MU.to_double(batch))
+            pred64 = model64(b64)
+            loss64 = MU.loss_fn(variant, pred64, b64.y) if variant != 'ogb' else \
+                torch.nn.BCEWithLogitsLoss()(pred64[b64.y.view(pred64.shape) == b64.y.view(pred64.shape)],
+                                             b64.y.view(pred64.shape)[b64.y.view(pred64.shape) == b64.y.view(pred64.shape)])
+            loss64.backward()
+            dig64, err32 = [], []
+            for k in keys:
+                g64 = dict(model64.named_parameters())[k].grad.detach()
+                dig64.append(MU.grad_digest(g64))
+                err32.append((g32[k] - g64).norm().item())
+            store[name + '/grad64_digest'] = np.stack(dig64)
+            store[name + '/grad_err32'] = np.array(err32, dtype=np.float64)
+            store[name + '/loss64'] = np.array([loss64.item()], dtype=np.float64)
+            store[name + '/pred64'] = pred64.detach().numpy()
         nparam = sum(p.numel() for p in model.parameters())
         print('%-12s params %8d  N %5d  E %6d  nnz %7d  loss %.6f  adam %s' % (
             name, nparam, batch.x.shape[0], batch.edge_index.shape[1], batch.pos_enc.numel(), loss.item(),

@@ -79,7 +79,24 @@ MODEL_CASES = {
     'ogb': ('ogb', 4, 12, dict(num_tasks=1, num_layer=3, emb_dim=64, drop_ratio=0.0, virtual_node=True, residual=True)),
     'qm9': ('qm9', 6, 20, dict(num_layers=3)),
     'ogb_full': ('ogb', 4, 8, dict(num_tasks=1, num_layer=6, emb_dim=300, drop_ratio=0.0, virtual_node=True, residual=False)),
+    # BASELINE.json shapes (configs[0..3]): the reference's own batch sizes, depths and widths; these cases also carry fp64
+    # gradient statistics of the reference class (`/grad64_digest`, `/grad_err32`)
+    'count_cfg1': ('count', 1, 128, dict(num_layers=5, hidden=256)),       # run_graphcount.py:465, batch 128, h=3
+    'zinc_cfg2': ('zinc', 2, 256, dict(num_layers=5)),                     # run_zinc.py:56 batch 256, h=3
+    'count_cfg3': ('count', 3, 32, dict(num_layers=5, hidden=256)),        # count_graphlet, h=4, batch 32
+    'ogb_cfg4': ('ogb', 4, 32, dict(num_tasks=1, num_layer=6, emb_dim=300, drop_ratio=0.0, virtual_node=True, residual=False)),
 }
+FP64_CASES = ('count_cfg1', 'zinc_cfg2', 'count_cfg3', 'ogb_cfg4')
+
+
+def to_double(batch):
+    """The same batch with every floating tensor in float64 (fp64 gradient truth runs)."""
+    import copy
+    b = copy.copy(batch)
+    for k, v in list(b.__dict__.items()):
+        if torch.is_tensor(v) and v.is_floating_point():
+            setattr(b, k, v.double())
+    return b
 
 
 def loss_fn(variant, pred, y):

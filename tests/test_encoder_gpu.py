@@ -205,6 +205,31 @@ def test_pre_transform_batched_equals_per_graph_calls():
             assert (o.edge_attr is None) == (w.edge_attr is None) and (o.edge_attr is None or torch.equal(o.edge_attr, w.edge_attr))
 
 
+def test_pre_transform_batched_single_edge_graphs_inside_a_chunk():
+    """A graph with exactly ONE output edge (one node + self_loop, or one directed edge) has last local ordinal 0, the same as
+    the next graph's first: record boundaries must come from the batch-wide edge ordinal, not from ordinal drops."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.dataset import pre_transform_batched
+    from esc_gnn_b200.transform import create_subgraphs
+    one_node = Data(x=torch.ones(1, 1), edge_index=torch.zeros((2, 0), dtype=torch.long), y=torch.tensor([0.0]))
+    one_node.num_nodes = 1
+    one_edge = Data(x=torch.ones(2, 1), edge_index=torch.tensor([[0], [1]]), y=torch.tensor([1.0]))
+
+    def big(i):
+        g = synth.make_graph(2, 40 + i)
+        return Data(x=torch.as_tensor(g['x']), edge_index=torch.as_tensor(g['edge_index']), y=torch.as_tensor(g['y']).view(1))
+    # self_loop=True: the one-node graph yields the single edge (0,0); self_loop=False: only the one-edge graph qualifies
+    for sl, graphs in ((True, [big(0), one_node, one_node, big(1), one_edge, one_node, big(2)]),
+                       (False, [one_edge, big(0), one_edge, one_edge, big(1), one_edge])):
+        got = pre_transform_batched(graphs, h=2, use_rd=False, self_loop=sl, chunk=64)
+        assert len(got) == len(graphs)
+        for d, o in zip(graphs, got):
+            w = create_subgraphs(d, 2, use_rd=False, self_loop=sl)
+            for k in ('edge_index', 'pos_enc', 'pos_index', 'pos_batch'):
+                assert torch.equal(o[k], w[k]), (sl, k)
+
+
 def test_encoded_dataset_processes_once_and_serves_from_cache(tmp_path):
     """N1: EncodedDataset.process() (batched encoder -> collate -> torch.save) then a second open from the cache alone;
     every served graph equals the oracle's per-graph encoding, and the loader batches it like any Data list."""

@@ -145,6 +145,29 @@ def test_distance_transform_matches_reference_formula():
             torch.testing.assert_close(out, want, rtol=1e-6, atol=1e-6)
 
 
+def test_distance_transform_matches_reference_fixtures():
+    """D1 pinned: outputs of the unmodified /root/reference/distance.py (tests/golden/make_golden_batch.py -> batch.npz), every
+    constructor option, 1-D / missing edge_attr, and the original_* branch (distance.py:49-63); CPU-resident and CUDA-resident
+    data.  fp32 tolerance 1e-6 relative (sqrt / division rounding; the reference is plain torch fp32)."""
+    import os
+    from esc_gnn_b200.data import Data
+    from esc_gnn_b200.distance import Distance
+    from tests import batch_cases as BC
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'batch.npz'))
+    for name, kw, has_attr, one_d, original in BC.DIST_CASES:
+        inp = {k.split('/', 2)[2][3:]: torch.as_tensor(fix[k]) for k in fix.files if k.startswith('dist/%s/in_' % name)}
+        assert ('edge_attr' in inp) == has_attr and ('original_pos' in inp) == original
+        for dev in ('cpu', 'cuda'):
+            d = Data(x=torch.ones(inp['pos'].size(0), 1), **{k: v.clone().to(dev) for k, v in inp.items()})
+            o = Distance(**kw)(d)
+            want = torch.as_tensor(fix['dist/%s/edge_attr' % name])
+            assert o.edge_attr.shape == want.shape and o.edge_attr.dtype == want.dtype, name
+            torch.testing.assert_close(o.edge_attr.cpu(), want, rtol=1e-6, atol=1e-6)
+            if original:
+                torch.testing.assert_close(o.original_edge_attr.cpu(), torch.as_tensor(fix['dist/%s/original_edge_attr' % name]),
+                                           rtol=1e-6, atol=1e-6)
+
+
 def test_ops_refuse_cpu_tensors():
     from esc_gnn_b200 import ops
     with pytest.raises(RuntimeError):
@@ -421,3 +444,207 @@ def test_bag_embed_backward_index_major_matches_atomic_version():
     mag = torch.zeros(1800, H, device='cuda', dtype=torch.float64)
     mag.index_add_(0, r.pos_index, g[r.pos_batch].double().abs() * r.pos_enc.view(-1, 1).double())
     assert ((dW.double() - ref).abs() <= 1e-5 * ref.abs() + 2e-6 * mag + 1e-6).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json shapes (batch 128 / 256 / 32 / 32, 5-6 layers, hidden 256 / 300) and the fp64 gradient yardstick
+def _fp64_truth(name):
+    """fp64 run of the oracle restatement (plain torch, on the GPU for speed) -- first pinned to the fp64 run of the reference's
+    own class (fixture `/grad64_digest`, 1e-9), then used as the truth both backward passes are measured against."""
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    m = MU.build_oracle_model(variant, kw).double()
+    sd = MU.det_state(m.state_dict(), seed=1234)
+    m.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()})
+    m = m.cuda().train()
+    b = MU.to_double(MU.ref_batch(config, 100, count))
+    for k, v in list(b.__dict__.items()):
+        if torch.is_tensor(v):
+            setattr(b, k, v.cuda())
+    loss = MU.loss_fn(variant, m(b), b.y) if variant != 'ogb' else None
+    if variant == 'ogb':
+        pred = m(b)
+        y = b.y.view(pred.shape)
+        loss = torch.nn.BCEWithLogitsLoss()(pred[y == y], y[y == y])
+    loss.backward()
+    g64 = {k: p.grad.detach() for k, p in m.named_parameters() if p.grad is not None}
+    assert abs(loss.item() - FIX_M[name + '/loss64'][0]) <= 1e-9 * max(1.0, abs(FIX_M[name + '/loss64'][0]))
+    for k, want in zip(FIX_M[name + '/grad_keys'], FIX_M[name + '/grad64_digest']):
+        got = MU.grad_digest(g64[str(k)])
+        assert abs(got[3] - want[3]) <= 1e-8 * max(want[3], 1e-12) + 1e-13, (str(k), got[3], want[3])     # ||g64||_2
+    return g64
+
+
+def _check_against_fp64(name, grads, g64, factor):
+    """||g - g64||_2 <= factor * ||g32_reference - g64||_2 + floor, per parameter tensor.  floor: 2e-6 of the tensor's norm
+    (fp32 resolution of the sum itself) -- it only matters where the reference's own error is ~0, i.e. gradients that are
+    mathematically zero (a Linear bias feeding BatchNorm), which the engine leaves at exactly 0."""
+    variant = MU.MODEL_CASES[name][0]
+    worst, bad = 0.0, []
+    gmax = max(float(v.norm()) for v in g64.values())
+    for k, ref_err in zip(FIX_M[name + '/grad_keys'], FIX_M[name + '/grad_err32']):
+        k = str(k)
+        if variant == 'count' and k.startswith('x_embedding.'):
+            continue                  # all-ones input: zero-variance BatchNorm, gradients are rounding noise times rsqrt(eps) (see run_case)
+        err = float((grads[k].double() - g64[k]).norm())
+        bound = factor * float(ref_err) + 2e-6 * float(g64[k].norm()) + 1e-9 * gmax
+        worst = max(worst, err / max(bound, 1e-30))
+        if err > bound:
+            bad.append((k, err, float(ref_err), float(g64[k].norm())))
+    assert not bad, (name, worst, bad[:6])
+    return worst
+
+
+@pytest.mark.parametrize('name', list(MU.FP64_CASES))
+def test_gradients_within_3x_of_reference_fp32_error(name):
+    """Drop-in module (autograd over the sm_100a kernels) AND the engine's hand-written backward, at the reference's own batch
+    sizes: per tensor, the distance to the fp64 gradient is at most 3x the distance of the REFERENCE's fp32 gradient to it."""
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g64 = _fp64_truth(name)
+    # module path
+    ref = build_product_model(variant, kw).cuda()
+    sd = MU.det_state(ref.state_dict(), seed=1234)
+    ref.load_state_dict({k: v.cuda() for k, v in sd.items()})
+    ref.train()
+    b = product_batch(config, 100, count)
+    MU.loss_fn(variant, ref(b), b.y).backward()
+    w_mod = _check_against_fp64(name, {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}, g64, 3.0)
+    # engine path (lr = 0 keeps the gradients in the flat buffer)
+    eng, model, raw = _engine_for(variant, config, count, kw, use_graph=False)
+    eng.opt.hyper[0] = 0.0
+    eng.opt._hyper_host = (0.0, 1.0); eng.opt.param_groups[0]['lr'] = 0.0
+    loss_e = float(eng.step(raw).item())
+    eng.check_errors()
+    assert abs(loss_e - FIX_M[name + '/loss64'][0]) <= RTOL * abs(FIX_M[name + '/loss64'][0]) + 1e-5
+    w_eng = _check_against_fp64(name, {k: p.grad for k, p in model.named_parameters()}, g64, 3.0)
+    print('%s: worst err/bound module %.2f engine %.2f' % (name, w_mod, w_eng))
+
+
+@pytest.mark.parametrize('name', ['count_cfg1', 'zinc_cfg2', 'count_cfg3'])
+def test_static_engine_baseline_shapes_match_reference_fixture(name):
+    """Three engine steps at BASELINE.json's batch sizes (cfg 1: 128 graphs h=3, cfg 2: 256 graphs, cfg 3: 32 graphs h=4) against
+    the loss trajectory of the reference's own class + torch Adam."""
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    eng, model, raw = _engine_for(variant, config, count, kw, True)
+    losses = [float(eng.step(raw).item()) for _ in range(3)]
+    eng.check_errors()
+    assert abs(losses[0] - FIX_M[name + '/loss'][0]) <= RTOL * abs(FIX_M[name + '/loss'][0]) + 1e-5
+    np.testing.assert_allclose(losses, FIX_M[name + '/adam_losses'], rtol=5e-3, atol=1e-4)
+
+
+def test_static_engine_ogb_baseline_shape_matches_reference_fixture():
+    name = 'ogb_cfg4'
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    eng, model, raw = _engine_for(variant, config, count, kw, True)
+    losses = [float(eng.step(raw).item()) for _ in range(3)]
+    eng.check_errors()
+    assert abs(losses[0] - FIX_M[name + '/loss'][0]) <= RTOL * abs(FIX_M[name + '/loss'][0]) + 1e-5
+    np.testing.assert_allclose(losses[:2], FIX_M[name + '/adam_losses'][:2], rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(losses[2], FIX_M[name + '/adam_losses'][2], rtol=5e-2, atol=1e-4)
+
+
+def test_zinc_engine_with_self_loops_rewrites_bond_types():
+    """flags['self_loop'] on the ZINC variant (run_zinc.py --self_loop): bond types go through E1 with the edge list (loop rows
+    dropped, N rows of 1 appended); engine loss and gradients equal the drop-in module fed the reference-contract batch."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.engine import StaticTrainEngine
+    from esc_gnn_b200.pipeline import RawBatch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    kw, count = dict(num_layers=3), 24
+    raw = RawBatch.synth(2, 100, count)
+    fl = dict(synth.ENCODER_FLAGS[2], self_loop=True)
+    for pipeline in (False, True):
+        model = build_product_model('zinc', kw).cuda()
+        sd = MU.det_state(model.state_dict(), seed=1234)
+        model.load_state_dict({k: v.cuda() for k, v in sd.items()})
+        model.train()
+        eng = StaticTrainEngine(model, 'zinc', fl, max_graphs=count, max_nodes_per_graph=64, max_edges_per_graph=256,
+                                nodes_cap=raw.num_nodes + 100, edges_cap=raw.src.numel() + 200, lr=0.0, use_graph=False,
+                                pipeline=pipeline)
+        eng.opt.hyper[0] = 0.0
+        eng.opt._hyper_host = (0.0, 1.0); eng.opt.param_groups[0]['lr'] = 0.0
+        if pipeline:
+            assert eng.step(raw) is None
+            loss_e = float(eng.drain().item())
+        else:
+            loss_e = float(eng.step(raw).item())
+        eng.check_errors()
+        ref = build_product_model('zinc', kw).cuda()
+        ref.load_state_dict({k: v.cuda() for k, v in sd.items()})
+        ref.train()
+        from esc_gnn_b200.batch import Batch
+        b = Batch.from_data_list([to_data(g) for g in MU.graph_dicts(2, 100, count, self_loop=True)]).to('cuda')
+        assert int((b.edge_attr == 1).sum()) >= b.x.size(0)          # the appended loop rows carry bond type 1
+        loss_m = MU.loss_fn('zinc', ref(b), b.y)
+        loss_m.backward()
+        assert abs(loss_e - loss_m.item()) <= 1e-5 * max(1.0, abs(loss_m.item())), (pipeline, loss_e, loss_m.item())
+        named_e = dict(model.named_parameters())
+        for k, p in ref.named_parameters():
+            err = (named_e[k].grad - p.grad).abs().max().item()
+            assert err <= 2e-2 * max(p.grad.abs().max().item(), 1e-6) + 1e-6, (k, err)
+
+
+def test_engine_error_counters_are_sticky_and_overflow_is_contained():
+    """A batch that exceeds the record capacity must not corrupt memory and must still be reported by check_errors() after LATER
+    clean batches (the per-call counters are zeroed every step, the sticky slots are not)."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.engine import StaticTrainEngine
+    from esc_gnn_b200.pipeline import RawBatch
+    count = 16
+    seeds = [100 + 50 * i for i in range(10)]
+    nnz = {s: int(MU.ref_batch(2, s, count).pos_enc.numel()) for s in seeds}
+    s_small, s_big = min(nnz, key=nnz.get), max(nnz, key=nnz.get)
+    small, big = RawBatch.synth(2, s_small, count), RawBatch.synth(2, s_big, count)
+    edges_cap = max(small.src.numel(), big.src.numel()) + 8
+    rpe = -(-nnz[s_small] // edges_cap)
+    assert edges_cap * rpe < nnz[s_big], 'seeds do not separate: %r' % (nnz, )
+    model = build_product_model('zinc', dict(num_layers=2)).cuda().train()
+    eng = StaticTrainEngine(model, 'zinc', synth.ENCODER_FLAGS[2], max_graphs=count, max_nodes_per_graph=64, max_edges_per_graph=256,
+                            nodes_cap=max(small.num_nodes, big.num_nodes) + 8, edges_cap=edges_cap, lr=1e-3, use_graph=False,
+                            records_per_edge=rpe)
+    loss = eng.step(big)                                             # overflows
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(loss).all())
+    nnz_edges = eng.rec_nnz[:int(eng.c.dims[1])]
+    assert int(nnz_edges.sum()) <= eng.rec.numel() and int((nnz_edges == 0).sum()) > 0     # edges without room own no records
+    assert int((eng.rec_off[:int(eng.c.dims[1])] + nnz_edges).max()) <= eng.rec.numel()
+    eng.step(small)                                                  # clean batch afterwards: per-call counters are reset ...
+    with pytest.raises(RuntimeError, match='record capacity'):
+        eng.check_errors()                                           # ... but the overflow is still reported
+    eng.step(small)
+    eng.check_errors()                                               # cleared by the read; clean since
+
+
+@pytest.mark.parametrize('name', ['zinc', 'count_h64', 'ogb'])
+def test_engine_trains_on_a_partial_last_batch(name):
+    """The last batch of an epoch has fewer graphs than the engine's capacity (the reference trains on it): same loss and
+    gradients as an engine built for exactly that many graphs."""
+    from esc_gnn_b200 import synth
+    from esc_gnn_b200.engine import StaticTrainEngine
+    from esc_gnn_b200.pipeline import RawBatch
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    part = max(2, count * 2 // 3)
+    full, raw = RawBatch.synth(config, 100, count), RawBatch.synth(config, 100, part)
+    out = []
+    for G in (count, part):
+        model = build_product_model(variant, kw).cuda()
+        sd = MU.det_state(model.state_dict(), seed=1234)
+        model.load_state_dict({k: v.cuda() for k, v in sd.items()})
+        model.train()
+        eng = StaticTrainEngine(model, variant, synth.ENCODER_FLAGS[config], max_graphs=G, max_nodes_per_graph=max(64, full.max_nodes),
+                                max_edges_per_graph=max(256, full.max_loop_edges), nodes_cap=full.num_nodes + 300,
+                                edges_cap=full.src.numel() + 700, lr=1e-3, use_graph=False)
+        eng.opt.hyper[0] = 0.0
+        eng.opt._hyper_host = (0.0, 1.0); eng.opt.param_groups[0]['lr'] = 0.0
+        if G == count:
+            eng.step(full)                       # a full batch first: its rows / graphs must not leak into the partial one
+        loss = float(eng.step(raw).item())
+        eng.check_errors()
+        assert int(eng.c.dims[2]) == part
+        out.append((loss, eng.opt.grad.clone()))
+    (la, ga), (lb, gb) = out
+    assert abs(la - lb) <= 1e-6 * max(1.0, abs(lb)), (la, lb)
+    assert (ga - gb).abs().max().item() <= 1e-4 * gb.abs().max().item()

@@ -8,7 +8,7 @@ import torch
 from tests import model_util as MU
 
 FIX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'model.npz'))
-CPU_CASES = ('count_h64', 'zinc_l2', 'ogb', 'zinc', 'qm9')
+CPU_CASES = ('count_h64', 'zinc_l2', 'ogb', 'zinc', 'qm9', 'count_cfg3', 'ogb_cfg4', 'count_cfg1', 'zinc_cfg2')
 
 
 def run_case(model, variant, batch, name, rtol, atol, check_adam=True):
@@ -77,6 +77,34 @@ def test_model_oracle_matches_reference_classes(name):
     model = MU.build_oracle_model(variant, kw)
     batch = MU.ref_batch(config, 100, count)
     run_case(model, variant, batch, name, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('name', ['count_cfg3', 'ogb_cfg4'])
+def test_fp64_oracle_matches_fp64_reference_class(name):
+    """The fp64 run of the oracle restatement reproduces the fp64 run of the reference's own class (loss and every gradient
+    norm to 1e-9): it is the truth the GPU gradient tests measure against (tests/test_model_gpu.py)."""
+    variant, config, count, kw = MU.MODEL_CASES[name]
+    torch.set_num_threads(4)
+    m = MU.build_oracle_model(variant, kw).double()
+    sd = MU.det_state(m.state_dict(), seed=1234)
+    m.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()})
+    m.train()
+    b = MU.to_double(MU.ref_batch(config, 100, count))
+    pred = m(b)
+    if variant == 'ogb':
+        y = b.y.view(pred.shape)
+        loss = torch.nn.BCEWithLogitsLoss()(pred[y == y], y[y == y])
+    else:
+        loss = MU.loss_fn(variant, pred, b.y)
+    loss.backward()
+    assert abs(loss.item() - FIX[name + '/loss64'][0]) <= 1e-10 * max(1.0, abs(FIX[name + '/loss64'][0]))
+    np.testing.assert_allclose(pred.detach().numpy(), FIX[name + '/pred64'], rtol=1e-9, atol=1e-10)
+    grads = dict(m.named_parameters())
+    for k, want in zip(FIX[name + '/grad_keys'], FIX[name + '/grad64_digest']):
+        got = MU.grad_digest(grads[str(k)].grad)
+        assert abs(got[3] - want[3]) <= 1e-8 * max(want[3], 1e-12) + 1e-13, str(k)
+    # and the reference's own fp32 error against it is small but not zero: the yardstick is meaningful
+    assert 0 < FIX[name + '/grad_err32'].max() < 1e-2 * FIX[name + '/grad64_digest'][:, 3].max()
 
 
 def test_state_dict_keys_match_reference_contract():
