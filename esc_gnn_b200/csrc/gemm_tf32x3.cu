@@ -94,6 +94,115 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused epilogues of the "TS" kernel (EPI template parameter): the Linear -> BatchNorm(training) -> activation chains of the
+// model (run_graphcount.py:54-61,78-87; zinc_models.py:513-522,538-566) as ONE launch each way.
+//   EPI 1 (forward):  y = A B^T + bias is kept in tensor memory; every CTA writes y (saved for the backward), reduces its
+//                     tile's column sums (sum y, sum y^2) with a shuffle-transposed warp reduction, publishes them, waits at a
+//                     grid barrier of its column block, sums the tile partials in a fixed order (deterministic), and normalises
+//                     + activates straight from tensor memory:  C = act(BN(y)).
+//   EPI 2 (backward): the tile is dgrad's output d(act(BN(x))); with the saved pre-BN x, mean, rstd the epilogue forms
+//                     dz = d * act'(BN(x)), reduces sum dz and sum dz*xhat the same way, and writes the gradient with respect
+//                     to x:  C = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)); dgamma / dbeta from the sums.
+//                     Columns >= bn_cols are stored as plain dgrad output (the edge-type columns of the concatenated z).
+// The grid barrier needs every CTA of a column block resident at once: the launcher only takes this path when the whole grid
+// fits the machine (cudaOccupancyMaxActiveBlocksPerMultiprocessor x SM count), and callers keep such launches on ONE stream.
+struct BnParams {
+    float* Y; int ldy;                         // EPI 1: pre-BN output (saved)
+    const float* X; int ldx;                   // EPI 2: pre-BN input saved by the forward
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var;   // EPI 1
+    float* mean; float* rstd;                  // EPI 1: written; EPI 2: read
+    float* dgamma; float* dbeta;               // EPI 2
+    float eps, momentum;
+    int act, bn_cols;
+    float* ws;                                 // [0,32) arrive tickets, [32,64) depart tickets (uint32, left zero), then [tile][2][ldp]
+    int ldp;
+};
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : expm1f(v);
+    return v;
+}
+__device__ __forceinline__ float epi_act_grad(float v, int act) {
+    if (act == 1) return v > 0.f ? 1.f : 0.f;
+    if (act == 2) return v > 0.f ? 1.f : expf(v);
+    return 1.f;
+}
+
+// v[j] of lane l = element (row l, column j) of a 32 x 32 block; returns in lane l the sum of column l over the 32 rows
+// (31 shuffles: every step halves the columns a lane is responsible for; fixed order -> deterministic)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+    #pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+        #pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = up ? v[j] : v[j + half];
+            const float keep = up ? v[j + half] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// one row chunk of 32 columns [nb, nb + 32) of a row-major buffer: 16-byte accesses when possible
+__device__ __forceinline__ void row_store32(float* rowp, int nb, int N, const float (&f)[32]) {
+    if (nb + 32 <= N && ((reinterpret_cast<uintptr_t>(rowp + nb) & 15) == 0)) {
+        #pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(rowp + nb + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+        #pragma unroll
+        for (int j = 0; j < 32; ++j) if (nb + j < N) rowp[nb + j] = f[j];
+    }
+}
+__device__ __forceinline__ void row_load32(const float* rowp, int nb, int N, float (&f)[32]) {
+    if (nb + 32 <= N && ((reinterpret_cast<uintptr_t>(rowp + nb) & 15) == 0)) {
+        #pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(rowp + nb + j));
+            f[j] = v.x; f[j + 1] = v.y; f[j + 2] = v.z; f[j + 3] = v.w;
+        }
+    } else {
+        #pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = nb + j < N ? __ldcg(rowp + nb + j) : 0.f;
+    }
+}
+
+// grid barrier over the `expected` active CTAs of one column block (called by the 128 epilogue threads; t = 0..127).
+// arrive: release (fence + atomic), spin: acquire; the last CTA to depart re-arms both tickets for the next launch.
+__device__ __forceinline__ void column_block_barrier(float* ws, int block_y, unsigned expected, int t) {
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t == 0) {
+        unsigned* arrive = reinterpret_cast<unsigned*>(ws) + block_y;
+        unsigned* depart = arrive + 32;
+        atomicAdd(arrive, 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+            if (seen < expected) __nanosleep(40);
+        } while (seen < expected);
+        if (atomicAdd(depart, 1u) == expected - 1u) { *depart = 0u; __threadfence(); atomicExch(arrive, 0u); }
+        __threadfence();
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2..5 = tf32 splitters during the main loop, then epilogue.
 // Shared memory: STAGES raw stages {A 16 KB, B BLOCK_N*128 B} filled by TMA, ONE lo buffer of the same shape written by the
 // splitter warps (lo = x - trunc_tf32(x), element-wise, so the swizzled placement is simply preserved).  Two CTAs are
