@@ -171,7 +171,7 @@ def run_own(args):
     edges_cap = int(max(b.src.numel() for b in host_pool) * 1.04) + 128
     eng = StaticTrainEngine(model, 'zinc', fl, max_graphs=BATCH, max_nodes_per_graph=40, max_edges_per_graph=96,
                             nodes_cap=nodes_cap, edges_cap=edges_cap, lr=LR, distributed=world > 1, use_graph=True,
-                            pipeline=bool(args.pipeline), encoder_ctas=args.encoder_ctas)
+                            pipeline=bool(args.pipeline), encoder_ctas=args.encoder_ctas, fuse_bn=bool(args.fuse_bn))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')     # > 126 MB L2
 
     def read(loss):                                         # pipelined engines return the previous batch's loss (None at first)
@@ -391,6 +391,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--pipeline', type=int, default=1, help='1: overlap the encoder of batch k with the training of batch k-1')
+    ap.add_argument('--fuse-bn', type=int, default=0, help='1: Linear+BatchNorm+act as one launch (GEMM epilogue behind a grid barrier)')
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-large', action='store_true', help='skip the 8192-graph section')

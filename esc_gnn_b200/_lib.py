@@ -76,6 +76,13 @@ SIGNATURES = {
     'escgnn_gemm_tf32x3': (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     'escgnn_gemm_tf32x3_bounded': (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
     'escgnn_gemm_set_split_target': (_i32, [_i32]),
+    'escgnn_linear_bn_fusable': (_i32, [_i32, _i32, _i32]),
+    'escgnn_linear_bn_resident_ctas': (_i32, [_i32, _i32, _i32]),
+    'escgnn_linear_bn_workspace_floats': (_i64, [_i32, _i32]),
+    'escgnn_linear_bn_act_fwd': (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32] + [_vp] * 7 + [_i32, ctypes.c_float, ctypes.c_float,
+                                        _vp, _i32, _vp, _i32, _vp, _i64, _vp]),
+    'escgnn_linear_bn_act_bwd': (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp,
+                                        _vp, _i32, _vp, _i64, _vp]),
     'escgnn_gemm_set_plan': (_i32, [_i32]),
     'escgnn_gemm_workspace_floats': (_i64, [_i32, _i32, _i32]),
     'escgnn_tf32_split_lo': (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp]),
@@ -116,7 +123,8 @@ KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'encod
                     'gine_aggregate_fwd': 1, 'gine_aggregate_bwd': 2, 'gine_aggregate_fwd_ld': 1, 'gine_aggregate_bwd_ld': 2, 'gine_aggregate_bwd_ld_noeps': 1, 'segment_pool_fwd': 1, 'segment_pool_bwd': 1,
                     'edge_distance': 2, 'all_pairs_spd': 1, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 1, 'bn_act_bwd': 1,
                     'act_fwd': 1, 'act_bwd': 1, 'colsum': 1, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
-                    'make_dims': 1, 'adam_step_device': 2, 'bag_embed_bwd_sorted': 4, 'bag_index_build': 3, 'bag_embed_bwd_indexed': 1, 'reduce_sum': 1, 'zero_tail_rows': 1, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1}
+                    'make_dims': 1, 'adam_step_device': 2, 'bag_embed_bwd_sorted': 4, 'bag_index_build': 3, 'bag_embed_bwd_indexed': 1, 'reduce_sum': 1, 'zero_tail_rows': 1, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1,
+                    'linear_bn_act_fwd': 1, 'linear_bn_act_bwd': 1}
 LAUNCHES = {'n': 0}
 PROFILE = None      # bench.py: a list; every mark() appends (label, cuda event) -> per-kernel durations by differencing
 PROFILE_EXTERNAL = False   # record graph-capturable ("external") events: per-kernel device times of a REPLAYED graph

@@ -5,7 +5,10 @@
 // from device memory (`d_rows`), so one captured CUDA graph serves batches of any size up to the capacity; rows at
 // or beyond the actual count are written as zeros, which keeps them inert in the GEMMs that follow.
 // Reductions are two-stage and ordered (per-tile partials, then a fixed-order sum): results are run-to-run
-// deterministic.  Reference semantics: torch.nn.BatchNorm1d (momentum 0.1, biased variance for normalisation,
+// deterministic.  Batch statistics are SHIFTED sums -- sum (x - x[0]) and sum (x - x[0])^2 per column, x[0] = the column's first row --
+// so the variance S2/m - (S1/m)^2 does not cancel when |mean| >> std (and is exactly 0 for a constant column), and the
+// normalisation is applied centred, (x - mean) * (rstd * gamma) + beta: both within ~1 ulp of torch's Welford statistics.
+// Reference semantics: torch.nn.BatchNorm1d (momentum 0.1, biased variance for normalisation,
 // unbiased for the running estimate) as used at run_graphcount.py:54-61,78-87; zinc_models.py:513-522;
 // ogb_mol_gnn.py:331-336,672.
 #include <cuda_runtime.h>
@@ -57,9 +60,11 @@ colstats_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ d_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCols + lane, r0 = blockIdx.y * kTileRows, rows = *d_rows;
     float a = 0.f, b = 0.f;
-    if (c < C)
+    if (c < C && rows > 0) {
+        const float shift = x[c];
         #pragma unroll 8
-        for (int r = r0 + warp; r < min(r0 + kTileRows, rows); r += 8) { const float v = x[(size_t)r * ldx + c]; a += v; b += v * v; }
+        for (int r = r0 + warp; r < min(r0 + kTileRows, rows); r += 8) { const float v = x[(size_t)r * ldx + c] - shift; a += v; b += v * v; }
+    }
     cta_reduce2(a, b, s);
     if (warp == 0 && c < C) { partial[((size_t)blockIdx.y * 2 + 0) * C + c] = a; partial[((size_t)blockIdx.y * 2 + 1) * C + c] = b; }
 }
@@ -79,9 +84,9 @@ bn_act_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
         if (training) {
             float s1 = 0.f, s2 = 0.f;
             for (int t = 0; t < tiles; ++t) { s1 += partial[((size_t)t * 2 + 0) * C + c]; s2 += partial[((size_t)t * 2 + 1) * C + c]; }
-            const float m = (float)max(rows, 1);
-            mean = s1 / m;
-            const float var = fmaxf(s2 / m - mean * mean, 0.f);
+            const float m = (float)max(rows, 1), m1 = s1 / m;
+            mean = (rows > 0 ? x[c] : 0.f) + m1;
+            const float var = fmaxf(s2 / m - m1 * m1, 0.f);
             rstd = rsqrtf(var + eps);
             if (blockIdx.y == 0 && warp == 0) {
                 mean_out[c] = mean; rstd_out[c] = rstd;
@@ -98,11 +103,11 @@ bn_act_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
         g = gamma ? gamma[c] : 1.f; bt = beta ? beta[c] : 0.f;
     }
     if (c >= C) return;
-    const float sc = rstd * g, sh = bt - mean * sc;
+    const float sc = rstd * g;
     #pragma unroll 8
     for (int r = r0 + warp; r < min(r0 + kTileRows, rows_cap); r += 8) {
         float o = 0.f;
-        if (r < rows) o = act_fwd(x[(size_t)r * ldx + c] * sc + sh, act);
+        if (r < rows) o = act_fwd((x[(size_t)r * ldx + c] - mean) * sc + bt, act);
         y[(size_t)r * ldy + c] = o;               // rows >= actual count are zeroed (inert in the next GEMM)
     }
 }
@@ -180,6 +185,18 @@ constexpr int kVRows = 64, kVCols = 128, kHdr = 64;
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+// act((v - mean) * sc + bt), per component
+__device__ __forceinline__ float4 bn_apply4(const float4& v, const float4& mean, const float4& sc, const float4& bt) {
+    return make_float4((v.x - mean.x) * sc.x + bt.x, (v.y - mean.y) * sc.y + bt.y, (v.z - mean.z) * sc.z + bt.z, (v.w - mean.w) * sc.w + bt.w);
+}
+// (S1, S2) shifted sums over m rows -> mean (shift added back) and biased variance, per component
+__device__ __forceinline__ void bn_finish4(const float4& s1, const float4& s2, const float4& shift, float m, float4& mean, float4& var) {
+    const float4 m1 = make_float4(s1.x / m, s1.y / m, s1.z / m, s1.w / m);
+    mean = make_float4(shift.x + m1.x, shift.y + m1.y, shift.z + m1.z, shift.w + m1.w);
+    var = make_float4(fmaxf(s2.x / m - m1.x * m1.x, 0.f), fmaxf(s2.y / m - m1.y * m1.y, 0.f), fmaxf(s2.z / m - m1.z * m1.z, 0.f),
+                      fmaxf(s2.w / m - m1.w * m1.w, 0.f));
+}
 
 // Per-CTA sums of (a, b) over its 8 warps -> tile partial; returns true (uniformly) in the last CTA of the column block.
 __device__ __forceinline__ bool tile_commit(const float4& a, const float4& b, float* ws, int C, float (*s)[2][kVCols], int* s_last) {
@@ -237,11 +254,12 @@ colstats_v4_kernel(const float* __restrict__ x, int ldx, const int* __restrict__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c4 = blockIdx.x * kVCols + lane * 4, rows = min(*d_rows, rows_cap);
     float4 a = zero4(), b = zero4();
+    const float4 sh = (MODE == 0 && c4 < C && rows > 0) ? ld4(x + c4) : zero4();       // statistics: sums shifted by the first row
     if (c4 < C) {
         for (int r0 = blockIdx.y * kVRows + warp; r0 < rows; r0 += gridDim.y * kVRows) {      // row chunks of this tile
             float4 v[kVRows / 8];
             #pragma unroll
-            for (int i = 0; i < kVRows / 8; ++i) v[i] = r0 + 8 * i < rows ? ld4(x + (size_t)(r0 + 8 * i) * ldx + c4) : zero4();
+            for (int i = 0; i < kVRows / 8; ++i) v[i] = r0 + 8 * i < rows ? sub4(ld4(x + (size_t)(r0 + 8 * i) * ldx + c4), sh) : zero4();
             #pragma unroll
             for (int i = 0; i < kVRows / 8; ++i) {
                 a.x += v[i].x; a.y += v[i].y; a.z += v[i].z; a.w += v[i].w;
@@ -255,7 +273,7 @@ colstats_v4_kernel(const float* __restrict__ x, int ldx, const int* __restrict__
     const int c = blockIdx.x * kVCols + threadIdx.x;
     if (threadIdx.x >= kVCols || c >= C) return;
     if (MODE == 1) { out_sum[c] = s1; return; }
-    const float m = (float)max(rows, 1), mean = s1 / m, var = fmaxf(s2 / m - mean * mean, 0.f);
+    const float m = (float)max(rows, 1), m1 = s1 / m, mean = (rows > 0 ? x[c] : 0.f) + m1, var = fmaxf(s2 / m - m1 * m1, 0.f);
     mean_out[c] = mean; rstd_out[c] = rsqrtf(var + eps);
     if (rows > 0) {
         const float unbiased = rows > 1 ? var * m / (m - 1.f) : var;
@@ -288,7 +306,6 @@ bn_act_fwd_v4_kernel(const float* __restrict__ x, int ldx, const float* __restri
     }
     const float4 g = gamma ? ld4(gamma + c4) : make_float4(1.f, 1.f, 1.f, 1.f), bt = beta ? ld4(beta + c4) : zero4();
     const float4 sc = make_float4(rstd.x * g.x, rstd.y * g.y, rstd.z * g.z, rstd.w * g.w);
-    const float4 sh = make_float4(bt.x - mean.x * sc.x, bt.y - mean.y * sc.y, bt.z - mean.z * sc.z, bt.w - mean.w * sc.w);
     float4 v[kVRows / 8];
     #pragma unroll
     for (int i = 0; i < kVRows / 8; ++i) v[i] = r0 + 8 * i < rows ? ld4(x + (size_t)(r0 + 8 * i) * ldx + c4) : zero4();
@@ -297,7 +314,7 @@ bn_act_fwd_v4_kernel(const float* __restrict__ x, int ldx, const float* __restri
         const int r = r0 + 8 * i;
         if (r >= rows_cap) break;
         float4 o = zero4();                           // rows >= actual count are zeroed (inert in the next GEMM)
-        if (r < rows) o = act_fwd4(make_float4(v[i].x * sc.x + sh.x, v[i].y * sc.y + sh.y, v[i].z * sc.z + sh.z, v[i].w * sc.w + sh.w), act);
+        if (r < rows) o = act_fwd4(bn_apply4(v[i], mean, sc, bt), act);
         st4(y + (size_t)r * ldy + c4, o);
     }
 }
@@ -474,11 +491,12 @@ bn_act_fwd_cluster_kernel(const float* __restrict__ x, int ldx, const float* __r
     const int c4 = blockIdx.x * T::kCols + 4 * cl, rows = min(*d_rows, rows_cap);
     const bool col_ok = c4 < C;
     float4 a = zero4(), b = zero4();
+    const float4 shift = (col_ok && rows > 0) ? ld4(x + c4) : zero4();
     if (col_ok)
         for (int r0 = rank * T::kSlots + rs; r0 < rows; r0 += kClFwdUnroll * T::kSweep) {
             float4 v[kClFwdUnroll];
             #pragma unroll
-            for (int k = 0; k < kClFwdUnroll; ++k) v[k] = r0 + k * T::kSweep < rows ? ld4(x + (size_t)(r0 + k * T::kSweep) * ldx + c4) : zero4();
+            for (int k = 0; k < kClFwdUnroll; ++k) v[k] = r0 + k * T::kSweep < rows ? sub4(ld4(x + (size_t)(r0 + k * T::kSweep) * ldx + c4), shift) : zero4();
             #pragma unroll
             for (int k = 0; k < kClFwdUnroll; ++k) {
                 a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
@@ -489,9 +507,8 @@ bn_act_fwd_cluster_kernel(const float* __restrict__ x, int ldx, const float* __r
     if (col_ok) {
         const float m = (float)max(rows, 1);
         const float4 s1 = ld4(&s_tot[0][4 * cl]), s2 = ld4(&s_tot[1][4 * cl]);
-        const float4 mean = make_float4(s1.x / m, s1.y / m, s1.z / m, s1.w / m);
-        const float4 var = make_float4(fmaxf(s2.x / m - mean.x * mean.x, 0.f), fmaxf(s2.y / m - mean.y * mean.y, 0.f),
-                                       fmaxf(s2.z / m - mean.z * mean.z, 0.f), fmaxf(s2.w / m - mean.w * mean.w, 0.f));
+        float4 mean, var;
+        bn_finish4(s1, s2, shift, m, mean, var);
         const float4 rstd = make_float4(rsqrtf(var.x + eps), rsqrtf(var.y + eps), rsqrtf(var.z + eps), rsqrtf(var.w + eps));
         if (rank == 0 && rs == 0) {
             st4(mean_out + c4, mean); st4(rstd_out + c4, rstd);
@@ -506,7 +523,6 @@ bn_act_fwd_cluster_kernel(const float* __restrict__ x, int ldx, const float* __r
         }
         const float4 g = gamma ? ld4(gamma + c4) : make_float4(1.f, 1.f, 1.f, 1.f), bt = beta ? ld4(beta + c4) : zero4();
         const float4 sc = make_float4(rstd.x * g.x, rstd.y * g.y, rstd.z * g.z, rstd.w * g.w);
-        const float4 sh = make_float4(bt.x - mean.x * sc.x, bt.y - mean.y * sc.y, bt.z - mean.z * sc.z, bt.w - mean.w * sc.w);
         for (int r0 = rank * T::kSlots + rs; r0 < rows_cap; r0 += kClFwdUnroll * T::kSweep) {
             float4 v[kClFwdUnroll];
             #pragma unroll
@@ -516,7 +532,7 @@ bn_act_fwd_cluster_kernel(const float* __restrict__ x, int ldx, const float* __r
                 const int r = r0 + k * T::kSweep;
                 if (r >= rows_cap) break;
                 float4 o = zero4();                   // rows >= actual count are zeroed (inert in the next GEMM)
-                if (r < rows) o = act_fwd4(make_float4(v[k].x * sc.x + sh.x, v[k].y * sc.y + sh.y, v[k].z * sc.z + sh.z, v[k].w * sc.w + sh.w), act);
+                if (r < rows) o = act_fwd4(bn_apply4(v[k], mean, sc, bt), act);
                 st4(y + (size_t)r * ldy + c4, o);
             }
         }
@@ -632,9 +648,10 @@ bn_act_fwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
     // behind it (one L2 round trip less on the critical path), then mask
     #pragma unroll
     for (int k = 0; k < R; ++k) v[k] = (col_ok && r_first + k * T::kSweep < rows_cap) ? ld4(x + (size_t)(r_first + k * T::kSweep) * ldx + c4) : zero4();
+    const float4 shift = col_ok ? ld4(x + c4) : zero4();          // row 0 is below the capacity: valid memory, used only when rows > 0
     const int rows = min(*d_rows, rows_cap);
     #pragma unroll
-    for (int k = 0; k < R; ++k) if (r_first + k * T::kSweep >= rows) v[k] = zero4();
+    for (int k = 0; k < R; ++k) v[k] = r_first + k * T::kSweep >= rows ? zero4() : sub4(v[k], shift);     // registers hold x - shift
     #pragma unroll
     for (int k = 0; k < R; ++k) {
         a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
@@ -645,9 +662,9 @@ bn_act_fwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
     if (col_ok) {
         const float m = (float)max(rows, 1);
         const float4 s1 = ld4(&s_tot[0][4 * cl]), s2 = ld4(&s_tot[1][4 * cl]);
-        const float4 mean = make_float4(s1.x / m, s1.y / m, s1.z / m, s1.w / m);
-        const float4 var = make_float4(fmaxf(s2.x / m - mean.x * mean.x, 0.f), fmaxf(s2.y / m - mean.y * mean.y, 0.f),
-                                       fmaxf(s2.z / m - mean.z * mean.z, 0.f), fmaxf(s2.w / m - mean.w * mean.w, 0.f));
+        float4 mean, var;
+        bn_finish4(s1, s2, shift, m, mean, var);
+        const float4 m1c = make_float4(s1.x / m, s1.y / m, s1.z / m, s1.w / m);      // mean - shift (the registers hold x - shift)
         const float4 rstd = make_float4(rsqrtf(var.x + eps), rsqrtf(var.y + eps), rsqrtf(var.z + eps), rsqrtf(var.w + eps));
         if (rank == 0 && rs == 0) {
             st4(mean_out + c4, mean); st4(rstd_out + c4, rstd);
@@ -662,13 +679,12 @@ bn_act_fwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
         }
         const float4 g = gamma ? ld4(gamma + c4) : make_float4(1.f, 1.f, 1.f, 1.f), bt = beta ? ld4(beta + c4) : zero4();
         const float4 sc = make_float4(rstd.x * g.x, rstd.y * g.y, rstd.z * g.z, rstd.w * g.w);
-        const float4 sh = make_float4(bt.x - mean.x * sc.x, bt.y - mean.y * sc.y, bt.z - mean.z * sc.z, bt.w - mean.w * sc.w);
         #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int r = r_first + k * T::kSweep;
             if (r < rows_cap) {
                 float4 o = zero4();                   // rows >= actual count are zeroed (inert in the next GEMM)
-                if (r < rows) o = act_fwd4(make_float4(v[k].x * sc.x + sh.x, v[k].y * sc.y + sh.y, v[k].z * sc.z + sh.z, v[k].w * sc.w + sh.w), act);
+                if (r < rows) o = act_fwd4(bn_apply4(v[k], m1c, sc, bt), act);      // v = x - shift, m1c = mean - shift
                 st4(y + (size_t)r * ldy + c4, o);
             }
         }
@@ -958,9 +974,10 @@ head_bn_linear_l1_kernel(const float* __restrict__ x, int ldx, const float* __re
     const int rows = min(*d_rows, rows_cap);
     const float m = (float)max(rows, 1);
     float s1 = 0.f, s2 = 0.f;
+    const float shift = (col_ok && rows > 0) ? x[c] : 0.f;         // shifted sums (see the header): xv holds x - x[0]
     #pragma unroll
     for (int i = 0; i < RPC; ++i) {
-        if (r_base + i >= rows) xv[i] = 0.f;
+        xv[i] = r_base + i >= rows ? 0.f : xv[i] - shift;
         s1 += xv[i]; s2 += xv[i] * xv[i];
     }
     s_stat[0][c] = s1; s_stat[1][c] = s2;
@@ -968,10 +985,10 @@ head_bn_linear_l1_kernel(const float* __restrict__ x, int ldx, const float* __re
     float t1 = 0.f, t2 = 0.f;
     #pragma unroll
     for (int r = 0; r < kClRanks; ++r) { t1 += *cluster.map_shared_rank(&s_stat[0][c], r); t2 += *cluster.map_shared_rank(&s_stat[1][c], r); }
-    const float mean = t1 / m, var = fmaxf(t2 / m - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+    const float mean = t1 / m, var = fmaxf(t2 / m - mean * mean, 0.f), rstd = rsqrtf(var + eps);      // mean of x - shift
     if (rank == 0 && col_ok && rows > 0) {
         const float ub = rows > 1 ? m / (m - 1.f) : 1.f;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mean + shift);
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * ub;
     }
     const float g = col_ok ? (gamma ? gamma[c] : 1.f) : 0.f, bt = col_ok ? (beta ? beta[c] : 0.f) : 0.f, w = col_ok ? w2[c] : 0.f;

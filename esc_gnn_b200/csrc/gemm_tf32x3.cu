@@ -18,6 +18,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/escgnn_b200.h"
 #include "launch.cuh"
@@ -86,6 +88,15 @@ struct Params {
     const int* rows_ptr;          // optional device-side row count (static-shape engine): rows_dim 1 = bounds M (tiles past it
     int rows_dim;                 // leave without touching C), 2 = bounds K (k-blocks past it are skipped)
 };
+
+// 3xTF32 split: hi = the raw fp32 value (the tensor core reads its top 19 bits, i.e. truncates), lo = x - trunc_tf32(x), exact in
+// fp32.  Rounded planes (cvt.rna on both) were measured and removed: the error floor of this kernel is not the split but the
+// tensor core's truncating accumulation (-2.6e-6 mean signed relative error at K = 256 either way, tools/bench_linear_bn.py),
+// and the in-place rounding of B cost 15 % of the main loop.
+__device__ __forceinline__ void split4(const float4& v, float4& l) {
+    l = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                    v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+}
 
 __device__ __forceinline__ void red_add4(float4* dst, const float4& v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -312,13 +323,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kStageBytes);
             #pragma unroll 4
             for (int q = t; q < kStageBytes / 16; q += 128) {
-                const float4 v = src[q];
-                float4 r;
-                r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                dst[q] = r;
+                float4 l;
+                split4(src[q], l);
+                dst[q] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to tcgen05.mma
             mbar_arrive(&split_bar[lb]);
@@ -413,9 +420,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         : "memory");
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS>
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0>
 __global__ void __launch_bounds__(kThreads, STAGES == 2 ? 2 : 1)
-gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p, const BnParams bn) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int kABytes = kBlockM * 128;           // 16 KB
     constexpr int kBBytes = BLOCK_N * 128;
@@ -425,6 +432,12 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[LO_BUFS], lo_free_bar[LO_BUFS], tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ float s_bias[BLOCK_N];
+    // fused epilogues: their scratch lives in the first raw stage, which is dead once the accumulator is complete (every TMA fill
+    // has been consumed by an MMA that has finished) -- the fused instantiations keep the shared-memory footprint, and with it
+    // the CTAs per SM, of the plain kernel
+    float (*s_part)[2][BLOCK_N] = reinterpret_cast<float (*)[2][BLOCK_N]>(smem);                        // [4] per-warp column sums
+    float (*s_col)[BLOCK_N] = reinterpret_cast<float (*)[BLOCK_N]>(smem + 8 * BLOCK_N * sizeof(float));   // [4] per-column constants
+    float (*s_fin)[BLOCK_N] = reinterpret_cast<float (*)[BLOCK_N]>(smem + 12 * BLOCK_N * sizeof(float));  // [2] EPI 2: mean(dz), mean(dz xhat)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
     const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -536,13 +549,9 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kBBytes);
             #pragma unroll 4
             for (int e = t; e < kBBytes / 16; e += 128) {
-                const float4 v = src[e];
-                float4 w;
-                w.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                w.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                w.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                w.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                dst[e] = w;
+                float4 l;
+                split4(src[e], l);
+                dst[e] = l;
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -550,13 +559,185 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             mbar_arrive(&split_bar[lb]);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int row = m0 + r;
+        if constexpr (EPI != 0) {
+            const int rows_eff = p.rows_ptr ? min(rows_now, p.M) : p.M;
+            float* crow = p.C + (size_t)row * p.ldc;
+            if (m0 >= rows_eff) {
+                // tile past the actual row count: its rows of C are kept zero (inert in the GEMMs that follow), no barrier
+                if (row < p.M) {
+                    float z[32];
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) z[j] = 0.f;
+                    for (int c = 0; c < BLOCK_N; c += 32) row_store32(crow, n0 + c, p.N, z);
+                }
+            } else {
+                const bool row_in = row < rows_eff;
+                const unsigned expected = (unsigned)((rows_eff + kBlockM - 1) / kBlockM);
+                const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+                float* part = bn.ws + 64;
+                mbar_wait(&tmem_full_bar, 0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (EPI == 2) {
+                    for (int i = t; i < BLOCK_N; i += 128) {
+                        const int n = n0 + i;
+                        const bool on = n < bn.bn_cols;
+                        s_col[0][i] = on ? bn.mean[n] : 0.f; s_col[1][i] = on ? bn.rstd[n] : 0.f;
+                        s_col[2][i] = on ? (bn.gamma ? bn.gamma[n] : 1.f) : 0.f; s_col[3][i] = on ? (bn.beta ? bn.beta[n] : 0.f) : 0.f;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                // ---- pass 1: per-tile column statistics.  EPI 1: tile mean, then the CENTRED sum of squares about it (a second read
+                // of tensor memory; no cancellation), combined across tiles with Chan's update; also stores the pre-BN output y.
+                // EPI 2: sum dz and sum dz * xhat.
+                #pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + (uint32_t)c, v);
+                    float a[32];
+                    if (EPI == 1) {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) a[j] = row_in ? __uint_as_float(v[j]) + s_bias[c + j] : 0.f;
+                        if (row_in && bn.Y) row_store32(bn.Y + (size_t)row * bn.ldy, n0 + c, p.N, a);
+                        s_part[q][0][c + lane] = warp_transpose_sum(a, lane);
+                    } else {
+                        float b[32];
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) b[j] = 0.f;
+                        if (row_in) row_load32(bn.X + (size_t)row * bn.ldx, n0 + c, min(p.N, bn.bn_cols), b);
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float xh = (b[j] - s_col[0][c + j]) * s_col[1][c + j];
+                            const float dz = __uint_as_float(v[j]) * epi_act_grad(xh * s_col[2][c + j] + s_col[3][c + j], bn.act);
+                            a[j] = (row_in && s_col[1][c + j] != 0.f) ? dz : 0.f;      // columns >= bn_cols (rstd slot 0) take no part
+                            b[j] = a[j] * xh;
+                        }
+                        const float sa = warp_transpose_sum(a, lane), sb = warp_transpose_sum(b, lane);
+                        s_part[q][0][c + lane] = sa; s_part[q][1][c + lane] = sb;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (EPI == 1) {
+                    const float n_t = (float)min(kBlockM, rows_eff - m0);
+                    for (int col = t; col < BLOCK_N; col += 128)
+                        s_col[2][col] = ((s_part[0][0][col] + s_part[1][0][col]) + (s_part[2][0][col] + s_part[3][0][col])) / n_t;     // tile mean
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    #pragma unroll 1
+                    for (int c = 0; c < BLOCK_N; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(trow + (uint32_t)c, v);
+                        float b[32];
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float d = row_in ? (__uint_as_float(v[j]) + s_bias[c + j]) - s_col[2][c + j] : 0.f;
+                            b[j] = d * d;
+                        }
+                        s_part[q][1][c + lane] = warp_transpose_sum(b, lane);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                for (int i = t; i < 2 * BLOCK_N; i += 128) {
+                    const int which = i / BLOCK_N, col = i % BLOCK_N;
+                    part[((size_t)blockIdx.x * 2 + which) * bn.ldp + n0 + col] = (EPI == 1 && which == 0) ? s_col[2][col] :
+                        (s_part[0][which][col] + s_part[1][which][col]) + (s_part[2][which][col] + s_part[3][which][col]);
+                }
+                column_block_barrier(bn.ws, blockIdx.y, expected, t);
+                // ---- every CTA combines the tile partials of its columns in a fixed order (deterministic): warp q takes tiles
+                // q, q+4, ... with a lane per 4 columns (independent 16-byte loads), then the four warps' results are merged
+                {
+                    float4 u = make_float4(0.f, 0.f, 0.f, 0.f), w = u;         // EPI 1: running mean / M2 (Chan); EPI 2: the two sums
+                    float cnt = 0.f;
+                    if (lane * 4 < BLOCK_N) {
+                        const float* base = part + n0 + lane * 4;
+                        #pragma unroll 4
+                        for (unsigned tl = q; tl < expected; tl += 4) {
+                            const float4 pa = __ldcg(reinterpret_cast<const float4*>(base + ((size_t)tl * 2 + 0) * bn.ldp));
+                            const float4 pb = __ldcg(reinterpret_cast<const float4*>(base + ((size_t)tl * 2 + 1) * bn.ldp));
+                            if (EPI == 1) {
+                                const float nb = (float)min(kBlockM, rows_eff - (int)tl * kBlockM), nab = cnt + nb, f = nb / nab, g2 = cnt * f;
+                                float d;
+                                d = pa.x - u.x; u.x += d * f; w.x += pb.x + d * d * g2;
+                                d = pa.y - u.y; u.y += d * f; w.y += pb.y + d * d * g2;
+                                d = pa.z - u.z; u.z += d * f; w.z += pb.z + d * d * g2;
+                                d = pa.w - u.w; u.w += d * f; w.w += pb.w + d * d * g2;
+                                cnt = nab;
+                            } else {
+                                u.x += pa.x; u.y += pa.y; u.z += pa.z; u.w += pa.w;
+                                w.x += pb.x; w.y += pb.y; w.z += pb.z; w.w += pb.w;
+                            }
+                        }
+                        *reinterpret_cast<float4*>(&s_part[q][0][lane * 4]) = u;
+                        *reinterpret_cast<float4*>(&s_part[q][1][lane * 4]) = w;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int col = t; col < BLOCK_N; col += 128) {
+                    const int n = n0 + col;
+                    const float m = (float)max(rows_eff, 1);
+                    if (EPI == 1) {
+                        float mean = 0.f, m2 = 0.f, cnt = 0.f;
+                        #pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4) {
+                            float nb = 0.f;                                     // rows behind warp w4's tiles
+                            for (unsigned tl = w4; tl < expected; tl += 4) nb += (float)min(kBlockM, rows_eff - (int)tl * kBlockM);
+                            if (nb > 0.f) {
+                                const float nab = cnt + nb, f = nb / nab, d = s_part[w4][0][col] - mean;
+                                mean += d * f; m2 += s_part[w4][1][col] + d * d * cnt * f; cnt = nab;
+                            }
+                        }
+                        const float var = fmaxf(m2 / m, 0.f), rstd = rsqrtf(var + bn.eps);
+                        const float g = (bn.gamma && n < p.N) ? bn.gamma[n] : 1.f, bt = (bn.beta && n < p.N) ? bn.beta[n] : 0.f;
+                        s_col[0][col] = rstd * g; s_col[1][col] = bt; s_col[3][col] = mean;
+                        if (blockIdx.x == 0 && n < p.N) {
+                            bn.mean[n] = mean; bn.rstd[n] = rstd;
+                            const float ub = rows_eff > 1 ? m / (m - 1.f) : 1.f;
+                            bn.running_mean[n] = (1.f - bn.momentum) * bn.running_mean[n] + bn.momentum * mean;
+                            bn.running_var[n] = (1.f - bn.momentum) * bn.running_var[n] + bn.momentum * var * ub;
+                        }
+                    } else {
+                        const float s1 = (s_part[0][0][col] + s_part[1][0][col]) + (s_part[2][0][col] + s_part[3][0][col]);
+                        const float s2 = (s_part[0][1][col] + s_part[1][1][col]) + (s_part[2][1][col] + s_part[3][1][col]);
+                        s_fin[0][col] = s1 / m; s_fin[1][col] = s2 / m;
+                        if (blockIdx.x == 0 && n < min(p.N, bn.bn_cols)) { if (bn.dgamma) bn.dgamma[n] = s2; if (bn.dbeta) bn.dbeta[n] = s1; }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // ---- pass 2: normalise (+ activation) / BatchNorm backward straight from tensor memory
+                #pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + (uint32_t)c, v);
+                    float o[32];
+                    if (EPI == 1) {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            o[j] = row_in ? epi_act(((__uint_as_float(v[j]) + s_bias[c + j]) - s_col[3][c + j]) * s_col[0][c + j] + s_col[1][c + j], bn.act) : 0.f;
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = 0.f;
+                        if (row_in) row_load32(bn.X + (size_t)row * bn.ldx, n0 + c, min(p.N, bn.bn_cols), o);
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float rs = s_col[1][c + j], g = s_col[2][c + j];
+                            const float xh = (o[j] - s_col[0][c + j]) * rs;
+                            const float d = __uint_as_float(v[j]);
+                            const float dz = d * epi_act_grad(xh * g + s_col[3][c + j], bn.act);
+                            const float bnv = g * rs * (dz - s_fin[0][c + j] - xh * s_fin[1][c + j]);
+                            o[j] = row_in ? (rs != 0.f ? bnv : d) : 0.f;
+                        }
+                    }
+                    if (row < p.M) row_store32(crow, n0 + c, p.N, o);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        } else {
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + r;
         const bool row_ok = row < p.M && !skip;
         float* out = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
         #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
+
             uint32_t v[32];
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
             if (num_kb > 0) {
@@ -602,6 +783,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -729,18 +911,68 @@ int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3
 
 int g_gemm_plan = -1;      // -1 auto, 0 dual, 1 deep (escgnn_gemm_set_plan; experiments / tests); +2: force the "SS" kernel for K-major A
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS>
-int launch_cfg_ts(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+// One-time setup of a TS instantiation: opt in to its dynamic shared memory; returns how many of its CTAs the device holds at once
+// (<= 0: a CUDA error, negated) -- the bound the grid-barrier epilogues need.
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI>
+int ts_resident_ctas() {
+    static int resident = 0;
+    if (resident != 0) return resident;
     const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + LO_BUFS * BLOCK_N * 128 + 1024;
-    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
+    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return -(int)e;
+    int per_sm = 0, dev = 0, sms = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return -(int)e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return -(int)e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return -(int)e;
+    if (getenv("ESCGNN_DEBUG_OCC")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        int smem_sm = 0, smem_blk = 0, resv = 0;
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&resv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+        fprintf(stderr, "[escgnn] ts<%d,%d,%d,%d,%d,%d> per_sm %d dyn %d static %d regs %d maxdyn %d | sm %d blk %d reserved %d\n", BLOCK_N, (int)A_MN,
+                (int)B_MN, STAGES, LO_BUFS, EPI, per_sm, smem, (int)fa.sharedSizeBytes, fa.numRegs, fa.maxDynamicSharedSizeBytes, smem_sm, smem_blk, resv);
     }
-    escgnn::launch_pdl(kern, grid, kThreads, smem, st, a, b, p);
+    resident = (per_sm > 2 ? 2 : per_sm) * sms;          // 256 of the 512 tensor-memory columns per CTA
+    if (resident <= 0) resident = -(int)cudaErrorLaunchOutOfResources;
+    return resident;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0>
+int launch_cfg_ts(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, const BnParams& bn = BnParams()) {
+    const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + LO_BUFS * BLOCK_N * 128 + 1024;
+    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI>;
+    const int resident = ts_resident_ctas<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI>();     // cached after the first call
+    if (resident <= 0) return -resident;
+    if (EPI != 0 && (int)(grid.x * grid.y * grid.z) > resident) return ESCGNN_ERR_TOO_LARGE;   // the grid barrier would deadlock
+    escgnn::launch_pdl(kern, grid, kThreads, smem, st, a, b, p, bn);
     return (int)cudaGetLastError();
+}
+
+template <int EPI>
+int bn_resident(int block_n, bool deep) {
+    constexpr bool B_MN = EPI == 2;
+    switch (block_n) {
+        case 32: return deep ? ts_resident_ctas<32, false, B_MN, 4, 2, EPI>() : ts_resident_ctas<32, false, B_MN, 2, 2, EPI>();
+        case 64: return deep ? ts_resident_ctas<64, false, B_MN, 4, 2, EPI>() : ts_resident_ctas<64, false, B_MN, 2, 2, EPI>();
+        case 96: return deep ? ts_resident_ctas<96, false, B_MN, 4, 2, EPI>() : ts_resident_ctas<96, false, B_MN, 2, 2, EPI>();
+        default: return deep ? ts_resident_ctas<128, false, B_MN, 4, 2, EPI>() : ts_resident_ctas<128, false, B_MN, 2, 2, EPI>();
+    }
+}
+
+// fused Linear + BatchNorm epilogues (EPI 1: forward, K-major A and B; EPI 2: dgrad, MN-major B)
+template <int EPI>
+int launch_bn(int block_n, const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, const BnParams& bn) {
+    const bool deep = (int)(grid.x * grid.y) <= 148;
+    constexpr bool B_MN = EPI == 2;
+    switch (block_n) {
+        case 32: return deep ? launch_cfg_ts<32, false, B_MN, 4, 2, EPI>(a, b, p, grid, st, bn) : launch_cfg_ts<32, false, B_MN, 2, 2, EPI>(a, b, p, grid, st, bn);
+        case 64: return deep ? launch_cfg_ts<64, false, B_MN, 4, 2, EPI>(a, b, p, grid, st, bn) : launch_cfg_ts<64, false, B_MN, 2, 2, EPI>(a, b, p, grid, st, bn);
+        case 96: return deep ? launch_cfg_ts<96, false, B_MN, 4, 2, EPI>(a, b, p, grid, st, bn) : launch_cfg_ts<96, false, B_MN, 2, 2, EPI>(a, b, p, grid, st, bn);
+        default: return deep ? launch_cfg_ts<128, false, B_MN, 4, 2, EPI>(a, b, p, grid, st, bn) : launch_cfg_ts<128, false, B_MN, 2, 2, EPI>(a, b, p, grid, st, bn);
+    }
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -872,6 +1104,83 @@ int escgnn_gemm_tf32x3_bounded(const float* d_a, int lda, int a_mn_major, const 
         rc = (int)cudaGetLastError();
     }
     return rc;
+}
+
+/* ---- fused Linear -> BatchNorm(training) -> activation, one launch each way (header: escgnn_linear_bn_act_fwd / _bwd) ---- */
+int escgnn_linear_bn_resident_ctas(int n_cols, int rows_cap, int backward) {
+    const int block_n = pick_block_n(n_cols);
+    const int ctas = ((rows_cap + kBlockM - 1) / kBlockM) * ((n_cols + block_n - 1) / block_n);
+    return backward ? bn_resident<2>(block_n, ctas <= 148) : bn_resident<1>(block_n, ctas <= 148);
+}
+
+int escgnn_linear_bn_fusable(int rows_cap, int n_out, int k_in) {
+    if (rows_cap <= 0 || n_out <= 0 || k_in <= 0 || (k_in & 3)) return 0;
+    const int block_n = pick_block_n(n_out);
+    const int ctas = ((rows_cap + kBlockM - 1) / kBlockM) * ((n_out + block_n - 1) / block_n);
+    if ((n_out + block_n - 1) / block_n > 32) return 0;          // one arrive / depart ticket per column block
+    // the whole grid must be resident at once (the same bound the launchers enforce), for the forward and the dgrad instantiation
+    return (ctas <= bn_resident<1>(block_n, ctas <= 148) && ctas <= bn_resident<2>(block_n, ctas <= 148)) ? 1 : 0;
+}
+
+static int bn_ldp(int n_cols) {            // tile partials are written for every column of every column block
+    const int block_n = pick_block_n(n_cols);
+    return (n_cols + block_n - 1) / block_n * block_n;
+}
+
+int64_t escgnn_linear_bn_workspace_floats(int rows_cap, int n_cols) {
+    return 64 + (int64_t)((rows_cap + kBlockM - 1) / kBlockM) * 2 * bn_ldp(n_cols);
+}
+
+int escgnn_linear_bn_act_fwd(const float* d_x, int ldx, const float* d_w, int ldw, const float* d_bias, int rows_cap, int n_out, int k_in,
+                             const int* d_rows, const float* d_gamma, const float* d_beta, float* d_running_mean, float* d_running_var,
+                             float* d_mean, float* d_rstd, int act, float eps, float momentum, float* d_y, int ldy, float* d_out,
+                             int ldo, float* d_ws, int64_t ws_floats, void* stream) {
+    if (rows_cap <= 0 || n_out <= 0 || k_in <= 0) return 0;
+    if ((ldx & 3) || (ldw & 3) || ((uintptr_t)d_x & 15) || ((uintptr_t)d_w & 15) || !d_ws || !d_mean || !d_rstd || !d_running_mean ||
+        !d_running_var || !d_out)
+        return ESCGNN_ERR_BAD_ARG;
+    if (ws_floats < escgnn_linear_bn_workspace_floats(rows_cap, n_out)) return ESCGNN_ERR_CAPACITY;
+    const int block_n = pick_block_n(n_out);
+    const int tiles_m = (rows_cap + kBlockM - 1) / kBlockM, n_tiles = (n_out + block_n - 1) / block_n;
+    if (n_tiles > 32) return ESCGNN_ERR_TOO_LARGE;
+    Params p;
+    p.C = d_out; p.ldc = ldo; p.bias = d_bias; p.M = rows_cap; p.N = n_out; p.K = k_in;
+    p.kb_total = (k_in + kBlockK - 1) / kBlockK; p.kb_per_split = p.kb_total;
+    p.partial = nullptr; p.accumulate = 0; p.atomic = 0; p.rows_ptr = d_rows; p.rows_dim = d_rows ? 1 : 0;
+    BnParams bn = BnParams();
+    bn.Y = d_y; bn.ldy = ldy; bn.gamma = d_gamma; bn.beta = d_beta; bn.running_mean = d_running_mean; bn.running_var = d_running_var;
+    bn.mean = d_mean; bn.rstd = d_rstd; bn.eps = eps; bn.momentum = momentum; bn.act = act; bn.bn_cols = n_out; bn.ws = d_ws;
+    bn.ldp = bn_ldp(n_out);
+    CUtensorMap a, b;
+    int rc = make_map(&a, d_x, k_in, rows_cap, ldx, kBlockK, kBlockM) | make_map(&b, d_w, k_in, n_out, ldw, kBlockK, block_n);
+    if (rc) return rc;
+    return launch_bn<1>(block_n, a, b, p, dim3((unsigned)tiles_m, (unsigned)n_tiles, 1), (cudaStream_t)stream, bn);
+}
+
+int escgnn_linear_bn_act_bwd(const float* d_dy, int lddy, const float* d_w, int ldw, int rows_cap, int n_in, int n_out, const int* d_rows,
+                             const float* d_x, int ldx, const float* d_mean, const float* d_rstd, const float* d_gamma,
+                             const float* d_beta, int act, int bn_cols, float* d_dgamma, float* d_dbeta, float* d_dx, int lddx,
+                             float* d_ws, int64_t ws_floats, void* stream) {
+    if (rows_cap <= 0 || n_out <= 0 || n_in <= 0) return 0;
+    if ((lddy & 3) || (ldw & 3) || ((uintptr_t)d_dy & 15) || ((uintptr_t)d_w & 15) || !d_ws || !d_mean || !d_rstd || !d_x || !d_dx ||
+        bn_cols < 0 || bn_cols > n_in)
+        return ESCGNN_ERR_BAD_ARG;
+    if (ws_floats < escgnn_linear_bn_workspace_floats(rows_cap, n_in)) return ESCGNN_ERR_CAPACITY;
+    // dX[rows, n_in] = dY[rows, n_out] W[n_out, n_in]: output width n_in, contraction over n_out; W is the MN-major B operand
+    const int block_n = pick_block_n(n_in);
+    const int tiles_m = (rows_cap + kBlockM - 1) / kBlockM, n_tiles = (n_in + block_n - 1) / block_n;
+    if (n_tiles > 32) return ESCGNN_ERR_TOO_LARGE;
+    Params p;
+    p.C = d_dx; p.ldc = lddx; p.bias = nullptr; p.M = rows_cap; p.N = n_in; p.K = n_out;
+    p.kb_total = (n_out + kBlockK - 1) / kBlockK; p.kb_per_split = p.kb_total;
+    p.partial = nullptr; p.accumulate = 0; p.atomic = 0; p.rows_ptr = d_rows; p.rows_dim = d_rows ? 1 : 0;
+    BnParams bn = BnParams();
+    bn.X = d_x; bn.ldx = ldx; bn.gamma = d_gamma; bn.beta = d_beta; bn.mean = const_cast<float*>(d_mean); bn.rstd = const_cast<float*>(d_rstd);
+    bn.dgamma = d_dgamma; bn.dbeta = d_dbeta; bn.act = act; bn.bn_cols = bn_cols; bn.ws = d_ws; bn.ldp = bn_ldp(n_in);
+    CUtensorMap a, b;
+    int rc = make_map(&a, d_dy, n_out, rows_cap, lddy, kBlockK, kBlockM) | make_map(&b, d_w, n_in, n_out, ldw, 32, kBlockK, true);
+    if (rc) return rc;
+    return launch_bn<2>(block_n, a, b, p, dim3((unsigned)tiles_m, (unsigned)n_tiles, 1), (cudaStream_t)stream, bn);
 }
 
 }  // extern "C"

@@ -93,7 +93,7 @@ class StaticTrainEngine(object):
     """One model variant at a fixed capacity: NestedGIN_eff 'zinc' / 'count', or 'ogb' = GNN(gnn_type='gin_eff')."""
 
     def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
-                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True, encoder_ctas=None, fused_head=True):
+                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True, encoder_ctas=None, fused_head=True, fuse_bn=False):
         if variant not in ('zinc', 'count', 'ogb'):
             raise NotImplementedError('engine variants: zinc, count, ogb')
         p0 = next(model.parameters())
@@ -170,6 +170,11 @@ class StaticTrainEngine(object):
         # in place with vector reductions (2) instead of going through partial tiles and a reduction launch (0)
         self.wgrad_mode = 2 if atomic_wgrad else 0
         self.bounded_gemm = True
+        # Linear -> BatchNorm -> activation as one launch each way (GEMM epilogues behind a grid barrier); only kernels of the MAIN
+        # branch take that path (two barrier kernels on concurrent branches could starve each other of SM slots)
+        self.fuse_bn = bool(fuse_bn) and tensor_cores
+        self.bn_ws = torch.zeros(int(self.c.L.escgnn_linear_bn_workspace_floats(max(caps['N'], caps['E'], caps['B']), 2048)),
+                                 dtype=torch.float32, device=dev)
         self.fused_head = fused_head
         self.encoder_ctas = int(encoder_ctas) if encoder_ctas else None
         self.gemm_ws = torch.zeros(8 * 1024 * 1024, dtype=torch.float32, device=dev)    # split-K partial tiles (wgrad)
@@ -240,7 +245,39 @@ class StaticTrainEngine(object):
             torch.cuda.current_stream(self.c.dev).wait_event(done)
             self._side_used = False
 
-    def _linear(self, x, lin, kind, out=None, dx=None, dx_accumulate=False, need_dx=True, feeds_bn=False, branch=False):
+    def _tc_ok(self, *ts):
+        return self.tensor_cores and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in ts)
+
+    def _bn_spec(self, bn, act, kind, x=None, dx=None, out=None):
+        """One training-mode BatchNorm + activation of the tape: x (pre-BN) -> out; dx = gradient wrt x.  mean / rstd are saved by
+        whichever kernel runs its forward (stand-alone or a GEMM epilogue) for whichever runs its backward."""
+        C = bn.num_features
+        return dict(bn=bn, act=act, kind=kind, x=x, dx=dx, out=out,
+                    mean=torch.zeros(C, dtype=torch.float32, device=self.c.dev), rstd=torch.ones(C, dtype=torch.float32, device=self.c.dev))
+
+    def _bn_fwd(self, s):
+        """Stand-alone forward of a BatchNorm spec (its backward may still be fused into the next Linear's dgrad)."""
+        c, bn, x, out, kind = self.c, s['bn'], s['x'], s['out'], s['kind']
+        self.fwd.append(lambda: _lib.check(c.L.escgnn_bn_act_fwd(
+            _p(x), x.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(s['mean']), _p(s['rstd']),
+            _p(c.partial), ACT[s['act']], bn.eps, bn.momentum, 1, _p(c.rows[kind]), c.caps[kind], x.size(1), _p(out), out.stride(0),
+            c.st()), 'bn_act_fwd'))
+        self._bns.append(bn)
+
+    def _bn_bwd(self, s, dout, dout2=None):
+        """Stand-alone backward of a BatchNorm spec: s['dx'] from dout (+ dout2; a callable is resolved when the tape runs)."""
+        c, bn, x, dx, kind = self.c, s['bn'], s['x'], s['dx'], s['kind']
+
+        def back():
+            d2 = dout2() if callable(dout2) else dout2
+            _lib.check(c.L.escgnn_bn_act_bwd(
+                _p(x), x.stride(0), _p(dout), dout.stride(0), _p(d2), d2.stride(0) if d2 is not None else 0, _p(s['mean']), _p(s['rstd']),
+                _p(bn.weight), _p(bn.bias), ACT[s['act']], 1, _p(c.partial), _p(c.rows[kind]), c.caps[kind], x.size(1),
+                _p(bn.weight.grad), _p(bn.bias.grad), _p(dx), dx.stride(0), c.st()), 'bn_act_bwd')
+        self.bwd.append(back)
+
+    def _linear(self, x, lin, kind, out=None, dx=None, dx_accumulate=False, need_dx=True, feeds_bn=False, branch=False,
+                fwd_bn=None, bwd_bn=None, dy=None):
         """y = x W^T + b over capacity rows.  Returns (y, dy) buffers; backward fills W.grad, b.grad and dx.
 
         feeds_bn: the output goes straight into a training-mode BatchNorm.  Its bias gradient is sum_rows(dBN/dx), which
@@ -248,19 +285,44 @@ class StaticTrainEngine(object):
         zero the step starts from; torch computes the same quantity as ~1e-9 rounding noise.
         branch: nothing downstream on the critical path needs this layer's output immediately (the conv.lin edge
         projections: every layer's depends only on z): forward and dgrad run on the side stream as well; the caller waits on
-        the returned events."""
+        the returned events.
+        fwd_bn: spec (_bn_spec) of the BatchNorm + activation that FOLLOWS this Linear: Linear, statistics, normalisation and
+        activation are one launch (GEMM epilogue behind a grid barrier, csrc/gemm_tf32x3.cu EPI 1); the spec's x / dx become
+        this Linear's y / dy.  Shapes the fused kernel cannot take run as GEMM + stand-alone BatchNorm.
+        bwd_bn: spec of the BatchNorm + activation that PRECEDES this Linear (its `out` is our x): the dgrad's epilogue applies
+        the activation / BatchNorm backward and writes the gradient wrt the spec's pre-BN x (EPI 2) -- `dx` is not needed."""
         c = self.c
         W, bvec = lin.weight, lin.bias
         n_out, k_in, rows = W.size(0), W.size(1), c.caps[kind]
         y = out if out is not None else c.buf(kind, n_out)
-        dy = c.buf(kind, n_out)
+        dy = dy if dy is not None else c.buf(kind, n_out)
+        fuse = self.fuse_bn and not branch
+        fuse_f = fwd_bn is not None and fuse and self._tc_ok(x, W) and c.L.escgnn_linear_bn_fusable(rows, n_out, k_in) == 1
+        fuse_b = bwd_bn is not None and fuse and need_dx and not dx_accumulate and self._tc_ok(dy, W) and \
+            c.L.escgnn_linear_bn_fusable(rows, k_in, n_out) == 1
+        if fwd_bn is not None:
+            fwd_bn['x'], fwd_bn['dx'] = y, dy
+            feeds_bn = True
         # forward: Y[rows, n_out] = X[rows, k_in] W[n_out, k_in]^T + b          (A, B K-major)
         fwd_gemm = lambda: self._gemm('gemm_fwd', x, False, W, False, y, bvec, rows, n_out, k_in, False, rows=kind)
         fwd_event = [None]
-        if branch:
+        if fuse_f:
+            bn, o = fwd_bn['bn'], fwd_bn['out']
+            self.fwd.append(lambda: _lib.check(c.L.escgnn_linear_bn_act_fwd(
+                _p(x), x.stride(0), _p(W), W.stride(0), _p(bvec), rows, n_out, k_in, _p(c.rows[kind]), _p(bn.weight), _p(bn.bias),
+                _p(bn.running_mean), _p(bn.running_var), _p(fwd_bn['mean']), _p(fwd_bn['rstd']), ACT[fwd_bn['act']], bn.eps, bn.momentum,
+                _p(y), y.stride(0), _p(o), o.stride(0), _p(self.bn_ws), self.bn_ws.numel(), c.st()), 'linear_bn_act_fwd'))
+            self._bns.append(bn)
+        elif branch:
             self.fwd.append(lambda: fwd_event.__setitem__(0, self._fork(fwd_gemm)))
         else:
             self.fwd.append(fwd_gemm)
+        if fwd_bn is not None and not fuse_f:
+            self._bn_fwd(fwd_bn)
+        if bwd_bn is not None and not fuse_b:
+            if dx is None:
+                dx = c.buf(kind, k_in)
+            self._bn_bwd(bwd_bn, dx)                 # registered first: runs right AFTER this Linear's dgrad
 
         def grads():
             # wgrad: dW[n_out, k_in] = dY^T X   (A = dY stored [rows, n_out] = MN-major, B = X stored [rows, k_in] = MN-major)
@@ -271,6 +333,14 @@ class StaticTrainEngine(object):
 
         def dgrad():
             # dgrad: dX[rows, k_in] = dY W      (A = dY K-major, B = W stored [n_out, k_in] = MN-major for this product)
+            if fuse_b:
+                b = bwd_bn
+                bn, xb, dxb = b['bn'], b['x'], b['dx']
+                _lib.check(c.L.escgnn_linear_bn_act_bwd(
+                    _p(dy), dy.stride(0), _p(W), W.stride(0), rows, k_in, n_out, _p(c.rows[kind]), _p(xb), xb.stride(0), _p(b['mean']),
+                    _p(b['rstd']), _p(bn.weight), _p(bn.bias), ACT[b['act']], bn.num_features, _p(bn.weight.grad), _p(bn.bias.grad),
+                    _p(dxb), dxb.stride(0), _p(self.bn_ws), self.bn_ws.numel(), c.st()), 'linear_bn_act_bwd')
+                return
             self._gemm('gemm_dgrad', dy, False, W, True, dx, None, rows, k_in, n_out, dx_accumulate, rows=kind)
 
         def back():
@@ -388,10 +458,14 @@ class StaticTrainEngine(object):
         self.bwd.append(lambda: (torch.cuda.current_stream(c.dev).wait_event(bag_ready[0]), _lib.check(
             c.L.escgnn_bag_embed_bwd_indexed(_p(dz0), H, c.caps['nnz'], _p(W0.grad), _p(bag_work), _p(bag_edge), _p(bag_cnt),
                                              c.st()), 'bag_embed_bwd_indexed')))
-        z1, dz1 = c.buf('E', H), c.buf('E', H)
-        self._bn_act(z0, dz0, m.z_embedding[1], act, 'E', z1, dz1)
-        z2, dz2 = self._linear(z1, m.z_embedding[3], 'E', dx=dz1, feeds_bn=True)
-        self._bn_act(z2, dz2, m.z_embedding[5], act, 'E', zcat[:, :H], dzcat[:, :H])
+        # z_embedding = BN, act, Linear, BN, act (zinc_models.py:513-522).  Forward: the first BatchNorm stand-alone, Linear + second
+        # BatchNorm + activation one launch.  Backward: the second BatchNorm's is the epilogue of the grouped projection dgrad below
+        # (which writes d z2 into the first H columns of `dzcat`), the first one's the epilogue of this Linear's dgrad.
+        z1 = c.buf('E', H)
+        bn_z1 = self._bn_spec(m.z_embedding[1], act, 'E', x=z0, dx=dz0, out=z1)
+        self._bn_fwd(bn_z1)
+        bn_z2 = self._bn_spec(m.z_embedding[5], act, 'E', out=zcat[:, :H])
+        self._linear(z1, m.z_embedding[3], 'E', fwd_bn=bn_z2, bwd_bn=bn_z1, dy=dzcat[:, :H])
         if self.variant == 'zinc':
             self._embedding_bwd(m.edge_type_embedding, self.in_ea, 'E', dzcat[:, H:])
         # JK buffer: [x_embedding(x) | x1 .. xL] for count, [x1 .. xL] for zinc
@@ -401,15 +475,15 @@ class StaticTrainEngine(object):
         if self.variant == 'count':       # xs[0] = x_embedding(data.x)   (run_graphcount.py:166)
             seq = m.x_embedding
             dxin = c.buf('N', 10)
-            a, da = self._linear(x0, seq[0], 'N', dx=dxin, need_dx=False, feeds_bn=True)
-            b_, db_ = c.buf('N', H), c.buf('N', H)
-            self._bn_act(a, da, seq[2], act, 'N', b_, db_)
-            d_, dd_ = self._linear(b_, seq[4], 'N', dx=db_, feeds_bn=True)
-            self._bn_act(d_, dd_, seq[6], act, 'N', xs[:, 0:H], dxs[:, 0:H])
+            b_ = c.buf('N', H)
+            bn_a = self._bn_spec(seq[2], act, 'N', out=b_)
+            self._linear(x0, seq[0], 'N', dx=dxin, need_dx=False, fwd_bn=bn_a)
+            bn_d = self._bn_spec(seq[6], act, 'N', out=xs[:, 0:H])
+            self._linear(b_, seq[4], 'N', fwd_bn=bn_d, bwd_bn=bn_a)
+            self._bn_bwd(bn_d, dxs[:, 0:H])            # registered last of the three: runs first in the backward pass
             slot0 = 1
         # M3 GINE layers
         x_prev, dx_prev = x0, dx0
-        self.bwd.append(self._join)               # (runs after every conv backward) dzcat is complete before z_embedding's backward
         # ---- edge projections of every layer in one GEMM: ee_all[E, sum C_in] = zcat @ W_cat^T + b_cat
         col, off = {}, 0
         for cv in self.lin_convs:
@@ -447,11 +521,30 @@ class StaticTrainEngine(object):
                        False, rows='E')
         self.fwd.append(first_projection)
 
+        # d zcat = dee_all W_cat.  Its first H columns are the output of z_embedding's last BatchNorm + activation: that BatchNorm's
+        # backward is the epilogue of this product (-> d z2 lands in dzcat[:, :H]); the edge-type columns (ZINC) only feed an
+        # embedding-table gradient, so their (narrow) product leaves the critical path
+        fuse_proj = self.fuse_bn and self._tc_ok(dee_all, W_cat) and c.L.escgnn_linear_bn_fusable(E_rows, H, n_tot) == 1
+        if not fuse_proj:
+            dz_act = c.buf('E', H)                # gradient wrt the activation output, BatchNorm backward as its own launch
+            self._bn_bwd(bn_z2, dz_act)           # (registered before proj_back: runs after it)
+
         def proj_back():                          # runs after every layer's backward has filled its slice of dee_all
-            self._fork(lambda: (self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, self.wgrad_mode, rows='E'),
-                                _lib.check(c.L.escgnn_colsum(_p(dee_all), dee_all.stride(0), _p(c.rows['E']), E_rows, n_tot,
-                                                             _p(self.side_partial), _p(db_cat), c.st()), 'colsum')))
-            self._gemm('gemm_dgrad', dee_all, False, W_cat, True, dzcat, None, E_rows, edge_dim, n_tot, False, rows='E')
+            def side():
+                self._gemm('gemm_wgrad', dee_all, True, zcat, True, dW_cat, None, n_tot, edge_dim, E_rows, self.wgrad_mode, rows='E')
+                _lib.check(c.L.escgnn_colsum(_p(dee_all), dee_all.stride(0), _p(c.rows['E']), E_rows, n_tot,
+                                             _p(self.side_partial), _p(db_cat), c.st()), 'colsum')
+                if edge_dim > H:
+                    self._gemm('gemm_dgrad', dee_all, False, W_cat[:, H:], True, dzcat[:, H:], None, E_rows, edge_dim - H, n_tot, False, rows='E')
+            self._fork(side)
+            if fuse_proj:
+                bn, b = bn_z2['bn'], bn_z2
+                _lib.check(c.L.escgnn_linear_bn_act_bwd(
+                    _p(dee_all), dee_all.stride(0), _p(W_cat), W_cat.stride(0), E_rows, H, n_tot, _p(c.rows['E']), _p(b['x']), b['x'].stride(0),
+                    _p(b['mean']), _p(b['rstd']), _p(bn.weight), _p(bn.bias), ACT[b['act']], H, _p(bn.weight.grad), _p(bn.bias.grad),
+                    _p(dzcat), dzcat.stride(0), _p(self.bn_ws), self.bn_ws.numel(), c.st()), 'linear_bn_act_bwd')
+            else:
+                self._gemm('gemm_dgrad', dee_all, False, W_cat[:, :H], True, dz_act, None, E_rows, H, n_tot, False, rows='E')
         self.bwd.append(proj_back)
         layer_dx_from_next = [None] * Lh          # gradient flowing into layer l's output from layer l+1's aggregation
         for l, conv in enumerate(convs):
@@ -468,16 +561,19 @@ class StaticTrainEngine(object):
                 dxin_buf = c.buf('N', H)
                 layer_dx_from_next[l - 1] = dxin_buf
             self._gine(xin, dxin_buf, ee, dee, conv.eps, agg, dagg)
+            # conv.nn = Linear, BN, act, Linear, BN, act: two fused launches forward; backward: the last BatchNorm stand-alone (its
+            # gradient arrives from two places), the middle one as the epilogue of the second Linear's dgrad
             seq = conv.nn
-            h1, dh1 = self._linear(agg, seq[0], 'N', dx=dagg, feeds_bn=True)
-            h2, dh2 = c.buf('N', H), c.buf('N', H)
-            self._bn_act(h1, dh1, seq[2], act, 'N', h2, dh2)
-            h3, dh3 = self._linear(h2, seq[4], 'N', dx=dh2, feeds_bn=True)
+            h2 = c.buf('N', H)
             out_slice = xs[:, (slot0 + l) * H:(slot0 + l + 1) * H]
             dout_slice = dxs[:, (slot0 + l) * H:(slot0 + l + 1) * H]
-            # the last BN of layer l: its backward needs layer l+1's dx, which is only known after the loop wiring;
-            # register forward now, backward through a late-bound closure
-            self._bn_act_late(h3, dh3, seq[6], act, out_slice, dout_slice, layer_dx_from_next, l)
+            bn_mid = self._bn_spec(seq[2], act, 'N', out=h2)
+            bn_out = self._bn_spec(seq[6], act, 'N', out=out_slice)
+            self._linear(agg, seq[0], 'N', dx=dagg, fwd_bn=bn_mid)
+            self._linear(h2, seq[4], 'N', fwd_bn=bn_out, bwd_bn=bn_mid)
+            # the gradient of layer l's output also comes from layer l+1's aggregation, known only after the loop wiring: resolved
+            # when the tape runs
+            self._bn_bwd(bn_out, dout_slice, dout2=lambda l=l: layer_dx_from_next[l])
         # M4 readout
         if self.variant == 'zinc':
             pooled, dpooled = c.buf('B', Lh * H), c.buf('B', Lh * H)
@@ -722,26 +818,6 @@ class StaticTrainEngine(object):
         self.fwd.append(lambda: _lib.check(c.L.escgnn_loss_fwd_bwd(_p(pred), pred.stride(0), _p(self.in_y), 1, _p(c.rows['B']), G, 1,
                                                                    _p(self.loss), _p(dpred), dpred.stride(0), c.st()),
                                            'loss_fwd_bwd'))
-
-    def _bn_act_late(self, x, dx, bn, act, out, dout, dx_from_next, l):
-        """Like _bn_act, but the second gradient source (next layer's aggregation) is resolved when the tape runs."""
-        c = self.c
-        C = x.size(1)
-        mean = torch.zeros(C, dtype=torch.float32, device=c.dev)
-        rstd = torch.ones(C, dtype=torch.float32, device=c.dev)
-        self.fwd.append(lambda: _lib.check(c.L.escgnn_bn_act_fwd(
-            _p(x), x.stride(0), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), _p(mean), _p(rstd),
-            _p(c.partial), ACT[act], bn.eps, bn.momentum, 1, _p(c.rows['N']), c.caps['N'], C, _p(out), out.stride(0),
-            c.st()), 'bn_act_fwd'))
-        self._bns.append(bn)
-
-        def back():
-            d2 = dx_from_next[l]
-            _lib.check(c.L.escgnn_bn_act_bwd(
-                _p(x), x.stride(0), _p(dout), dout.stride(0), _p(d2), d2.stride(0) if d2 is not None else 0, _p(mean), _p(rstd),
-                _p(bn.weight), _p(bn.bias), ACT[act], 1, _p(c.partial), _p(c.rows['N']), c.caps['N'], C, _p(bn.weight.grad),
-                _p(bn.bias.grad), _p(dx), dx.stride(0), c.st()), 'bn_act_bwd')
-        self.bwd.append(back)
 
     # ------------------------------------------------------------------ one step
     def _encode_and_index(self, t=None):

@@ -328,6 +328,31 @@ int escgnn_gemm_tf32x3_bounded(const float* d_a, int lda, int a_mn_major, const 
                                int ldc, const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace,
                                int64_t workspace_floats, const int* d_rows, int rows_dim, void* stream);
 int64_t escgnn_gemm_workspace_floats(int M, int N, int K);
+/* Fused Linear -> BatchNorm1d(training) -> activation, ONE launch each way (replaces the Linear, BN, act triples of
+ * nn.Sequential(Linear, Dropout, BN, act, ...): run_graphcount.py:54-61,78-87; zinc_models.py:513-522,538-566). The GEMM
+ * (tcgen05 3xTF32, as escgnn_gemm_tf32x3_bounded) keeps its tile in tensor memory; column statistics are reduced per tile,
+ * exchanged through d_ws behind a grid barrier and summed in a fixed order (deterministic).
+ *   fwd: y = x W^T + b -> d_y (pre-BN, kept for the backward; may be NULL), d_out = act(BN(y)); saves d_mean / d_rstd, updates the
+ *        running statistics like torch. Rows [*d_rows, rows_cap) of d_out are written as zeros.
+ *   bwd: given d_dy = gradient wrt the output of the NEXT Linear (weights d_w [n_out, n_in]) whose input was act(BN(x)),
+ *        computes d(act(BN(x))) = d_dy W on the tensor cores and, in the epilogue, the gradient wrt x (the saved pre-BN d_x):
+ *        d_dx [rows_cap, n_in]; d_dgamma / d_dbeta [bn_cols]. Columns [bn_cols, n_in) of d_dx receive the plain product
+ *        (concatenated inputs whose tail did not come through the BatchNorm).
+ * The grid barrier needs the whole grid resident: escgnn_linear_bn_fusable() tells whether a shape qualifies on this device
+ * (ESCGNN_ERR_TOO_LARGE from the launchers otherwise: use the separate entry points), and two such launches must not run
+ * concurrently on different streams. d_ws: escgnn_linear_bn_workspace_floats() floats, zero before first use. */
+int escgnn_linear_bn_fusable(int rows_cap, int n_out, int k_in);
+/* CTAs of the fused kernel for this shape that the current device keeps resident at once (<= 0: CUDA error, negated) */
+int escgnn_linear_bn_resident_ctas(int n_cols, int rows_cap, int backward);
+int64_t escgnn_linear_bn_workspace_floats(int rows_cap, int n_cols);
+int escgnn_linear_bn_act_fwd(const float* d_x, int ldx, const float* d_w, int ldw, const float* d_bias, int rows_cap, int n_out, int k_in,
+                             const int* d_rows, const float* d_gamma, const float* d_beta, float* d_running_mean, float* d_running_var,
+                             float* d_mean, float* d_rstd, int act, float eps, float momentum, float* d_y, int ldy, float* d_out,
+                             int ldo, float* d_ws, int64_t ws_floats, void* stream);
+int escgnn_linear_bn_act_bwd(const float* d_dy, int lddy, const float* d_w, int ldw, int rows_cap, int n_in, int n_out, const int* d_rows,
+                             const float* d_x, int ldx, const float* d_mean, const float* d_rstd, const float* d_gamma,
+                             const float* d_beta, int act, int bn_cols, float* d_dgamma, float* d_dbeta, float* d_dx, int lddx,
+                             float* d_ws, int64_t ws_floats, void* stream);
 /* shared-memory plan of the GEMM: -1 auto, 0 = 2 stages (2 CTAs/SM), 1 = 4 stages (1 CTA/SM); +2 = the variant that keeps
  * both planes of A in shared memory instead of tensor memory (experiments / tests) */
 int escgnn_gemm_set_plan(int plan);

@@ -170,3 +170,122 @@ def test_gemm_simple_atomic_split_k(M, N, K):
     ref = A.double() @ B.double().t() + C0.double()
     scale = (A.double().abs() @ B.double().abs().t()).max().item()
     assert (C.double() - ref).abs().max().item() <= 2e-6 * scale
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused Linear -> BatchNorm(training) -> activation (one launch each way) against fp64 torch
+def _bn_ref(y, gamma, beta, eps, act):
+    mean = y.mean(0)
+    var = y.var(0, unbiased=False)
+    xh = (y - mean) / torch.sqrt(var + eps)
+    z = xh * gamma + beta
+    o = torch.relu(z) if act == 1 else torch.nn.functional.elu(z) if act == 2 else z
+    return o, mean, var
+
+
+@pytest.mark.parametrize('act', [1, 2])
+@pytest.mark.parametrize('rows_cap,rows,n_out,k_in', [(6302, 5906, 256, 256), (9400, 9300, 256, 256), (700, 700, 300, 600), (130, 1, 64, 32),
+                                                      (1000, 513, 96, 40), (2048, 0, 256, 64)])
+def test_linear_bn_act_fwd_matches_fp64(act, rows_cap, rows, n_out, k_in):
+    from esc_gnn_b200 import _lib
+    L = _lib.lib()
+    assert L.escgnn_linear_bn_fusable(rows_cap, n_out, k_in) == 1, L.escgnn_linear_bn_resident_ctas(n_out, rows_cap, 0)
+    g = torch.Generator(device='cuda').manual_seed(rows_cap + n_out)
+    x = torch.randn(rows_cap, k_in, device='cuda', generator=g)
+    x[rows:] = 0
+    w = torch.randn(n_out, k_in, device='cuda', generator=g) / k_in ** 0.5
+    bias = torch.randn(n_out, device='cuda', generator=g)
+    gamma = 1 + 0.1 * torch.randn(n_out, device='cuda', generator=g)
+    beta = 0.1 * torch.randn(n_out, device='cuda', generator=g)
+    rm0, rv0 = torch.randn(n_out, device='cuda', generator=g), 1 + torch.rand(n_out, device='cuda', generator=g)
+    rm, rv = rm0.clone(), rv0.clone()
+    mean, rstd = torch.zeros(n_out, device='cuda'), torch.zeros(n_out, device='cuda')
+    ld = n_out + 32                                       # output is a column slice of a wider buffer
+    y = torch.full((rows_cap, n_out), float('nan'), device='cuda')
+    out = torch.full((rows_cap, ld), float('nan'), device='cuda')
+    d_rows = torch.tensor([rows], dtype=torch.int32, device='cuda')
+    ws_n = L.escgnn_linear_bn_workspace_floats(rows_cap, n_out)
+    ws = torch.zeros(ws_n, device='cuda')
+    for rep in range(2):                                  # second launch: the barrier tickets were re-armed
+        if rep:
+            rm.copy_(rm0); rv.copy_(rv0)
+        _lib.check(L.escgnn_linear_bn_act_fwd(_p(x), k_in, _p(w), k_in, _p(bias), rows_cap, n_out, k_in, _p(d_rows), _p(gamma), _p(beta),
+                                              _p(rm), _p(rv), _p(mean), _p(rstd), act, 1e-5, 0.1, _p(y), n_out, _p(out[:, 16:]), ld,
+                                              _p(ws), ws_n, _st()), 'linear_bn_act_fwd')
+        torch.cuda.synchronize()
+        assert int(ws[:64].view(torch.int32).abs().sum()) == 0
+        assert torch.equal(out[rows:, 16:16 + n_out], torch.zeros_like(out[rows:, 16:16 + n_out]))
+        assert torch.isnan(out[:, :16]).all() and torch.isnan(out[:, 16 + n_out:]).all()
+        if rows == 0:
+            continue
+        yr = x[:rows].double() @ w.double().t() + bias.double()
+        scale = (x[:rows].double().abs() @ w.double().abs().t()).max().item() + 1.0
+        assert (y[:rows].double() - yr).abs().max().item() <= 4e-6 * scale
+        o, m, v = _bn_ref(yr, gamma.double(), beta.double(), 1e-5, act)
+        if rows > 1:
+            assert (out[:rows, 16:16 + n_out].double() - o).abs().max().item() <= 2e-4 * max(o.abs().max().item(), 1.0)
+            torch.testing.assert_close(mean.double(), m, rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(rstd.double(), 1 / torch.sqrt(v + 1e-5), rtol=2e-4, atol=1e-5)
+            ub = v * rows / (rows - 1)
+            torch.testing.assert_close(rv.double(), 0.9 * rv0.double() + 0.1 * ub, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(rm.double(), 0.9 * rm0.double() + 0.1 * m, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('act', [1, 2])
+@pytest.mark.parametrize('rows_cap,rows,n_in,n_out,bn_cols', [(6302, 5906, 256, 256, 256), (6200, 6092, 288, 1056, 256),
+                                                              (700, 650, 600, 300, 600), (300, 77, 64, 96, 32)])
+def test_linear_bn_act_bwd_matches_fp64(act, rows_cap, rows, n_in, n_out, bn_cols):
+    """dX = BN'(act'(.)) applied to dY W in the dgrad epilogue; columns >= bn_cols are the plain product."""
+    from esc_gnn_b200 import _lib
+    L = _lib.lib()
+    assert L.escgnn_linear_bn_fusable(rows_cap, n_in, n_out) == 1
+    g = torch.Generator(device='cuda').manual_seed(rows_cap + n_in)
+    dy = torch.randn(rows_cap, n_out, device='cuda', generator=g)
+    dy[rows:] = 0
+    w = torch.randn(n_out, n_in, device='cuda', generator=g) / n_out ** 0.5
+    x = torch.randn(rows_cap, bn_cols, device='cuda', generator=g) * 2 + 0.5
+    gamma = 1 + 0.1 * torch.randn(bn_cols, device='cuda', generator=g)
+    beta = 0.1 * torch.randn(bn_cols, device='cuda', generator=g)
+    x64 = x[:rows].double().requires_grad_(True)
+    mean = x64.mean(0)
+    var = x64.var(0, unbiased=False)
+    o, _, _ = _bn_ref(x64, gamma.double(), beta.double(), 1e-5, act)
+    d_act = dy[:rows].double() @ w.double()
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    o2, _, _ = _bn_ref(x64, g64, b64, 1e-5, act)
+    (o2 * d_act[:, :bn_cols]).sum().backward()
+    mean32, rstd32 = mean.detach().float().contiguous(), (1 / torch.sqrt(var.detach() + 1e-5)).float().contiguous()
+    dx = torch.full((rows_cap, n_in), float('nan'), device='cuda')
+    dgamma, dbeta = torch.zeros(bn_cols, device='cuda'), torch.zeros(bn_cols, device='cuda')
+    d_rows = torch.tensor([rows], dtype=torch.int32, device='cuda')
+    ws_n = L.escgnn_linear_bn_workspace_floats(rows_cap, n_in)
+    ws = torch.zeros(ws_n, device='cuda')
+    for rep in range(2):
+        _lib.check(L.escgnn_linear_bn_act_bwd(_p(dy), n_out, _p(w), n_in, rows_cap, n_in, n_out, _p(d_rows), _p(x), bn_cols, _p(mean32),
+                                              _p(rstd32), _p(gamma), _p(beta), act, bn_cols, _p(dgamma), _p(dbeta), _p(dx), n_in, _p(ws),
+                                              ws_n, _st()), 'linear_bn_act_bwd')
+        torch.cuda.synchronize()
+        assert int(ws[:64].view(torch.int32).abs().sum()) == 0
+        assert torch.equal(dx[rows:], torch.zeros_like(dx[rows:]))
+        sc = d_act.abs().max().item()
+        assert (dx[:rows, :bn_cols].double() - x64.grad).abs().max().item() <= 3e-4 * sc
+        if bn_cols < n_in:
+            assert (dx[:rows, bn_cols:].double() - d_act[:, bn_cols:]).abs().max().item() <= 1e-5 * sc
+        torch.testing.assert_close(dgamma.double(), g64.grad, rtol=2e-4, atol=2e-4 * g64.grad.abs().max().item())
+        torch.testing.assert_close(dbeta.double(), b64.grad, rtol=2e-4, atol=2e-4 * b64.grad.abs().max().item())
+
+
+def test_linear_bn_refuses_grids_that_do_not_fit_the_machine():
+    from esc_gnn_b200 import _lib
+    L = _lib.lib()
+    assert L.escgnn_linear_bn_fusable(128 * 400, 256, 256) == 0
+    rows_cap, n, k = 128 * 400, 256, 64
+    x = torch.zeros(rows_cap, k, device='cuda')
+    w = torch.zeros(n, k, device='cuda')
+    v = [torch.zeros(n, device='cuda') for _ in range(6)]
+    out = torch.zeros(rows_cap, n, device='cuda')
+    ws_n = L.escgnn_linear_bn_workspace_floats(rows_cap, n)
+    ws = torch.zeros(ws_n, device='cuda')
+    rc = L.escgnn_linear_bn_act_fwd(_p(x), k, _p(w), k, None, rows_cap, n, k, None, _p(v[0]), _p(v[1]), _p(v[2]), _p(v[3]), _p(v[4]),
+                                    _p(v[5]), 1, 1e-5, 0.1, None, 0, _p(out), n, _p(ws), ws_n, _st())
+    assert rc == -2
