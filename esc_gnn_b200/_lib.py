@@ -37,6 +37,9 @@ SIGNATURES = {
     'escgnn_ctx_destroy': (None, [_vp]),
     'escgnn_encode_host_run': (_i32, [_vp] * 5 + [_i64, _i32, _i32, _i32, _i32, _i64p, _i64p, _u32p]),
     'escgnn_encode_host_fetch': (_i32, [_vp] * 7),
+    'escgnn_encode_host_submit': (_i32, [_vp, _i32] + [_vp] * 4 + [_i64, _i32, _i32, _i32]),
+    'escgnn_encode_host_wait': (_i32, [_vp, _i32, _i64p, _i64p, _u32p] + [ctypes.POINTER(ctypes.c_void_p)] * 6),
+    'escgnn_expand_records_host': (_i32, [_vp] * 4 + [_i64, _i32, _vp, _vp, _vp, _i32]),
     'escgnn_encode_host_device_results': (_i32, [_vp] * 6),
     'escgnn_csr_build': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'escgnn_sorted_ids_to_ptr': (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),

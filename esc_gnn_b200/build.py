@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libescgnn_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
-         '-Xcompiler', '-O2', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-O2', '-Xcompiler', '-fopenmp', '--expt-relaxed-constexpr']
 
 
 def sources():
@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    subprocess.check_call([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart'])
+    subprocess.check_call([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart', '-lgomp'])
     return LIB
 
 

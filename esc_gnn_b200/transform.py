@@ -9,6 +9,7 @@ in compact form for the model's bag-embed kernel, or expanded to the reference's
 No CPU fallback: without libescgnn_b200.so / a CUDA device these functions raise.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -46,38 +47,144 @@ class EncodedBatch(object):
         self.__dict__.update(kw)
 
 
+def _np_view(ptr, n, dtype):
+    """numpy view of `n` items of pinned host memory owned by the encoder context (no copy)."""
+    if n == 0 or not ptr:
+        return np.empty(0, dtype=dtype)
+    ctype = {np.uint32: ctypes.c_uint32, np.int32: ctypes.c_int32, np.int64: ctypes.c_int64}[dtype]
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(n, ))
+
+
+class HostEncodedBatch(object):
+    """Result of the host front end in COMPACT form (what crosses PCIe): `rec` uint32 [nnz] = index | count << 11, ascending
+    inside an edge, the records of edge e at rec[rec_off[e] : rec_off[e] + rec_nnz[e]]; `edge_index` int64 [2, E_out] and
+    `edge_ptr` int64 [G+1] after the self-loop rewrite.  The arrays are views of pinned memory owned by the encoder context
+    and stay valid until the same slot is submitted again (`detach()` copies them out).
+
+    The reference's int64 triple (`pos_enc`, `pos_index`, `pos_batch`, utils_edge_efficient.py:139-151) is produced on
+    first access, on the host, by all cores (`expand()`)."""
+
+    def __init__(self, rec, rec_off, rec_nnz, eo_src, eo_dst, edge_ptr, num_edges, nnz, local_ordinals):
+        self.rec, self.rec_off, self.rec_nnz = rec, rec_off, rec_nnz
+        self._eo_src, self._eo_dst, self._edge_ptr = eo_src, eo_dst, edge_ptr
+        self.num_edges, self.nnz, self.local_ordinals = num_edges, nnz, local_ordinals
+        self._triple = None
+
+    @property
+    def edge_index(self):
+        return torch.from_numpy(np.stack([self._eo_src, self._eo_dst]))
+
+    @property
+    def edge_ptr(self):
+        return torch.from_numpy(np.array(self._edge_ptr))
+
+    def detach(self):
+        """Copy the compact arrays out of the context's pinned arena (they are overwritten by the slot's next run)."""
+        for k in ('rec', 'rec_off', 'rec_nnz', '_eo_src', '_eo_dst', '_edge_ptr'):
+            setattr(self, k, np.array(getattr(self, k)))
+        return self
+
+    def expand(self, out=None, threads=None):
+        """(pos_enc, pos_index, pos_batch) as int64 CPU tensors; `out` = dict of preallocated (e.g. pinned) tensors."""
+        if self._triple is None:
+            K = self.nnz
+            if out is not None:
+                pe, pi, pb = out['pos_enc'][:K], out['pos_index'][:K], out['pos_batch'][:K]
+            else:
+                pe, pi, pb = (torch.empty(K, dtype=torch.int64) for _ in range(3))
+            ep = np.ascontiguousarray(self._edge_ptr)
+            p = lambda a: ctypes.c_void_p(a.ctypes.data)
+            _lib.check(_lib.lib().escgnn_expand_records_host(p(self.rec), p(self.rec_off), p(self.rec_nnz), p(ep), len(ep) - 1,
+                                                             int(self.local_ordinals), _ptr(pe), _ptr(pi), _ptr(pb),
+                                                             int(threads or os.cpu_count() or 1)), 'expand_records_host')
+            self._triple = (pe, pi, pb)
+        return self._triple
+
+    pos_enc = property(lambda self: self.expand()[0])
+    pos_index = property(lambda self: self.expand()[1])
+    pos_batch = property(lambda self: self.expand()[2])
+
+
+class HostEncoder(object):
+    """Pipelined host front end over the two slots of an encoder context (C-ABI escgnn_encode_host_submit / _wait).
+
+        enc = HostEncoder(h=3, use_rd=True)
+        for result in enc.stream(chunks):        # chunks: iterable of (src, dst, edge_ptr, node_ptr) int64 host arrays
+            ...                                  # HostEncodedBatch, valid until two more chunks have been submitted
+
+    While the caller consumes chunk k, the kernels of chunk k+1 are already running and its own D2H ran under them."""
+
+    def __init__(self, h, use_rd=False, self_loop=False, local_ordinals=False, device=0):
+        self.h, self.use_rd, self.self_loop, self.local_ordinals = int(h), bool(use_rd), bool(self_loop), bool(local_ordinals)
+        self.device = int(device)
+        self.ctx = _ctx(self.device)
+        self.L = _lib.lib()
+
+    def submit(self, slot, src, dst, edge_ptr, node_ptr):
+        a = [np.ascontiguousarray(x.numpy() if torch.is_tensor(x) else x, dtype=np.int64) for x in (src, dst, edge_ptr, node_ptr)]
+        G = a[2].shape[0] - 1
+        p = lambda x: ctypes.c_void_p(x.ctypes.data)
+        _lib.check(self.L.escgnn_encode_host_submit(self.ctx, slot, p(a[0]), p(a[1]), p(a[2]), p(a[3]), G, self.h,
+                                                    int(self.use_rd), int(self.self_loop)), 'encode_host_submit')
+        return G
+
+    def wait(self, slot, G):
+        e_out, nnz, bits = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_uint32(0)
+        ptrs = [ctypes.c_void_p() for _ in range(6)]
+        rc = self.L.escgnn_encode_host_wait(self.ctx, slot, ctypes.byref(e_out), ctypes.byref(nnz), ctypes.byref(bits),
+                                            *[ctypes.byref(q) for q in ptrs])
+        if rc == -4:
+            _lib.raise_data_errors(bits.value)
+        _lib.check(rc, 'encode_host_wait')
+        E, K = e_out.value, nnz.value
+        v = [q.value for q in ptrs]
+        return HostEncodedBatch(_np_view(v[0], K, np.uint32), _np_view(v[1], E, np.int64), _np_view(v[2], E, np.int32),
+                                _np_view(v[3], E, np.int64), _np_view(v[4], E, np.int64), _np_view(v[5], G + 1, np.int64), E, K,
+                                self.local_ordinals)
+
+    def encode(self, src, dst, edge_ptr, node_ptr):
+        """One chunk, synchronously (slot 0)."""
+        return self.wait(0, self.submit(0, src, dst, edge_ptr, node_ptr))
+
+    def stream(self, chunks):
+        pending = None
+        k = 0
+        for chunk in chunks:
+            slot = k & 1
+            G = self.submit(slot, *chunk)
+            if pending is not None:
+                yield self.wait(*pending)
+            pending = (slot, G)
+            k += 1
+        if pending is not None:
+            yield self.wait(*pending)
+
+
 def encode_batch_host(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=False, local_ordinals=False,
-                      device=0, out=None):
+                      device=0, out=None, compact=False):
     """HOST buffers in, HOST buffers out through the C-ABI host front end (H2D + kernels + D2H inside the call).
 
-    src/dst/edge_ptr/node_ptr: int64 numpy arrays or CPU tensors (graph-local node ids). Returns an EncodedBatch
-    of CPU tensors (pinned when `out` supplies pinned buffers)."""
-    L = _lib.lib()
-    src = torch.as_tensor(src, dtype=torch.int64).contiguous()
-    dst = torch.as_tensor(dst, dtype=torch.int64).contiguous()
-    edge_ptr = torch.as_tensor(edge_ptr, dtype=torch.int64).contiguous()
-    node_ptr = torch.as_tensor(node_ptr, dtype=torch.int64).contiguous()
-    G = edge_ptr.numel() - 1
-    c = _ctx(device)
-    e_out, nnz, bits = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_uint32(0)
-    rc = L.escgnn_encode_host_run(c, _ptr(src), _ptr(dst), _ptr(edge_ptr), _ptr(node_ptr), G, int(h), int(use_rd),
-                                  int(self_loop), int(local_ordinals), ctypes.byref(e_out), ctypes.byref(nnz),
-                                  ctypes.byref(bits))
-    if rc == -4:
-        _lib.raise_data_errors(bits.value)
-    _lib.check(rc, 'encode_host_run')
-    E, K = e_out.value, nnz.value
+    src/dst/edge_ptr/node_ptr: int64 numpy arrays or CPU tensors (graph-local node ids).  Only the compact records cross
+    PCIe (4 bytes per record, pinned staging on both sides); `compact=True` returns them as a HostEncodedBatch (views of the
+    context's pinned arena, the triple expanded lazily), otherwise the reference's int64 triple is expanded on the host
+    (all cores) into `out` (dict of preallocated tensors, e.g. pinned) or fresh tensors and an EncodedBatch of CPU
+    tensors is returned."""
+    G = len(edge_ptr) - 1
+    if G == 0:
+        z = lambda *shape: torch.zeros(shape, dtype=torch.int64)
+        return EncodedBatch(edge_index=z(2, 0), edge_ptr=z(1), pos_enc=z(0), pos_index=z(0), pos_batch=z(0), num_edges=0, nnz=0)
+    enc = HostEncoder(h, use_rd, self_loop, local_ordinals, device)
+    r = enc.encode(src, dst, edge_ptr, node_ptr)
+    if compact:
+        return r
+    E, K = r.num_edges, r.nnz
+    pe, pi, pb = r.expand(out)
     if out is not None:
         ei, eptr = out['edge_index'][:, :E], out['edge_ptr'][:G + 1]
-        pe, pi, pb = out['pos_enc'][:K], out['pos_index'][:K], out['pos_batch'][:K]
-        ei0, ei1 = out['edge_index'][0], out['edge_index'][1]
+        ei[0].copy_(torch.from_numpy(r._eo_src)); ei[1].copy_(torch.from_numpy(r._eo_dst))
+        eptr.copy_(torch.from_numpy(r._edge_ptr))
     else:
-        ei = torch.empty((2, E), dtype=torch.int64)
-        eptr = torch.empty(G + 1, dtype=torch.int64)
-        pe, pi, pb = (torch.empty(K, dtype=torch.int64) for _ in range(3))
-        ei0, ei1 = ei[0], ei[1]
-    _lib.check(L.escgnn_encode_host_fetch(c, _ptr(ei0), _ptr(ei1), _ptr(eptr), _ptr(pe), _ptr(pi), _ptr(pb)),
-               'encode_host_fetch')
+        ei, eptr = r.edge_index, r.edge_ptr
     return EncodedBatch(edge_index=ei, edge_ptr=eptr, pos_enc=pe, pos_index=pi, pos_batch=pb, num_edges=E, nnz=K)
 
 

@@ -116,6 +116,27 @@ int escgnn_encode_host_fetch(escgnn_ctx* ctx, int64_t* h_eo_src, int64_t* h_eo_d
 int escgnn_encode_host_device_results(escgnn_ctx* ctx, const uint32_t** d_rec, const int64_t** d_rec_off,
                                       const int32_t** d_rec_nnz, const int64_t** d_eo_src, const int64_t** d_eo_dst);
 
+/* Throughput form of the host front end: two slots per context, each with its own stream, device workspace and grow-only
+ * PINNED staging / result arenas (no allocation after warm-up).
+ *   _submit(slot): copies the inputs into the slot's pinned staging (the caller's buffers are free on return), queues H2D and the
+ *                  E1 / E5 / E2-E4 kernels on the slot's stream and returns without waiting.
+ *   _wait(slot):   waits for the kernels, then fetches the COMPACT result into the slot's pinned arena -- records uint32 [nnz]
+ *                  (index | count << ESCGNN_REC_IDX_BITS, ascending inside an edge; the records of edge e are
+ *                  h_rec[h_rec_off[e] .. + h_rec_nnz[e])), and the output edge list (graph-local ids, after E1) with its
+ *                  per-graph pointers.  4 bytes per record cross PCIe instead of the 24 of the int64 triple.  The returned
+ *                  pointers stay valid until the slot is submitted again.
+ * Submitting chunk k+1 on the other slot before waiting for chunk k overlaps the D2H of k with the kernels of k+1.
+ * escgnn_expand_records_host: E6 on the host (OpenMP over graphs) for callers that need the reference's int64 triple
+ * (utils_edge_efficient.py:139-151); pos_batch = per-graph edge ordinal when local_ordinals != 0, else the batch-wide one. */
+int escgnn_encode_host_submit(escgnn_ctx* ctx, int slot, const int64_t* h_src, const int64_t* h_dst, const int64_t* h_edge_ptr,
+                              const int64_t* h_node_ptr, int64_t n_graphs, int h, int use_rd, int self_loop);
+int escgnn_encode_host_wait(escgnn_ctx* ctx, int slot, int64_t* out_num_edges, int64_t* out_nnz, uint32_t* out_error_bits,
+                            const uint32_t** h_rec, const int64_t** h_rec_off, const int32_t** h_rec_nnz,
+                            const int64_t** h_eo_src, const int64_t** h_eo_dst, const int64_t** h_eo_ptr);
+int escgnn_expand_records_host(const uint32_t* h_rec, const int64_t* h_rec_off, const int32_t* h_rec_nnz, const int64_t* h_eo_ptr,
+                               int64_t n_graphs, int local_ordinals, int64_t* h_pos_enc, int64_t* h_pos_index,
+                               int64_t* h_pos_batch, int threads);
+
 /* ================= model step; fp32, row-major, device pointers ========
  * Static-shape convention: where an entry point takes `const int* d_count` (may be NULL), the size argument before
  * it is a CAPACITY and the actual count is read from device memory, so one captured CUDA graph serves every batch;
