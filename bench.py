@@ -214,7 +214,8 @@ def build_engine(config, variant, batch, host_pool, world, args, pipeline=None):
     pipe = bool(args.pipeline) if pipeline is None else pipeline
     return StaticTrainEngine(build_model(variant), variant, fl, max_graphs=batch, max_nodes_per_graph=mx_n, max_edges_per_graph=mx_e,
                              nodes_cap=nodes_cap, edges_cap=edges_cap, lr=LR, distributed=world > 1, use_graph=True, pipeline=pipe,
-                             encoder_ctas=args.encoder_ctas if pipe else None, fuse_bn=bool(args.fuse_bn))
+                             encoder_ctas=args.encoder_ctas if pipe else None, fuse_bn=bool(args.fuse_bn),
+                             exchange=getattr(args, 'exchange', 'nccl'))
 
 
 def zinc_flops(n_nodes, e_out, graphs):
@@ -584,7 +585,7 @@ def run_own(args):
                            l2='flushed between timed iterations (256 MB write)', lr=LR,
                            pipeline=('encoder of batch k overlaps training of batch k-1 (one encode + one train step per step); '
                                      'encoder grids capped at %d CTAs' % args.encoder_ctas if args.pipeline else 'off'),
-                           fused_linear_bn=bool(args.fuse_bn)),
+                           fused_linear_bn=bool(args.fuse_bn), exchange=(args.exchange if world > 1 else 'none')),
                clocks=clk,
                e2e=dict(value=e2e_value, unit='graphs/s', h2d_bytes_per_step=host_pool[0].h2d_bytes(), d2h_bytes_per_step=4,
                         ms_per_step=ms_step_e2e),
@@ -608,6 +609,7 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--pipeline', type=int, default=1, help='1: overlap the encoder of batch k with the training of batch k-1')
     ap.add_argument('--fuse-bn', type=int, default=0, help='1: Linear+BatchNorm+act as one launch (GEMM epilogue behind a grid barrier)')
+    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'p2p'], help='data-parallel exchange: NCCL all-reduce between two graphs, or the fused NVLink peer-memory kernel')
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-large', action='store_true', help='skip the 8192-graph sections (extraction, extraction_e2e, large_batch)')

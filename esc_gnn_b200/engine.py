@@ -93,13 +93,20 @@ class StaticTrainEngine(object):
     """One model variant at a fixed capacity: NestedGIN_eff 'zinc' / 'count', or 'ogb' = GNN(gnn_type='gin_eff')."""
 
     def __init__(self, model, variant, flags, max_graphs, max_nodes_per_graph, max_edges_per_graph, nodes_cap, edges_cap,
-                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True, encoder_ctas=None, fused_head=True, fuse_bn=False):
+                 lr=1e-3, distributed=False, records_per_edge=64, use_graph=True, tensor_cores=True, pipeline=False, atomic_wgrad=True, encoder_ctas=None, fused_head=True, fuse_bn=False,
+                 exchange='nccl'):
         if variant not in ('zinc', 'count', 'ogb'):
             raise NotImplementedError('engine variants: zinc, count, ogb')
         p0 = next(model.parameters())
         if not p0.is_cuda:
             raise RuntimeError('StaticTrainEngine needs a CUDA model; there is no CPU fallback')
         self.model, self.variant, self.flags = model, variant, dict(flags)
+        # data-parallel exchange: 'p2p' = reduce-scatter + Adam + all-gather as one kernel over NVLink peer memory, a node of the
+        # step's single graph (csrc/p2p.cu); 'nccl' = one all-reduce of the flat gradient between two captured graphs
+        if exchange not in ('nccl', 'p2p'):
+            raise ValueError("exchange: 'nccl' or 'p2p'")
+        self.exchange = exchange if distributed else 'none'
+        p2p_group = None if self.exchange == 'p2p' else False
         # the edge projections `conv.lin` of ALL layers read the same z, so they are one GEMM against the row-concatenation
         # of their weights: lay those tensors out adjacently (256-wide layers first, the narrow first layer last)
         if variant == 'ogb':
@@ -112,11 +119,11 @@ class StaticTrainEngine(object):
             first += [e.weight for e in gn.node_encoder.atom_embedding_list]
             for cv in gn.convs:
                 first += [e.weight for e in cv.edge_encoder.bond_embedding_list]
-            self.opt = FlatAdam(model.parameters(), lr=lr, first=first)
+            self.opt = FlatAdam(model.parameters(), lr=lr, first=first, p2p_group=p2p_group)
         else:
             self.lin_convs = list(model.convs) + [model.conv1]
             self.opt = FlatAdam(model.parameters(), lr=lr, first=[cv.lin.weight for cv in self.lin_convs] +
-                                [cv.lin.bias for cv in self.lin_convs])
+                                [cv.lin.bias for cv in self.lin_convs], p2p_group=p2p_group)
         self.distributed, self.use_graph = distributed, use_graph
         dev = p0.device
         self.G = int(max_graphs)
@@ -910,11 +917,14 @@ class StaticTrainEngine(object):
 
     @torch.no_grad()
     def _run_opt(self):
-        self.opt.step_device()
+        if self.exchange == 'p2p':
+            self.opt.step_exchange_device()      # exchange + update in one launch (every rank runs the same number of steps)
+        else:
+            self.opt.step_device()
 
     def _run(self):
         self._run_main()
-        if self.distributed:
+        if self.exchange == 'nccl':
             self.opt.all_reduce_grads()
         self._run_opt()
 
@@ -962,7 +972,7 @@ class StaticTrainEngine(object):
         self.opt.sync_hyper(self._world())
         self.live.buf.copy_(self.stage.buf)
         self._run_train()
-        if self.distributed:
+        if self.exchange == 'nccl':
             self.opt.all_reduce_grads()
         self._run_opt()
         self._primed = False
@@ -996,14 +1006,14 @@ class StaticTrainEngine(object):
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
                     self._run_main()
-                    if not self.distributed:
+                    if self.exchange != 'nccl':
                         self._run_opt()
-                if self.distributed:             # the NCCL exchange stays outside the captured graphs
+                if self.exchange == 'nccl':      # the NCCL exchange stays outside the captured graphs
                     self.graph_opt = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self.graph_opt):
                         self._run_opt()
             self.graph.replay()
-            if self.distributed:
+            if self.exchange == 'nccl':
                 self.opt.all_reduce_grads()
                 self.graph_opt.replay()
         self.steps += 1
@@ -1022,7 +1032,7 @@ class StaticTrainEngine(object):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._run_main()
-            self._run_opt()
+            self.opt.step_device()               # rank-local: no exchange inside the profiling replay
             _lib.mark('end')
         marks, _lib.PROFILE, _lib.PROFILE_EXTERNAL, self.inline_branches = _lib.PROFILE, None, False, False
         ms, calls = {}, {}
@@ -1060,3 +1070,5 @@ class StaticTrainEngine(object):
                                'raise records_per_edge)' % (worst, self.rec.numel()))
         if int(self.idx_err.cpu()[0]):
             raise RuntimeError('edge_index out of range after collation')
+        if self.opt.peers is not None and self.opt.peers.timed_out():
+            raise RuntimeError('gradient exchange: a peer did not arrive within 4 s (ranks must run the same number of steps)')

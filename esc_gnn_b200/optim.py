@@ -11,10 +11,61 @@ import torch
 from . import _lib
 
 
+class _RawCuda(object):
+    """CUDA array interface over a raw device allocation of the library (zero-copy torch view of peer-shareable memory)."""
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = dict(shape=(n, ), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+class PeerBuffers(object):
+    """Gradient / parameter / flag buffers of every rank of the node, opened through CUDA IPC (one process per GPU), for the
+    fused exchange kernel escgnn_allreduce_adam (csrc/p2p.cu).  Collective: every rank of `group` must construct it."""
+
+    def __init__(self, n_floats, device, group=None):
+        import torch.distributed as dist
+        L = _lib.lib()
+        self.L, self.world, self.rank = L, dist.get_world_size(group), dist.get_rank(group)
+        self.n = int(n_floats)
+        flag_words = int(L.escgnn_p2p_flag_words(self.world))
+        sizes = dict(grad=4 * self.n, param=4 * self.n, flags=8 * flag_words)
+        self.own, handles = {}, {}
+        for k, b in sizes.items():
+            ptr, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+            _lib.check(L.escgnn_p2p_alloc(b, ctypes.byref(ptr), h), 'p2p_alloc')
+            self.own[k], handles[k] = ptr.value, bytes(h)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=group)
+        self.peer, self._opened = {k: [0] * self.world for k in sizes}, []
+        for r, hs in enumerate(gathered):
+            for k in sizes:
+                if r == self.rank:
+                    self.peer[k][r] = self.own[k]
+                else:
+                    ptr = ctypes.c_void_p()
+                    _lib.check(L.escgnn_p2p_open((ctypes.c_ubyte * 64).from_buffer_copy(hs[k]), ctypes.byref(ptr)), 'p2p_open')
+                    self.peer[k][r] = ptr.value
+                    self._opened.append(ptr.value)
+        self.arrays = {k: (ctypes.c_void_p * self.world)(*v) for k, v in self.peer.items()}     # host arrays of device pointers
+        self.grad = torch.as_tensor(_RawCuda(self.own['grad'], self.n, '<f4'), device=device)
+        self.param = torch.as_tensor(_RawCuda(self.own['param'], self.n, '<f4'), device=device)
+        self.flags = torch.as_tensor(_RawCuda(self.own['flags'], flag_words, '<i8'), device=device)
+        dist.barrier(group=group)
+
+    def timed_out(self):
+        return int(self.flags[2 * self.world + 2].item()) != 0
+
+    def close(self):
+        for p in self._opened:
+            self.L.escgnn_p2p_close(ctypes.c_void_p(p))
+        self._opened = []
+
+
 class FlatAdam(object):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, first=()):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, first=(), p2p_group=False):
         """`first`: parameters to lay out first and in this order (tensors the engine wants adjacent in memory, e.g. the
-        edge-projection weights of all layers so they form ONE [sum C_in, edge_dim] operand); the rest keep their order."""
+        edge-projection weights of all layers so they form ONE [sum C_in, edge_dim] operand); the rest keep their order.
+        `p2p_group`: None / a process group = keep parameters and gradients in peer-shareable memory and run the data-parallel
+        exchange fused with the update (`step_exchange_device`); False = local buffers (+ `all_reduce_grads` over NCCL)."""
         params = [p for p in params if p.requires_grad]
         head = [p for p in first if p.requires_grad]
         ids = {id(p) for p in head}
@@ -25,8 +76,13 @@ class FlatAdam(object):
         sizes = [p.numel() for p in self.params]
         pad = [(-s) % 4 for s in sizes]                       # keep every tensor 16-byte aligned in the flat buffer
         total = sum(s + q for s, q in zip(sizes, pad))
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.peers = None
+        if p2p_group is not False:
+            self.peers = PeerBuffers(total, dev, group=p2p_group)
+            self.flat, self.grad = self.peers.param, self.peers.grad
+        else:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         off = 0
@@ -66,6 +122,16 @@ class FlatAdam(object):
         _lib.check(_lib.lib().escgnn_adam_step_device(P(self.flat), P(self.grad), P(self.exp_avg), P(self.exp_avg_sq),
                                                       self.flat.numel(), P(self.hyper), P(self.state), st),
                    'adam_step_device')
+
+    def step_exchange_device(self):
+        """Gradient exchange over NVLink peer memory + Adam in one graph-capturable launch pair (csrc/p2p.cu): every rank must
+        call it the same number of times.  Averages the gradients (hyper[4] = 1 / world, see sync_hyper)."""
+        pb = self.peers
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().escgnn_allreduce_adam(pb.arrays['grad'], pb.arrays['param'], pb.arrays['flags'], pb.rank, pb.world,
+                                                    self.flat.numel(), P(self.exp_avg), P(self.exp_avg_sq), P(self.hyper), P(self.state),
+                                                    st), 'allreduce_adam')
 
     def sync_hyper(self, world_size=1):
         want = (self.param_groups[0]['lr'], 1.0 / world_size)

@@ -5,8 +5,8 @@ communication -- the batched replacement of the reference's per-graph `pre_trans
 
 Every chunk goes through `encode_batch(..., expand=True)`, i.e. the reference contract (rewritten edge_index + int64
 pos_enc / pos_index / pos_batch) is materialised in HBM, and is reduced to (edges, records, sum of counts) so sweeps of any
-length fit.  `digest()` is the order-independent checksum the C oracle's batch driver computes (oracle/encode_ref.c); the
-caller (bench.py / tests) compares a prefix of the sweep against it -- this module never touches the oracle.
+length fit.  `digest()` is an order-independent checksum of an encoded batch, defined so that the CPU checker's batch driver
+(outside this package) computes the same four numbers; the caller (bench.py / tests) compares a prefix of the sweep with it.
 """
 import numpy as np
 import torch

@@ -387,6 +387,23 @@ int escgnn_tf32_split_lo(const float* d_x, int ldx, float* d_lo, int ldlo, int64
 int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c, int ldc,
                        const float* d_bias, int M, int N, int K, int accumulate, void* stream);
 
+/* ---- data-parallel exchange over NVLink peer memory (the reference is single-GPU, run_zinc.py:266-289) ----
+ * escgnn_p2p_alloc: cudaMalloc'd, zero-filled buffer + its 64-byte CUDA IPC handle; the peers open it with escgnn_p2p_open
+ * (one process per GPU; peer access is enabled lazily).  escgnn_allreduce_adam: ONE exchange + optimiser step, graph-capturable:
+ * reduce-scatter of the gradients read from the peers' HBM, Adam on the owned slice (same update rule as escgnn_adam_step_device;
+ * moments are only maintained for the owned slice), all-gather of the new parameters by stores into every rank's buffer, with
+ * the two cross-GPU barriers inside the kernel (epoch flags; a peer that never arrives sets the error word after 4 s instead of
+ * hanging).  h_peer_* are HOST arrays of `world` device pointers (index = rank; entry `rank` is this rank's own buffer):
+ * gradients [n], parameters [n], flags [escgnn_p2p_flag_words(world)] (zero-initialised; word 2*world+2 != 0 after a timeout).
+ * n must be a multiple of 4; every rank must call it the same number of times. */
+int escgnn_p2p_alloc(int64_t bytes, void** d_ptr, unsigned char* handle64);
+int escgnn_p2p_open(const unsigned char* handle64, void** d_ptr);
+int escgnn_p2p_close(void* d_ptr);
+int escgnn_p2p_free(void* d_ptr);
+int64_t escgnn_p2p_flag_words(int world);
+int escgnn_allreduce_adam(const float* const* h_peer_grads, float* const* h_peer_params, unsigned long long* const* h_peer_flags, int rank,
+                          int world, int64_t n, float* d_exp_avg, float* d_exp_avg_sq, float* d_hyper, long long* d_state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
