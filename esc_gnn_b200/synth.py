@@ -21,7 +21,9 @@ ENCODER_FLAGS = {
     4: dict(h=4, use_rd=True, self_loop=True),     # run_ogb_mol.py:329-332
     5: dict(h=3, use_rd=False, self_loop=False),   # sweep: h in 1..4, rd off
     6: dict(h=3, use_rd=True, self_loop=True),     # run_qm9.py:203-205 (QM9 variant)
+    7: dict(h=3, use_rd=True, self_loop=True),     # run_csl.py:79-80 (graph classification, kernel/gin.py variant, N3)
 }
+KGIN_FEATURES, KGIN_CLASSES = 7, 3                 # graph-classification variant (kernel/gin.py:200-379): dataset.num_features / num_classes
 QM9_FEATURES = 11                                  # dataset.num_features of the reference's QM9 (run_qm9.py:216-231)
 
 
@@ -76,7 +78,7 @@ def symmetrise(und):
 
 
 def make_graph(config, i):
-    """One synthetic graph of `config` (1..6) as a dict of numpy arrays: edge_index, num_nodes, x, y[, edge_attr]."""
+    """One synthetic graph of `config` (1..7) as a dict of numpy arrays: edge_index, num_nodes, x, y[, edge_attr]."""
     rng = np.random.Generator(np.random.PCG64(1000 * config + i))
     if config in (1, 3):
         n = int(rng.integers(10, 31))
@@ -106,6 +108,11 @@ def make_graph(config, i):
         return dict(edge_index=symmetrise(und), num_nodes=n, x=rng.random((n, QM9_FEATURES)).astype(np.float32),
                     pos=(1.5 * rng.normal(size=(n, 3))).astype(np.float32), node_type=rng.integers(0, 5, size=n).astype(np.int64),
                     edge_attr=np.concatenate([bond, bond], axis=0), y=np.float32(rng.normal()))
+    if config == 7:      # graph classification (CSL / EXP / TU style): continuous node features, one integer class per graph
+        n = int(rng.integers(10, 31))
+        und = random_graph(rng, n, int(round(1.66 * n)))
+        return dict(edge_index=symmetrise(und), num_nodes=n, x=rng.random((n, KGIN_FEATURES)).astype(np.float32),
+                    y=np.int64(rng.integers(0, KGIN_CLASSES)))
     if config == 5:
         n = int(rng.integers(25, 501))
         und = random_graph(rng, n, int(1.25 * n))

@@ -105,6 +105,37 @@ class NestedGINEffCount(torch.nn.Module):
         return x if self.use_cycle else F.log_softmax(x, dim=-1)
 
 
+class NestedGINEffKernel(torch.nn.Module):
+    """kernel/gin.py:200-379 (graph classification): use_id None; JK = cat of the layer outputs, mean pooling, log_softmax."""
+    def __init__(self, num_layers, hidden, num_features, num_classes, dropout=0.0, graph_pred=True, use_cycle=False):
+        super().__init__()
+        self.graph_pred, self.dropout, self.use_cycle = graph_pred, dropout, use_cycle
+        self.z_initial = torch.nn.Embedding(1800, hidden)
+        self.z_embedding = _z_embedding(hidden, dropout, ReLU)
+        self.conv1 = GINEConv(_mlp(num_features, hidden, dropout, ReLU), train_eps=True, edge_dim=hidden)
+        self.convs = torch.nn.ModuleList(
+            [GINEConv(_mlp(hidden, hidden, dropout, ReLU), train_eps=True, edge_dim=hidden) for _ in range(num_layers - 1)])
+        self.lin1 = Linear(num_layers * hidden, hidden)
+        self.bn_lin1 = BN(hidden, eps=1e-5, momentum=0.1)
+        self.lin2 = Linear(hidden, 1 if use_cycle else num_classes)
+
+    def forward(self, data):
+        x, edge_index, batch = data.x, data.edge_index, data.batch
+        z = self.z_embedding(bag_embed(self.z_initial.weight, data.pos_index, data.pos_enc, data.pos_batch))
+        x = self.conv1(x, edge_index, z)
+        xs = [x]
+        for conv in self.convs:
+            x = conv(x, edge_index, z)
+            xs += [x]
+        x = global_mean_pool(torch.cat(xs, dim=1), batch) if self.graph_pred else torch.cat(xs, dim=1)
+        x = self.lin1(x)
+        if x.size(0) > 1:
+            x = self.bn_lin1(x)
+        x = F.relu(F.dropout(x, p=self.dropout, training=self.training))
+        x = self.lin2(x)
+        return x if self.use_cycle else F.log_softmax(x, dim=-1)
+
+
 class NestedGINEffZinc(torch.nn.Module):
     """zinc_models.py:504-611 (hidden 256 and dropout 0 are hard-coded there; parameterised here for small tests)."""
     def __init__(self, num_layers, hidden=256, dropout=0.0):

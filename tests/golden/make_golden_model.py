@@ -72,6 +72,12 @@ def build_reference_model(variant, kw):
     if variant == 'zinc':
         ns = extract('/root/reference/zinc_models.py', {'NestedGIN_eff'})
         return ns['NestedGIN_eff'](_DS(), kw['num_layers'])                  # run_zinc.py:241-257
+    if variant == 'kgin':
+        ns = extract('/root/reference/kernel/gin.py', {'NestedGIN_eff'})
+
+        class _TU(object):
+            num_features, num_classes = synth.KGIN_FEATURES, synth.KGIN_CLASSES
+        return ns['NestedGIN_eff'](_TU(), kw['num_layers'], kw['hidden'], use_rd=True, dropout=0)
     if variant == 'qm9':
         ns = extract('/root/reference/qm9_models.py', {'NestedGIN_eff'})
 

@@ -78,6 +78,7 @@ MODEL_CASES = {
     'zinc_l2': ('zinc', 2, 3, dict(num_layers=2)),
     'ogb': ('ogb', 4, 12, dict(num_tasks=1, num_layer=3, emb_dim=64, drop_ratio=0.0, virtual_node=True, residual=True)),
     'qm9': ('qm9', 6, 20, dict(num_layers=3)),
+    'kgin': ('kgin', 7, 20, dict(num_layers=3, hidden=64)),            # kernel/gin.py graph-classification variant
     'ogb_full': ('ogb', 4, 8, dict(num_tasks=1, num_layer=6, emb_dim=300, drop_ratio=0.0, virtual_node=True, residual=False)),
     # BASELINE.json shapes (configs[0..3]): the reference's own batch sizes, depths and widths; these cases also carry fp64
     # gradient statistics of the reference class (`/grad64_digest`, `/grad_err32`)
@@ -106,6 +107,8 @@ def loss_fn(variant, pred, y):
         return torch.nn.BCEWithLogitsLoss()(pred.to(torch.float32)[lab], y[lab])      # run_ogb_mol.py:58-74
     if variant == 'qm9':
         return torch.nn.functional.mse_loss(pred, y.view(-1))                          # run_qm9.py:348
+    if variant == 'kgin':
+        return torch.nn.functional.nll_loss(pred, y.view(-1))                          # kernel/train_eval.py (F.nll_loss on log_softmax)
     return torch.nn.L1Loss()(pred, y.view(-1, 1))                                      # run_graphcount.py:494-500
 
 
@@ -116,5 +119,7 @@ def build_oracle_model(variant, kw):
         return model_ref.NestedGINEffZinc(kw['num_layers'])
     if variant == 'qm9':
         return model_ref.NestedGINEffQM9(kw['num_layers'], synth.QM9_FEATURES)
+    if variant == 'kgin':
+        return model_ref.NestedGINEffKernel(kw['num_layers'], kw['hidden'], synth.KGIN_FEATURES, synth.KGIN_CLASSES)
     return model_ref.GNNOgbEff(kw['num_tasks'], kw['num_layer'], kw['emb_dim'], kw['virtual_node'], kw['residual'],
                                kw['drop_ratio'])

@@ -45,6 +45,12 @@ def build_product_model(variant, kw):
         class _QM9(object):
             num_features = synth.QM9_FEATURES
         return qm9_model.NestedGIN_eff(_QM9(), kw['num_layers'])
+    if variant == 'kgin':
+        from esc_gnn_b200 import kernel_gin_model
+
+        class _TU(object):
+            num_features, num_classes = synth.KGIN_FEATURES, synth.KGIN_CLASSES
+        return kernel_gin_model.NestedGIN_eff(_TU(), kw['num_layers'], kw['hidden'], use_rd=True, dropout=0)
     if variant == 'count':
         return graphcount_model.NestedGIN_eff(None, kw['num_layers'], kw['hidden'], use_rd=True, graph_pred=False,
                                               dropout=0, edge_nest=True, use_cycle=True)

@@ -8,7 +8,7 @@ import torch
 from tests import model_util as MU
 
 FIX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'model.npz'))
-CPU_CASES = ('count_h64', 'zinc_l2', 'ogb', 'zinc', 'qm9', 'count_cfg3', 'ogb_cfg4', 'count_cfg1', 'zinc_cfg2')
+CPU_CASES = ('count_h64', 'zinc_l2', 'ogb', 'zinc', 'qm9', 'kgin', 'count_cfg3', 'ogb_cfg4', 'count_cfg1', 'zinc_cfg2')
 
 
 def reference_worst_relative_error(name, variant):
