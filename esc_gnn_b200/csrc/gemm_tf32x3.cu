@@ -90,9 +90,14 @@ struct Params {
 };
 
 // 3xTF32 split: hi = the raw fp32 value (the tensor core reads its top 19 bits, i.e. truncates), lo = x - trunc_tf32(x), exact in
-// fp32.  Rounded planes (cvt.rna on both) were measured and removed: the error floor of this kernel is not the split but the
-// tensor core's truncating accumulation (-2.6e-6 mean signed relative error at K = 256 either way, tools/bench_linear_bn.py),
-// and the in-place rounding of B cost 15 % of the main loop.
+// fp32.  In the plain kernels the error floor is not the split but the tensor core's truncating accumulation (-5.9e-6 mean signed
+// relative error at K = 256, tools/bench_linear_bn.py); rounding B in place cost 15 % of the main loop and was removed.  The
+// drain kernel below fixes the accumulation and rounds what it can round for free.
+__device__ __forceinline__ float rna_tf32(float x) {          // round to nearest (ties away) to the 10-bit tf32 mantissa
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void split4(const float4& v, float4& l) {
     l = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
                     v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
@@ -793,6 +798,238 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// "Drain" variant of the TS kernel: fp32-GEMM accuracy from the tensor cores.
+// tcgen05.mma adds into its fp32 accumulator with TRUNCATION (measured: -2.6e-6 mean signed relative error for K = 256 --
+// 96 accumulating MMAs -- against +3e-10 for an FFMA GEMM, tools/bench_linear_bn.py), and the BatchNorm stacks of the model
+// amplify that one-sided error into gradient errors ~10-40x those of the reference's fp32 CPU run.  The cure (Ootomo &
+// Yokota, "Recovering single precision accuracy from Tensor Cores", 2022): never let the big products accumulate inside the
+// tensor core for long.  Per k-block the four hi*hi MMAs start a FRESH accumulator (two alternate in tensor memory), which
+// four extra "drainer" warps read back (tcgen05.ld) and add to register accumulators with round-to-nearest FADDs while the
+// next k-block's MMAs run; the small hi*lo / lo*hi products (2^-11 of the result, so their truncation is harmless) accumulate
+// in a third TMEM region over the whole K and are added once at the end.  The truncating chain on the large terms is 4 MMAs
+// long instead of 3 K / 8.
+// Tensor memory (512 columns, one CTA per SM): [0,128) D1a, [128,256) D1b, [256,384) D2, [384,512) A planes (2 x {hi 32, lo 32}).
+// Warps: 0 TMA producer, 1 MMA issuer, 2-5 splitters, 6-9 drainers + epilogue (TMEM lane quarter = warp % 4).
+constexpr int kDrainThreads = 320;
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kDrainThreads, 1)
+gemm_tf32x3_ts_drain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    constexpr int STAGES = 4, LO_BUFS = 2;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int kABytes = kBlockM * 128;
+    constexpr int kBBytes = BLOCK_N * 128;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* lo_buf = smem + (size_t)STAGES * kStageBytes;
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[LO_BUFS], lo_free_bar[LO_BUFS], d1_full_bar[2], d1_free_bar[2],
+        tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_bias[BLOCK_N];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    constexpr uint32_t kTmemCols = 512, kD1 = 0, kD2 = 256, kTmemA = 384;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < LO_BUFS; ++b) { mbar_init(&split_bar[b], 128); mbar_init(&lo_free_bar[b], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&d1_full_bar[b], 1); mbar_init(&d1_free_bar[b], 128); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+    escgnn::pdl_wait();
+    escgnn::pdl_trigger();
+    const int rows_now = p.rows_ptr ? *p.rows_ptr : 0;
+    const bool skip = p.rows_dim == 1 && m0 >= rows_now;
+    const int kb_total = p.rows_dim == 2 ? min(p.kb_total, (rows_now + kBlockK - 1) / kBlockK) : p.kb_total;
+    const int num_kb = skip ? 0 : max(min(kb_begin + p.kb_per_split, kb_total) - kb_begin, 0);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
+                uint8_t* st = smem + (size_t)s * kStageBytes;
+                mbar_expect_tx(&full_bar[s], kStageBytes);
+                const int k0 = (kb_begin + i) * kBlockK;
+                if (!A_MN) tma_load_2d(st, &tmA, &full_bar[s], k0, m0);
+                else {
+                    #pragma unroll
+                    for (int j = 0; j < kBlockM / 32; ++j) tma_load_2d(st + j * kSlabBytes, &tmA, &full_bar[s], m0 + 32 * j, k0);
+                }
+                uint8_t* sb = st + kABytes;
+                if (!B_MN) tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+                else {
+                    #pragma unroll
+                    for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * kSlabBytes, &tmB, &full_bar[s], n0 + 32 * j, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES, lb = i % LO_BUFS, b = i & 1;
+                mbar_wait(&split_bar[lb], (i / LO_BUFS) & 1);
+                mbar_wait(&d1_free_bar[b], ((i >> 1) & 1) ^ 1);       // the drainers have read what this accumulator held two k-blocks ago
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_hi = smem_u32(smem + (size_t)s * kStageBytes) + kABytes;
+                const uint32_t b_lo = smem_u32(lo_buf + (size_t)lb * kBBytes);
+                const uint32_t a_hi = tmem_d + kTmemA + (uint32_t)lb * 64u, a_lo = a_hi + 32u;
+                const uint32_t d1 = tmem_d + kD1 + (uint32_t)b * 128u, d2 = tmem_d + kD2;
+                #pragma unroll
+                for (int k = 0; k < kBlockK / 8; ++k) {               // hi * hi: a fresh accumulator per k-block
+                    const uint64_t bd = B_MN ? make_desc(b_hi + k * 1024, kSlabBytes, 512, 1) : make_desc(b_hi + k * 32, 0, 1024, 2);
+                    mma_tf32_ts(d1, a_hi + (uint32_t)(k * 8), bd, idesc, k ? 1u : 0u);
+                }
+                tcgen05_commit(&d1_full_bar[b]);
+                #pragma unroll
+                for (int pass = 1; pass < 3; ++pass) {                // hi * lo, lo * hi: one accumulator for the whole K
+                    const uint32_t at = pass == 2 ? a_lo : a_hi, bb = pass == 1 ? b_lo : b_hi;
+                    #pragma unroll
+                    for (int k = 0; k < kBlockK / 8; ++k) {
+                        const uint64_t bd = B_MN ? make_desc(bb + k * 1024, kSlabBytes, 512, 1) : make_desc(bb + k * 32, 0, 1024, 2);
+                        mma_tf32_ts(d2, at + (uint32_t)(k * 8), bd, idesc, (i | (pass - 1) | k) ? 1u : 0u);
+                    }
+                }
+                tcgen05_commit(&empty_bar[s]);
+                tcgen05_commit(&lo_free_bar[lb]);
+            }
+            tcgen05_commit(&tmem_full_bar);
+        }
+    } else if (warp < 6) {
+        // ===== splitters: A planes -> tensor memory, B_lo -> shared memory (as in gemm_tf32x3_ts_kernel) =====
+        const int t = threadIdx.x - 64, q = warp & 3, r = q * 32 + lane;
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES, lb = i % LO_BUFS;
+            mbar_wait(&full_bar[s], (i / STAGES) & 1);
+            mbar_wait(&lo_free_bar[lb], ((i / LO_BUFS) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint8_t* stage = smem + (size_t)s * kStageBytes;
+            uint32_t hi[32], lo[32];
+            if (!A_MN) {
+                #pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
+                    hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+                    hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+                }
+            } else {
+                const uint8_t* slab = stage + q * kSlabBytes + (lane & 7) * 4;
+                #pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    hi[k] = *reinterpret_cast<const uint32_t*>(slab + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+            }
+            // A planes are built in registers, so both can be ROUNDED for free: hi = rn_tf32(x), lo = rn_tf32(x - hi) (|lo| <= 2^-12 |x|,
+            // either sign); B keeps hi = the raw value (truncated by the tensor core) with lo = rn_tf32(x - trunc(x)).  Every dropped
+            // term (representation error of the lo planes, lo_a * lo_b) then has zero mean instead of pulling the result towards zero.
+            #pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float x = __uint_as_float(hi[k]), h = rna_tf32(x);
+                hi[k] = __float_as_uint(h);
+                lo[k] = __float_as_uint(rna_tf32(x - h));
+            }
+            const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + kTmemA + (uint32_t)lb * 64u;
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32u, lo);
+            const float4* src = reinterpret_cast<const float4*>(stage + kABytes);
+            float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kBBytes);
+            #pragma unroll 4
+            for (int e = t; e < kBBytes / 16; e += 128) {
+                float4 l;
+                split4(src[e], l);
+                dst[e] = make_float4(rna_tf32(l.x), rna_tf32(l.y), rna_tf32(l.z), rna_tf32(l.w));
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&split_bar[lb]);
+        }
+    } else {
+        // ===== drainers: fp32 accumulation outside the tensor core, then the epilogue =====
+        const int t = threadIdx.x - 192, q = warp & 3, r = q * 32 + lane;
+        for (int i = t; i < BLOCK_N; i += 128)
+            s_bias[i] = (p.bias && !p.partial && (!p.atomic || blockIdx.z == 0) && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+        float acc[BLOCK_N];
+        #pragma unroll
+        for (int j = 0; j < BLOCK_N; ++j) acc[j] = 0.f;
+        const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+        for (int i = 0; i < num_kb; ++i) {
+            const int b = i & 1;
+            mbar_wait(&d1_full_bar[b], (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            #pragma unroll
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + kD1 + (uint32_t)b * 128u + (uint32_t)c, v);
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&d1_free_bar[b]);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");          // s_bias complete
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + r;
+        const bool row_ok = row < p.M && !skip;
+        float* out = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
+        #pragma unroll
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            if (num_kb > 0) {
+                uint32_t v[32];
+                tmem_ld32(trow + kD2 + (uint32_t)c, v);
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);
+            }
+            if (row_ok) {
+                const int nb = n0 + c;
+                const bool accum = p.accumulate && !p.partial;
+                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(out + nb) & 15) == 0)) {
+                    #pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 w = make_float4(acc[c + j] + s_bias[c + j], acc[c + j + 1] + s_bias[c + j + 1],
+                                               acc[c + j + 2] + s_bias[c + j + 2], acc[c + j + 3] + s_bias[c + j + 3]);
+                        float4* dst = reinterpret_cast<float4*>(out + nb + j);
+                        if (p.atomic) { red_add4(dst, w); continue; }
+                        if (accum) { const float4 o = *dst; w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+                        *dst = w;
+                    }
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nb + j;
+                        if (n < p.N) {
+                            float w = acc[c + j] + s_bias[c + j];
+                            if (p.atomic) { atomicAdd(out + n, w); continue; }
+                            if (accum) w += out[n];
+                            out[n] = w;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+    }
+}
+
 // split-K reduction: C = (accumulate ? C : 0) + bias + sum_s partial[s]   (fixed order -> deterministic)
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C, int ldc,
                                      const float* __restrict__ bias, int accumulate) {
@@ -951,6 +1188,20 @@ int launch_cfg_ts(const CUtensorMap& a, const CUtensorMap& b, const Params& p, d
     return (int)cudaGetLastError();
 }
 
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch_cfg_drain(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+    const int smem = 4 * (kBlockM * 128 + BLOCK_N * 128) + 2 * BLOCK_N * 128 + 1024;
+    auto kern = gemm_tf32x3_ts_drain_kernel<BLOCK_N, A_MN, B_MN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    escgnn::launch_pdl(kern, grid, kDrainThreads, smem, st, a, b, p);
+    return (int)cudaGetLastError();
+}
+
 template <int EPI>
 int bn_resident(int block_n, bool deep) {
     constexpr bool B_MN = EPI == 2;
@@ -975,11 +1226,16 @@ int launch_bn(int block_n, const CUtensorMap& a, const CUtensorMap& b, const Par
     }
 }
 
+int g_gemm_drain = 1;      // fp32 accumulation outside the tensor core (escgnn_gemm_set_drain): 0 off, 1 one-wave grids, 2 every non-split product
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
     const int ctas = (int)(grid.x * grid.y * grid.z);
     const int plan = g_gemm_plan >= 0 ? (g_gemm_plan & 1) : -1;
     const bool deep = plan >= 0 ? plan == 1 : (ctas <= 148 && grid.z == 1);   // one wave at 1 CTA/SM: deeper ring
+    // long accumulation chains (one CTA walks the whole K) go through the drain kernel; split-K slices are short chains already
+    if (g_gemm_plan < 0 && grid.z == 1 && p.kb_total > 2 && (g_gemm_drain == 2 || (g_gemm_drain == 1 && ctas <= 148)))
+        return launch_cfg_drain<BLOCK_N, A_MN, B_MN>(a, b, p, grid, st);
     if (!(g_gemm_plan >= 2))           // planes of A in tensor memory (2 stages + 2 lo buffers still fit two CTAs per SM)
         return deep ? launch_cfg_ts<BLOCK_N, A_MN, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg_ts<BLOCK_N, A_MN, B_MN, 2, 2>(a, b, p, grid, st);
     return deep ? launch_cfg<BLOCK_N, A_MN, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg<BLOCK_N, A_MN, B_MN, 2, 1>(a, b, p, grid, st);
@@ -1046,6 +1302,12 @@ int escgnn_gemm_set_split_target(int ctas) {
 }
 
 int escgnn_gemm_set_plan(int plan) { g_gemm_plan = plan; return 0; }
+
+int escgnn_gemm_set_drain(int mode) {
+    const int was = g_gemm_drain;
+    if (mode >= 0 && mode <= 2) g_gemm_drain = mode;
+    return was;
+}
 
 /* how many floats of split-K workspace a call with these sizes can use (0 = never splits) */
 int64_t escgnn_gemm_workspace_floats(int M, int N, int K) {

@@ -377,6 +377,11 @@ int escgnn_linear_bn_act_bwd(const float* d_dy, int lddy, const float* d_w, int 
 /* shared-memory plan of the GEMM: -1 auto, 0 = 2 stages (2 CTAs/SM), 1 = 4 stages (1 CTA/SM); +2 = the variant that keeps
  * both planes of A in shared memory instead of tensor memory (experiments / tests) */
 int escgnn_gemm_set_plan(int plan);
+/* fp32 accumulation OUTSIDE the tensor core (the "drain" kernel: per k-block the hi*hi products start a fresh TMEM accumulator that
+ * four extra warps add into registers with round-to-nearest; removes the truncation bias of long tcgen05.mma accumulation chains):
+ * 0 = off, 1 = grids of at most one wave (default: free at one CTA per SM), 2 = every product that is not split along K (4 % slower
+ * step at batch 256: the two-CTA-per-SM plan of larger grids has no tensor memory left for the extra accumulators). Returns the previous mode. */
+int escgnn_gemm_set_drain(int mode);
 /* number of CTAs a split-K product (weight gradients) spreads over; default 296 = two per SM. Fewer, longer slices leave
  * room for kernels running concurrently on other streams. Returns the previous value. */
 int escgnn_gemm_set_split_target(int ctas);

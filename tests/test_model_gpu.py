@@ -488,7 +488,7 @@ def _check_against_fp64(name, grads, g64, factor):
     (fp32 resolution of the sum itself) -- it only matters where the reference's own error is ~0, i.e. gradients that are
     mathematically zero (a Linear bias feeding BatchNorm), which the engine leaves at exactly 0."""
     variant = MU.MODEL_CASES[name][0]
-    worst, bad = 0.0, []
+    worst, bad, strict = 0.0, [], []
     gmax = max(float(v.norm()) for v in g64.values())
     from tests.test_model_oracle_cpu import reference_worst_relative_error
     case_rel = 10.0 * reference_worst_relative_error(name, variant)
@@ -501,11 +501,21 @@ def _check_against_fp64(name, grads, g64, factor):
         # of the reference's own worst tensor in this case.  The product's floor is the tensor core: tcgen05.mma accumulates
         # with truncation (measured: -2.6e-6 mean signed relative error at K = 256 against +3e-10 for an FFMA GEMM,
         # tools/bench_linear_bn.py), which the BatchNorm stacks amplify like any other fp32 rounding.
-        bound = max(factor * float(ref_err) + 2e-6 * float(g64[k].norm()), case_rel * float(g64[k].norm())) + 1e-9 * gmax
+        strict_bound = factor * float(ref_err) + 2e-6 * float(g64[k].norm()) + 1e-9 * gmax
+        strict.append(err / max(strict_bound, 1e-30))
+        bound = max(strict_bound, case_rel * float(g64[k].norm()) + 1e-9 * gmax)
         worst = max(worst, err / max(bound, 1e-30))
         if err > bound:
             bad.append((k, err, float(ref_err), float(g64[k].norm())))
     assert not bad, (name, worst, bad[:6])
+    # The STRICT per-tensor bound (3x the reference's own fp32 error on that tensor) holds for the typical tensor -- the median
+    # ratio is 0.2 .. 0.5, i.e. the product is usually CLOSER to the fp64 truth than the reference's CPU run.  It cannot hold for
+    # every tensor of every case: a ReLU whose pre-activation is within rounding of zero takes the other branch under any fp32
+    # perturbation (tools/debug_relu_flips.py: 5 of the 12.7 M GINE message entries of the 256-graph ZINC batch do, with
+    # |pre-activation| < 1.6e-6), and each crossing shifts the gradients downstream of it by ~1e-4 of their norm -- which is what
+    # the looser case-level bound above absorbs.
+    strict.sort()
+    assert strict[len(strict) // 2] <= 1.0, (name, 'median strict ratio', strict[len(strict) // 2])
     return worst
 
 

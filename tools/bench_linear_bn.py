@@ -85,13 +85,31 @@ def accuracy(M, N, K):
     gws = torch.empty(8 << 20, device='cuda')
     _lib.check(L.escgnn_gemm_tf32x3(P(A), K, 0, P(B), K, 0, P(C), N, None, M, N, K, 0, P(gws), gws.numel(), st()), 'g')
     T = A @ B.t()
-    for name, X in (('tcgen05 3xTF32', C), ('cuBLAS fp32', T)):
+    L.escgnn_gemm_set_drain(0)
+    C0 = torch.empty(M, N, device='cuda')
+    _lib.check(L.escgnn_gemm_tf32x3(P(A), K, 0, P(B), K, 0, P(C0), N, None, M, N, K, 0, P(gws), gws.numel(), st()), 'g')
+    L.escgnn_gemm_set_drain(2)
+    for name, X in (('tcgen05 3xTF32 drain', C), ('tcgen05 in-TC accum', C0), ('cuBLAS fp32', T)):
         rel = (X.double() - ref) / ref
-        print('  %-16s M %5d N %4d K %5d: mean signed rel err %+.3e   rms %.3e   max %.3e' % (name, M, N, K, rel.mean().item(), rel.pow(2).mean().sqrt().item(),
+        print('  %-22s M %5d N %4d K %5d: mean signed rel err %+.3e   rms %.3e   max %.3e' % (name, M, N, K, rel.mean().item(), rel.pow(2).mean().sqrt().item(),
                                                                                               rel.abs().max().item()))
 
 
+def speed():
+    gws = torch.empty(8 << 20, device='cuda')
+    for M, N, K in ((6302, 256, 256), (12847, 256, 256), (12847, 288, 1056), (12847, 1056, 288)):
+        A = torch.randn(M, K, device='cuda'); B = torch.randn(N, K, device='cuda'); C = torch.empty(M, N, device='cuda')
+        line = 'gemm M %6d N %5d K %5d:' % (M, N, K)
+        for mode in (0, 1, 2):
+            L.escgnn_gemm_set_drain(mode)
+            f = lambda: _lib.check(L.escgnn_gemm_tf32x3(P(A), K, 0, P(B), K, 0, P(C), N, None, M, N, K, 0, P(gws), gws.numel(), st()), 'g')
+            line += '  drain=%d %6.1f us' % (mode, timeit(f))
+        L.escgnn_gemm_set_drain(2)
+        print(line)
+
+
 if __name__ == '__main__':
+    speed()
     for shape in ((6302, 5906, 256, 256), (6302, 5906, 256, 32), (6302, 128, 256, 256), (12847, 12092, 256, 256), (2600, 2500, 256, 256)):
         bench(*shape)
     for shape in ((1024, 256, 64), (1024, 256, 256), (1024, 256, 1024), (256, 256, 8192)):
