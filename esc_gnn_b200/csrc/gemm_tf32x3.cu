@@ -1226,7 +1226,7 @@ int launch_bn(int block_n, const CUtensorMap& a, const CUtensorMap& b, const Par
     }
 }
 
-int g_gemm_drain = 1;      // fp32 accumulation outside the tensor core (escgnn_gemm_set_drain): 0 off, 1 one-wave grids, 2 every non-split product
+int g_gemm_drain = 0;      // fp32 accumulation outside the tensor core (escgnn_gemm_set_drain): 0 off, 1 one-wave grids, 2 every non-split product
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {

@@ -289,3 +289,32 @@ def test_linear_bn_refuses_grids_that_do_not_fit_the_machine():
     rc = L.escgnn_linear_bn_act_fwd(_p(x), k, _p(w), k, None, rows_cap, n, k, None, _p(v[0]), _p(v[1]), _p(v[2]), _p(v[3]), _p(v[4]),
                                     _p(v[5]), 1, 1e-5, 0.1, None, 0, _p(out), n, _p(ws), ws_n, _st())
     assert rc == -2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the drain kernel: fp32 accumulation outside the tensor core (escgnn_gemm_set_drain)
+@pytest.mark.parametrize('a_mn,b_mn', [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize('M,N,K', [(256, 256, 256), (1000, 288, 256), (300, 160, 96), (6302, 256, 256), (700, 96, 1056)])
+def test_drain_gemm_matches_fp64_and_beats_in_tensor_core_accumulation(a_mn, b_mn, M, N, K):
+    from esc_gnn_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    A = torch.randn(M, K, device='cuda', generator=g).abs() + 0.1        # positive operands: the accumulation bias shows as a relative error
+    B = torch.randn(N, K, device='cuda', generator=g).abs() + 0.1
+    bias = torch.randn(N, device='cuda', generator=g)
+    ref = A.double() @ B.double().t()
+    was = L.escgnn_gemm_set_drain(2)
+    try:
+        check(A, B, a_mn, b_mn, bias=bias)
+        C0 = torch.randn(M, N, device='cuda', generator=g)
+        check(A, B, a_mn, b_mn, C0=C0)
+        drained = run_gemm(A, B, a_mn, b_mn)
+        L.escgnn_gemm_set_drain(0)
+        plain = run_gemm(A, B, a_mn, b_mn)
+    finally:
+        L.escgnn_gemm_set_drain(was)
+    e_d = ((drained.double() - ref) / ref).abs().mean().item()
+    e_p = ((plain.double() - ref) / ref).abs().mean().item()
+    assert e_d <= 4e-7, e_d                                # fp32-GEMM quality (cuBLAS fp32: ~2e-7 on these shapes)
+    if K >= 256:
+        assert e_d < 0.5 * e_p, (e_d, e_p)                 # the long in-tensor-core chains are what the drain removes

@@ -47,7 +47,7 @@ def run(label, linear=None, bn=None):
         rows.append((err / max(3 * ref_err[k] + 2e-6 * float(g64[k].norm()), 1e-30), k, err, ref_err[k], float(g64[k].norm())))
     rows.sort(reverse=True)
     print('== %-34s worst err/bound %.2f   median %.2f' % (label, rows[0][0], rows[len(rows) // 2][0]))
-    for r in rows[:5]:
+    for r in rows[:8]:
         print('     %-30s ratio %6.2f err %.3e ref_err %.3e norm %.3e' % (r[1], r[0], r[2], r[3], r[4]))
     return g
 
@@ -55,6 +55,10 @@ def run(label, linear=None, bn=None):
 torch_linear = lambda self, x: F.linear(x, self.weight, self.bias)
 torch_bn = lambda self, x: F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training, self.momentum, self.eps)
 run('product kernels')
+from esc_gnn_b200 import _lib
+_lib.lib().escgnn_set_cluster_bn(0)
+run('product kernels, cluster BN off (stats + apply kernels)')
+_lib.lib().escgnn_set_cluster_bn(1)
 run('torch Linear (cuBLAS fp32)', linear=torch_linear)
 run('torch BatchNorm', bn=torch_bn)
 run('torch Linear + torch BatchNorm', linear=torch_linear, bn=torch_bn)
