@@ -9,8 +9,9 @@ One "step" = one pass of the hot path over one batch of synthetic input: a batch
 run_zinc.py:141-146), collated and run through one NestedGIN_eff train step (5 layers, hidden 256; forward, L1
 loss, backward, Adam).  `value` = graphs/s with the raw graphs already resident in HBM; `e2e` = the same step fed
 from pinned HOST buffers (H2D of the raw graphs and D2H of the loss inside the timed region).
-Multi-GPU: weak scaling, every rank encodes and trains on its own 256 graphs; the only exchange is one NCCL
-all-reduce of the flat gradient per step.
+Multi-GPU: weak scaling, every rank encodes and trains on its own 256 graphs; the only exchange is the gradient exchange of the
+data-parallel step: reduce-scatter + Adam + all-gather fused into one kernel over NVLink peer memory (`config.exchange` = 'p2p';
+'nccl' = one NCCL all-reduce of the flat gradient between two captured graphs, the fallback).
 
 Beside the headline the same JSON line carries (none of them is the judged `value`):
   configs          the other BASELINE.json model configs through the same engine: cfg 1 (count_cycle-shaped, batch 128, h=3),
@@ -215,7 +216,7 @@ def build_engine(config, variant, batch, host_pool, world, args, pipeline=None):
     return StaticTrainEngine(build_model(variant), variant, fl, max_graphs=batch, max_nodes_per_graph=mx_n, max_edges_per_graph=mx_e,
                              nodes_cap=nodes_cap, edges_cap=edges_cap, lr=LR, distributed=world > 1, use_graph=True, pipeline=pipe,
                              encoder_ctas=args.encoder_ctas if pipe else None, fuse_bn=bool(args.fuse_bn),
-                             exchange=getattr(args, 'exchange', 'nccl'))
+                             exchange=getattr(args, 'exchange', 'auto'))
 
 
 def zinc_flops(n_nodes, e_out, graphs):
@@ -585,7 +586,7 @@ def run_own(args):
                            l2='flushed between timed iterations (256 MB write)', lr=LR,
                            pipeline=('encoder of batch k overlaps training of batch k-1 (one encode + one train step per step); '
                                      'encoder grids capped at %d CTAs' % args.encoder_ctas if args.pipeline else 'off'),
-                           fused_linear_bn=bool(args.fuse_bn), exchange=(args.exchange if world > 1 else 'none')),
+                           fused_linear_bn=bool(args.fuse_bn), exchange=eng.exchange),
                clocks=clk,
                e2e=dict(value=e2e_value, unit='graphs/s', h2d_bytes_per_step=host_pool[0].h2d_bytes(), d2h_bytes_per_step=4,
                         ms_per_step=ms_step_e2e),
@@ -609,7 +610,8 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--pipeline', type=int, default=1, help='1: overlap the encoder of batch k with the training of batch k-1')
     ap.add_argument('--fuse-bn', type=int, default=0, help='1: Linear+BatchNorm+act as one launch (GEMM epilogue behind a grid barrier)')
-    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'p2p'], help='data-parallel exchange: NCCL all-reduce between two graphs, or the fused NVLink peer-memory kernel')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'nccl', 'p2p'],
+                    help='data-parallel exchange: the fused NVLink peer-memory kernel (p2p), one NCCL all-reduce between two graphs (nccl), or p2p with nccl as the fallback (auto)')
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-large', action='store_true', help='skip the 8192-graph sections (extraction, extraction_e2e, large_batch)')

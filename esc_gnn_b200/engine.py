@@ -103,10 +103,10 @@ class StaticTrainEngine(object):
         self.model, self.variant, self.flags = model, variant, dict(flags)
         # data-parallel exchange: 'p2p' = reduce-scatter + Adam + all-gather as one kernel over NVLink peer memory, a node of the
         # step's single graph (csrc/p2p.cu); 'nccl' = one all-reduce of the flat gradient between two captured graphs
-        if exchange not in ('nccl', 'p2p'):
-            raise ValueError("exchange: 'nccl' or 'p2p'")
+        if exchange not in ('nccl', 'p2p', 'auto'):
+            raise ValueError("exchange: 'nccl', 'p2p' or 'auto' (p2p when the peers' memory can be mapped, else nccl)")
         self.exchange = exchange if distributed else 'none'
-        p2p_group = None if self.exchange == 'p2p' else False
+        p2p_group = None if self.exchange in ('p2p', 'auto') else False
         # the edge projections `conv.lin` of ALL layers read the same z, so they are one GEMM against the row-concatenation
         # of their weights: lay those tensors out adjacently (256-wide layers first, the narrow first layer last)
         if variant == 'ogb':
@@ -119,11 +119,17 @@ class StaticTrainEngine(object):
             first += [e.weight for e in gn.node_encoder.atom_embedding_list]
             for cv in gn.convs:
                 first += [e.weight for e in cv.edge_encoder.bond_embedding_list]
-            self.opt = FlatAdam(model.parameters(), lr=lr, first=first, p2p_group=p2p_group)
         else:
             self.lin_convs = list(model.convs) + [model.conv1]
-            self.opt = FlatAdam(model.parameters(), lr=lr, first=[cv.lin.weight for cv in self.lin_convs] +
-                                [cv.lin.bias for cv in self.lin_convs], p2p_group=p2p_group)
+            first = [cv.lin.weight for cv in self.lin_convs] + [cv.lin.bias for cv in self.lin_convs]
+        try:
+            self.opt = FlatAdam(model.parameters(), lr=lr, first=first, p2p_group=p2p_group)
+        except RuntimeError:
+            if self.exchange != 'auto':
+                raise
+            self.opt = FlatAdam(model.parameters(), lr=lr, first=first, p2p_group=False)       # (the failure is collective: every rank lands here)
+        if self.exchange == 'auto':
+            self.exchange = 'p2p' if self.opt.peers is not None else 'nccl'
         self.distributed, self.use_graph = distributed, use_graph
         dev = p0.device
         self.G = int(max_graphs)

@@ -36,15 +36,27 @@ class PeerBuffers(object):
         gathered = [None] * self.world
         dist.all_gather_object(gathered, handles, group=group)
         self.peer, self._opened = {k: [0] * self.world for k in sizes}, []
+        failed = 0
         for r, hs in enumerate(gathered):
             for k in sizes:
                 if r == self.rank:
                     self.peer[k][r] = self.own[k]
                 else:
                     ptr = ctypes.c_void_p()
-                    _lib.check(L.escgnn_p2p_open((ctypes.c_ubyte * 64).from_buffer_copy(hs[k]), ctypes.byref(ptr)), 'p2p_open')
+                    rc = L.escgnn_p2p_open((ctypes.c_ubyte * 64).from_buffer_copy(hs[k]), ctypes.byref(ptr))
+                    if rc != 0:
+                        failed = rc
+                        continue
                     self.peer[k][r] = ptr.value
                     self._opened.append(ptr.value)
+        # every rank takes the same decision: one rank that cannot map a peer (IPC disabled, no peer access) fails all of them
+        flag = torch.tensor([1 if failed else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag[0]):
+            self.close()
+            for ptr in self.own.values():
+                L.escgnn_p2p_free(ctypes.c_void_p(ptr))
+            raise RuntimeError('peer-memory exchange unavailable on this node (cudaIpcOpenMemHandle failed on some rank: %d)' % failed)
         self.arrays = {k: (ctypes.c_void_p * self.world)(*v) for k, v in self.peer.items()}     # host arrays of device pointers
         self.grad = torch.as_tensor(_RawCuda(self.own['grad'], self.n, '<f4'), device=device)
         self.param = torch.as_tensor(_RawCuda(self.own['param'], self.n, '<f4'), device=device)
