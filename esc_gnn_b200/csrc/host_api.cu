@@ -78,6 +78,18 @@ struct Slot {
 
 constexpr int kSlots = 2;
 
+// the context's device is made current for the duration of a call and the caller's device restored afterwards (the host thread
+// usually belongs to a framework that tracks its own current device)
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 }  // namespace
 
 struct escgnn_ctx {
@@ -198,7 +210,8 @@ int scan_sizes(Slot& s, const int64_t* h_edge_ptr, const int64_t* h_node_ptr, in
 extern "C" {
 
 escgnn_ctx* escgnn_ctx_create(int device) {
-    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return nullptr;
     escgnn_ctx* c = new escgnn_ctx();
     c->device = device;
     for (int i = 0; i < kSlots; ++i) {
@@ -215,7 +228,7 @@ escgnn_ctx* escgnn_ctx_create(int device) {
 
 void escgnn_ctx_destroy(escgnn_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     for (int i = 0; i < kSlots; ++i) {
         if (c->slot[i].stream) cudaStreamSynchronize(c->slot[i].stream);
         c->slot[i].release();
@@ -227,7 +240,8 @@ int escgnn_encode_host_run(escgnn_ctx* c, const int64_t* h_src, const int64_t* h
                            const int64_t* h_node_ptr, int64_t G, int h, int use_rd, int self_loop,
                            int local_ordinals, int64_t* out_num_edges, int64_t* out_nnz, uint32_t* out_error_bits) {
     if (!c || G < 0 || h < 1 || h > 4) return ESCGNN_ERR_BAD_ARG;
-    ESC_TRY(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    ESC_TRY(guard.err);
     Slot& s = c->slot[0];
     if (s.busy) return ESCGNN_ERR_BAD_ARG;      // a pipelined submit is in flight on this slot
     *out_num_edges = 0; *out_nnz = 0; *out_error_bits = 0;
@@ -256,7 +270,8 @@ int escgnn_encode_host_run(escgnn_ctx* c, const int64_t* h_src, const int64_t* h
 int escgnn_encode_host_fetch(escgnn_ctx* c, int64_t* h_eo_src, int64_t* h_eo_dst, int64_t* h_eo_ptr,
                              int64_t* h_pos_enc, int64_t* h_pos_index, int64_t* h_pos_batch) {
     if (!c) return ESCGNN_ERR_BAD_ARG;
-    ESC_TRY(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    ESC_TRY(guard.err);
     Slot& s = c->slot[0];
     cudaStream_t st = s.stream;
     if (s.n_graphs > 0) {
@@ -285,7 +300,8 @@ int escgnn_encode_host_device_results(escgnn_ctx* c, const uint32_t** d_rec, con
 int escgnn_encode_host_submit(escgnn_ctx* c, int slot, const int64_t* h_src, const int64_t* h_dst, const int64_t* h_edge_ptr,
                               const int64_t* h_node_ptr, int64_t G, int h, int use_rd, int self_loop) {
     if (!c || slot < 0 || slot >= kSlots || G < 1 || h < 1 || h > 4) return ESCGNN_ERR_BAD_ARG;
-    ESC_TRY(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    ESC_TRY(guard.err);
     Slot& s = c->slot[slot];
     if (s.busy) return ESCGNN_ERR_BAD_ARG;      // wait() first
     ESC_TRY(scan_sizes(s, h_edge_ptr, h_node_ptr, G, h, use_rd, self_loop));
@@ -308,7 +324,8 @@ int escgnn_encode_host_wait(escgnn_ctx* c, int slot, int64_t* out_num_edges, int
                             const uint32_t** h_rec, const int64_t** h_rec_off, const int32_t** h_rec_nnz,
                             const int64_t** h_eo_src, const int64_t** h_eo_dst, const int64_t** h_eo_ptr) {
     if (!c || slot < 0 || slot >= kSlots) return ESCGNN_ERR_BAD_ARG;
-    ESC_TRY(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    ESC_TRY(guard.err);
     Slot& s = c->slot[slot];
     if (!s.busy) return ESCGNN_ERR_BAD_ARG;
     s.busy = false;

@@ -9,7 +9,7 @@ import torch
 from .transform import encode_batch_host
 
 
-def pre_transform_batched(data_list, h=1, use_rd=False, self_loop=False, chunk=4096, device=0):
+def pre_transform_batched(data_list, h=1, use_rd=False, self_loop=False, chunk=4096, device=None):
     """Equivalent to `[create_subgraphs(d, h, use_rd=use_rd, self_loop=self_loop) for d in data_list]`."""
     out = []
     for lo in range(0, len(data_list), chunk):
@@ -95,7 +95,7 @@ class EncodedDataset(object):
     (run_graphcount.py:395-401)."""
 
     def __init__(self, root, raw_graphs, h, use_rd=False, self_loop=False, transform=None, pre_filter=None, chunk=4096,
-                 device=0, name='data'):
+                 device=None, name='data'):
         import os
         self.root, self.transform = root, transform
         self.flags = dict(h=h, use_rd=bool(use_rd), self_loop=bool(self_loop))

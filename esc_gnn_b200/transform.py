@@ -114,8 +114,10 @@ class HostEncoder(object):
 
     While the caller consumes chunk k, the kernels of chunk k+1 are already running and its own D2H ran under them."""
 
-    def __init__(self, h, use_rd=False, self_loop=False, local_ordinals=False, device=0):
+    def __init__(self, h, use_rd=False, self_loop=False, local_ordinals=False, device=None):
         self.h, self.use_rd, self.self_loop, self.local_ordinals = int(h), bool(use_rd), bool(self_loop), bool(local_ordinals)
+        if device is None:          # the calling thread's current CUDA device
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self.device = int(device)
         self.ctx = _ctx(self.device)
         self.L = _lib.lib()
@@ -161,7 +163,7 @@ class HostEncoder(object):
 
 
 def encode_batch_host(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=False, local_ordinals=False,
-                      device=0, out=None, compact=False):
+                      device=None, out=None, compact=False):
     """HOST buffers in, HOST buffers out through the C-ABI host front end (H2D + kernels + D2H inside the call).
 
     src/dst/edge_ptr/node_ptr: int64 numpy arrays or CPU tensors (graph-local node ids).  Only the compact records cross
