@@ -99,6 +99,7 @@ SIGNATURES = {
     'escgnn_p2p_free': (_i32, [_vp]),
     'escgnn_p2p_flag_words': (_i64, [_i32]),
     'escgnn_allreduce_adam': (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'escgnn_allreduce_adam_range': (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     'escgnn_adam_step': (_i32, [_vp, _vp, _vp, _vp, _i64] + [ctypes.c_float] * 4 + [_i64, ctypes.c_float, _vp]),
     'escgnn_all_pairs_spd_smem_bytes': (_i64, [_i64, _i64]),
     'escgnn_all_pairs_spd': (_i32, [_vp] * 4 + [_i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
@@ -136,7 +137,7 @@ KERNELS_PER_CALL = {'rewrite_self_loops': 5, 'encode_rd': 1, 'encode': 1, 'encod
                     'edge_distance': 2, 'all_pairs_spd': 1, 'adam_step': 1, 'collate_edges': 1, 'ptr_to_ids': 1, 'bn_act_fwd': 1, 'bn_act_bwd': 1,
                     'act_fwd': 1, 'act_bwd': 1, 'colsum': 1, 'embedding_fwd': 1, 'embedding_bwd': 1, 'loss_fwd_bwd': 1,
                     'make_dims': 1, 'adam_step_device': 2, 'bag_embed_bwd_sorted': 4, 'bag_index_build': 3, 'bag_embed_bwd_indexed': 1, 'reduce_sum': 1, 'zero_tail_rows': 1, 'gemm_tf32x3': 1, 'tf32_split_lo': 1, 'gemm_simple': 1,
-                    'linear_bn_act_fwd': 1, 'linear_bn_act_bwd': 1, 'allreduce_adam': 2}
+                    'linear_bn_act_fwd': 1, 'linear_bn_act_bwd': 1, 'allreduce_adam': 1}
 LAUNCHES = {'n': 0}
 PROFILE = None      # bench.py: a list; every mark() appends (label, cuda event) -> per-kernel durations by differencing
 PROFILE_EXTERNAL = False   # record graph-capturable ("external") events: per-kernel device times of a REPLAYED graph

@@ -4,6 +4,8 @@
 // step's single CUDA graph (the reference itself is single-GPU: run_zinc.py:266-289 steps torch.optim.Adam on one device).
 //
 //   every rank r owns slice r of the flat parameter vector (n / world elements):
+//   (escgnn_allreduce_adam_range splits the vector into buckets that are exchanged independently: the engine sends everything but
+//   the parameters whose gradients arrive last on a side branch, under the tail of the backward pass.)
 //     phase 0  announce "my gradients are complete" to every peer (release store of this step's epoch into the peer's flag
 //              word), wait until every peer has announced the same epoch (acquire spin on local memory);
 //     phase 1  for the owned slice: g = sum over ranks (fixed order -> bit-identical replicas) of the peers' gradient slices,
@@ -56,33 +58,33 @@ __device__ __forceinline__ void spin_until(const unsigned long long* p, unsigned
     }
 }
 
-// step counter, bias corrections (as adam_tick_kernel of optim.cu) and the exchange epoch
-__global__ void p2p_tick_kernel(float* hyper, long long* state, unsigned long long* my_flags, int world) {
-    escgnn::pdl_enter();
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const long long t = ++state[0];
-        hyper[5] = (float)(1.0 - pow((double)hyper[1], (double)t));
-        hyper[6] = (float)sqrt(1.0 - pow((double)hyper[2], (double)t));
-        my_flags[2 * world] += 1ull;
-    }
-}
-
+// One bucket [lo4, hi4) (float4 units) of the flat vector.  `tick` != 0: this launch opens a new optimiser step -- every CTA derives
+// t = state + 1 and the bias corrections itself, and the last CTA to finish publishes them (state, hyper[5..6]) for the launches of
+// the same step that follow (tick == 0: they read what the first one stored).  Each bucket has its own flag block (epoch counter
+// included), so a bucket whose gradients are complete early can be exchanged on a side branch while the backward pass continues.
 __global__ void __launch_bounds__(256)
-allreduce_adam_kernel(const Peers peers, int rank, int world, int64_t n4, int64_t slice4, float* __restrict__ m, float* __restrict__ v,
-                      const float* __restrict__ hyper) {
+allreduce_adam_kernel(const Peers peers, int rank, int world, int64_t lo4, int64_t hi4, int64_t flag_base, int tick, float* __restrict__ m,
+                      float* __restrict__ v, float* hyper, long long* state) {
     escgnn::pdl_enter();
-    unsigned long long* mine = peers.flags[rank];
+    unsigned long long* mine = peers.flags[rank] + flag_base;
     unsigned long long* err = mine + 2 * world + 2;
-    const unsigned long long epoch = mine[2 * world];                 // written by the tick kernel that precedes this launch
+    const unsigned long long epoch = mine[2 * world] + 1ull;          // the last CTA stores it back in phase 2
     __shared__ int s_last;
     // ---- phase 0: gradients of every rank complete
-    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
+    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + flag_base + rank, epoch);
     if (threadIdx.x < world) spin_until(mine + threadIdx.x, epoch, err);
     __syncthreads();
-    // ---- phase 1: reduce the owned slice, Adam, broadcast the new parameters
-    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], gs = hyper[4], bc1 = hyper[5], bc2s = hyper[6];
+    // ---- phase 1: reduce the owned slice of the bucket, Adam, broadcast the new parameters
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], gs = hyper[4];
+    float bc1 = hyper[5], bc2s = hyper[6];
+    const long long t_now = state[0] + (tick ? 1 : 0);
+    if (tick) {
+        bc1 = (float)(1.0 - pow((double)b1, (double)t_now));
+        bc2s = (float)sqrt(1.0 - pow((double)b2, (double)t_now));
+    }
     const float step = lr / bc1;
-    const int64_t lo = (int64_t)rank * slice4, hi = min(lo + slice4, n4);
+    const int64_t n4 = hi4 - lo4, slice4 = (n4 + world - 1) / world;
+    const int64_t lo = lo4 + (int64_t)rank * slice4, hi = min(lo + slice4, hi4);
     for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         #pragma unroll 4
@@ -108,9 +110,13 @@ allreduce_adam_kernel(const Peers peers, int rank, int world, int64_t n4, int64_
     if (threadIdx.x == 0) s_last = atomicAdd(mine + 2 * world + 1, 1ull) == (unsigned long long)gridDim.x - 1ull;
     __syncthreads();
     if (s_last) {
-        if (threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + world + rank, epoch);
+        if (threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + flag_base + world + rank, epoch);
         if (threadIdx.x < world) spin_until(mine + world + threadIdx.x, epoch, err);
-        if (threadIdx.x == 0) mine[2 * world + 1] = 0ull;            // ticket re-armed for the next launch
+        if (threadIdx.x == 0) {
+            mine[2 * world + 1] = 0ull;                              // ticket re-armed for the next launch
+            mine[2 * world] = epoch;
+            if (tick) { state[0] = t_now; hyper[5] = bc1; hyper[6] = bc2s; }
+        }
     }
 }
 
@@ -140,22 +146,29 @@ int escgnn_p2p_open(const unsigned char* handle64, void** d_ptr) {
 int escgnn_p2p_close(void* d_ptr) { return d_ptr ? (int)cudaIpcCloseMemHandle(d_ptr) : 0; }
 int escgnn_p2p_free(void* d_ptr) { return d_ptr ? (int)cudaFree(d_ptr) : 0; }
 
-int64_t escgnn_p2p_flag_words(int world) { return 2 * (int64_t)world + 8; }
+int64_t escgnn_p2p_flag_words(int world) { return 4 * (2 * (int64_t)world + 8); }      // four independent buckets
 
 int escgnn_allreduce_adam(const float* const* h_peer_grads, float* const* h_peer_params, unsigned long long* const* h_peer_flags, int rank,
                           int world, int64_t n, float* d_exp_avg, float* d_exp_avg_sq, float* d_hyper, long long* d_state, void* stream) {
-    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n <= 0 || (n & 3)) return ESCGNN_ERR_BAD_ARG;
+    return escgnn_allreduce_adam_range(h_peer_grads, h_peer_params, h_peer_flags, rank, world, 0, n, 0, 1, d_exp_avg, d_exp_avg_sq, d_hyper,
+                                       d_state, stream);
+}
+
+int escgnn_allreduce_adam_range(const float* const* h_peer_grads, float* const* h_peer_params, unsigned long long* const* h_peer_flags,
+                                int rank, int world, int64_t begin, int64_t end, int bucket, int tick, float* d_exp_avg,
+                                float* d_exp_avg_sq, float* d_hyper, long long* d_state, void* stream) {
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || begin < 0 || end <= begin || ((begin | end) & 3) || bucket < 0 ||
+        bucket > 3)
+        return ESCGNN_ERR_BAD_ARG;
     Peers p;
     for (int i = 0; i < kMaxWorld; ++i) { p.grad[i] = nullptr; p.param[i] = nullptr; p.flags[i] = nullptr; }
     for (int i = 0; i < world; ++i) { p.grad[i] = h_peer_grads[i]; p.param[i] = h_peer_params[i]; p.flags[i] = h_peer_flags[i]; }
-    const int64_t n4 = n >> 2, slice4 = (n4 + world - 1) / world;
+    const int64_t lo4 = begin >> 2, hi4 = end >> 2, slice4 = (hi4 - lo4 + world - 1) / world;
     int64_t blocks = (slice4 + 255) / 256;
     if (blocks > 148) blocks = 148;                      // every CTA spins on the ready flags: all must be resident at once
     if (blocks < 1) blocks = 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    escgnn::launch_pdl(p2p_tick_kernel, 1, 32, 0, st, d_hyper, d_state, p.flags[rank], world);
-    escgnn::launch_pdl(allreduce_adam_kernel, (unsigned)blocks, 256, 0, st, p, rank, world, n4, slice4, d_exp_avg, d_exp_avg_sq,
-                       (const float*)d_hyper);
+    escgnn::launch_pdl(allreduce_adam_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, p, rank, world, lo4, hi4,
+                       (int64_t)bucket * (2 * world + 8), tick, d_exp_avg, d_exp_avg_sq, d_hyper, d_state);
     return (int)cudaGetLastError();
 }
 

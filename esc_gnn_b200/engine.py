@@ -119,15 +119,22 @@ class StaticTrainEngine(object):
             first += [e.weight for e in gn.node_encoder.atom_embedding_list]
             for cv in gn.convs:
                 first += [e.weight for e in cv.edge_encoder.bond_embedding_list]
+            last = []
         else:
             self.lin_convs = list(model.convs) + [model.conv1]
             first = [cv.lin.weight for cv in self.lin_convs] + [cv.lin.bias for cv in self.lin_convs]
+            # parameters whose gradients are produced by the LAST kernels of the backward pass (the z path, the input embeddings):
+            # one contiguous tail of the flat vector = the late bucket of the peer-memory exchange; everything before it is
+            # exchanged on the side branch while those kernels still run
+            last = [model.z_initial.weight] + list(model.z_embedding.parameters())
+            last += list(model.x_embedding.parameters()) if variant == 'count' else \
+                [model.node_type_embedding.weight, model.edge_type_embedding.weight]
         try:
-            self.opt = FlatAdam(model.parameters(), lr=lr, first=first, p2p_group=p2p_group)
+            self.opt = FlatAdam(model.parameters(), lr=lr, first=first, p2p_group=p2p_group, last=last)
         except RuntimeError:
             if self.exchange != 'auto':
                 raise
-            self.opt = FlatAdam(model.parameters(), lr=lr, first=first, p2p_group=False)       # (the failure is collective: every rank lands here)
+            self.opt = FlatAdam(model.parameters(), lr=lr, first=first, p2p_group=False, last=last)    # (collective failure: every rank lands here)
         if self.exchange == 'auto':
             self.exchange = 'p2p' if self.opt.peers is not None else 'nccl'
         self.distributed, self.use_graph = distributed, use_graph
@@ -183,6 +190,8 @@ class StaticTrainEngine(object):
         # in place with vector reductions (2) instead of going through partial tiles and a reduction launch (0)
         self.wgrad_mode = 2 if atomic_wgrad else 0
         self.bounded_gemm = True
+        self.bucketed_exchange, self._early_done, self._xchg_done = True, False, None
+        self.xchg = torch.cuda.Stream(device=dev)
         # Linear -> BatchNorm -> activation as one launch each way (GEMM epilogues behind a grid barrier); only kernels of the MAIN
         # branch take that path (two barrier kernels on concurrent branches could starve each other of SM slots)
         self.fuse_bn = bool(fuse_bn) and tensor_cores
@@ -558,6 +567,21 @@ class StaticTrainEngine(object):
                     _p(dzcat), dzcat.stride(0), _p(self.bn_ws), self.bn_ws.numel(), c.st()), 'linear_bn_act_bwd')
             else:
                 self._gemm('gemm_dgrad', dee_all, False, W_cat[:, :H], True, dz_act, None, E_rows, H, n_tot, False, rows='E')
+            # every gradient outside the late bucket is complete once the side branch has passed this point, and nothing below
+            # reads the parameters of the early bucket any more (this dgrad was the last reader of W_cat): exchange + update them
+            # on the side branch, under the z path's backward
+            if self.exchange == 'p2p' and self.bucketed_exchange and not self.inline_branches and self.opt.tail_begin > 0:
+                main = torch.cuda.current_stream(c.dev)             # its own branch: behind this dgrad AND behind the side branch's
+                ev_m, ev_s = torch.cuda.Event(), torch.cuda.Event()  # weight gradients, but not in front of the side work still to come
+                ev_m.record(main)
+                ev_s.record(self.side)
+                with torch.cuda.stream(self.xchg):
+                    self.xchg.wait_event(ev_m)
+                    self.xchg.wait_event(ev_s)
+                    self.opt.step_exchange_device(0, self.opt.tail_begin, bucket=0, tick=True)
+                    self._xchg_done = torch.cuda.Event()
+                    self._xchg_done.record(self.xchg)
+                self._early_done = True
         self.bwd.append(proj_back)
         layer_dx_from_next = [None] * Lh          # gradient flowing into layer l's output from layer l+1's aggregation
         for l, conv in enumerate(convs):
@@ -889,6 +913,9 @@ class StaticTrainEngine(object):
         for b in reversed(self.bwd):
             b()
         self._join()                                 # every weight gradient is in place before the optimiser / exchange
+        if self._xchg_done is not None:              # ... and so is the early bucket of the peer-memory exchange
+            torch.cuda.current_stream(self.c.dev).wait_event(self._xchg_done)
+            self._xchg_done = None
 
     @torch.no_grad()
     def _run_main(self):
@@ -923,8 +950,12 @@ class StaticTrainEngine(object):
 
     @torch.no_grad()
     def _run_opt(self):
-        if self.exchange == 'p2p':
-            self.opt.step_exchange_device()      # exchange + update in one launch (every rank runs the same number of steps)
+        if self.exchange == 'p2p':               # exchange + update in one launch (every rank runs the same number of steps)
+            if self._early_done:                 # the early bucket went out on the side branch (joined by _run_train): the tail is left
+                self.opt.step_exchange_device(self.opt.tail_begin, None, bucket=1, tick=False)
+                self._early_done = False
+            else:
+                self.opt.step_exchange_device()
         else:
             self.opt.step_device()
 

@@ -64,7 +64,8 @@ class PeerBuffers(object):
         dist.barrier(group=group)
 
     def timed_out(self):
-        return int(self.flags[2 * self.world + 2].item()) != 0
+        block = 2 * self.world + 8
+        return any(int(self.flags[b * block + 2 * self.world + 2].item()) != 0 for b in range(4))
 
     def close(self):
         for p in self._opened:
@@ -73,15 +74,16 @@ class PeerBuffers(object):
 
 
 class FlatAdam(object):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, first=(), p2p_group=False):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, first=(), p2p_group=False, last=()):
         """`first`: parameters to lay out first and in this order (tensors the engine wants adjacent in memory, e.g. the
         edge-projection weights of all layers so they form ONE [sum C_in, edge_dim] operand); the rest keep their order.
         `p2p_group`: None / a process group = keep parameters and gradients in peer-shareable memory and run the data-parallel
         exchange fused with the update (`step_exchange_device`); False = local buffers (+ `all_reduce_grads` over NCCL)."""
         params = [p for p in params if p.requires_grad]
         head = [p for p in first if p.requires_grad]
-        ids = {id(p) for p in head}
-        self.params = head + [p for p in params if id(p) not in ids]
+        tail = [p for p in last if p.requires_grad]             # `last`: laid out at the END (the engine puts the parameters whose
+        ids = {id(p) for p in head} | {id(p) for p in tail}     # gradients arrive last there: one contiguous late exchange bucket)
+        self.params = head + [p for p in params if id(p) not in ids] + tail
         if not self.params or not self.params[0].is_cuda:
             raise RuntimeError('FlatAdam needs CUDA parameters; there is no CPU fallback')
         dev = self.params[0].device
@@ -98,6 +100,7 @@ class FlatAdam(object):
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         off = 0
+        self.tail_begin = total - sum(s + q for (p, s, q) in zip(self.params, sizes, pad) if any(p is t for t in tail))
         for p, s, q in zip(self.params, sizes, pad):
             self.flat[off:off + s].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + s].view(p.shape)
@@ -135,15 +138,18 @@ class FlatAdam(object):
                                                       self.flat.numel(), P(self.hyper), P(self.state), st),
                    'adam_step_device')
 
-    def step_exchange_device(self):
-        """Gradient exchange over NVLink peer memory + Adam in one graph-capturable launch pair (csrc/p2p.cu): every rank must
-        call it the same number of times.  Averages the gradients (hyper[4] = 1 / world, see sync_hyper)."""
+    def step_exchange_device(self, begin=0, end=None, bucket=0, tick=True):
+        """Gradient exchange over NVLink peer memory + Adam in one graph-capturable launch (csrc/p2p.cu) for the element range
+        [begin, end): every rank must issue the same sequence of calls.  Averages the gradients (hyper[4] = 1 / world, see
+        sync_hyper).  A step may be split into buckets (`bucket` 0..3 = independent barrier flags): `tick=True` on the first call
+        of the step only, and the later calls must be ordered after it on the device."""
         pb = self.peers
+        end = self.flat.numel() if end is None else end
         st = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
         P = lambda t: ctypes.c_void_p(t.data_ptr())
-        _lib.check(_lib.lib().escgnn_allreduce_adam(pb.arrays['grad'], pb.arrays['param'], pb.arrays['flags'], pb.rank, pb.world,
-                                                    self.flat.numel(), P(self.exp_avg), P(self.exp_avg_sq), P(self.hyper), P(self.state),
-                                                    st), 'allreduce_adam')
+        _lib.check(_lib.lib().escgnn_allreduce_adam_range(pb.arrays['grad'], pb.arrays['param'], pb.arrays['flags'], pb.rank, pb.world,
+                                                          int(begin), int(end), int(bucket), int(bool(tick)), P(self.exp_avg),
+                                                          P(self.exp_avg_sq), P(self.hyper), P(self.state), st), 'allreduce_adam')
 
     def sync_hyper(self, world_size=1):
         want = (self.param_groups[0]['lr'], 1.0 / world_size)

@@ -401,13 +401,21 @@ int escgnn_gemm_simple(const float* d_a, int lda, int a_mn_major, const float* d
  * moments are only maintained for the owned slice), all-gather of the new parameters by stores into every rank's buffer, with
  * the two cross-GPU barriers inside the kernel (epoch flags; a peer that never arrives sets the error word after 4 s instead of
  * hanging).  h_peer_* are HOST arrays of `world` device pointers (index = rank; entry `rank` is this rank's own buffer):
- * gradients [n], parameters [n], flags [escgnn_p2p_flag_words(world)] (zero-initialised; word 2*world+2 != 0 after a timeout).
+ * gradients [n], parameters [n], flags [escgnn_p2p_flag_words(world)] (zero-initialised; word 2*world+2 of a bucket's block
+ * of 2*world+8 words != 0 after a timeout).
  * n must be a multiple of 4; every rank must call it the same number of times. */
 int escgnn_p2p_alloc(int64_t bytes, void** d_ptr, unsigned char* handle64);
 int escgnn_p2p_open(const unsigned char* handle64, void** d_ptr);
 int escgnn_p2p_close(void* d_ptr);
 int escgnn_p2p_free(void* d_ptr);
 int64_t escgnn_p2p_flag_words(int world);
+/* The same over the element range [begin, end) only (multiples of 4), with flag block `bucket` (0..3: buckets of one step may be in
+ * flight concurrently on different streams).  tick != 0 on the FIRST launch of an optimiser step (it advances the step counter and
+ * the bias corrections), 0 on the others, which must be ordered after it on the device.  The union of a step's ranges must cover
+ * [0, n) exactly once. */
+int escgnn_allreduce_adam_range(const float* const* h_peer_grads, float* const* h_peer_params, unsigned long long* const* h_peer_flags,
+                                int rank, int world, int64_t begin, int64_t end, int bucket, int tick, float* d_exp_avg,
+                                float* d_exp_avg_sq, float* d_hyper, long long* d_state, void* stream);
 int escgnn_allreduce_adam(const float* const* h_peer_grads, float* const* h_peer_params, unsigned long long* const* h_peer_flags, int rank,
                           int world, int64_t n, float* d_exp_avg, float* d_exp_avg_sq, float* d_hyper, long long* d_state, void* stream);
 

@@ -19,9 +19,10 @@ class A(object):
 
 pool = [RawBatch.synth(bench.CONFIG, rank * 1_000_000 + i * bench.BATCH, bench.BATCH).cuda(non_blocking=False) for i in range(6)]
 out = {}
-for mode in ('nccl', 'p2p'):
-    A.exchange = mode
+for mode in ('nccl', 'p2p-one', 'p2p'):
+    A.exchange = mode.split('-')[0]
     eng = bench.build_engine(bench.CONFIG, 'zinc', bench.BATCH, pool, world, A)
+    eng.bucketed_exchange = mode == 'p2p'
     losses = []
     for i in range(8):
         l = eng.step(pool[i % 6])
@@ -45,10 +46,11 @@ for mode in ('nccl', 'p2p'):
     ok = torch.tensor([int(same)], device='cuda'); dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     out[mode] = (losses, float(t[0]), bool(ok[0]), flat)
     if rank == 0:
-        print('%-5s ms/step %.4f  graphs/s %.0f  replicas identical %s  losses %s' % (mode, float(t[0]), bench.BATCH * world / float(t[0]) * 1e3,
+        print('%-8s ms/step %.4f  graphs/s %.0f  replicas identical %s  losses %s' % (mode, float(t[0]), bench.BATCH * world / float(t[0]) * 1e3,
                                                                                    bool(ok[0]), ['%.5f' % v for v in losses[:6]]), flush=True)
 if rank == 0:
     la, lb = out['nccl'][0], out['p2p'][0]
     d = max(abs(x - y) / max(1.0, abs(x)) for x, y in zip(la[:4], lb[:4]))
-    print('loss agreement over the first steps (rel): %.2e' % d, 'PASS' if d < 2e-3 and out['p2p'][2] else 'FAIL')
+    d2 = max(abs(x - y) / max(1.0, abs(x)) for x, y in zip(out['p2p-one'][0][:6], lb[:6]))
+    print('loss agreement nccl vs p2p (rel): %.2e, one bucket vs two: %.2e' % (d, d2), 'PASS' if d < 2e-3 and d2 < 2e-3 and out['p2p'][2] and out['p2p-one'][2] else 'FAIL')
 dist.destroy_process_group()
