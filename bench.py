@@ -372,11 +372,13 @@ def run_own(args):
                       pos_batch=torch.empty(nnz_l + 1024, dtype=torch.int64).pin_memory())
         k_h = 12
 
+        host_threads = max(1, (os.cpu_count() or 1) // world)      # the ranks of one box share its cores
+
         def host_run(expand):
             tot = 0
             for r in henc.stream(h_arrays for _ in range(k_h)):
                 if expand:
-                    r.expand(out=pinned)
+                    r.expand(out=pinned, threads=host_threads)
                 tot += r.nnz
             return tot
         res = {}
@@ -393,7 +395,7 @@ def run_own(args):
         extraction_e2e = dict(chunk_graphs=LG, chunks=k_h, compact=res['compact'], int64_triple=res['int64_triple'],
                               what='HostEncoder.stream: numpy int64 arrays in -> pinned host arrays out; compact = records (index | count<<11) + '
                                    'per-edge offsets / counts (what crosses PCIe); int64_triple = plus the host-side expansion to the '
-                                   'reference contract (escgnn_expand_records_host, %d threads)' % (os.cpu_count() or 1),
+                                   'reference contract (escgnn_expand_records_host, %d host threads per rank)' % host_threads,
                               timing='wall clock incl. host staging copies, max over ranks')
         del henc, pinned
     # ---- config-5 sweep (strong scaling: the total number of graphs is fixed, chunks are dealt round-robin to the ranks)

@@ -38,7 +38,7 @@ for lab, a in agg.items():
     out[lab] = dict(launches=n, avg_us=a['us'] / n, dram_read_bytes_per_launch=a['rd'] / n, dram_write_bytes_per_launch=a['wr'] / n,
                     dram_bytes_per_launch=(a['rd'] + a['wr']) / n, share_of_captured_kernel_time=a['us'] / total_us,
                     source='%s (ncu --set full --clock-control none, one eager step of config 2 / batch 256 on one stream, cold L2; '
-                           'tools/profile_step.py + tools/ncu_traffic.py)' % sys.argv[2].replace('_traffic.json', '_step_kernels.txt'))
+                           'tools/profile_step.py + tools/ncu_traffic.py)' % 'profiles/r02_step_kernels.txt')
 json.dump(out, open(sys.argv[2], 'w'), indent=1)
 if len(sys.argv) > 3:
     open(sys.argv[3], 'w').write('\n'.join(lines) + '\n')
