@@ -17,6 +17,7 @@ import torch
 from . import _lib
 
 _ctx_cache = {}
+_host_encoders = {}
 
 
 def _ctx(device_index):
@@ -96,7 +97,8 @@ class HostEncodedBatch(object):
             p = lambda a: ctypes.c_void_p(a.ctypes.data)
             _lib.check(_lib.lib().escgnn_expand_records_host(p(self.rec), p(self.rec_off), p(self.rec_nnz), p(ep), len(ep) - 1,
                                                              int(self.local_ordinals), _ptr(pe), _ptr(pi), _ptr(pb),
-                                                             int(threads or os.cpu_count() or 1)), 'expand_records_host')
+                                                             int(threads or (1 if K < (1 << 16) else (os.cpu_count() or 1)))),
+                       'expand_records_host')        # (a single graph is not worth waking a thread team for)
             self._triple = (pe, pi, pb)
         return self._triple
 
@@ -175,7 +177,10 @@ def encode_batch_host(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=F
     if G == 0:
         z = lambda *shape: torch.zeros(shape, dtype=torch.int64)
         return EncodedBatch(edge_index=z(2, 0), edge_ptr=z(1), pos_enc=z(0), pos_index=z(0), pos_batch=z(0), num_edges=0, nnz=0)
-    enc = HostEncoder(h, use_rd, self_loop, local_ordinals, device)
+    key = (int(h), bool(use_rd), bool(self_loop), bool(local_ordinals), device)
+    enc = _host_encoders.get(key)
+    if enc is None:
+        enc = _host_encoders[key] = HostEncoder(h, use_rd, self_loop, local_ordinals, device)
     r = enc.encode(src, dst, edge_ptr, node_ptr)
     if compact:
         return r
