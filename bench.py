@@ -226,6 +226,15 @@ def zinc_flops(n_nodes, e_out, graphs):
                   graphs * (LAYERS * H * H + H))
 
 
+def zinc_gemm_bytes(n_nodes, e_out, graphs):
+    """Algorithmic operand bytes (A + B read, C written, fp32) of the Linear layers of one forward pass; dgrad and wgrad move the
+    same three matrices in other roles, so each role's bytes equal this."""
+    L1, H = LAYERS - 1, HIDDEN
+    lin = [(e_out, H, H), (e_out, H + 32, 32 + L1 * H), (n_nodes, 32, H), (n_nodes, H, H)] + [(n_nodes, H, H)] * (2 * L1) + \
+          [(graphs, LAYERS * H, H), (graphs, H, 1)]
+    return 4.0 * sum(m * k + n * k + m * n for m, k, n in lin)
+
+
 def run_own(args):
     import torch
     import torch.distributed as dist
@@ -532,7 +541,7 @@ def run_own(args):
         roofline = dict(bound='tensor', kernel='gemm_tf32x3_ts_kernel (%s)' % ' + '.join(gemm_labels), achieved=achieved, peak=tensor_peak,
                         unit='TFLOP/s', frac=achieved / tensor_peak,
                         traffic=(tr['dram_bytes_per_launch'] if tr else None), traffic_source=(tr['source'] if tr else None),
-                        algorithmic_operand_bytes_per_launch=(tr.get('algorithmic_bytes_per_launch') if tr else None),
+                        algorithmic_operand_bytes_per_launch=zinc_gemm_bytes(n_nodes, e_out, BATCH) * len(roles) / max(g_calls, 1),
                         peak_source=peak_src + ' dense bf16, sustained',
                         share_of_step=g_ms / sum_ms, algorithmic_flops_per_step=flops, launches_per_step=g_calls,
                         launch_ms=g_ms / max(g_calls, 1), frac_of_3xtf32_ceiling=achieved / (tensor_peak / 6.0), roles=roles,

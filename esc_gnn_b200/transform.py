@@ -177,7 +177,9 @@ def encode_batch_host(src, dst, edge_ptr, node_ptr, h, use_rd=False, self_loop=F
     if G == 0:
         z = lambda *shape: torch.zeros(shape, dtype=torch.int64)
         return EncodedBatch(edge_index=z(2, 0), edge_ptr=z(1), pos_enc=z(0), pos_index=z(0), pos_batch=z(0), num_edges=0, nnz=0)
-    key = (int(h), bool(use_rd), bool(self_loop), bool(local_ordinals), device)
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    key = (int(h), bool(use_rd), bool(self_loop), bool(local_ordinals), int(device))
     enc = _host_encoders.get(key)
     if enc is None:
         enc = _host_encoders[key] = HostEncoder(h, use_rd, self_loop, local_ordinals, device)
