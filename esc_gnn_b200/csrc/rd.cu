@@ -57,9 +57,16 @@ __device__ __forceinline__ unsigned long long column_mask(const double* M, int m
 // from the last column back.  The warp-per-pair variant walks only the NON-ZERO entries of each factor column (ballot
 // masks): molecular graphs are nearly trees, so a column holds 1-3 entries instead of m/2.
 // Returns error bits (uniform in the group).
+// Pendant trees are peeled before the linear algebra (warp mode, u != v): a node whose only remaining neighbour p is joined to it by
+// a single edge adds exactly 1 to every resistance measured from the rest of the graph, R(r, w) = R(r, p) + 1, so leaves are
+// removed round by round (u and v are kept) and only the remaining core -- the rings and the paths between them, often just {u, v} for
+// a molecule -- goes through LDL^T / Takahashi.  Eliminating a unit-weight leaf leaves the Laplacian of the induced core
+// (Schur complement), and the added path lengths are exact integers in fp64, so the histogram bins are unchanged.
+// aux (per warp, may be nullptr = no peeling): rnd[stride] u8 (0 = core, else the round it was peeled in), dep[stride] u8 (path
+// length to the core), par[stride] u16, anc[stride] u16 (the core node the pendant tree hangs from).
 template <int H, bool kCta>
 __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_t* sub, int* hist_u, int* hist_v, double* s_red,
-                            int* s_cnt) {
+                            int* s_cnt, unsigned char* aux = nullptr, int aux_stride = 0) {
     const int gt = kCta ? threadIdx.x : (threadIdx.x & 31);        // thread id inside the group
     const int gn = kCta ? blockDim.x : 32;                         // group size
     const int lane = threadIdx.x & 31;
@@ -68,13 +75,60 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
     const uint32_t* rowV = g.dist + (size_t)v * rw;
     const bool phantom = u == v;
     if (gt < ESCGNN_RD_SLOTS) { hist_u[gt] = 0; hist_v[gt] = 0; }
+    // ---- peel pendant trees
+    const bool peel = !kCta && aux != nullptr && !phantom && n <= 64;
+    uint8_t* rnd = aux;
+    uint8_t* dep = aux + aux_stride;
+    uint16_t* par = reinterpret_cast<uint16_t*>(aux + 2 * aux_stride);
+    uint16_t* anc = par + aux_stride;
+    if (peel) {
+        for (int w = lane; w < n; w += 32) { rnd[w] = 0; dep[w] = 0; }
+        __syncwarp();
+        int rounds = 0;
+        for (int r = 1; r < 250; ++r) {
+            int cand[2] = {-1, -1}, cpar[2] = {0, 0};
+            int slot = 0;
+            for (int w = lane; w < n; w += 32, ++slot) {
+                const uint32_t du = nib(rowU, w), dv = nib(rowV, w);
+                if ((du == kFar && dv == kFar) || rnd[w] != 0 || w == u || w == v) continue;
+                int b0 = -1, mult = 0;
+                bool other = false;
+                const uint32_t ka = g.out_ptr[w], kb = g.out_ptr[w + 1];
+                for (uint32_t k = ka; k < kb; ++k) {
+                    const int b = g.out_adj[k];
+                    if (b == w) continue;
+                    const uint32_t bu = nib(rowU, b), bv = nib(rowV, b);
+                    if (!((du != kFar && bu != kFar) || (dv != kFar && bv != kFar))) continue;      // edge not in F
+                    if (rnd[b] != 0) continue;                                                      // neighbour already peeled
+                    if (b0 < 0) { b0 = b; mult = 1; } else if (b == b0) ++mult; else other = true;
+                }
+                if (b0 >= 0 && !other && mult == 1) { cand[slot] = w; cpar[slot] = b0; }            // a unit-weight leaf
+            }
+            if (!__any_sync(kFull, cand[0] >= 0 || cand[1] >= 0)) break;
+            __syncwarp();                                        // every lane has finished reading this round's state
+            #pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (cand[q] >= 0) { rnd[cand[q]] = (uint8_t)r; par[cand[q]] = (uint16_t)cpar[q]; }
+            __syncwarp();
+            rounds = r;
+        }
+        for (int r = rounds; r >= 1; --r) {                      // parents were peeled later (or never): latest rounds first
+            for (int w = lane; w < n; w += 32)
+                if (rnd[w] == r) {
+                    const int pp = par[w];
+                    if (rnd[pp] == 0) { anc[w] = (uint16_t)pp; dep[w] = 1; }
+                    else { anc[w] = anc[pp]; dep[w] = (uint8_t)(dep[pp] + 1); }
+                }
+            __syncwarp();
+        }
+    }
     // ---- matrix index of every member of S (node order); u is grounded (no row) unless phantom
     int m = 0;
     if (!kCta || threadIdx.x < 32) {
         for (int w0 = 0; w0 < n; w0 += 32) {
             const int w = w0 + lane;
             bool in = false;
-            if (w < n) in = (nib(rowU, w) != kFar || nib(rowV, w) != kFar) && (phantom || w != u);
+            if (w < n) in = (nib(rowU, w) != kFar || nib(rowV, w) != kFar) && (phantom || w != u) && (!peel || rnd[w] == 0);
             const unsigned b = __ballot_sync(kFull, in);
             if (w < n) sub[w] = in ? (uint16_t)(m + __popc(b & ((1u << lane) - 1))) : (uint16_t)0xffff;
             m += __popc(b);
@@ -99,6 +153,7 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
             if (b == w) continue;                                      // scipy laplacian ignores loops
             const uint32_t bu = nib(rowU, b), bv = nib(rowV, b);
             if (!((du != kFar && bu != kFar) || (dv != kFar && bv != kFar))) continue;
+            if (peel && rnd[b] != 0) continue;                         // peeled leaves are gone from the core's Laplacian
             deg += 1.0;
             const int j = sub[b];
             if (j != 0xffff && j < i) rowi[j] -= 1.0;
@@ -203,7 +258,22 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
     const double zvv = phantom ? 0.0 : M[tidx(iv, iv)];
     for (int w = gt; w < n; w += gn) {
         const int i = sub[w];
-        if (i == 0xffff) continue;
+        if (i == 0xffff) {
+            if (peel && rnd[w] != 0) {                               // pendant node: its anchor's resistances plus the path length
+                const int a = anc[w];
+                const double d = (double)dep[w];
+                const int ia = a == u ? 0 : sub[a];
+                const double zaa = a == u ? 0.0 : M[tidx(ia, ia)];
+                double rv;
+                if (a == v) rv = d;
+                else if (a == u) rv = zvv + d;
+                else rv = zvv + zaa - 2.0 * (ia >= iv ? M[tidx(ia, iv)] : M[tidx(iv, ia)]) + d;
+                const int bu = (int)truncf((float)(zaa + d)), bv = (int)truncf((float)rv);
+                if (bu < 0 || bu >= ESCGNN_RD_SLOTS || bv < 0 || bv >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD;
+                else { atomicAdd(&hist_u[bu], 1); atomicAdd(&hist_v[bv], 1); }
+            }
+            continue;
+        }
         const double zww = M[tidx(i, i)];
         if (phantom) {
             const int b = (int)truncf((float)(zww - fill));
@@ -234,7 +304,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
               const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int n_graphs,
               uint16_t* __restrict__ rdh, unsigned long long* counters, long long graph_smem_bytes,
               long long mat_region_doubles, int sub_stride, unsigned char* scratch, long long slab_bytes,
-              long long slab_graph_bytes, int parts) {
+              long long slab_graph_bytes, int parts, int aux_stride) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     __shared__ int s_misc[2];
@@ -245,7 +315,8 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     double* mat_region = reinterpret_cast<double*>(smem);
     uint16_t* sub_region = reinterpret_cast<uint16_t*>(smem + mat_region_doubles * 8);
-    unsigned char* graph_smem = smem + align16(mat_region_doubles * 8 + (long long)nw * sub_stride * 2);
+    unsigned char* aux_region = smem + align16(mat_region_doubles * 8 + (long long)nw * sub_stride * 2);      // aux_stride == 0: none
+    unsigned char* graph_smem = aux_region + align16((long long)nw * aux_stride * 6);
     const long long warp_cap = mat_region_doubles / nw;
 
     for (;;) {
@@ -304,7 +375,8 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
                     if (__any_sync(kFull, dup)) first = false;
                 }
                 if (!first) continue;
-                err |= rd_pair<H, false>(g, u, v, M, sub, s_hist[warp][0], s_hist[warp][1], nullptr, nullptr);
+                err |= rd_pair<H, false>(g, u, v, M, sub, s_hist[warp][0], s_hist[warp][1], nullptr, nullptr,
+                                         aux_stride ? aux_region + (size_t)warp * aux_stride * 6 : nullptr, aux_stride);
                 for (int q0 = 0; q0 < e; q0 += 32) {
                     const int q = q0 + lane;
                     if (q < e) {
@@ -345,9 +417,14 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
     }
 }
 
+inline int& rd_peel_enabled() {
+    static int on = 1;
+    return on;
+}
+
 struct RdPlan {
     int64_t mat_doubles, smem, graph_bytes, slab, slab_graph;
-    int sub_stride;
+    int sub_stride, aux_stride;
 };
 
 static RdPlan plan_rd(int64_t max_nodes, int64_t max_edges, int smem_optin) {
@@ -360,11 +437,13 @@ static RdPlan plan_rd(int64_t max_nodes, int64_t max_edges, int smem_optin) {
     if (p.sub_stride > 1024) p.sub_stride = 1024;
     int64_t sub_bytes = (int64_t)kNw * p.sub_stride * 2;
     p.graph_bytes = need_graph <= 48 * 1024 ? need_graph : 0;
-    int64_t avail = budget - sub_bytes - p.graph_bytes - 16;
+    p.aux_stride = max_nodes <= 64 ? (p.sub_stride + 15) & ~15 : 0;                     // pendant-tree peeling state (warp mode)
+    const int64_t aux_bytes = align16((int64_t)kNw * p.aux_stride * 6);
+    int64_t avail = budget - sub_bytes - aux_bytes - p.graph_bytes - 16;
     if (t * 8 * kNw <= 96 * 1024 && t * 8 * kNw <= avail) p.mat_doubles = t * kNw;      // warp mode for every graph
     else if (t * 8 <= avail) p.mat_doubles = ((t + kNw - 1) / kNw) * kNw;               // CTA mode, on chip
     else p.mat_doubles = (64 * 1024 / 8 / kNw) * kNw;                                    // small graphs stay on chip
-    p.smem = align16(p.mat_doubles * 8 + sub_bytes) + p.graph_bytes;
+    p.smem = align16(p.mat_doubles * 8 + sub_bytes) + aux_bytes + p.graph_bytes;
     p.slab_graph = align16(need_graph);
     p.slab = 0;
     if (p.graph_bytes < need_graph || t > p.mat_doubles || max_nodes > (int64_t)kNw * p.sub_stride)
@@ -403,7 +482,7 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
                                                             counters, (long long)p.graph_bytes,
                                                             (long long)p.mat_doubles, p.sub_stride,
                                                             (unsigned char*)scratch, (long long)p.slab,
-                                                            (long long)p.slab_graph, parts);
+                                                            (long long)p.slab_graph, parts, rd_peel_enabled() ? p.aux_stride : 0);
     return (int)cudaGetLastError();
 }
 
@@ -412,6 +491,12 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
 using namespace escgnn;
 
 extern "C" {
+
+int escgnn_set_rd_peel(int on) {
+    const int was = rd_peel_enabled();
+    rd_peel_enabled() = on ? 1 : 0;
+    return was;
+}
 
 int64_t escgnn_encode_rd_scratch_bytes(int64_t max_nodes, int64_t max_edges, int h) {
     (void)h;

@@ -273,6 +273,9 @@ int escgnn_set_pdl(int on);
  * pipelined training step, where the encoder of the next batch has a whole step of slack and should leave most SMs to the
  * latency-critical kernels of the current batch. Returns the previous cap. */
 int escgnn_set_encoder_grid_cap(int ctas);
+/* Pendant-tree peeling in the resistance-distance kernel (graphs of at most 64 nodes; see csrc/rd.cu): on by default, 0 solves the
+ * full system of every pair (same histograms; A/B timing and tests). Returns the previous setting. */
+int escgnn_set_rd_peel(int on);
 /* One-launch cluster BatchNorm kernels (rows_cap <= 65536, training mode): on by default; 0 = statistics + apply kernel pair
  * (same results up to summation order). Returns the previous setting. */
 int escgnn_set_cluster_bn(int on);

@@ -325,3 +325,33 @@ def test_pipelined_host_encoder_matches_oracle(config):
             assert r.nnz == want[1].shape[0] and int(r.rec_nnz.sum()) == r.nnz
             seen += 1
         assert seen == len(chunks)
+
+
+@pytest.mark.parametrize('config', [2, 4, 1])
+def test_rd_pendant_tree_peeling_leaves_the_histograms_unchanged(config):
+    """ego_rd peels pendant trees before the linear algebra (R(r, leaf) = R(r, parent) + 1): same records as the full solve of
+    every pair system, on molecule-shaped batches and on a multigraph whose doubled edges must NOT be peeled (weight 2)."""
+    from esc_gnn_b200 import _lib, synth
+    from esc_gnn_b200.transform import encode_batch
+    L = _lib.lib()
+    fl = synth.ENCODER_FLAGS[config]
+    src, dst, eptr, nptr = synth.make_batch_arrays(config, 8000, 192)
+    # append one hand-made multigraph: a triangle 0-1-2 with a pendant path 2-3-4 and a DOUBLE pendant edge 0=5 (both directions twice)
+    und = [(0, 1), (1, 2), (0, 2), (2, 3), (3, 4), (0, 5), (0, 5)]
+    ms = np.array([a for a, b in und] + [b for a, b in und], dtype=np.int64)
+    md = np.array([b for a, b in und] + [a for a, b in und], dtype=np.int64)
+    src, dst = np.concatenate([src, ms]), np.concatenate([dst, md])
+    eptr, nptr = np.append(eptr, eptr[-1] + len(ms)), np.append(nptr, nptr[-1] + 6)
+    args = (torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), torch.as_tensor(eptr), torch.as_tensor(nptr), fl['h'], True,
+            fl['self_loop'])
+    was = L.escgnn_set_rd_peel(1)
+    try:
+        a = encode_batch(*args)
+        L.escgnn_set_rd_peel(0)
+        b = encode_batch(*args)
+    finally:
+        L.escgnn_set_rd_peel(was)
+    for k in ('pos_enc', 'pos_index', 'pos_batch'):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    want = _oracle_batch(src, dst, eptr, nptr, fl['h'], True, fl['self_loop'])
+    assert np.array_equal(a.pos_enc.cpu().numpy(), want[1]) and np.array_equal(a.pos_index.cpu().numpy(), want[2])
