@@ -5,7 +5,7 @@
 // (one_hot(rd.long(), 100)) under parity policy E5: float64 arithmetic, bin = trunc((float)rd).
 //
 // For a symmetric, connected (S, F):  u != v: rd(w) = R(u,w) = [(L with row/col u removed)^-1]_ww, rd(u) = 0;
-// u == v (phantom root): rd(w) = [pinv(L_ball)]_ww = [(L_ball + J/m)^-1]_ww - 1/m, rd(phantom) = 0.
+// u == v (phantom root): rd(w) = [pinv(L_ball)]_ww, rd(phantom) = 0; pinv from the same grounded inverse (see rd_pair).
 // Both are "diagonal of the inverse of an SPD matrix": LDL^T in place on a packed lower triangle held in shared
 // memory, then the Takahashi recurrence Z_ij = delta_ij/D_j - sum_{k>j} Z_ik L_kj run from the last column back.
 // Each thread owns matrix rows (row i -> thread i mod group), so assembly and both sweeps need no atomics.
@@ -52,7 +52,7 @@ __device__ __forceinline__ unsigned long long column_mask(const double* M, int m
 // (u, v) and hist_v = that of (v, u) -- both directions share S and F, only the root differs.
 //   u != v : ground u.  M = L without row/col u (SPD, and as sparse as the molecule), Z = M^-1:
 //            R(u,w) = Z_ww,  R(v,w) = Z_vv + Z_ww - 2 Z_vw,  R(v,u) = Z_vv.
-//   u == v : phantom root: Z = (L_ball + J/m)^-1, rd(w) = pinv(L)_ww = Z_ww - 1/m, rd(phantom) = 0.
+//   u == v : phantom root: ground u as well; rd(w) = pinv(L)_ww = Z_ww - 2 r_w / mm + S / mm^2, rd(phantom) = 0.
 // LDL^T in place on the packed lower triangle, then the Takahashi recurrence Z_ij = delta_ij/D_j - (1/D_j) sum_{k>j} Z_ik W_kj
 // from the last column back.  The warp-per-pair variant walks only the NON-ZERO entries of each factor column (ballot
 // masks): molecular graphs are nearly trees, so a column holds 1-3 entries instead of m/2.
@@ -128,7 +128,7 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
         for (int w0 = 0; w0 < n; w0 += 32) {
             const int w = w0 + lane;
             bool in = false;
-            if (w < n) in = (nib(rowU, w) != kFar || nib(rowV, w) != kFar) && (phantom || w != u) && (!peel || rnd[w] == 0);
+            if (w < n) in = (nib(rowU, w) != kFar || nib(rowV, w) != kFar) && w != u && (!peel || rnd[w] == 0);
             const unsigned b = __ballot_sync(kFull, in);
             if (w < n) sub[w] = in ? (uint16_t)(m + __popc(b & ((1u << lane) - 1))) : (uint16_t)0xffff;
             m += __popc(b);
@@ -137,8 +137,7 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
     }
     group_sync<kCta>();
     if (kCta) m = *s_cnt;
-    const double fill = phantom ? 1.0 / (double)m : 0.0;
-    for (int t = gt; t < (int)tri(m); t += gn) M[t] = fill;
+    for (int t = gt; t < (int)tri(m); t += gn) M[t] = 0.0;
     group_sync<kCta>();
     // ---- assemble: the thread owning node w writes row sub[w] (diagonal = degree in F without loops)
     for (int w = gt; w < n; w += gn) {
@@ -256,7 +255,29 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
     unsigned err = 0;
     const int iv = phantom ? 0 : sub[v];
     const double zvv = phantom ? 0.0 : M[tidx(iv, iv)];
-    for (int w = gt; w < n; w += gn) {
+    // phantom root: pinv(L_ball) from the SAME grounded inverse (any symmetric generalised inverse G of L gives L^+ = H G H with the
+    // centring H = I - J/mm): L^+_ww = Z_ww - (2/mm) r_w + S/mm^2 with r_w = sum_b Z_wb, S = sum_w r_w, and Z_u. = 0 for the ground
+    // u -- the sparse grounded system replaces the dense (L + J/mm) one the first version factorised for every node of the graph.
+    double rsum[4] = {0.0, 0.0, 0.0, 0.0}, S = 0.0;
+    const double mm = (double)(m + 1);
+    if (phantom) {
+        double part = 0.0;
+        int cnt = 0;
+        for (int w = gt; w < n; w += gn, ++cnt) {
+            const int i = sub[w];
+            if (i == 0xffff) continue;
+            double r = 0.0;
+            int pr = tidx(i, 0);
+            for (int b = 0; b <= i; ++b) r += M[pr + b];
+            int pc = tidx(i + 1, i);
+            for (int b = i + 1; b < m; ++b) { r += M[pc]; pc += b + 1; }
+            if (cnt < 4) rsum[cnt] = r;
+            part += r;
+        }
+        S = group_sum<kCta>(part, s_red);
+    }
+    int cnt_w = 0;
+    for (int w = gt; w < n; w += gn, ++cnt_w) {
         const int i = sub[w];
         if (i == 0xffff) {
             if (peel && rnd[w] != 0) {                               // pendant node: its anchor's resistances plus the path length
@@ -276,7 +297,7 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
         }
         const double zww = M[tidx(i, i)];
         if (phantom) {
-            const int b = (int)truncf((float)(zww - fill));
+            const int b = (int)truncf((float)(zww - 2.0 * rsum[cnt_w < 4 ? cnt_w : 3] / mm + S / (mm * mm)));
             if (b < 0 || b >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD; else atomicAdd(&hist_u[b], 1);
         } else {
             const double zvw = i >= iv ? M[tidx(i, iv)] : M[tidx(iv, i)];
@@ -287,8 +308,11 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
         }
     }
     if (gt == 0) {
-        if (phantom) atomicAdd(&hist_u[0], 1);             // the phantom root itself (rd = 0)
-        else {
+        if (phantom) {
+            atomicAdd(&hist_u[0], 1);                      // the phantom root itself (rd = 0)
+            const int b = (int)truncf((float)(S / (mm * mm)));       // the real root u: the grounded node, Z_u. = 0
+            if (b < 0 || b >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD; else atomicAdd(&hist_u[b], 1);
+        } else {
             atomicAdd(&hist_u[0], 1);                      // rd_u(u) = 0
             const int b = (int)truncf((float)zvv);          // rd_v(u) = R(v, u) = Z_vv
             if (b < 0 || b >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD; else atomicAdd(&hist_v[b], 1);
@@ -304,7 +328,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
               const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int n_graphs,
               uint16_t* __restrict__ rdh, unsigned long long* counters, long long graph_smem_bytes,
               long long mat_region_doubles, int sub_stride, unsigned char* scratch, long long slab_bytes,
-              long long slab_graph_bytes, int parts, int aux_stride) {
+              long long slab_graph_bytes, int parts, int aux_stride, int n_lo, int n_hi) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     __shared__ int s_misc[2];
@@ -330,7 +354,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
         const long long e0 = eo_ptr[gi];
         const int e = (int)(eo_ptr[gi + 1] - e0);
         const int n = (int)(node_ptr[gi + 1] - node_ptr[gi]);
-        if (e == 0) continue;
+        if (e == 0 || n < n_lo || n > n_hi) continue;             // (size classes: each launch takes the graphs of its node range)
         GraphLayout L(n, e);
         unsigned char* slab = scratch + (size_t)blockIdx.x * slab_bytes;
         unsigned char* base = (L.total <= graph_smem_bytes) ? graph_smem : slab;
@@ -437,11 +461,15 @@ static RdPlan plan_rd(int64_t max_nodes, int64_t max_edges, int smem_optin) {
     if (p.sub_stride > 1024) p.sub_stride = 1024;
     int64_t sub_bytes = (int64_t)kNw * p.sub_stride * 2;
     p.graph_bytes = need_graph <= 48 * 1024 ? need_graph : 0;
-    p.aux_stride = max_nodes <= 64 ? (p.sub_stride + 15) & ~15 : 0;                     // pendant-tree peeling state (warp mode)
+    p.aux_stride = max_nodes <= 64 ? (p.sub_stride + 15) & ~15 : 64;                    // pendant-tree peeling state (graphs of <= 64 nodes)
     const int64_t aux_bytes = align16((int64_t)kNw * p.aux_stride * 6);
     int64_t avail = budget - sub_bytes - aux_bytes - p.graph_bytes - 16;
     if (t * 8 * kNw <= 96 * 1024 && t * 8 * kNw <= avail) p.mat_doubles = t * kNw;      // warp mode for every graph
-    else if (t * 8 <= avail) p.mat_doubles = ((t + kNw - 1) / kNw) * kNw;               // CTA mode, on chip
+    else if (t * 8 <= avail) {                                                          // CTA mode on chip for the largest graphs ...
+        p.mat_doubles = ((t + kNw - 1) / kNw) * kNw;
+        const int64_t t64 = tri(65) * kNw;                                              // ... and a warp per pair up to 64 nodes, if it fits
+        if (max_nodes > 64 && t64 > p.mat_doubles && t64 * 8 <= avail) p.mat_doubles = t64;
+    }
     else p.mat_doubles = (64 * 1024 / 8 / kNw) * kNw;                                    // small graphs stay on chip
     p.smem = align16(p.mat_doubles * 8 + sub_bytes) + aux_bytes + p.graph_bytes;
     p.slab_graph = align16(need_graph);
@@ -460,30 +488,41 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const RdPlan p = plan_rd(max_nodes, max_edges, smem_optin);
-    auto kern = ego_rd_kernel<H>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    if (err != cudaSuccess) return (int)err;
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, (size_t)p.smem);
-    if (occ < 1) occ = 1;
-    int64_t grid = (int64_t)sms * occ;
-    if (encoder_grid_cap() > 0 && grid > encoder_grid_cap()) grid = encoder_grid_cap();
-    int parts = (int)(grid / n_graphs);                      // CTAs left over by a small batch share its graphs
-    parts = parts < 1 ? 1 : parts > 8 ? 8 : parts;
-    if (grid > n_graphs * parts) grid = n_graphs * parts;
-    if (p.slab) {
-        if (scratch == nullptr || scratch_bytes < p.slab) return ESCGNN_ERR_BAD_ARG;
-        const int64_t fit = scratch_bytes / p.slab;
-        if (grid > fit) grid = fit;
+    // size classes: a batch whose largest graph needs the whole-CTA path (more than kSmall nodes) is encoded by two launches, so the
+    // small graphs keep the small plan (three CTAs per SM, a warp per pair, peeling) instead of inheriting the large one
+    constexpr int kSmall = 41;
+    const int n_class = max_nodes > kSmall ? 2 : 1;
+    for (int cls = 0; cls < n_class; ++cls) {
+        const int n_lo = cls == 0 ? 0 : kSmall + 1, n_hi = (n_class == 2 && cls == 0) ? kSmall : (int)max_nodes;
+        const RdPlan p = plan_rd(n_hi, max_edges, smem_optin);
+        auto kern = ego_rd_kernel<H>;
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        if (err != cudaSuccess) return (int)err;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, (size_t)p.smem);
+        if (occ < 1) occ = 1;
+        int64_t grid = (int64_t)sms * occ;
+        if (encoder_grid_cap() > 0 && grid > encoder_grid_cap()) grid = encoder_grid_cap();
+        int parts = (int)(grid / n_graphs);                      // CTAs left over by a small batch share its graphs
+        parts = parts < 1 ? 1 : parts > 8 ? 8 : parts;
+        if (grid > n_graphs * parts) grid = n_graphs * parts;
+        if (p.slab) {
+            if (scratch == nullptr || scratch_bytes < p.slab) return ESCGNN_ERR_BAD_ARG;
+            const int64_t fit = scratch_bytes / p.slab;
+            if (grid > fit) grid = fit;
+        }
+        if (grid < 1) grid = 1;
+        if (cls > 0) {                                            // the work ticket starts again for the second class
+            err = cudaMemsetAsync(counters + ESCGNN_CTR_TICKET_RD, 0, sizeof(unsigned long long), st);
+            if (err != cudaSuccess) return (int)err;
+        }
+        kern<<<(unsigned)grid, kThreads, (size_t)p.smem, st>>>(eo_src, eo_dst, eo_ptr, node_ptr, (int)n_graphs, rdh, counters,
+                                                                (long long)p.graph_bytes, (long long)p.mat_doubles, p.sub_stride,
+                                                                (unsigned char*)scratch, (long long)p.slab, (long long)p.slab_graph,
+                                                                parts, rd_peel_enabled() ? p.aux_stride : 0, n_lo, n_hi);
+        if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
     }
-    if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kThreads, (size_t)p.smem, st>>>(eo_src, eo_dst, eo_ptr, node_ptr, (int)n_graphs, rdh,
-                                                            counters, (long long)p.graph_bytes,
-                                                            (long long)p.mat_doubles, p.sub_stride,
-                                                            (unsigned char*)scratch, (long long)p.slab,
-                                                            (long long)p.slab_graph, parts, rd_peel_enabled() ? p.aux_stride : 0);
-    return (int)cudaGetLastError();
+    return 0;
 }
 
 }  // namespace escgnn
@@ -501,7 +540,8 @@ int escgnn_set_rd_peel(int on) {
 int64_t escgnn_encode_rd_scratch_bytes(int64_t max_nodes, int64_t max_edges, int h) {
     (void)h;
     const RdPlan p = plan_rd(max_nodes, max_edges, 227 * 1024);
-    return p.slab * 148 * 2;
+    const RdPlan q = plan_rd(max_nodes > 41 ? 41 : max_nodes, max_edges, 227 * 1024);
+    return (p.slab > q.slab ? p.slab : q.slab) * 148 * 3;
 }
 
 int escgnn_encode_rd(const int64_t* d_eo_src, const int64_t* d_eo_dst, const int64_t* d_eo_ptr,
