@@ -76,7 +76,8 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
     const bool phantom = u == v;
     if (gt < ESCGNN_RD_SLOTS) { hist_u[gt] = 0; hist_v[gt] = 0; }
     // ---- peel pendant trees
-    const bool peel = !kCta && aux != nullptr && !phantom && n <= 64;
+    // (worth it on sparse, molecule-like graphs only: with ~4 edges per node almost nothing is pendant and the scan is pure overhead)
+    const bool peel = !kCta && aux != nullptr && !phantom && n <= 64 && 10 * g.e <= 33 * n;
     uint8_t* rnd = aux;
     uint8_t* dep = aux + aux_stride;
     uint16_t* par = reinterpret_cast<uint16_t*>(aux + 2 * aux_stride);
