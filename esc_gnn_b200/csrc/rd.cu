@@ -259,7 +259,7 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
     // phantom root: pinv(L_ball) from the SAME grounded inverse (any symmetric generalised inverse G of L gives L^+ = H G H with the
     // centring H = I - J/mm): L^+_ww = Z_ww - (2/mm) r_w + S/mm^2 with r_w = sum_b Z_wb, S = sum_w r_w, and Z_u. = 0 for the ground
     // u -- the sparse grounded system replaces the dense (L + J/mm) one the first version factorised for every node of the graph.
-    double rsum[4] = {0.0, 0.0, 0.0, 0.0}, S = 0.0;
+    double rs0 = 0.0, rs1 = 0.0, rs2 = 0.0, rs3 = 0.0, S = 0.0;       // row sums of the nodes this thread owns (<= 4: registers)
     const double mm = (double)(m + 1);
     if (phantom) {
         double part = 0.0;
@@ -272,7 +272,7 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
             for (int b = 0; b <= i; ++b) r += M[pr + b];
             int pc = tidx(i + 1, i);
             for (int b = i + 1; b < m; ++b) { r += M[pc]; pc += b + 1; }
-            if (cnt < 4) rsum[cnt] = r;
+            if (cnt == 0) rs0 = r; else if (cnt == 1) rs1 = r; else if (cnt == 2) rs2 = r; else rs3 = r;
             part += r;
         }
         S = group_sum<kCta>(part, s_red);
@@ -298,7 +298,8 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
         }
         const double zww = M[tidx(i, i)];
         if (phantom) {
-            const int b = (int)truncf((float)(zww - 2.0 * rsum[cnt_w < 4 ? cnt_w : 3] / mm + S / (mm * mm)));
+            const double rw = cnt_w == 0 ? rs0 : cnt_w == 1 ? rs1 : cnt_w == 2 ? rs2 : rs3;
+            const int b = (int)truncf((float)(zww - 2.0 * rw / mm + S / (mm * mm)));
             if (b < 0 || b >= ESCGNN_RD_SLOTS) err = ESCGNN_DATA_RD; else atomicAdd(&hist_u[b], 1);
         } else {
             const double zvw = i >= iv ? M[tidx(i, iv)] : M[tidx(iv, i)];
@@ -324,7 +325,7 @@ __device__ unsigned rd_pair(const GraphView& g, int u, int v, double* M, uint16_
 }
 
 template <int H>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)          // three CTAs per SM is what the shared-memory plan of molecule-sized batches allows
 ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo_dst,
               const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int n_graphs,
               uint16_t* __restrict__ rdh, unsigned long long* counters, long long graph_smem_bytes,
