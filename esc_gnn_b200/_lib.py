@@ -67,6 +67,7 @@ SIGNATURES = {
     'escgnn_set_pdl': (_i32, [_i32]),
     'escgnn_set_encoder_grid_cap': (_i32, [_i32]),
     'escgnn_set_rd_peel': (_i32, [_i32]),
+    'escgnn_set_rd_fast': (_i32, [_i32]),
     'escgnn_set_cluster_bn': (_i32, [_i32]),
     'escgnn_dense_partial_floats': (_i64, [_i32, _i32]),
     'escgnn_bn_act_fwd': (_i32, [_vp, _i32] + [_vp] * 7 + [_i32, ctypes.c_float, ctypes.c_float, _i32, _vp, _i32, _i32, _vp, _i32, _vp]),

@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "graph_smem.cuh"
+#include "rd_fast.cuh"
 
 namespace escgnn {
 
@@ -330,7 +331,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
               const int64_t* __restrict__ eo_ptr, const int64_t* __restrict__ node_ptr, int n_graphs,
               uint16_t* __restrict__ rdh, unsigned long long* counters, long long graph_smem_bytes,
               long long mat_region_doubles, int sub_stride, unsigned char* scratch, long long slab_bytes,
-              long long slab_graph_bytes, int parts, int aux_stride, int n_lo, int n_hi) {
+              long long slab_graph_bytes, int parts, int aux_stride, int n_lo, int n_hi, int fast_done) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     __shared__ int s_misc[2];
@@ -357,6 +358,12 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
         const int e = (int)(eo_ptr[gi + 1] - e0);
         const int n = (int)(node_ptr[gi + 1] - node_ptr[gi]);
         if (e == 0 || n < n_lo || n > n_hi) continue;             // (size classes: each launch takes the graphs of its node range)
+        if (fast_done) {
+            // the cycle-space kernel (ego_rd_fast_kernel below) ran first: only the edges it marked are still to be solved
+            int any = 0;
+            for (int i = tid; i < e; i += blockDim.x) any |= rdh[(size_t)(e0 + i) * ESCGNN_RD_SLOTS] == rdfast::kSentinel;
+            if (!__syncthreads_or(any)) continue;
+        }
         GraphLayout L(n, e);
         unsigned char* slab = scratch + (size_t)blockIdx.x * slab_bytes;
         unsigned char* base = (L.total <= graph_smem_bytes) ? graph_smem : slab;
@@ -401,6 +408,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
                     if (__any_sync(kFull, dup)) first = false;
                 }
                 if (!first) continue;
+                if (fast_done && rdh[(size_t)(e0 + ed) * ESCGNN_RD_SLOTS] != rdfast::kSentinel) continue;     // solved by the fast path
                 err |= rd_pair<H, false>(g, u, v, M, sub, s_hist[warp][0], s_hist[warp][1], nullptr, nullptr,
                                          aux_stride ? aux_region + (size_t)warp * aux_stride * 6 : nullptr, aux_stride);
                 for (int q0 = 0; q0 < e; q0 += 32) {
@@ -428,6 +436,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
                 for (int q = tid; q < ed; q += blockDim.x)
                     if ((int)eo_src[e0 + q] == u && (int)eo_dst[e0 + q] == v) first = false;
                 if (__syncthreads_or(!first)) continue;
+                if (fast_done && rdh[(size_t)(e0 + ed) * ESCGNN_RD_SLOTS] != rdfast::kSentinel) continue;
                 err |= rd_pair<H, true>(g, u, v, M, sub, s_hist[0][0], s_hist[0][1], s_red, &s_cnt);
                 for (int q = tid; q < e; q += blockDim.x) {
                     const int a = (int)eo_src[e0 + q], b = (int)eo_dst[e0 + q];
@@ -441,6 +450,202 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
         }
         if (err) atomicOr(&counters[ESCGNN_CTR_ERROR], (unsigned long long)err);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path (rd_fast.cuh): a warp per graph, a lane per unordered pair / self-loop edge, cycle-space resistance distances.
+// Takes symmetric simple graphs of at most `nf` nodes / `ef` directed edges; per pair at most kFastCmax independent cycles inside
+// the ego-net.  Whatever it declines gets the sentinel in slot 0 of its histogram and is solved by ego_rd_kernel afterwards.
+constexpr int kFastCmax = 4;
+constexpr int kFastSmall = 41;        // size classes, as for the general solver: molecule-sized graphs keep a small workspace
+
+__device__ __forceinline__ unsigned long long spread4(uint32_t x) {         // four 8-bit counts -> four uint16
+    return (unsigned long long)(x & 0xffu) | ((unsigned long long)((x >> 8) & 0xffu) << 16) |
+           ((unsigned long long)((x >> 16) & 0xffu) << 32) | ((unsigned long long)(x >> 24) << 48);
+}
+__device__ __forceinline__ void store_hist(uint16_t* rdh, long long edge, const rdfast::Hist& h) {
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(rdh + (size_t)edge * ESCGNN_RD_SLOTS);     // 24-byte rows
+    out[0] = spread4((uint32_t)h.lo);
+    out[1] = spread4((uint32_t)(h.lo >> 32));
+    out[2] = spread4(h.hi);
+}
+
+template <int H>
+__global__ void __launch_bounds__(256)
+ego_rd_fast_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo_dst, const int64_t* __restrict__ eo_ptr,
+                   const int64_t* __restrict__ node_ptr, int n_graphs, uint16_t* __restrict__ rdh, unsigned long long* counters,
+                   int nf, int ef, int warp_bytes, int n_lo, int n_hi) {
+    static_assert(ESCGNN_RD_SLOTS == rdfast::kSlots, "histogram width");
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    rdfast::Ws ws;
+    rdfast::ws_carve(ws, smem + (size_t)warp * warp_bytes, nf, ef);
+    for (;;) {
+        int gi = 0;
+        if (lane == 0) gi = (int)atomicAdd(&counters[ESCGNN_CTR_TICKET_RD], 1ull);
+        gi = __shfl_sync(kFull, gi, 0);
+        if (gi >= n_graphs) break;
+        const long long e0 = eo_ptr[gi];
+        const int e = (int)(eo_ptr[gi + 1] - e0);
+        const int n = (int)(node_ptr[gi + 1] - node_ptr[gi]);
+        if (e == 0 || n < n_lo || n > n_hi) continue;              // another launch's size class
+        const int64_t* src = eo_src + e0;
+        const int64_t* dst = eo_dst + e0;
+        __syncwarp();
+        bool bad = n > nf || e > ef || n < 1;
+        if (!bad) {
+            // ---- CSR by source (counting sort; the cursors alias the distance matrix, which is initialised afterwards)
+            ws.n = n; ws.e = e; ws.rws = rdfast::row_stride(n);
+            uint32_t* cnt = ws.dist;
+            for (int i = lane; i <= n; i += 32) cnt[i] = 0;
+            __syncwarp();
+            for (int i = lane; i < e; i += 32) {
+                const long long s = src[i], t = dst[i];
+                if (s < 0 || s >= n || t < 0 || t >= n) bad = true;
+                else atomicAdd(&cnt[s + 1], 1u);
+            }
+            bad = __any_sync(kFull, bad);
+        }
+        if (!bad) {
+            __syncwarp();
+            uint32_t carry = 0;
+            for (int i0 = 0; i0 <= n; i0 += 32) {
+                const int i = i0 + lane;
+                uint32_t v = i <= n ? ws.dist[i] : 0u;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, v, d);
+                    if (lane >= d) v += t;
+                }
+                if (i <= n) ws.optr[i] = (uint16_t)(v + carry);
+                carry += __shfl_sync(kFull, v, 31);
+            }
+            __syncwarp();
+            uint32_t* cur = ws.dist + (n + 1);
+            for (int i = lane; i < n; i += 32) cur[i] = ws.optr[i];
+            __syncwarp();
+            for (int i = lane; i < e; i += 32) {
+                const int s = (int)src[i], t = (int)dst[i];
+                const uint32_t slot = atomicAdd(&cur[s], 1u);
+                ws.oadj[slot] = (uint8_t)t;
+                ws.oeid[slot] = (uint16_t)i;
+            }
+            __syncwarp();
+            // ---- ascending adjacency (deterministic trees), simple, symmetric
+            for (int w = lane; w < n; w += 32) {
+                const int ka = ws.optr[w], kb = ws.optr[w + 1];
+                for (int k = ka + 1; k < kb; ++k) {
+                    const uint8_t t = ws.oadj[k];
+                    const uint16_t id = ws.oeid[k];
+                    int j = k - 1;
+                    while (j >= ka && ws.oadj[j] > t) { ws.oadj[j + 1] = ws.oadj[j]; ws.oeid[j + 1] = ws.oeid[j]; --j; }
+                    ws.oadj[j + 1] = t; ws.oeid[j + 1] = id;
+                }
+                for (int k = ka + 1; k < kb; ++k) bad |= ws.oadj[k] == ws.oadj[k - 1];        // multi-edge
+            }
+            __syncwarp();
+            for (int w = lane; w < n; w += 32) {
+                const int ka = ws.optr[w], kb = ws.optr[w + 1];
+                for (int k = ka; k < kb; ++k) {
+                    const int b = ws.oadj[k];
+                    bool back = false;
+                    for (int q = ws.optr[b]; q < ws.optr[b + 1]; ++q) back |= ws.oadj[q] == w;
+                    bad |= !back;                                                            // asymmetric
+                }
+            }
+            bad = __any_sync(kFull, bad);
+        }
+        if (bad) {                                                 // left to the general solver (which also raises the data errors)
+            for (int i = lane; i < e; i += 32) rdh[(size_t)(e0 + i) * ESCGNN_RD_SLOTS] = rdfast::kSentinel;
+            continue;
+        }
+        __syncwarp();
+        // ---- E2: a lane per root
+        for (int i = lane; i < n * ws.rws; i += 32) ws.dist[i] = 0xffffffffu;
+        __syncwarp();
+        for (int r0 = 0; r0 < n; r0 += 32) {
+            const int r = r0 + lane;
+            if (r < n) rdfast::bfs_root<H>(ws, r);
+        }
+        __syncwarp();
+        // ---- one system per unordered pair / self-loop edge
+        int pairs = 0;
+        for (int i0 = 0; i0 < e; i0 += 32) {
+            const int i = i0 + lane;
+            const bool is = i < e && src[i] <= dst[i];
+            const unsigned b = __ballot_sync(kFull, is);
+            if (is) ws.list[pairs + __popc(b & ((1u << lane) - 1u))] = (uint16_t)i;
+            pairs += __popc(b);
+        }
+        __syncwarp();
+        unsigned err = 0;
+        for (int p0 = 0; p0 < pairs; p0 += 32) {
+            const int p = p0 + lane;
+            if (p < pairs) {
+                const int ed = ws.list[p];
+                const int u = (int)src[ed], v = (int)dst[ed];
+                rdfast::Hist hu, hv;
+                const int rc = rdfast::solve_pair<H, kFastCmax>(ws, lane, u, v, hu, hv);
+                int rev = -1;
+                if (u != v)
+                    for (int q = ws.optr[v]; q < ws.optr[v + 1]; ++q) if (ws.oadj[q] == u) rev = ws.oeid[q];
+                if (rc == -1) {
+                    rdh[(size_t)(e0 + ed) * ESCGNN_RD_SLOTS] = rdfast::kSentinel;
+                    if (rev >= 0) rdh[(size_t)(e0 + rev) * ESCGNN_RD_SLOTS] = rdfast::kSentinel;
+                } else {
+                    if (rc < 0) err = ESCGNN_DATA_RD;
+                    store_hist(rdh, e0 + ed, hu);
+                    if (rev >= 0) store_hist(rdh, e0 + rev, hv);
+                }
+            }
+            __syncwarp();
+        }
+        if (err) atomicOr(&counters[ESCGNN_CTR_ERROR], (unsigned long long)err);
+    }
+}
+
+inline int& rd_fast_enabled() {
+    static int on = 1;
+    return on;
+}
+
+template <int H>
+static int launch_rd_fast(const int64_t* eo_src, const int64_t* eo_dst, const int64_t* eo_ptr, const int64_t* node_ptr,
+                          int64_t n_graphs, uint16_t* rdh, unsigned long long* counters, int64_t max_nodes, int64_t max_edges,
+                          cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_class = max_nodes > kFastSmall ? 2 : 1;
+    for (int cls = 0; cls < n_class; ++cls) {
+        // class 0: molecule-sized graphs, 8 warps per CTA; class 1: up to 128 nodes, 4 warps per CTA.  A single class owns every graph.
+        const int nf = cls == 0 ? (int)(max_nodes < kFastSmall ? (max_nodes < 8 ? 8 : max_nodes) : kFastSmall) : (int)(max_nodes < rdfast::kMaxNodes ? max_nodes : rdfast::kMaxNodes);
+        const int64_t e_cap = cls == 0 ? 8 * kFastSmall : 1536;
+        const int ef = (int)(max_edges < e_cap ? (max_edges < 16 ? 16 : max_edges) : e_cap);
+        const int n_lo = cls == 0 ? 0 : kFastSmall + 1, n_hi = (n_class == 2 && cls == 0) ? kFastSmall : 0x7fffffff;
+        const int warps = cls == 0 ? 8 : 4;
+        const int64_t wb = (rdfast::ws_bytes(nf, ef, kFastCmax) + 15) & ~int64_t(15);
+        const size_t smem = (size_t)(wb * warps);
+        auto kern = ego_rd_fast_kernel<H>;
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
+        if (occ < 1) occ = 1;
+        int64_t grid = (int64_t)sms * occ;
+        if (encoder_grid_cap() > 0 && grid > encoder_grid_cap()) grid = encoder_grid_cap();
+        const int64_t need = (n_graphs + warps - 1) / warps;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        if (cls > 0) {
+            err = cudaMemsetAsync(counters + ESCGNN_CTR_TICKET_RD, 0, sizeof(unsigned long long), st);
+            if (err != cudaSuccess) return (int)err;
+        }
+        kern<<<(unsigned)grid, warps * 32, smem, st>>>(eo_src, eo_dst, eo_ptr, node_ptr, (int)n_graphs, rdh, counters, nf, ef, (int)wb,
+                                                       n_lo, n_hi);
+        if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
+    }
+    return (int)cudaMemsetAsync(counters + ESCGNN_CTR_TICKET_RD, 0, sizeof(unsigned long long), st);     // for the general solver
 }
 
 inline int& rd_peel_enabled() {
@@ -486,6 +691,12 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
                      int64_t n_graphs, uint16_t* rdh, unsigned long long* counters, int64_t max_nodes,
                      int64_t max_edges, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
     constexpr int kThreads = 256;
+    // the cycle-space kernel first (rd_fast.cuh): it solves the sparse systems and marks the rest for the general solver below
+    const int fast_done = rd_fast_enabled() && max_edges <= 65535 ? 1 : 0;
+    if (fast_done) {
+        const int rc = launch_rd_fast<H>(eo_src, eo_dst, eo_ptr, node_ptr, n_graphs, rdh, counters, max_nodes, max_edges, st);
+        if (rc != 0) return rc;
+    }
     int dev = 0, sms = 148, smem_optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -521,7 +732,7 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
         kern<<<(unsigned)grid, kThreads, (size_t)p.smem, st>>>(eo_src, eo_dst, eo_ptr, node_ptr, (int)n_graphs, rdh, counters,
                                                                 (long long)p.graph_bytes, (long long)p.mat_doubles, p.sub_stride,
                                                                 (unsigned char*)scratch, (long long)p.slab, (long long)p.slab_graph,
-                                                                parts, rd_peel_enabled() ? p.aux_stride : 0, n_lo, n_hi);
+                                                                parts, rd_peel_enabled() ? p.aux_stride : 0, n_lo, n_hi, fast_done);
         if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
     }
     return 0;
@@ -532,6 +743,12 @@ static int launch_rd(const int64_t* eo_src, const int64_t* eo_dst, const int64_t
 using namespace escgnn;
 
 extern "C" {
+
+int escgnn_set_rd_fast(int on) {
+    const int was = rd_fast_enabled();
+    rd_fast_enabled() = on ? 1 : 0;
+    return was;
+}
 
 int escgnn_set_rd_peel(int on) {
     const int was = rd_peel_enabled();

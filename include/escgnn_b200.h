@@ -276,6 +276,11 @@ int escgnn_set_encoder_grid_cap(int ctas);
 /* Pendant-tree peeling in the resistance-distance kernel (graphs of at most 64 nodes; see csrc/rd.cu): on by default, 0 solves the
  * full system of every pair (same histograms; A/B timing and tests). Returns the previous setting. */
 int escgnn_set_rd_peel(int on);
+/* Cycle-space fast path of the resistance-distance block (csrc/rd_fast.cuh: a warp per graph, a thread per pair system; symmetric
+ * simple graphs of at most 128 nodes whose ego-nets hold at most 4 independent cycles -- everything else falls through to the
+ * LDL^T / Takahashi solver): on by default, 0 = general solver for every pair (same histograms; A/B timing and tests).
+ * Replaces utils_edge_efficient.py:92-107,130-131 like escgnn_encode_rd itself. Returns the previous setting. */
+int escgnn_set_rd_fast(int on);
 /* One-launch cluster BatchNorm kernels (rows_cap <= 65536, training mode): on by default; 0 = statistics + apply kernel pair
  * (same results up to summation order). Returns the previous setting. */
 int escgnn_set_cluster_bn(int on);

@@ -355,3 +355,39 @@ def test_rd_pendant_tree_peeling_leaves_the_histograms_unchanged(config):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
     want = _oracle_batch(src, dst, eptr, nptr, fl['h'], True, fl['self_loop'])
     assert np.array_equal(a.pos_enc.cpu().numpy(), want[1]) and np.array_equal(a.pos_index.cpu().numpy(), want[2])
+
+
+@pytest.mark.parametrize('config,count', [(2, 300), (4, 200), (1, 64), (6, 100)])
+def test_rd_cycle_space_fast_path_equals_the_general_solver(config, count):
+    """ego_rd_fast_kernel (csrc/rd_fast.cuh: a thread per pair system, resistance distances from the cycle space) in front of the
+    LDL^T / Takahashi solver: same records with the fast path on and off, and equal to the oracle -- on molecule-shaped batches
+    (everything solved by the fast path), on count-shaped ones (mostly declined: > 4 cycles per ego-net), with 42..130-node graphs
+    (second size class), a multigraph and an asymmetric-free single-node graph in the batch."""
+    from esc_gnn_b200 import _lib, synth
+    from esc_gnn_b200.transform import encode_batch
+    L = _lib.lib()
+    fl = synth.ENCODER_FLAGS[config]
+    src, dst, eptr, nptr = synth.make_batch_arrays(config, 12000, count)
+    rng = np.random.Generator(np.random.PCG64(3))
+    extra = []
+    for n in (60, 128, 130, 42):                     # 130 nodes: beyond the fast path's 128
+        extra.append((synth.symmetrise(synth.random_graph(rng, n, n + 2, max_degree=4)), n))
+    und = [(0, 1), (1, 2), (0, 2), (2, 3), (3, 4), (0, 5), (0, 5)]        # doubled edge 0=5: multigraph -> general solver
+    extra.append((np.array([[a for a, b in und] + [b for a, b in und], [b for a, b in und] + [a for a, b in und]], dtype=np.int64), 6))
+    extra.append((np.array([[0, 1], [1, 0]], dtype=np.int64), 2))
+    for ei, n in extra:
+        src, dst = np.concatenate([src, ei[0]]), np.concatenate([dst, ei[1]])
+        eptr, nptr = np.append(eptr, eptr[-1] + ei.shape[1]), np.append(nptr, nptr[-1] + n)
+    args = (torch.as_tensor(src).cuda(), torch.as_tensor(dst).cuda(), torch.as_tensor(eptr), torch.as_tensor(nptr), fl['h'], True,
+            fl['self_loop'])
+    was = L.escgnn_set_rd_fast(1)
+    try:
+        a = encode_batch(*args)
+        L.escgnn_set_rd_fast(0)
+        b = encode_batch(*args)
+    finally:
+        L.escgnn_set_rd_fast(was)
+    for k in ('pos_enc', 'pos_index', 'pos_batch'):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    want = _oracle_batch(src, dst, eptr, nptr, fl['h'], True, fl['self_loop'])
+    assert np.array_equal(a.pos_enc.cpu().numpy(), want[1]) and np.array_equal(a.pos_index.cpu().numpy(), want[2])

@@ -1,4 +1,5 @@
-"""ego_rd with and without pendant-tree peeling: ms per 8192 graphs of the config shapes (CUDA events)."""
+"""ego_rd: general solver with / without pendant-tree peeling, and with the cycle-space fast path in front of it (the default):
+ms per 8192 graphs of the config shapes (CUDA events)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,8 +15,9 @@ for config, G in ((2, 8192), (4, 8192), (1, 8192)):
     ep = torch.as_tensor(np.concatenate([[0], np.cumsum(np.tile(np.diff(eptr), reps))]))
     npt = torch.as_tensor(np.concatenate([[0], np.cumsum(np.tile(np.diff(nptr), reps))]))
     line = 'cfg%d h=%d loops=%d  %d graphs:' % (config, fl['h'], fl['self_loop'], G)
-    for peel in (0, 1):
+    for peel, fast in ((0, 0), (1, 0), (1, 1)):
         L.escgnn_set_rd_peel(peel)
+        L.escgnn_set_rd_fast(fast)
         tm = {}
         for _ in range(3):
             encode_batch(s, d, ep, npt, fl['h'], True, fl['self_loop'], expand=False)
@@ -24,6 +26,7 @@ for config, G in ((2, 8192), (4, 8192), (1, 8192)):
             encode_batch(s, d, ep, npt, fl['h'], True, fl['self_loop'], expand=False, timings=tm)
         torch.cuda.synchronize()
         ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in tm.items()}
-        line += '   peel=%d ego_rd %.3f ms ego_encode %.3f ms' % (peel, ms.get('ego_rd', 0), ms.get('ego_encode', 0))
+        line += '   peel=%d fast=%d ego_rd %.3f ms ego_encode %.3f ms' % (peel, fast, ms.get('ego_rd', 0), ms.get('ego_encode', 0))
     L.escgnn_set_rd_peel(1)
+    L.escgnn_set_rd_fast(1)
     print(line, flush=True)
