@@ -470,20 +470,41 @@ __device__ __forceinline__ void store_hist(uint16_t* rdh, long long edge, const 
     out[2] = spread4(h.hi);
 }
 
-template <int H>
-__global__ void __launch_bounds__(256)
+// kCta = false: a warp per graph (molecule-sized graphs: the pairs of one graph fill one or two chunks of 32 lanes);
+// kCta = true: a CTA per graph -- the graph's CSR / distance matrix are built once by all warps (a thread per BFS root) and the
+// chunks of 32 pair systems are dealt to the warps, so a 120-node graph does not serialise 8 chunks on one warp.
+template <int H, bool kCta>
+__global__ void __launch_bounds__(256, kCta ? 1 : 3)
 ego_rd_fast_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo_dst, const int64_t* __restrict__ eo_ptr,
                    const int64_t* __restrict__ node_ptr, int n_graphs, uint16_t* __restrict__ rdh, unsigned long long* counters,
-                   int nf, int ef, int warp_bytes, int n_lo, int n_hi) {
+                   int nf, int ef, int graph_part, int lane_part, int n_lo, int n_hi) {
     static_assert(ESCGNN_RD_SLOTS == rdfast::kSlots, "histogram width");
     extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_share[4];                                    // CTA mode: ticket, loops, pairs, n_pair
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int gt = kCta ? (int)threadIdx.x : lane, gn = kCta ? (int)blockDim.x : 32;      // thread id / size of the group owning a graph
+    auto gsync = [&]() { if (kCta) __syncthreads(); else __syncwarp(); };
+    auto gany = [&](bool x) -> bool { return kCta ? __syncthreads_or(x) != 0 : __any_sync(kFull, x) != 0; };
     rdfast::Ws ws;
-    rdfast::ws_carve(ws, smem + (size_t)warp * warp_bytes, nf, ef);
+    if (kCta) {
+        rdfast::carve_graph(ws, smem, nf, ef);
+        rdfast::carve_lanes(ws, smem + graph_part + (size_t)warp * lane_part, nf);
+    } else {
+        unsigned char* base = smem + (size_t)warp * (graph_part + lane_part);
+        rdfast::carve_graph(ws, base, nf, ef);
+        rdfast::carve_lanes(ws, base + graph_part, nf);
+    }
     for (;;) {
         int gi = 0;
-        if (lane == 0) gi = (int)atomicAdd(&counters[ESCGNN_CTR_TICKET_RD], 1ull);
-        gi = __shfl_sync(kFull, gi, 0);
+        if (kCta) {
+            __syncthreads();                                      // everyone is done with the previous graph
+            if (threadIdx.x == 0) { s_share[0] = (int)atomicAdd(&counters[ESCGNN_CTR_TICKET_RD], 1ull); s_share[1] = 0; }
+            __syncthreads();
+            gi = s_share[0];
+        } else {
+            if (lane == 0) gi = (int)atomicAdd(&counters[ESCGNN_CTR_TICKET_RD], 1ull);
+            gi = __shfl_sync(kFull, gi, 0);
+        }
         if (gi >= n_graphs) break;
         const long long e0 = eo_ptr[gi];
         const int e = (int)(eo_ptr[gi + 1] - e0);
@@ -491,48 +512,61 @@ ego_rd_fast_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict
         if (e == 0 || n < n_lo || n > n_hi) continue;              // another launch's size class
         const int64_t* src = eo_src + e0;
         const int64_t* dst = eo_dst + e0;
-        __syncwarp();
-        bool bad = n > nf || e > ef || n < 1;
+        gsync();
+        bool bad = n > nf || e > ef || n < 1;                      // (uniform)
         if (!bad) {
             // ---- CSR by source (counting sort; the cursors alias the distance matrix, which is initialised afterwards)
             ws.n = n; ws.e = e; ws.rws = rdfast::row_stride(n);
             uint32_t* cnt = ws.dist;
-            for (int i = lane; i <= n; i += 32) cnt[i] = 0;
-            __syncwarp();
-            for (int i = lane; i < e; i += 32) {
+            for (int i = gt; i <= n; i += gn) cnt[i] = 0;
+            gsync();
+            int loops = 0;
+            for (int i = gt; i < e; i += gn) {
                 const long long s = src[i], t = dst[i];
                 if (s < 0 || s >= n || t < 0 || t >= n) bad = true;
-                else atomicAdd(&cnt[s + 1], 1u);
+                else { atomicAdd(&cnt[s + 1], 1u); loops += s == t; }
             }
-            bad = __any_sync(kFull, bad);
+            if (kCta) {
+                if (loops) atomicAdd(&s_share[1], loops);
+                __syncthreads();
+                loops = s_share[1];
+            } else {
+                #pragma unroll
+                for (int d = 16; d; d >>= 1) loops += __shfl_xor_sync(kFull, loops, d);
+            }
+            // cyclomatic number of the whole graph (if connected): an upper bound for every ego-net.  Dense graphs (count_cycle-like,
+            // ~1.66 edges per node) would be declined pair by pair anyway: skip their setup
+            bad |= (e - loops) / 2 - n + 1 > 2 * kFastCmax;
+            bad = gany(bad);
         }
         if (!bad) {
-            __syncwarp();
-            uint32_t carry = 0;
-            for (int i0 = 0; i0 <= n; i0 += 32) {
-                const int i = i0 + lane;
-                uint32_t v = i <= n ? ws.dist[i] : 0u;
-                #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(kFull, v, d);
-                    if (lane >= d) v += t;
+            if (warp == 0 || !kCta) {
+                uint32_t carry = 0;
+                for (int i0 = 0; i0 <= n; i0 += 32) {
+                    const int i = i0 + lane;
+                    uint32_t v = i <= n ? ws.dist[i] : 0u;
+                    #pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(kFull, v, d);
+                        if (lane >= d) v += t;
+                    }
+                    if (i <= n) ws.optr[i] = (uint16_t)(v + carry);
+                    carry += __shfl_sync(kFull, v, 31);
                 }
-                if (i <= n) ws.optr[i] = (uint16_t)(v + carry);
-                carry += __shfl_sync(kFull, v, 31);
             }
-            __syncwarp();
+            gsync();
             uint32_t* cur = ws.dist + (n + 1);
-            for (int i = lane; i < n; i += 32) cur[i] = ws.optr[i];
-            __syncwarp();
-            for (int i = lane; i < e; i += 32) {
+            for (int i = gt; i < n; i += gn) cur[i] = ws.optr[i];
+            gsync();
+            for (int i = gt; i < e; i += gn) {
                 const int s = (int)src[i], t = (int)dst[i];
                 const uint32_t slot = atomicAdd(&cur[s], 1u);
                 ws.oadj[slot] = (uint8_t)t;
                 ws.oeid[slot] = (uint16_t)i;
             }
-            __syncwarp();
+            gsync();
             // ---- ascending adjacency (deterministic trees), simple, symmetric
-            for (int w = lane; w < n; w += 32) {
+            for (int w = gt; w < n; w += gn) {
                 const int ka = ws.optr[w], kb = ws.optr[w + 1];
                 for (int k = ka + 1; k < kb; ++k) {
                     const uint8_t t = ws.oadj[k];
@@ -543,8 +577,8 @@ ego_rd_fast_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict
                 }
                 for (int k = ka + 1; k < kb; ++k) bad |= ws.oadj[k] == ws.oadj[k - 1];        // multi-edge
             }
-            __syncwarp();
-            for (int w = lane; w < n; w += 32) {
+            gsync();
+            for (int w = gt; w < n; w += gn) {
                 const int ka = ws.optr[w], kb = ws.optr[w + 1];
                 for (int k = ka; k < kb; ++k) {
                     const int b = ws.oadj[k];
@@ -553,35 +587,40 @@ ego_rd_fast_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict
                     bad |= !back;                                                            // asymmetric
                 }
             }
-            bad = __any_sync(kFull, bad);
+            bad = gany(bad);
         }
         if (bad) {                                                 // left to the general solver (which also raises the data errors)
-            for (int i = lane; i < e; i += 32) rdh[(size_t)(e0 + i) * ESCGNN_RD_SLOTS] = rdfast::kSentinel;
+            for (int i = gt; i < e; i += gn) rdh[(size_t)(e0 + i) * ESCGNN_RD_SLOTS] = rdfast::kSentinel;
             continue;
         }
-        __syncwarp();
-        // ---- E2: a lane per root
-        for (int i = lane; i < n * ws.rws; i += 32) ws.dist[i] = 0xffffffffu;
-        __syncwarp();
-        for (int r0 = 0; r0 < n; r0 += 32) {
-            const int r = r0 + lane;
-            if (r < n) rdfast::bfs_root<H>(ws, r);
+        gsync();
+        // ---- E2: a thread per root
+        for (int i = gt; i < n * ws.rws; i += gn) ws.dist[i] = 0xffffffffu;
+        gsync();
+        for (int r = gt; r < n; r += gn) rdfast::bfs_root<H>(ws, r);
+        // ---- one system per unordered pair / self-loop edge (pairs first, self-loops after them, in separate chunks of 32: the two
+        // kinds of system run different code)
+        int pairs = 0, n_pair = 0;
+        if (warp == 0 || !kCta) {
+            for (int kind = 0; kind < 2; ++kind) {
+                for (int i0 = 0; i0 < e; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool is = i < e && (kind == 0 ? src[i] < dst[i] : src[i] == dst[i]);
+                    const unsigned b = __ballot_sync(kFull, is);
+                    if (is) ws.list[pairs + __popc(b & ((1u << lane) - 1u))] = (uint16_t)i;
+                    pairs += __popc(b);
+                }
+                if (kind == 0) n_pair = pairs;
+            }
+            if (kCta && lane == 0) { s_share[2] = pairs; s_share[3] = n_pair; }
         }
-        __syncwarp();
-        // ---- one system per unordered pair / self-loop edge
-        int pairs = 0;
-        for (int i0 = 0; i0 < e; i0 += 32) {
-            const int i = i0 + lane;
-            const bool is = i < e && src[i] <= dst[i];
-            const unsigned b = __ballot_sync(kFull, is);
-            if (is) ws.list[pairs + __popc(b & ((1u << lane) - 1u))] = (uint16_t)i;
-            pairs += __popc(b);
-        }
-        __syncwarp();
+        gsync();
+        if (kCta) { pairs = s_share[2]; n_pair = s_share[3]; }
+        const int c_pair = (n_pair + 31) >> 5, c_all = c_pair + ((pairs - n_pair + 31) >> 5);
         unsigned err = 0;
-        for (int p0 = 0; p0 < pairs; p0 += 32) {
-            const int p = p0 + lane;
-            if (p < pairs) {
+        for (int ci = kCta ? warp : 0; ci < c_all; ci += kCta ? nw : 1) {
+            const int p = (ci < c_pair ? ci * 32 : n_pair + (ci - c_pair) * 32) + lane;
+            if (p < (ci < c_pair ? n_pair : pairs)) {
                 const int ed = ws.list[p];
                 const int u = (int)src[ed], v = (int)dst[ed];
                 rdfast::Hist hu, hv;
@@ -609,6 +648,29 @@ inline int& rd_fast_enabled() {
     return on;
 }
 
+template <int H, bool kCta>
+static int launch_rd_fast_class(const int64_t* eo_src, const int64_t* eo_dst, const int64_t* eo_ptr, const int64_t* node_ptr,
+                                int64_t n_graphs, uint16_t* rdh, unsigned long long* counters, int nf, int ef, int n_lo, int n_hi,
+                                int sms, cudaStream_t st) {
+    const int warps = 8;
+    const int64_t gp = (rdfast::graph_bytes(nf, ef) + 15) & ~int64_t(15), lp = (rdfast::lane_bytes(nf, kFastCmax) + 15) & ~int64_t(15);
+    const size_t smem = (size_t)(kCta ? gp + warps * lp : warps * (gp + lp));
+    auto kern = ego_rd_fast_kernel<H, kCta>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)sms * occ;
+    if (encoder_grid_cap() > 0 && grid > encoder_grid_cap()) grid = encoder_grid_cap();
+    const int64_t need = kCta ? n_graphs : (n_graphs + warps - 1) / warps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, warps * 32, smem, st>>>(eo_src, eo_dst, eo_ptr, node_ptr, (int)n_graphs, rdh, counters, nf, ef, (int)gp, (int)lp,
+                                                   n_lo, n_hi);
+    return (int)cudaGetLastError();
+}
+
 template <int H>
 static int launch_rd_fast(const int64_t* eo_src, const int64_t* eo_dst, const int64_t* eo_ptr, const int64_t* node_ptr,
                           int64_t n_graphs, uint16_t* rdh, unsigned long long* counters, int64_t max_nodes, int64_t max_edges,
@@ -616,34 +678,23 @@ static int launch_rd_fast(const int64_t* eo_src, const int64_t* eo_dst, const in
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int n_class = max_nodes > kFastSmall ? 2 : 1;
-    for (int cls = 0; cls < n_class; ++cls) {
-        // class 0: molecule-sized graphs, 8 warps per CTA; class 1: up to 128 nodes, 4 warps per CTA.  A single class owns every graph.
-        const int nf = cls == 0 ? (int)(max_nodes < kFastSmall ? (max_nodes < 8 ? 8 : max_nodes) : kFastSmall) : (int)(max_nodes < rdfast::kMaxNodes ? max_nodes : rdfast::kMaxNodes);
-        const int64_t e_cap = cls == 0 ? 8 * kFastSmall : 1536;
-        const int ef = (int)(max_edges < e_cap ? (max_edges < 16 ? 16 : max_edges) : e_cap);
-        const int n_lo = cls == 0 ? 0 : kFastSmall + 1, n_hi = (n_class == 2 && cls == 0) ? kFastSmall : 0x7fffffff;
-        const int warps = cls == 0 ? 8 : 4;
-        const int64_t wb = (rdfast::ws_bytes(nf, ef, kFastCmax) + 15) & ~int64_t(15);
-        const size_t smem = (size_t)(wb * warps);
-        auto kern = ego_rd_fast_kernel<H>;
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
-        if (occ < 1) occ = 1;
-        int64_t grid = (int64_t)sms * occ;
-        if (encoder_grid_cap() > 0 && grid > encoder_grid_cap()) grid = encoder_grid_cap();
-        const int64_t need = (n_graphs + warps - 1) / warps;
-        if (grid > need) grid = need;
-        if (grid < 1) grid = 1;
-        if (cls > 0) {
-            err = cudaMemsetAsync(counters + ESCGNN_CTR_TICKET_RD, 0, sizeof(unsigned long long), st);
-            if (err != cudaSuccess) return (int)err;
-        }
-        kern<<<(unsigned)grid, warps * 32, smem, st>>>(eo_src, eo_dst, eo_ptr, node_ptr, (int)n_graphs, rdh, counters, nf, ef, (int)wb,
-                                                       n_lo, n_hi);
-        if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
+    // class 0: molecule-sized graphs (<= kFastSmall nodes), a warp per graph; class 1 (only when the batch holds larger graphs): up to
+    // 128 nodes, a CTA per graph.  The last class owns every graph above its range too (it marks them for the general solver).
+    const bool two = max_nodes > kFastSmall;
+    const int nf0 = (int)(max_nodes < kFastSmall ? (max_nodes < 8 ? 8 : max_nodes) : kFastSmall);
+    const int64_t cap0 = 8 * kFastSmall;
+    const int ef0 = (int)(max_edges < cap0 ? (max_edges < 16 ? 16 : max_edges) : cap0);
+    int rc = launch_rd_fast_class<H, false>(eo_src, eo_dst, eo_ptr, node_ptr, n_graphs, rdh, counters, nf0, ef0, 0,
+                                            two ? kFastSmall : 0x7fffffff, sms, st);
+    if (rc != 0) return rc;
+    if (two) {
+        rc = (int)cudaMemsetAsync(counters + ESCGNN_CTR_TICKET_RD, 0, sizeof(unsigned long long), st);
+        if (rc != 0) return rc;
+        const int nf1 = (int)(max_nodes < rdfast::kMaxNodes ? max_nodes : rdfast::kMaxNodes);
+        const int ef1 = (int)(max_edges < 1536 ? max_edges : 1536);
+        rc = launch_rd_fast_class<H, true>(eo_src, eo_dst, eo_ptr, node_ptr, n_graphs, rdh, counters, nf1, ef1, kFastSmall + 1, 0x7fffffff,
+                                           sms, st);
+        if (rc != 0) return rc;
     }
     return (int)cudaMemsetAsync(counters + ESCGNN_CTR_TICKET_RD, 0, sizeof(unsigned long long), st);     // for the general solver
 }

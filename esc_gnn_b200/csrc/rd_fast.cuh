@@ -48,11 +48,14 @@ RDF_HD int popc64(uint64_t x) {
 #endif
 }
 
-// number of equal bytes of two packed paths
+// lambda(x, y) from two packed root paths: the ancestors agree from the root down to the lowest common ancestor, so the number of
+// equal bytes is the index of the first differing byte (the filler marks of any two paths differ, so there always is one)
 RDF_HD int equal_bytes(uint64_t a, uint64_t b) {
-    const uint64_t z = a ^ b, m = 0x7f7f7f7f7f7f7f7full;
-    const uint64_t t = ~(((z & m) + m) | z | m);            // 0x80 in every byte of z that is zero
-    return popc64(t);
+#ifdef __CUDA_ARCH__
+    return (__ffsll((long long)(a ^ b)) - 1) >> 3;
+#else
+    return __builtin_ctzll(a ^ b) >> 3;
+#endif
 }
 
 // one warp's workspace
@@ -73,27 +76,26 @@ RDF_HD int row_stride(int n) { return ((n + 7) >> 3) | 1; }
 
 RDF_HD uint32_t nibr(const uint32_t* row, int w) { return (row[w >> 3] >> ((w & 7) << 2)) & 15u; }
 
-// bytes of one warp's workspace for graphs of at most nf nodes / ef directed edges
-RDF_HD int64_t ws_bytes(int64_t nf, int64_t ef, int cmax) {
-    auto al = [](int64_t x) { return (x + 7) & ~int64_t(7); };
-    int64_t d = nf * row_stride((int)nf);
-    if (d < 2 * nf + 2) d = 2 * nf + 2;
-    return al(2 * (nf + 1)) + al(ef) + al(2 * ef) + al(2 * ef) + al(4 * d) + 3 * al(nf * kLanes) + 8 * 2 * (int64_t)cmax * kLanes;
+RDF_HD int64_t al8(int64_t x) { return (x + 7) & ~int64_t(7); }
+RDF_HD int64_t dist_words(int64_t nf) {            // the counting-sort cursors (2 nf + 2 words) alias the distance matrix
+    const int64_t d = nf * row_stride((int)nf);
+    return d < 2 * nf + 2 ? 2 * nf + 2 : d;
 }
+// bytes of the per-graph part (CSR + distance matrix) and of one warp's per-lane part, for graphs of <= nf nodes / ef directed edges
+RDF_HD int64_t graph_bytes(int64_t nf, int64_t ef) { return al8(4 * dist_words(nf)) + al8(2 * (nf + 1)) + 2 * al8(2 * ef) + al8(ef); }
+RDF_HD int64_t lane_bytes(int64_t nf, int cmax) { return 3 * al8(nf * kLanes) + 8 * 2 * (int64_t)cmax * kLanes; }
 
-RDF_HD void ws_carve(Ws& ws, unsigned char* base, int64_t nf, int64_t ef) {
-    auto al = [](int64_t x) { return (x + 7) & ~int64_t(7); };
-    int64_t d = nf * row_stride((int)nf);
-    if (d < 2 * nf + 2) d = 2 * nf + 2;
-    // base is 8-byte aligned and every region is padded to 8 bytes
-    ws.dist = reinterpret_cast<uint32_t*>(base); base += al(4 * d);
-    ws.optr = reinterpret_cast<uint16_t*>(base); base += al(2 * (nf + 1));
-    ws.oeid = reinterpret_cast<uint16_t*>(base); base += al(2 * ef);
-    ws.list = reinterpret_cast<uint16_t*>(base); base += al(2 * ef);
-    ws.oadj = base; base += al(ef);
-    ws.par = base; base += al(nf * kLanes);
-    ws.dep = base; base += al(nf * kLanes);
-    ws.siz = base; base += al(nf * kLanes);
+RDF_HD void carve_graph(Ws& ws, unsigned char* base, int64_t nf, int64_t ef) {        // base 8-byte aligned
+    ws.dist = reinterpret_cast<uint32_t*>(base); base += al8(4 * dist_words(nf));
+    ws.optr = reinterpret_cast<uint16_t*>(base); base += al8(2 * (nf + 1));
+    ws.oeid = reinterpret_cast<uint16_t*>(base); base += al8(2 * ef);
+    ws.list = reinterpret_cast<uint16_t*>(base); base += al8(2 * ef);
+    ws.oadj = base;
+}
+RDF_HD void carve_lanes(Ws& ws, unsigned char* base, int64_t nf) {
+    ws.par = base; base += al8(nf * kLanes);
+    ws.dep = base; base += al8(nf * kLanes);
+    ws.siz = base; base += al8(nf * kLanes);
     ws.path = reinterpret_cast<uint64_t*>(base);
 }
 
@@ -181,9 +183,8 @@ RDF_HD int solve_pair(const Ws& ws, int lane, int u, int v, Hist& hu, Hist& hv) 
     auto pack = [&](int x, uint8_t mark, int* sum_siz) -> uint64_t {
         uint64_t P = 0x0101010101010101ull * mark;
         int a = 0;
-        for (int k = dep[x * L]; k >= 1; --k) {
-            const int sh = 8 * (k - 1);
-            P = (P & ~(0xffull << sh)) | ((uint64_t)x << sh);
+        for (int k = dep[x * L]; k >= 1; --k) {               // x itself enters at byte 0 and is shifted up to byte depth - 1
+            P = (P << 8) | (uint64_t)x;
             if (sum_siz) a += siz[x * L];
             x = par[x * L];
         }

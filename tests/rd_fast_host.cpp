@@ -14,12 +14,13 @@ using namespace escgnn::rdfast;
 template <int H, int CMAX>
 static int run(const int64_t* src, const int64_t* dst, int64_t e, int64_t n, uint16_t* rdh, int* max_chords) {
     if (n < 1 || n > kMaxNodes || e < 1 || e > 60000) return 1;
-    std::vector<unsigned char> buf(ws_bytes(n, e, CMAX) + 16);
+    std::vector<unsigned char> buf(graph_bytes(n, e) + lane_bytes(n, CMAX) + 16);
     Ws ws;
     ws.n = (int)n; ws.e = (int)e; ws.rws = row_stride((int)n);
     unsigned char* base = buf.data();
     base += (8 - (reinterpret_cast<uintptr_t>(base) & 7)) & 7;
-    ws_carve(ws, base, n, e);
+    carve_graph(ws, base, n, e);
+    carve_lanes(ws, base + graph_bytes(n, e), n);
     std::vector<std::vector<std::pair<int, int>>> adj(n);
     for (int64_t i = 0; i < e; ++i) {
         if (src[i] < 0 || src[i] >= n || dst[i] < 0 || dst[i] >= n) return 2;
