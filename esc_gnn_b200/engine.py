@@ -19,6 +19,7 @@ Dense contractions (every nn.Linear forward / dgrad / wgrad) run on the hand-wri
 kernels of csrc/*.cu.  No library GEMM is on the path.
 """
 import ctypes
+import os
 
 import torch
 
@@ -206,6 +207,14 @@ class StaticTrainEngine(object):
         self.side = torch.cuda.Stream(device=dev)
         self.side_partial = torch.zeros_like(c.partial)
         self._side_used = False
+        # the z path's share of the backward pass starts with d z = sum over layers of (d edge projection) W_l.  Opt-in
+        # (ESCGNN_SPLIT_PROJ=1): each layer's term is formed on a third branch as soon as that layer's aggregation backward has
+        # produced it, so only the first layer's (narrow) term is left when the layer chain ends.  Measured SLOWER at batch 256
+        # (1.228 vs 1.159 ms per step): the 190-CTA edge-level products evict the node-level GEMMs of the critical chain from the SMs,
+        # which costs more than the 55 us the shorter tail saves.  Default: one product over all layers at the end.
+        self.split_proj = os.environ.get('ESCGNN_SPLIT_PROJ', '0') == '1'
+        self.proj_stream = torch.cuda.Stream(device=dev)
+        self.gemm_ws_proj = torch.zeros(1024 * 1024, dtype=torch.float32, device=dev)
         self.inline_branches = False
         self.fwd, self.bwd, self._bns, self._emb_ready = [], [], [], []
         # bond attributes go through E1 on the device whenever the edge list does (dropped loops, appended loop rows = 1:
@@ -232,7 +241,8 @@ class StaticTrainEngine(object):
         ok = all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (A, B)) and self.tensor_cores
         if ok:
             # split-K partials: one workspace per stream (GEMMs of the two graph branches may run concurrently)
-            ws = self.gemm_ws_side if torch.cuda.current_stream(c.dev) == self.side else self.gemm_ws
+            cur = torch.cuda.current_stream(c.dev)
+            ws = self.gemm_ws_side if cur == self.side else self.gemm_ws_proj if cur == self.proj_stream else self.gemm_ws
             d_rows = _p(c.rows[rows]) if (rows is not None and self.bounded_gemm) else None
             _lib.check(c.L.escgnn_gemm_tf32x3_bounded(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C),
                                                       C.stride(0), _p(bias), M, N, K, int(accumulate), _p(ws), ws.numel(), d_rows,
@@ -242,22 +252,25 @@ class StaticTrainEngine(object):
                                               _p(bias), M, N, K, int(accumulate), c.st()), tag + '_simple')
 
     # ---- graph branches: work that is off the critical path runs on the side stream (captured as a parallel branch)
-    def _fork(self, fn):
-        """Run fn on the side stream after everything issued so far on the main stream; returns its completion event."""
+    def _fork(self, fn, stream=None):
+        """Run fn on the side stream (or `stream`) after everything issued so far on the main stream; returns its completion event.
+        Work forked to the side stream is joined by _join(); the caller waits for the event of any other stream itself."""
         main = torch.cuda.current_stream(self.c.dev)
         if self.inline_branches:                  # profiling: one stream, so every interval belongs to exactly one kernel
             fn()
             done = torch.cuda.Event()
             done.record(main)
             return done
+        side = self.side if stream is None else stream
         ready = torch.cuda.Event()
         ready.record(main)
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ready)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
             fn()
             done = torch.cuda.Event()
-            done.record(self.side)
-        self._side_used = True
+            done.record(side)
+        if stream is None:
+            self._side_used = True
         return done
 
     def _join(self):
@@ -547,6 +560,8 @@ class StaticTrainEngine(object):
         # backward is the epilogue of this product (-> d z2 lands in dzcat[:, :H]); the edge-type columns (ZINC) only feed an
         # embedding-table gradient, so their (narrow) product leaves the critical path
         fuse_proj = self.fuse_bn and self._tc_ok(dee_all, W_cat) and c.L.escgnn_linear_bn_fusable(E_rows, H, n_tot) == 1
+        split_proj = self.split_proj and not fuse_proj
+        proj_done = [None]                        # completion of the latest per-layer term (they run in order on one branch)
         if not fuse_proj:
             dz_act = c.buf('E', H)                # gradient wrt the activation output, BatchNorm backward as its own launch
             self._bn_bwd(bn_z2, dz_act)           # (registered before proj_back: runs after it)
@@ -565,6 +580,8 @@ class StaticTrainEngine(object):
                     _p(dee_all), dee_all.stride(0), _p(W_cat), W_cat.stride(0), E_rows, H, n_tot, _p(c.rows['E']), _p(b['x']), b['x'].stride(0),
                     _p(b['mean']), _p(b['rstd']), _p(bn.weight), _p(bn.bias), ACT[b['act']], H, _p(bn.weight.grad), _p(bn.bias.grad),
                     _p(dzcat), dzcat.stride(0), _p(self.bn_ws), self.bn_ws.numel(), c.st()), 'linear_bn_act_bwd')
+            elif split_proj:                      # every layer's term is already on its way: wait for the last one
+                torch.cuda.current_stream(c.dev).wait_event(proj_done[0])
             else:
                 self._gemm('gemm_dgrad', dee_all, False, W_cat[:, :H], True, dz_act, None, E_rows, H, n_tot, False, rows='E')
             # every gradient outside the late bucket is complete once the side branch has passed this point, and nothing below
@@ -597,6 +614,13 @@ class StaticTrainEngine(object):
                 xin = xs[:, (slot0 + l - 1) * H:(slot0 + l) * H]
                 dxin_buf = c.buf('N', H)
                 layer_dx_from_next[l - 1] = dxin_buf
+            if split_proj:
+                # (registered before the aggregation: runs right after its backward)  d z (+)= dee_l W_l[:, :H]; the last layer's
+                # backward runs first and overwrites, the others accumulate
+                def proj_term(l=l, dee=dee, c0=c0, cin=cin):
+                    proj_done[0] = self._fork(lambda: self._gemm('gemm_dgrad', dee, False, W_cat[c0:c0 + cin, :H], True, dz_act, None,
+                                                                 E_rows, H, cin, l != Lh - 1, rows='E'), stream=self.proj_stream)
+                self.bwd.append(proj_term)
             self._gine(xin, dxin_buf, ee, dee, conv.eps, agg, dagg)
             # conv.nn = Linear, BN, act, Linear, BN, act: two fused launches forward; backward: the last BatchNorm stand-alone (its
             # gradient arrives from two places), the middle one as the epilogue of the second Linear's dgrad
