@@ -89,6 +89,7 @@ SIGNATURES = {
     'escgnn_linear_bn_act_bwd': (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp,
                                         _vp, _i32, _vp, _i64, _vp]),
     'escgnn_gemm_set_plan': (_i32, [_i32]),
+    'escgnn_gemm_set_wide': (_i32, [_i32]),
     'escgnn_gemm_set_drain': (_i32, [_i32]),
     'escgnn_gemm_workspace_floats': (_i64, [_i32, _i32, _i32]),
     'escgnn_tf32_split_lo': (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp]),
@@ -124,6 +125,8 @@ def lib():
             L.escgnn_gemm_set_split_target(int(os.environ['ESCGNN_SPLIT_TARGET']))
         if os.environ.get('ESCGNN_GEMM_DRAIN'):
             L.escgnn_gemm_set_drain(int(os.environ['ESCGNN_GEMM_DRAIN']))
+        if os.environ.get('ESCGNN_GEMM_WIDE', '1') == '0':   # A/B switch: 128-wide tiles everywhere
+            L.escgnn_gemm_set_wide(0)
         if os.environ.get('ESCGNN_CLUSTER_BN', '1') == '0':
             L.escgnn_set_cluster_bn(0)
         if os.environ.get('ESCGNN_PDL', '1') == '0':      # A/B switch: plain stream-ordered launches

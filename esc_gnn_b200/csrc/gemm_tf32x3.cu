@@ -446,7 +446,8 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
     const int kb_begin = blockIdx.z * p.kb_per_split;
-    constexpr uint32_t kTmemCols = 256, kTmemA = 128;
+    // accumulator [0, BLOCK_N) then the A planes; a 256-wide tile takes the whole tensor memory (one CTA per SM)
+    constexpr uint32_t kTmemCols = BLOCK_N <= 128 ? 256 : 512, kTmemA = BLOCK_N <= 128 ? 128 : 256;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -1241,8 +1242,18 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 gri
     return deep ? launch_cfg<BLOCK_N, A_MN, B_MN, 4, 2>(a, b, p, grid, st) : launch_cfg<BLOCK_N, A_MN, B_MN, 2, 1>(a, b, p, grid, st);
 }
 
+// "wide" plan: one CTA per 128 x 256 tile (3 raw stages + 2 lo buffers = 208 KB, the whole tensor memory).  For edge-level products
+// with a 256-column output (z_embedding's Linear, the projection dgrad with K = 1056) it replaces two 128-wide CTAs per SM that
+// share one tensor pipe through a 2-stage ring: the A tile is fetched once, the ring is deep enough to cover the TMA latency, and
+// one UTCHMMA covers N = 256.
+int g_gemm_wide = 1;       // escgnn_gemm_set_wide
+
 template <bool A_MN, bool B_MN>
 int dispatch_n(int block_n, const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
+    if (block_n == 256) {
+        if constexpr (!A_MN) return launch_cfg_ts<256, false, B_MN, 3, 2>(a, b, p, grid, st);
+        else return ESCGNN_ERR_BAD_ARG;
+    }
     switch (block_n) {
         case 32: return launch<32, A_MN, B_MN>(a, b, p, grid, st);
         case 64: return launch<64, A_MN, B_MN>(a, b, p, grid, st);
@@ -1303,6 +1314,12 @@ int escgnn_gemm_set_split_target(int ctas) {
 
 int escgnn_gemm_set_plan(int plan) { g_gemm_plan = plan; return 0; }
 
+int escgnn_gemm_set_wide(int on) {
+    const int was = g_gemm_wide;
+    g_gemm_wide = on ? 1 : 0;
+    return was;
+}
+
 int escgnn_gemm_set_drain(int mode) {
     const int was = g_gemm_drain;
     if (mode >= 0 && mode <= 2) g_gemm_drain = mode;
@@ -1332,12 +1349,19 @@ int escgnn_gemm_tf32x3_bounded(const float* d_a, int lda, int a_mn_major, const 
     if ((lda & 3) || (ldb & 3) || ((uintptr_t)d_a & 15) || ((uintptr_t)d_b & 15))
         return ESCGNN_ERR_BAD_ARG;            // TMA needs 16-byte aligned bases and row pitches
     cudaStream_t st = (cudaStream_t)stream;
-    const int block_n = pick_block_n(N);
-    const int tiles_m = (M + kBlockM - 1) / kBlockM, n_tiles = (N + block_n - 1) / block_n;
+    int block_n = pick_block_n(N);
+    const int tiles_m = (M + kBlockM - 1) / kBlockM;
+    int n_tiles = (N + block_n - 1) / block_n;
     const int kb_total = (K + kBlockK - 1) / kBlockK;
     const bool atomic = accumulate == 2;       // C += A B^T with the K-slices added by fp32 reductions (order not fixed)
-    int splits = atomic ? pick_splits(tiles_m * n_tiles, kb_total, M, N, (int64_t)1 << 40)
-                        : d_workspace ? pick_splits(tiles_m * n_tiles, kb_total, M, N, workspace_floats) : 1;
+    // one wave of 128 x 256 tiles when the output is 256 columns wide and the 128-wide tiles would need two CTAs per SM (more than 74
+    // row tiles; below that the 128-wide grid fits one CTA per SM with the deep ring and is faster: 12.9 vs 19.0 us at 65 row tiles,
+    // against 22.5 vs 20.2 us at 95, tools/bench_gemm_wide.py)
+    const bool wide = g_gemm_wide && g_gemm_plan < 0 && g_gemm_drain == 0 && !a_mn_major && !atomic && N % 256 == 0 &&
+                      tiles_m * (N / 128) > 148 && tiles_m * (N / 256) <= 148;
+    if (wide) { block_n = 256; n_tiles = N / 256; }
+    int splits = wide ? 1 : atomic ? pick_splits(tiles_m * n_tiles, kb_total, M, N, (int64_t)1 << 40)
+                                   : d_workspace ? pick_splits(tiles_m * n_tiles, kb_total, M, N, workspace_floats) : 1;
     Params p;
     p.C = d_c; p.ldc = ldc; p.bias = d_bias; p.M = M; p.N = N; p.K = K;
     p.kb_total = kb_total; p.kb_per_split = (kb_total + splits - 1) / splits;

@@ -385,6 +385,10 @@ int escgnn_linear_bn_act_bwd(const float* d_dy, int lddy, const float* d_w, int 
 /* shared-memory plan of the GEMM: -1 auto, 0 = 2 stages (2 CTAs/SM), 1 = 4 stages (1 CTA/SM); +2 = the variant that keeps
  * both planes of A in shared memory instead of tensor memory (experiments / tests) */
 int escgnn_gemm_set_plan(int plan);
+/* 128 x 256 output tiles (one CTA per SM, 3-stage ring, the whole tensor memory) for products with a 256-column output, K-major A and
+ * 64..148 row tiles -- the edge-level Linear layers of a reference batch (zinc_models.py:513-522, GINEConv.lin dgrad): on by default,
+ * 0 = always 128-wide tiles (A/B timing and tests).  Returns the previous setting. */
+int escgnn_gemm_set_wide(int on);
 /* fp32 accumulation OUTSIDE the tensor core (the "drain" kernel: per k-block the hi*hi products start a fresh TMEM accumulator that
  * four extra warps add into registers with round-to-nearest; the A planes are rounded, not truncated).  tcgen05.mma accumulates with
  * truncation: -5.9e-6 mean signed relative error at K = 256 for the plain kernels, -8e-8 (rms 1.0e-7; cuBLAS fp32: 2.3e-7) with the

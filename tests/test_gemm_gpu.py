@@ -320,3 +320,28 @@ def test_drain_gemm_matches_fp64_and_beats_in_tensor_core_accumulation(a_mn, b_m
     assert e_d <= 4e-7, e_d                                # fp32-GEMM quality (cuBLAS fp32: ~2e-7 on these shapes)
     if K >= 256:
         assert e_d < 0.5 * e_p, (e_d, e_p)                 # the long in-tensor-core chains are what the drain removes
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the "wide" plan: one CTA per 128 x 256 tile (escgnn_gemm_set_wide) for 256-column outputs with 64..148 row tiles
+@pytest.mark.parametrize('b_mn', [False, True])
+@pytest.mark.parametrize('M,N,K', [(12092, 256, 256), (12092, 256, 1056), (9700, 256, 288), (18900, 256, 64), (9000, 512, 96)])
+def test_wide_tile_gemm_matches_fp64_and_the_128_wide_tiles(b_mn, M, N, K):
+    from esc_gnn_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    A = torch.randn(M, K, device='cuda', generator=g)
+    B = torch.randn(N, K, device='cuda', generator=g)
+    bias = torch.randn(N, device='cuda', generator=g)
+    was = L.escgnn_gemm_set_wide(1)
+    try:
+        check(A, B, False, b_mn, bias=bias)
+        check(A, B, False, b_mn, C0=torch.randn(M, N, device='cuda', generator=g))
+        wide = run_gemm(A, B, False, b_mn, bias=bias)
+        L.escgnn_gemm_set_wide(0)
+        narrow = run_gemm(A, B, False, b_mn, bias=bias)
+    finally:
+        L.escgnn_gemm_set_wide(was)
+    # same products, same k order inside a tile: the two plans agree to rounding of the in-tensor-core accumulation
+    scale = (A.abs().double() @ B.abs().double().t()).max().item()
+    assert (wide.double() - narrow.double()).abs().max().item() <= 4e-6 * scale
