@@ -246,7 +246,7 @@ class StaticTrainEngine(object):
             d_rows = _p(c.rows[rows]) if (rows is not None and self.bounded_gemm) else None
             _lib.check(c.L.escgnn_gemm_tf32x3_bounded(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C),
                                                       C.stride(0), _p(bias), M, N, K, int(accumulate), _p(ws), ws.numel(), d_rows,
-                                                      2 if tag == 'gemm_wgrad' else 1, c.st()), tag)
+                                                      (2 if tag == 'gemm_wgrad' else 1) | 4, c.st()), tag)      # | 4: counts final long before
         else:
             _lib.check(c.L.escgnn_gemm_simple(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(C), C.stride(0),
                                               _p(bias), M, N, K, int(accumulate), c.st()), tag + '_simple')

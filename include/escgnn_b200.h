@@ -352,7 +352,10 @@ int escgnn_gemm_tf32x3(const float* d_a, int lda, int a_mn_major, const float* d
 /* Same product for the static-shape engine, where M (forward / dgrad) or K (wgrad) is a row CAPACITY and the actual row
  * count lives in device memory: rows_dim = 1 -> output tiles that start at or past *d_rows leave without touching C (their
  * rows of C keep their previous contents); rows_dim = 2 -> k-blocks past *d_rows are skipped. Keeps the launch shape static
- * (CUDA-graph capturable) while the work follows the batch; d_rows = NULL: identical to escgnn_gemm_tf32x3. */
+ * (CUDA-graph capturable) while the work follows the batch; d_rows = NULL: identical to escgnn_gemm_tf32x3.
+ * rows_dim | 4: *d_rows was final before the kernel PRECEDING this launch on the stream was launched (a static-shape engine writes
+ * its counts once at the start of the step): the kernel then reads it ahead of its programmatic-dependency wait, which takes an
+ * L2-missing load off the path between the wait and the first TMA issue. */
 int escgnn_gemm_tf32x3_bounded(const float* d_a, int lda, int a_mn_major, const float* d_b, int ldb, int b_mn_major, float* d_c,
                                int ldc, const float* d_bias, int M, int N, int K, int accumulate, float* d_workspace,
                                int64_t workspace_floats, const int* d_rows, int rows_dim, void* stream);
