@@ -210,6 +210,13 @@ RDF_HD int solve_pair(const Ws& ws, int lane, int u, int v, Hist& hu, Hist& hv) 
             ++c;
         }
     }
+    // the unrolled per-chord code below runs for the largest chord count among the lanes of the warp only (uniform branches): a chunk
+    // of tree-like ego-nets skips the Gram matrix and the triangular solves altogether
+#ifdef __CUDA_ARCH__
+    const int cw = __reduce_max_sync(__activemask(), c);
+#else
+    const int cw = c;
+#endif
     if (over) return -1;
     // ---- Gram matrix of the fundamental cycles and its Cholesky factor (identity beyond c: the unrolled code is uniform)
     uint64_t pa[CMAX], pb[CMAX];
@@ -224,7 +231,9 @@ RDF_HD int solve_pair(const Ws& ws, int lane, int u, int v, Hist& hu, Hist& hv) 
         #pragma unroll
         for (int j = 0; j <= i; ++j) {
             int val;
-            if (i == j) {
+            if (i >= cw) {
+                val = i == j ? 1 : 0;
+            } else if (i == j) {
                 const int da = 8 - popc64(pa[i] & 0x8080808080808080ull), db = 8 - popc64(pb[i] & 0x8080808080808080ull);
                 val = i < c ? da + db - 2 * equal_bytes(pa[i], pb[i]) + 1 : 1;                          // the cycle's length
             } else {
@@ -237,19 +246,22 @@ RDF_HD int solve_pair(const Ws& ws, int lane, int u, int v, Hist& hu, Hist& hv) 
     bool bad = false;
     #pragma unroll
     for (int j = 0; j < CMAX; ++j) {
-        double d = g[j][j];
-        #pragma unroll
-        for (int k = 0; k < j; ++k) d -= g[j][k] * g[j][k];
-        if (!(d > 1e-12)) { bad = true; d = 1.0; }
-        const double l = sqrt(d);
-        inv_d[j] = 1.0 / l;
-        g[j][j] = l;
-        #pragma unroll
-        for (int i = j + 1; i < CMAX; ++i) {
-            double s = g[i][j];
+        inv_d[j] = 1.0;
+        if (j < cw) {
+            double d = g[j][j];
             #pragma unroll
-            for (int k = 0; k < j; ++k) s -= g[i][k] * g[j][k];
-            g[i][j] = s * inv_d[j];
+            for (int k = 0; k < j; ++k) d -= g[j][k] * g[j][k];
+            if (!(d > 1e-12)) { bad = true; d = 1.0; }
+            const double l = sqrt(d);
+            inv_d[j] = 1.0 / l;
+            g[j][j] = l;
+            #pragma unroll
+            for (int i = j + 1; i < CMAX; ++i) {
+                double s = g[i][j];
+                #pragma unroll
+                for (int k = 0; k < j; ++k) s -= g[i][k] * g[j][k];
+                g[i][j] = s * inv_d[j];
+            }
         }
     }
     if (bad) return -2;
@@ -257,10 +269,13 @@ RDF_HD int solve_pair(const Ws& ws, int lane, int u, int v, Hist& hu, Hist& hv) 
     auto solve_y = [&](uint64_t P, double (&y)[CMAX]) {
         #pragma unroll
         for (int i = 0; i < CMAX; ++i) {
-            double s = (double)(equal_bytes(P, pb[i]) - equal_bytes(P, pa[i]));
-            #pragma unroll
-            for (int k = 0; k < i; ++k) s -= g[i][k] * y[k];
-            y[i] = s * inv_d[i];
+            y[i] = 0.0;
+            if (i < cw) {
+                double s = (double)(equal_bytes(P, pb[i]) - equal_bytes(P, pa[i]));
+                #pragma unroll
+                for (int k = 0; k < i; ++k) s -= g[i][k] * y[k];
+                y[i] = s * inv_d[i];
+            }
         }
     };
     bool ok = true;

@@ -6,7 +6,7 @@ duration and average DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) p
 """
 import csv, json, subprocess, sys
 
-LABELS = [('gemm_tf32x3', 'gemm'), ('ego_encode_kernel', 'encode'), ('ego_rd_kernel', 'encode_rd'), ('bag_embed_fwd', 'bag_embed_fwd'),
+LABELS = [('gemm_tf32x3', 'gemm'), ('ego_encode_kernel', 'encode'), ('ego_rd', 'encode_rd'), ('bag_embed_fwd', 'bag_embed_fwd'),
           ('bag_embed_bwd_indexed', 'bag_embed_bwd_indexed'), ('bag_reduce', 'bag_embed_bwd_indexed'), ('bag_count', 'bag_index_build'),
           ('bag_fill', 'bag_index_build'), ('bag_scan', 'bag_index_build'), ('gine_fwd', 'gine_aggregate_fwd_ld'),
           ('gine_bwd', 'gine_aggregate_bwd_ld_noeps'), ('segment_pool_fwd', 'segment_pool_fwd'), ('segment_pool_bwd', 'segment_pool_bwd'),
