@@ -340,6 +340,7 @@ ego_rd_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict__ eo
     __shared__ int s_cnt;
     __shared__ unsigned s_err;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    if (fast_done && counters[ESCGNN_CTR_RD_DECLINED] == 0ull) return;       // the cycle-space kernel solved every edge of the batch
     double* mat_region = reinterpret_cast<double*>(smem);
     uint16_t* sub_region = reinterpret_cast<uint16_t*>(smem + mat_region_doubles * 8);
     unsigned char* aux_region = smem + align16(mat_region_doubles * 8 + (long long)nw * sub_stride * 2);      // aux_stride == 0: none
@@ -591,6 +592,7 @@ ego_rd_fast_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict
         }
         if (bad) {                                                 // left to the general solver (which also raises the data errors)
             for (int i = gt; i < e; i += gn) rdh[(size_t)(e0 + i) * ESCGNN_RD_SLOTS] = rdfast::kSentinel;
+            if (gt == 0) atomicAdd(&counters[ESCGNN_CTR_RD_DECLINED], (unsigned long long)e);
             continue;
         }
         gsync();
@@ -631,6 +633,7 @@ ego_rd_fast_kernel(const int64_t* __restrict__ eo_src, const int64_t* __restrict
                 if (rc == -1) {
                     rdh[(size_t)(e0 + ed) * ESCGNN_RD_SLOTS] = rdfast::kSentinel;
                     if (rev >= 0) rdh[(size_t)(e0 + rev) * ESCGNN_RD_SLOTS] = rdfast::kSentinel;
+                    atomicAdd(&counters[ESCGNN_CTR_RD_DECLINED], 1ull);
                 } else {
                     if (rc < 0) err = ESCGNN_DATA_RD;
                     store_hist(rdh, e0 + ed, hu);
@@ -680,11 +683,13 @@ static int launch_rd_fast(const int64_t* eo_src, const int64_t* eo_dst, const in
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // class 0: molecule-sized graphs (<= kFastSmall nodes), a warp per graph; class 1 (only when the batch holds larger graphs): up to
     // 128 nodes, a CTA per graph.  The last class owns every graph above its range too (it marks them for the general solver).
+    int rc = (int)cudaMemsetAsync(counters + ESCGNN_CTR_RD_DECLINED, 0, sizeof(unsigned long long), st);
+    if (rc != 0) return rc;
     const bool two = max_nodes > kFastSmall;
     const int nf0 = (int)(max_nodes < kFastSmall ? (max_nodes < 8 ? 8 : max_nodes) : kFastSmall);
     const int64_t cap0 = 8 * kFastSmall;
     const int ef0 = (int)(max_edges < cap0 ? (max_edges < 16 ? 16 : max_edges) : cap0);
-    int rc = launch_rd_fast_class<H, false>(eo_src, eo_dst, eo_ptr, node_ptr, n_graphs, rdh, counters, nf0, ef0, 0,
+    rc = launch_rd_fast_class<H, false>(eo_src, eo_dst, eo_ptr, node_ptr, n_graphs, rdh, counters, nf0, ef0, 0,
                                             two ? kFastSmall : 0x7fffffff, sms, st);
     if (rc != 0) return rc;
     if (two) {

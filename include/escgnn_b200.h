@@ -36,6 +36,7 @@ extern "C" {
 #define ESCGNN_CTR_TICKET_RD 3
 #define ESCGNN_CTR_STICKY_ERROR 4     /* OR of every ERROR word seen by escgnn_make_dims since the caller last cleared it */
 #define ESCGNN_CTR_MAX_NNZ 5          /* max of every NNZ seen by escgnn_make_dims (record-capacity overflow detection) */
+#define ESCGNN_CTR_RD_DECLINED 6      /* edges the cycle-space rd kernel left to the general solver (zeroed by escgnn_encode_rd itself) */
 #define ESCGNN_CTR_PER_CALL 4         /* slots [0, 4) are per-call state: a caller that keeps the sticky slots zeroes only these */
 #define ESCGNN_NUM_COUNTERS 8
 
