@@ -90,6 +90,9 @@ SIGNATURES = {
                                         _vp, _i32, _vp, _i64, _vp]),
     'escgnn_gemm_set_plan': (_i32, [_i32]),
     'escgnn_gemm_set_wide': (_i32, [_i32]),
+    'escgnn_gemm_set_trace': (_i32, [_vp]),
+    'escgnn_gemm_set_split_warps': (_i32, [_i32]),
+    'escgnn_gemm_set_staged_store': (_i32, [_i32]),
     'escgnn_gemm_set_drain': (_i32, [_i32]),
     'escgnn_gemm_workspace_floats': (_i64, [_i32, _i32, _i32]),
     'escgnn_tf32_split_lo': (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp]),
@@ -125,6 +128,10 @@ def lib():
             L.escgnn_gemm_set_split_target(int(os.environ['ESCGNN_SPLIT_TARGET']))
         if os.environ.get('ESCGNN_GEMM_DRAIN'):
             L.escgnn_gemm_set_drain(int(os.environ['ESCGNN_GEMM_DRAIN']))
+        if os.environ.get('ESCGNN_GEMM_SPLIT_WARPS'):        # A/B switch: 4 or 8 splitter / epilogue warps
+            L.escgnn_gemm_set_split_warps(int(os.environ['ESCGNN_GEMM_SPLIT_WARPS']))
+        if os.environ.get('ESCGNN_GEMM_STAGED', '1') == '0':   # A/B switch: accumulator rows stored straight from registers
+            L.escgnn_gemm_set_staged_store(0)
         if os.environ.get('ESCGNN_GEMM_WIDE', '1') == '0':   # A/B switch: 128-wide tiles everywhere
             L.escgnn_gemm_set_wide(0)
         if os.environ.get('ESCGNN_CLUSTER_BN', '1') == '0':

@@ -88,7 +88,17 @@ struct Params {
     const int* rows_ptr;          // optional device-side row count (static-shape engine): rows_dim 1 = bounds M (tiles past it
     int rows_dim;                 // leave without touching C), 2 = bounds K (k-blocks past it are skipped)
     int rows_early;               // the count was final before the PRECEDING kernel was launched: read it ahead of griddepcontrol.wait
+    unsigned long long* trace;    // debugging (escgnn_gemm_set_trace): 8 globaltimer stamps per CTA of the TS kernel, nullptr = off
+    int stage_out;                // full tiles are written out row-contiguously through shared memory (escgnn_gemm_set_staged_store)
 };
+
+__device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
+}
 
 // 3xTF32 split: hi = the raw fp32 value (the tensor core reads its top 19 bits, i.e. truncates), lo = x - trunc_tf32(x), exact in
 // fp32.  In the plain kernels the error floor is not the split but the tensor core's truncating accumulation (-5.9e-6 mean signed
@@ -429,8 +439,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         : "memory");
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0>
-__global__ void __launch_bounds__(kThreads, STAGES == 2 ? 2 : 1)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+// SW = splitter / epilogue warps: 4 (one per tensor-memory lane quarter; the fused-BatchNorm epilogues are written for this shape) or
+// 8 (two per quarter, each taking half of the A tile's 32 columns, half of the B_lo split and every other 32-column chunk of the
+// epilogue).  In-kernel %globaltimer stamps (tools/trace_gemm.py) showed the 4-warp splitter, not the tensor pipe, pacing the main
+// loop of a node-level product (0.68 us per k-block against 0.39 us of MMA time) and the epilogue taking 2.5 of its 9.5 us.
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0, int SW = 4>
+__global__ void __launch_bounds__(64 + 32 * SW, STAGES == 2 ? 2 : 1)
 gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p, const BnParams bn) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int kABytes = kBlockM * 128;           // 16 KB
@@ -450,6 +473,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM, n0 = blockIdx.y * BLOCK_N;
     const int kb_begin = blockIdx.z * p.kb_per_split;
+    if (threadIdx.x == 0) trace_stamp(p, 0);                                   // CTA start
     // accumulator [0, BLOCK_N) then the A planes; a 256-wide tile takes the whole tensor memory (one CTA per SM)
     constexpr uint32_t kTmemCols = BLOCK_N <= 128 ? 256 : 512, kTmemA = BLOCK_N <= 128 ? 128 : 256;
 
@@ -458,7 +482,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < LO_BUFS; ++b) { mbar_init(&split_bar[b], 128); mbar_init(&lo_free_bar[b], 1); }
+        for (int b = 0; b < LO_BUFS; ++b) { mbar_init(&split_bar[b], 32 * SW); mbar_init(&lo_free_bar[b], 1); }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -473,8 +497,10 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // the row count of a static-shape engine is written at the start of the step, many kernels ahead of this one: its (L2-missing)
     // read need not sit between the dependency wait and the first TMA issue
     int rows_now = (p.rows_ptr && p.rows_early) ? __ldg(p.rows_ptr) : 0;
+    if (threadIdx.x == 0) trace_stamp(p, 1);                                   // prologue done (barriers, tensor memory)
     escgnn::pdl_wait();
     escgnn::pdl_trigger();
+    if (threadIdx.x == 0) trace_stamp(p, 2);                                   // predecessor complete
     if (p.rows_ptr && !p.rows_early) rows_now = *p.rows_ptr;
     const bool skip = p.rows_dim == 1 && m0 >= rows_now;
     const int kb_total = p.rows_dim == 2 ? min(p.kb_total, (rows_now + kBlockK - 1) / kBlockK) : p.kb_total;
@@ -509,6 +535,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES, lb = i % LO_BUFS;
                 mbar_wait(&split_bar[lb], (i / LO_BUFS) & 1);    // A planes in TMEM, B_lo in shared memory (implies the stage landed)
+                if (i == 0) trace_stamp(p, 4);                                // first k-block split
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t b_hi = smem_u32(smem + (size_t)s * kStageBytes) + kABytes;
                 const uint32_t b_lo = smem_u32(lo_buf + (size_t)lb * kBBytes);
@@ -526,45 +553,53 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tcgen05_commit(&lo_free_bar[lb]);
             }
             tcgen05_commit(&tmem_full_bar);
+            trace_stamp(p, 5);                                                // last MMA issued
         }
     } else {
+        static_assert(SW == 4 || (SW == 8 && EPI == 0), "the fused epilogues are written for four warps");
         const int t = threadIdx.x - 64, q = warp & 3, r = q * 32 + lane;       // r: this thread's row of the A tile = its TMEM lane
-        for (int i = t; i < BLOCK_N; i += 128)
+        constexpr int kACols = 128 / SW;                                       // columns of the A tile per thread: 32 or 16
+        const int half = SW == 8 ? (warp - 2) >> 2 : 0;                        // which half of the columns / chunks this warp takes
+        for (int i = t; i < BLOCK_N; i += 32 * SW)
             s_bias[i] = (p.bias && !p.partial && (!p.atomic || blockIdx.z == 0) && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
         for (int i = 0; i < num_kb; ++i) {
             const int s = i % STAGES, lb = i % LO_BUFS;
             mbar_wait(&full_bar[s], (i / STAGES) & 1);
+            if (i == 0 && t == 0) trace_stamp(p, 3);                            // first stage landed
             mbar_wait(&lo_free_bar[lb], ((i / LO_BUFS) & 1) ^ 1);     // MMAs that read TMEM A buffer / B_lo buffer `lb` are done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint8_t* stage = smem + (size_t)s * kStageBytes;
-            uint32_t hi[32], lo[32];
+            uint32_t hi[kACols], lo[kACols];
             if (!A_MN) {
                 #pragma unroll
-                for (int c = 0; c < 8; ++c) {              // 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+                for (int cc = 0; cc < kACols / 4; ++cc) {  // 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+                    const int c = half * (kACols / 4) + cc;
                     const float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
-                    hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
-                    hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+                    hi[4 * cc + 0] = __float_as_uint(v.x); hi[4 * cc + 1] = __float_as_uint(v.y);
+                    hi[4 * cc + 2] = __float_as_uint(v.z); hi[4 * cc + 3] = __float_as_uint(v.w);
                 }
             } else {
                 // MN-major tile: slab q holds rows 32q..32q+31 as [k][32 m] lines of 128 B whose 32-byte units are XOR-ed with
                 // (k & 3) (SWIZZLE_128B_ATOM_32B); a warp reads one permuted line per k -- conflict-free, and transposed for free
                 const uint8_t* slab = stage + q * kSlabBytes + (lane & 7) * 4;
                 #pragma unroll
-                for (int k = 0; k < 32; ++k)
-                    hi[k] = *reinterpret_cast<const uint32_t*>(slab + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+                for (int kk = 0; kk < kACols; ++kk) {
+                    const int k = half * kACols + kk;
+                    hi[kk] = *reinterpret_cast<const uint32_t*>(slab + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+                }
             }
             #pragma unroll
-            for (int k = 0; k < 32; ++k) {
+            for (int k = 0; k < kACols; ++k) {
                 const float x = __uint_as_float(hi[k]);
                 lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
             }
-            const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + kTmemA + (uint32_t)lb * 64u;
-            tmem_st32(ta, hi);
-            tmem_st32(ta + 32u, lo);
+            const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + kTmemA + (uint32_t)lb * 64u + (uint32_t)(half * kACols);
+            if constexpr (SW == 4) { tmem_st32(ta, hi); tmem_st32(ta + 32u, lo); }
+            else { tmem_st16(ta, hi); tmem_st16(ta + 32u, lo); }
             const float4* src = reinterpret_cast<const float4*>(stage + kABytes);
             float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kBBytes);
             #pragma unroll 4
-            for (int e = t; e < kBBytes / 16; e += 128) {
+            for (int e = t; e < kBBytes / 16; e += 32 * SW) {
                 float4 l;
                 split4(src[e], l);
                 dst[e] = l;
@@ -574,7 +609,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&split_bar[lb]);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * SW) : "memory");
         const int row = m0 + r;
         if constexpr (EPI != 0) {
             const int rows_eff = p.rows_ptr ? min(rows_now, p.M) : p.M;
@@ -749,50 +784,100 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         } else {
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool row_ok = row < p.M && !skip;
-        float* out = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
-        #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-
-            uint32_t v[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
-            if (num_kb > 0) {
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
-                #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-            if (row_ok) {
-                const int nb = n0 + c;
-                const bool acc = p.accumulate && !p.partial;
-                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(out + nb) & 15) == 0)) {
+        if (t == 0) trace_stamp(p, 6);                                          // accumulator complete
+        // Full tiles leave through shared memory: a thread owns a ROW of the accumulator (its tensor-memory lane), so storing straight
+        // from the registers makes every 16-byte store instruction touch 32 different rows -- 4096 half-sector writes per tile,
+        // 2.6 of the 9.5 us of a node-level product (tools/trace_gemm.py).  The operand stages are dead by now (every fill was consumed
+        // by an MMA that has completed): the tile is parked there with a 4-float row pad (conflict-free 16-byte stores), then written
+        // out row-contiguously, 512 bytes per warp instruction.
+        const int ldo = p.partial ? p.N : p.ldc;
+        float* obase = p.partial ? p.partial + (size_t)blockIdx.z * p.M * p.N : p.C;
+        const bool staged = p.stage_out && n0 + BLOCK_N <= p.N && (ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(obase + n0) & 15) == 0);
+        if (staged) {
+            constexpr int kLd = BLOCK_N + 4;
+            float* stg = reinterpret_cast<float*>(smem);
+            if (!skip) {
+                #pragma unroll 1
+                for (int c = 32 * half; c < BLOCK_N; c += 32 * (SW / 4)) {
+                    uint32_t v[32];
+                    if (num_kb > 0) {
+                        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0u;
+                    }
+                    float* dst = stg + r * kLd + c;
                     #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 w = make_float4(__uint_as_float(v[j]) + s_bias[c + j], __uint_as_float(v[j + 1]) + s_bias[c + j + 1],
-                                               __uint_as_float(v[j + 2]) + s_bias[c + j + 2], __uint_as_float(v[j + 3]) + s_bias[c + j + 3]);
-                        float4* dst = reinterpret_cast<float4*>(out + nb + j);
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) =
+                            make_float4(__uint_as_float(v[j]) + s_bias[c + j], __uint_as_float(v[j + 1]) + s_bias[c + j + 1],
+                                        __uint_as_float(v[j + 2]) + s_bias[c + j + 2], __uint_as_float(v[j + 3]) + s_bias[c + j + 3]);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * SW) : "memory");
+            if (!skip) {
+                constexpr int kLanesPerRow = BLOCK_N / 4, kRowsPerPass = (32 * SW) / kLanesPerRow;
+                const bool acc = p.accumulate && !p.partial;
+                if (t < kRowsPerPass * kLanesPerRow) {
+                    const int col = (t % kLanesPerRow) * 4;
+                    #pragma unroll 4
+                    for (int rr = t / kLanesPerRow; rr < kBlockM; rr += kRowsPerPass) {
+                        const int grow = m0 + rr;
+                        if (grow >= p.M) break;
+                        float4 w = *reinterpret_cast<const float4*>(stg + rr * kLd + col);
+                        float4* dst = reinterpret_cast<float4*>(obase + (size_t)grow * ldo + n0 + col);
                         if (p.atomic) { red_add4(dst, w); continue; }
                         if (acc) { const float4 o = *dst; w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
                         *dst = w;
                     }
+                }
+            }
+        } else {
+            const bool row_ok = row < p.M && !skip;
+            float* out = p.partial ? p.partial + ((size_t)blockIdx.z * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
+            #pragma unroll 1
+            for (int c = 32 * half; c < BLOCK_N; c += 32 * (SW / 4)) {      // SW == 8: the two warps of a lane quarter alternate chunks
+
+                uint32_t v[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+                if (num_kb > 0) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 } else {
                     #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = nb + j;
-                        if (n < p.N) {
-                            float w = __uint_as_float(v[j]) + s_bias[c + j];
-                            if (p.atomic) { atomicAdd(out + n, w); continue; }
-                            if (acc) w += out[n];
-                            out[n] = w;
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (row_ok) {
+                    const int nb = n0 + c;
+                    const bool acc = p.accumulate && !p.partial;
+                    if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(out + nb) & 15) == 0)) {
+                        #pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 w = make_float4(__uint_as_float(v[j]) + s_bias[c + j], __uint_as_float(v[j + 1]) + s_bias[c + j + 1],
+                                                   __uint_as_float(v[j + 2]) + s_bias[c + j + 2], __uint_as_float(v[j + 3]) + s_bias[c + j + 3]);
+                            float4* dst = reinterpret_cast<float4*>(out + nb + j);
+                            if (p.atomic) { red_add4(dst, w); continue; }
+                            if (acc) { const float4 o = *dst; w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+                            *dst = w;
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nb + j;
+                            if (n < p.N) {
+                                float w = __uint_as_float(v[j]) + s_bias[c + j];
+                                if (p.atomic) { atomicAdd(out + n, w); continue; }
+                                if (acc) w += out[n];
+                                out[n] = w;
+                            }
                         }
                     }
                 }
@@ -802,6 +887,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) trace_stamp(p, 7);                                   // epilogue stored
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1164,16 +1250,18 @@ int g_gemm_plan = -1;      // -1 auto, 0 dual, 1 deep (escgnn_gemm_set_plan; exp
 
 // One-time setup of a TS instantiation: opt in to its dynamic shared memory; returns how many of its CTAs the device holds at once
 // (<= 0: a CUDA error, negated) -- the bound the grid-barrier epilogues need.
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI>
+int g_gemm_split_warps = 8;   // escgnn_gemm_set_split_warps: splitter / epilogue warps of the plain TS kernel (4 or 8)
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI, int SW = 4>
 int ts_resident_ctas() {
     static int resident = 0;
     if (resident != 0) return resident;
     const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + LO_BUFS * BLOCK_N * 128 + 1024;
-    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI>;
+    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return -(int)e;
     int per_sm = 0, dev = 0, sms = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return -(int)e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64 + 32 * SW, smem)) != cudaSuccess) return -(int)e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return -(int)e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return -(int)e;
     if (getenv("ESCGNN_DEBUG_OCC")) {
@@ -1191,15 +1279,23 @@ int ts_resident_ctas() {
     return resident;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0>
-int launch_cfg_ts(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, const BnParams& bn = BnParams()) {
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0, int SW = 4>
+int launch_cfg_ts_sw(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, const BnParams& bn) {
     const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + LO_BUFS * BLOCK_N * 128 + 1024;
-    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI>;
-    const int resident = ts_resident_ctas<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI>();     // cached after the first call
+    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW>;
+    const int resident = ts_resident_ctas<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW>();     // cached after the first call
     if (resident <= 0) return -resident;
     if (EPI != 0 && (int)(grid.x * grid.y * grid.z) > resident) return ESCGNN_ERR_TOO_LARGE;   // the grid barrier would deadlock
-    escgnn::launch_pdl(kern, grid, kThreads, smem, st, a, b, p, bn);
+    escgnn::launch_pdl(kern, grid, 64 + 32 * SW, smem, st, a, b, p, bn);
     return (int)cudaGetLastError();
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0>
+int launch_cfg_ts(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, const BnParams& bn = BnParams()) {
+    if constexpr (EPI == 0) {
+        if (g_gemm_split_warps == 8) return launch_cfg_ts_sw<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, 0, 8>(a, b, p, grid, st, bn);
+    }
+    return launch_cfg_ts_sw<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, 4>(a, b, p, grid, st, bn);
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -1260,6 +1356,8 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 gri
 // share one tensor pipe through a 2-stage ring: the A tile is fetched once, the ring is deep enough to cover the TMA latency, and
 // one UTCHMMA covers N = 256.
 int g_gemm_wide = 1;       // escgnn_gemm_set_wide
+unsigned long long* g_gemm_trace = nullptr;      // escgnn_gemm_set_trace
+int g_gemm_staged = 1;     // escgnn_gemm_set_staged_store
 
 template <bool A_MN, bool B_MN>
 int dispatch_n(int block_n, const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st) {
@@ -1327,6 +1425,20 @@ int escgnn_gemm_set_split_target(int ctas) {
 
 int escgnn_gemm_set_plan(int plan) { g_gemm_plan = plan; return 0; }
 
+int escgnn_gemm_set_trace(unsigned long long* d_stamps) { g_gemm_trace = d_stamps; return 0; }
+
+int escgnn_gemm_set_staged_store(int on) {
+    const int was = g_gemm_staged;
+    g_gemm_staged = on ? 1 : 0;
+    return was;
+}
+
+int escgnn_gemm_set_split_warps(int warps) {
+    const int was = g_gemm_split_warps;
+    if (warps == 4 || warps == 8) g_gemm_split_warps = warps;
+    return was;
+}
+
 int escgnn_gemm_set_wide(int on) {
     const int was = g_gemm_wide;
     g_gemm_wide = on ? 1 : 0;
@@ -1383,6 +1495,7 @@ int escgnn_gemm_tf32x3_bounded(const float* d_a, int lda, int a_mn_major, const 
     p.accumulate = accumulate;
     p.atomic = atomic ? 1 : 0;
     p.rows_ptr = d_rows; p.rows_dim = d_rows ? (rows_dim & 3) : 0; p.rows_early = (d_rows && (rows_dim & 4)) ? 1 : 0;
+    p.trace = g_gemm_trace; p.stage_out = g_gemm_staged;
     CUtensorMap a, b;
     int rc = 0;
     if (!a_mn_major) rc |= make_map(&a, d_a, K, M, lda, kBlockK, kBlockM);          // [M, K] row-major: inner = K
@@ -1445,7 +1558,7 @@ int escgnn_linear_bn_act_fwd(const float* d_x, int ldx, const float* d_w, int ld
     Params p;
     p.C = d_out; p.ldc = ldo; p.bias = d_bias; p.M = rows_cap; p.N = n_out; p.K = k_in;
     p.kb_total = (k_in + kBlockK - 1) / kBlockK; p.kb_per_split = p.kb_total;
-    p.partial = nullptr; p.accumulate = 0; p.atomic = 0; p.rows_ptr = d_rows; p.rows_dim = d_rows ? 1 : 0; p.rows_early = 0;
+    p.partial = nullptr; p.accumulate = 0; p.atomic = 0; p.rows_ptr = d_rows; p.rows_dim = d_rows ? 1 : 0; p.rows_early = 0; p.trace = nullptr; p.stage_out = 0;
     BnParams bn = BnParams();
     bn.Y = d_y; bn.ldy = ldy; bn.gamma = d_gamma; bn.beta = d_beta; bn.running_mean = d_running_mean; bn.running_var = d_running_var;
     bn.mean = d_mean; bn.rstd = d_rstd; bn.eps = eps; bn.momentum = momentum; bn.act = act; bn.bn_cols = n_out; bn.ws = d_ws;
@@ -1472,7 +1585,7 @@ int escgnn_linear_bn_act_bwd(const float* d_dy, int lddy, const float* d_w, int 
     Params p;
     p.C = d_dx; p.ldc = lddx; p.bias = nullptr; p.M = rows_cap; p.N = n_in; p.K = n_out;
     p.kb_total = (n_out + kBlockK - 1) / kBlockK; p.kb_per_split = p.kb_total;
-    p.partial = nullptr; p.accumulate = 0; p.atomic = 0; p.rows_ptr = d_rows; p.rows_dim = d_rows ? 1 : 0; p.rows_early = 0;
+    p.partial = nullptr; p.accumulate = 0; p.atomic = 0; p.rows_ptr = d_rows; p.rows_dim = d_rows ? 1 : 0; p.rows_early = 0; p.trace = nullptr; p.stage_out = 0;
     BnParams bn = BnParams();
     bn.X = d_x; bn.ldx = ldx; bn.gamma = d_gamma; bn.beta = d_beta; bn.mean = const_cast<float*>(d_mean); bn.rstd = const_cast<float*>(d_rstd);
     bn.dgamma = d_dgamma; bn.dbeta = d_dbeta; bn.act = act; bn.bn_cols = bn_cols; bn.ws = d_ws; bn.ldp = bn_ldp(n_in);

@@ -393,6 +393,19 @@ int escgnn_gemm_set_plan(int plan);
  * 64..148 row tiles -- the edge-level Linear layers of a reference batch (zinc_models.py:513-522, GINEConv.lin dgrad): on by default,
  * 0 = always 128-wide tiles (A/B timing and tests).  Returns the previous setting. */
 int escgnn_gemm_set_wide(int on);
+/* Debugging aid (tools/trace_gemm.py): when d_stamps is not NULL every CTA of the following escgnn_gemm_tf32x3* launches writes 8
+ * %globaltimer values (ns) to d_stamps[(tile_n * tiles_m + tile_m) * 8 + i]: 0 CTA start, 1 prologue done, 2 predecessor complete
+ * (griddepcontrol.wait returned), 3 first operand stage landed, 4 first k-block split, 5 last MMA issued, 6 accumulator complete,
+ * 7 epilogue stored.  NULL switches it off (the default; one predictable branch per stamp). */
+int escgnn_gemm_set_trace(unsigned long long* d_stamps);
+/* Warps that split the operand tiles into their tf32 planes during the main loop and drain the accumulator afterwards: 8 (default:
+ * two per tensor-memory lane quarter; with the staged epilogue 1.072 against 1.116 ms per training step at batch 256) or 4 (A/B
+ * timing and tests; the fused-BatchNorm epilogues always run with 4).  Returns the previous value. */
+int escgnn_gemm_set_split_warps(int warps);
+/* Epilogue of the GEMM: 1 (default) = full output tiles are parked in the dead operand stages and written out row-contiguously
+ * (512 bytes per warp instruction); 0 = every thread stores its accumulator row straight from registers (A/B timing and tests; tiles
+ * that cross the N extent or an unaligned C always take this path).  Returns the previous setting. */
+int escgnn_gemm_set_staged_store(int on);
 /* fp32 accumulation OUTSIDE the tensor core (the "drain" kernel: per k-block the hi*hi products start a fresh TMEM accumulator that
  * four extra warps add into registers with round-to-nearest; the A planes are rounded, not truncated).  tcgen05.mma accumulates with
  * truncation: -5.9e-6 mean signed relative error at K = 256 for the plain kernels, -8e-8 (rms 1.0e-7; cuBLAS fp32: 2.3e-7) with the
