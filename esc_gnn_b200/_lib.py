@@ -93,6 +93,7 @@ SIGNATURES = {
     'escgnn_gemm_set_trace': (_i32, [_vp]),
     'escgnn_gemm_set_split_warps': (_i32, [_i32]),
     'escgnn_gemm_set_staged_store': (_i32, [_i32]),
+    'escgnn_gemm_set_kb_groups': (_i32, [_i32]),
     'escgnn_gemm_set_drain': (_i32, [_i32]),
     'escgnn_gemm_workspace_floats': (_i64, [_i32, _i32, _i32]),
     'escgnn_tf32_split_lo': (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _vp]),
@@ -130,6 +131,8 @@ def lib():
             L.escgnn_gemm_set_drain(int(os.environ['ESCGNN_GEMM_DRAIN']))
         if os.environ.get('ESCGNN_GEMM_SPLIT_WARPS'):        # A/B switch: 4 or 8 splitter / epilogue warps
             L.escgnn_gemm_set_split_warps(int(os.environ['ESCGNN_GEMM_SPLIT_WARPS']))
+        if os.environ.get('ESCGNN_GEMM_KB_GROUPS'):          # A/B switch: 1 or 2 k-block groups of splitter warps
+            L.escgnn_gemm_set_kb_groups(int(os.environ['ESCGNN_GEMM_KB_GROUPS']))
         if os.environ.get('ESCGNN_GEMM_STAGED', '1') == '0':   # A/B switch: accumulator rows stored straight from registers
             L.escgnn_gemm_set_staged_store(0)
         if os.environ.get('ESCGNN_GEMM_WIDE', '1') == '0':   # A/B switch: 128-wide tiles everywhere

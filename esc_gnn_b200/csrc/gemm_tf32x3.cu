@@ -452,7 +452,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 // 8 (two per quarter, each taking half of the A tile's 32 columns, half of the B_lo split and every other 32-column chunk of the
 // epilogue).  In-kernel %globaltimer stamps (tools/trace_gemm.py) showed the 4-warp splitter, not the tensor pipe, pacing the main
 // loop of a node-level product (0.68 us per k-block against 0.39 us of MMA time) and the epilogue taking 2.5 of its 9.5 us.
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0, int SW = 4>
+// KBG = 2 (needs SW = 8 and LO_BUFS = 4): the two groups of four warps split ALTERNATE k-blocks (each group a whole 128 x 32 A tile and
+// B_lo plane, two lo buffers per group) instead of halves of the same one.  One split is a latency chain of ~0.6 us (stage wait,
+// shared-memory reads, tcgen05.st + wait, proxy fence, barrier) against 0.39 us of MMA time per k-block: two of them in flight make
+// the tensor pipe the pacer of a node-level product's main loop.
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0, int SW = 4, int KBG = 1>
 __global__ void __launch_bounds__(64 + 32 * SW, STAGES == 2 ? 2 : 1)
 gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p, const BnParams bn) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -475,14 +479,16 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int kb_begin = blockIdx.z * p.kb_per_split;
     if (threadIdx.x == 0) trace_stamp(p, 0);                                   // CTA start
     // accumulator [0, BLOCK_N) then the A planes; a 256-wide tile takes the whole tensor memory (one CTA per SM)
-    constexpr uint32_t kTmemCols = BLOCK_N <= 128 ? 256 : 512, kTmemA = BLOCK_N <= 128 ? 128 : 256;
+    constexpr uint32_t kTmemA = BLOCK_N <= 128 ? 128 : 256, kTmemCols = kTmemA + 64 * LO_BUFS <= 256 ? 256 : 512;
+    static_assert(kTmemA + 64 * LO_BUFS <= 512, "tensor memory");
+    static_assert(KBG == 1 || (KBG == 2 && SW == 8 && LO_BUFS % 2 == 0 && EPI == 0), "k-block groups");
 
     if (threadIdx.x == 0) {
         // (the descriptors live in the kernel's parameter space: fetching them is legal ahead of the dependency wait)
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < LO_BUFS; ++b) { mbar_init(&split_bar[b], 32 * SW); mbar_init(&lo_free_bar[b], 1); }
+        for (int b = 0; b < LO_BUFS; ++b) { mbar_init(&split_bar[b], 32 * SW / KBG); mbar_init(&lo_free_bar[b], 1); }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -558,11 +564,15 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else {
         static_assert(SW == 4 || (SW == 8 && EPI == 0), "the fused epilogues are written for four warps");
         const int t = threadIdx.x - 64, q = warp & 3, r = q * 32 + lane;       // r: this thread's row of the A tile = its TMEM lane
-        constexpr int kACols = 128 / SW;                                       // columns of the A tile per thread: 32 or 16
-        const int half = SW == 8 ? (warp - 2) >> 2 : 0;                        // which half of the columns / chunks this warp takes
+        constexpr int kSplitThreads = 32 * SW / KBG;                           // threads working on one k-block
+        constexpr int kACols = 4096 / kSplitThreads;                           // columns of the A tile per thread: 32 or 16
+        const int half = SW == 8 ? (warp - 2) >> 2 : 0;                        // epilogue: which 32-column chunks this warp takes
+        const int grp = KBG == 2 ? half : 0;                                   // main loop: which k-blocks (i % KBG == grp) ...
+        const int ahalf = KBG == 2 ? 0 : half;                                 // ... or which half of every A tile's columns
+        const int tg = KBG == 2 ? (t & 127) : t;                               // thread index within the group splitting a k-block
         for (int i = t; i < BLOCK_N; i += 32 * SW)
             s_bias[i] = (p.bias && !p.partial && (!p.atomic || blockIdx.z == 0) && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-        for (int i = 0; i < num_kb; ++i) {
+        for (int i = grp; i < num_kb; i += KBG) {
             const int s = i % STAGES, lb = i % LO_BUFS;
             mbar_wait(&full_bar[s], (i / STAGES) & 1);
             if (i == 0 && t == 0) trace_stamp(p, 3);                            // first stage landed
@@ -573,7 +583,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (!A_MN) {
                 #pragma unroll
                 for (int cc = 0; cc < kACols / 4; ++cc) {  // 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
-                    const int c = half * (kACols / 4) + cc;
+                    const int c = ahalf * (kACols / 4) + cc;
                     const float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
                     hi[4 * cc + 0] = __float_as_uint(v.x); hi[4 * cc + 1] = __float_as_uint(v.y);
                     hi[4 * cc + 2] = __float_as_uint(v.z); hi[4 * cc + 3] = __float_as_uint(v.w);
@@ -584,7 +594,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const uint8_t* slab = stage + q * kSlabBytes + (lane & 7) * 4;
                 #pragma unroll
                 for (int kk = 0; kk < kACols; ++kk) {
-                    const int k = half * kACols + kk;
+                    const int k = ahalf * kACols + kk;
                     hi[kk] = *reinterpret_cast<const uint32_t*>(slab + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
                 }
             }
@@ -593,13 +603,13 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const float x = __uint_as_float(hi[k]);
                 lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
             }
-            const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + kTmemA + (uint32_t)lb * 64u + (uint32_t)(half * kACols);
-            if constexpr (SW == 4) { tmem_st32(ta, hi); tmem_st32(ta + 32u, lo); }
+            const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + kTmemA + (uint32_t)lb * 64u + (uint32_t)(ahalf * kACols);
+            if constexpr (kACols == 32) { tmem_st32(ta, hi); tmem_st32(ta + 32u, lo); }
             else { tmem_st16(ta, hi); tmem_st16(ta + 32u, lo); }
             const float4* src = reinterpret_cast<const float4*>(stage + kABytes);
             float4* dst = reinterpret_cast<float4*>(lo_buf + (size_t)lb * kBBytes);
             #pragma unroll 4
-            for (int e = t; e < kBBytes / 16; e += 32 * SW) {
+            for (int e = tg; e < kBBytes / 16; e += kSplitThreads) {
                 float4 l;
                 split4(src[e], l);
                 dst[e] = l;
@@ -1250,14 +1260,15 @@ int g_gemm_plan = -1;      // -1 auto, 0 dual, 1 deep (escgnn_gemm_set_plan; exp
 
 // One-time setup of a TS instantiation: opt in to its dynamic shared memory; returns how many of its CTAs the device holds at once
 // (<= 0: a CUDA error, negated) -- the bound the grid-barrier epilogues need.
+int g_gemm_kb_groups = 2;     // escgnn_gemm_set_kb_groups: 2 = with 8 warps and one CTA per SM the warp groups take alternate k-blocks
 int g_gemm_split_warps = 8;   // escgnn_gemm_set_split_warps: splitter / epilogue warps of the plain TS kernel (4 or 8)
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI, int SW = 4>
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI, int SW = 4, int KBG = 1>
 int ts_resident_ctas() {
     static int resident = 0;
     if (resident != 0) return resident;
     const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + LO_BUFS * BLOCK_N * 128 + 1024;
-    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW>;
+    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW, KBG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return -(int)e;
     int per_sm = 0, dev = 0, sms = 0;
@@ -1279,11 +1290,11 @@ int ts_resident_ctas() {
     return resident;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0, int SW = 4>
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0, int SW = 4, int KBG = 1>
 int launch_cfg_ts_sw(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, const BnParams& bn) {
     const int smem = STAGES * (kBlockM * 128 + BLOCK_N * 128) + LO_BUFS * BLOCK_N * 128 + 1024;
-    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW>;
-    const int resident = ts_resident_ctas<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW>();     // cached after the first call
+    auto kern = gemm_tf32x3_ts_kernel<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW, KBG>;
+    const int resident = ts_resident_ctas<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, SW, KBG>();     // cached after the first call
     if (resident <= 0) return -resident;
     if (EPI != 0 && (int)(grid.x * grid.y * grid.z) > resident) return ESCGNN_ERR_TOO_LARGE;   // the grid barrier would deadlock
     escgnn::launch_pdl(kern, grid, 64 + 32 * SW, smem, st, a, b, p, bn);
@@ -1293,6 +1304,11 @@ int launch_cfg_ts_sw(const CUtensorMap& a, const CUtensorMap& b, const Params& p
 template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int LO_BUFS, int EPI = 0>
 int launch_cfg_ts(const CUtensorMap& a, const CUtensorMap& b, const Params& p, dim3 grid, cudaStream_t st, const BnParams& bn = BnParams()) {
     if constexpr (EPI == 0) {
+        // one CTA per SM (the deep ring): room for four lo buffers, the two warp groups split alternate k-blocks
+        if constexpr (STAGES == 4 && LO_BUFS == 2 && BLOCK_N <= 128) {
+            if (g_gemm_split_warps == 8 && g_gemm_kb_groups == 2)
+                return launch_cfg_ts_sw<BLOCK_N, A_MN, B_MN, 4, 4, 0, 8, 2>(a, b, p, grid, st, bn);
+        }
         if (g_gemm_split_warps == 8) return launch_cfg_ts_sw<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, 0, 8>(a, b, p, grid, st, bn);
     }
     return launch_cfg_ts_sw<BLOCK_N, A_MN, B_MN, STAGES, LO_BUFS, EPI, 4>(a, b, p, grid, st, bn);
@@ -1426,6 +1442,12 @@ int escgnn_gemm_set_split_target(int ctas) {
 int escgnn_gemm_set_plan(int plan) { g_gemm_plan = plan; return 0; }
 
 int escgnn_gemm_set_trace(unsigned long long* d_stamps) { g_gemm_trace = d_stamps; return 0; }
+
+int escgnn_gemm_set_kb_groups(int groups) {
+    const int was = g_gemm_kb_groups;
+    if (groups == 1 || groups == 2) g_gemm_kb_groups = groups;
+    return was;
+}
 
 int escgnn_gemm_set_staged_store(int on) {
     const int was = g_gemm_staged;

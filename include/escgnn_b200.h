@@ -402,6 +402,10 @@ int escgnn_gemm_set_trace(unsigned long long* d_stamps);
  * two per tensor-memory lane quarter; with the staged epilogue 1.072 against 1.116 ms per training step at batch 256) or 4 (A/B
  * timing and tests; the fused-BatchNorm epilogues always run with 4).  Returns the previous value. */
 int escgnn_gemm_set_split_warps(int warps);
+/* With 8 warps and the one-CTA-per-SM plan: 2 (default) = the two groups of four warps split ALTERNATE k-blocks (four lo buffers), so
+ * two of the ~0.6 us split latency chains are in flight per 0.39 us of MMA time; 1 = both groups work on halves of the same k-block.
+ * Returns the previous value. */
+int escgnn_gemm_set_kb_groups(int groups);
 /* Epilogue of the GEMM: 1 (default) = full output tiles are parked in the dead operand stages and written out row-contiguously
  * (512 bytes per warp instruction); 0 = every thread stores its accumulator row straight from registers (A/B timing and tests; tiles
  * that cross the N extent or an unaligned C always take this path).  Returns the previous setting. */

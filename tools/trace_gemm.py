@@ -45,12 +45,14 @@ def chain(M, N, K, reps=12, b_mn=0):
     print('   kernel span (first wait return -> last store) %.2f us; GEMM+act period %.2f us; last store -> next GEMM released %.2f us (the act kernel + 2 boundaries)' % (span, period, gap))
 
 
-for sw, staged in ((4, 0), (4, 1), (8, 1)):
+for sw, staged, kbg in ((4, 0, 1), (4, 1, 1), (8, 1, 1), (8, 1, 2)):
     L.escgnn_gemm_set_split_warps(sw)
     L.escgnn_gemm_set_staged_store(staged)
-    print('---- %d splitter / epilogue warps, %s epilogue' % (sw, 'staged (row-contiguous)' if staged else 'register-row'))
+    L.escgnn_gemm_set_kb_groups(kbg)
+    print('---- %d splitter / epilogue warps, %s epilogue, %d k-block group(s)' % (sw, 'staged (row-contiguous)' if staged else 'register-row', kbg))
     chain(5906, 256, 256)
     chain(5906, 256, 256, b_mn=1)
     chain(640, 256, 256)
-L.escgnn_gemm_set_split_warps(4)
+L.escgnn_gemm_set_split_warps(8)
 L.escgnn_gemm_set_staged_store(1)
+L.escgnn_gemm_set_kb_groups(2)
