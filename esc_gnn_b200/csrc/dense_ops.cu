@@ -31,7 +31,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
     if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return v > 0.f ? v : expm1f(v);
+    if (act == 2) return v > 0.f ? v : expm1f(v);   // (a Taylor / exp(v) - 1 hybrid was measured SLOWER than the library expm1f: tools/trace_bn.py)
     return v;
 }
 __device__ __forceinline__ float act_grad(float v, int act) {
@@ -438,6 +438,16 @@ constexpr int kClRanks = 8;
 constexpr int kClMaxRows = 1 << 16;          // above this the two-kernel path (all SMs busy) wins
 constexpr int kClFwdUnroll = 8, kClBwdUnroll = 4;    // independent row loads in flight per thread
 
+// debugging (escgnn_bn_set_trace, tools/trace_bn.py): 6 %globaltimer stamps per CTA of the register-resident cluster kernels
+__constant__ unsigned long long* g_bn_trace = nullptr;     // (constant bank: the disabled check costs one cached load)
+__device__ __forceinline__ void bn_stamp(int slot) {
+    if (g_bn_trace != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_bn_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 6 + slot] = t;
+    }
+}
+
 template <int LANES>
 struct ClusterTile {
     static constexpr int kCols = 4 * LANES, kSlots = 256 / LANES, kSweep = kClRanks * kSlots;
@@ -631,7 +641,9 @@ bn_act_fwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
                               float* running_mean, float* running_var, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                               int act, float eps, float momentum, const int* __restrict__ d_rows, int rows_cap, int C,
                               float* __restrict__ y, int ldy) {
+    bn_stamp(0);
     escgnn::pdl_enter();
+    bn_stamp(1);
     using T = ClusterTile<LANES>;
     __shared__ __align__(16) float s_w[8][2][T::kCols];
     __shared__ __align__(16) float s_part[2][T::kCols];
@@ -657,7 +669,9 @@ bn_act_fwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
         a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
         b.x += v[k].x * v[k].x; b.y += v[k].y * v[k].y; b.z += v[k].z * v[k].z; b.w += v[k].w * v[k].w;
     }
+    bn_stamp(2);
     t.reduce(a, b, cluster);
+    bn_stamp(3);
     cluster.barrier_arrive();                         // this CTA is done reading its peers' shared memory ...
     if (col_ok) {
         const float m = (float)max(rows, 1);
@@ -689,7 +703,9 @@ bn_act_fwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
             }
         }
     }
+    bn_stamp(4);
     cluster.barrier_wait();                           // ... and leaves only when every peer is done reading its own
+    bn_stamp(5);
 }
 
 template <int LANES, int R>
@@ -699,7 +715,9 @@ bn_act_bwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
                               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                               int act, const int* __restrict__ d_rows, int rows_cap, int C, float* __restrict__ dgamma,
                               float* __restrict__ dbeta, float* __restrict__ dx, int lddx) {
+    bn_stamp(0);
     escgnn::pdl_enter();
+    bn_stamp(1);
     using T = ClusterTile<LANES>;
     __shared__ __align__(16) float s_w[8][2][T::kCols];
     __shared__ __align__(16) float s_part[2][T::kCols];
@@ -735,7 +753,9 @@ bn_act_bwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
             a.x += z.x; a.y += z.y; a.z += z.z; a.w += z.w;
             b.x += z.x * h.x; b.y += z.y * h.y; b.z += z.z * h.z; b.w += z.w * h.w;
         }
+    bn_stamp(2);
     t.reduce(a, b, cluster);
+    bn_stamp(3);
     cluster.barrier_arrive();
     if (col_ok) {
         const float4 s1 = ld4(&s_tot[0][4 * cl]), s2 = ld4(&s_tot[1][4 * cl]);
@@ -756,7 +776,9 @@ bn_act_bwd_cluster_reg_kernel(const float* __restrict__ x, int ldx, const float*
             }
         }
     }
+    bn_stamp(4);
     cluster.barrier_wait();
+    bn_stamp(5);
 }
 
 // (lanes, registers) plan of the one-launch BatchNorm: as many clusters as the column count allows, rows in registers when they fit
@@ -1100,6 +1122,10 @@ int escgnn_head_bn_linear_l1(const float* d_x, int ldx, const float* d_gamma, co
                                    d_running_mean, d_running_var, act, eps, momentum, d_w2, d_b2, d_target, d_rows, rows_cap, channels,
                                    d_pred, d_loss, d_dx, lddx, d_dgamma, d_dbeta, d_dw2, d_db2);
     return (int)cudaGetLastError();
+}
+
+int escgnn_bn_set_trace(unsigned long long* d_stamps) {
+    return (int)cudaMemcpyToSymbol(g_bn_trace, &d_stamps, sizeof(d_stamps));
 }
 
 int escgnn_set_cluster_bn(int on) {

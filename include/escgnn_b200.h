@@ -285,6 +285,10 @@ int escgnn_set_rd_fast(int on);
 /* One-launch cluster BatchNorm kernels (rows_cap <= 65536, training mode): on by default; 0 = statistics + apply kernel pair
  * (same results up to summation order). Returns the previous setting. */
 int escgnn_set_cluster_bn(int on);
+/* Debugging aid (tools/trace_bn.py): every CTA of the following register-resident cluster BatchNorm launches writes 6 %globaltimer
+ * values (ns) to d_stamps[cta * 6 + i]: 0 CTA start, 1 dependency wait returned, 2 tile loaded and summed, 3 cluster reduction done,
+ * 4 outputs stored, 5 cluster released.  NULL (default) switches it off. */
+int escgnn_bn_set_trace(unsigned long long* d_stamps);
 int escgnn_dense_tile_rows(void);     /* rows per reduction tile of the scalar fallback kernels */
 /* floats the reduction workspace `d_partial` of bn_act_fwd / bn_act_bwd / colsum needs. It must be zero before its
  * first use (its first 64 words are arrival tickets, which every launch leaves at zero again), and two launches that
