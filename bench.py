@@ -301,7 +301,12 @@ def run_own(args):
         barrier()
         ms_v = max_over_ranks(ms_v)
         barrier()
-        ms_e = timed(lambda b: read(eng.step(b)), host_pool, k_steps)
+        # e2e: inputs from pinned host memory every step, and every step's loss read by the host -- through step_read(), which copies
+        # the 4 bytes to a pinned slot behind the step and hands the host the PREVIOUS step's value (its event has fired), so that
+        # reading the result does not idle the device once per step; the last loss is read inside the timed function's final sync
+        ms_e = timed(lambda b: eng.step_read(b), host_pool, k_steps)
+        last = eng.last_read()
+        assert last is None or last == last, 'loss is NaN'
         barrier()
         ms_e = max_over_ranks(ms_e)
         eng.check_errors()
@@ -600,7 +605,9 @@ def run_own(args):
                            fused_linear_bn=bool(args.fuse_bn), exchange=eng.exchange),
                clocks=clk,
                e2e=dict(value=e2e_value, unit='graphs/s', h2d_bytes_per_step=host_pool[0].h2d_bytes(), d2h_bytes_per_step=4,
-                        ms_per_step=ms_step_e2e),
+                        ms_per_step=ms_step_e2e,
+                        how='engine.step_read(RawBatch in pinned host memory): H2D of the raw batch and D2H of the 4-byte loss inside every '
+                            'timed step; the host reads step k-1\'s loss (pinned slot + event) after launching step k'),
                gpu_launches=launches_per_step * args.steps, launches_per_step=launches_per_step,
                kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
                roofline=roofline, cpu_baseline=cpu, sequential=sequential, large_batch=large, configs=configs, extraction=extraction,

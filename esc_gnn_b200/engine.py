@@ -192,6 +192,7 @@ class StaticTrainEngine(object):
         self.wgrad_mode = 2 if atomic_wgrad else 0
         self.bounded_gemm = True
         self.bucketed_exchange, self._early_done, self._xchg_done = True, False, None
+        self._loss_host = None                   # step_read(): pinned slots for the host's copy of the loss
         self.xchg = torch.cuda.Stream(device=dev)
         # Linear -> BatchNorm -> activation as one launch each way (GEMM epilogues behind a grid barrier); only kernels of the MAIN
         # branch take that path (two barrier kernels on concurrent branches could starve each other of SM slots)
@@ -1079,6 +1080,36 @@ class StaticTrainEngine(object):
                 self.graph_opt.replay()
         self.steps += 1
         return self.loss
+
+    def step_read(self, raw):
+        """step(raw) with the loss read on the host WITHOUT draining the device: the 4-byte result of this call is copied to a pinned
+        slot behind the step's graph (an event marks it), and what is returned is the float of the PREVIOUS call, whose event has
+        long fired -- the host stays one launch ahead of the device instead of idling it once per step on `.item()`.
+        Returns None until a loss is available (pipelined engines train on the batch of the call before, so the first two calls);
+        last_read() hands out the final one."""
+        if self._loss_host is None:
+            self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self._loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._loss_calls, self._loss_valid = 0, [False, False]
+        out = self.last_read()
+        loss = self.step(raw)
+        k = self._loss_calls & 1
+        self._loss_valid[k] = loss is not None
+        if loss is not None:
+            self._loss_host[k:k + 1].copy_(loss.view(-1)[:1], non_blocking=True)
+            self._loss_ev[k].record(torch.cuda.current_stream(self.c.dev))
+        self._loss_calls += 1
+        return out
+
+    def last_read(self):
+        """The loss of the latest step_read() call as a float (waits for that step only); None if it produced none."""
+        if self._loss_host is None or self._loss_calls == 0:
+            return None
+        k = (self._loss_calls - 1) & 1
+        if not self._loss_valid[k]:
+            return None
+        self._loss_ev[k].synchronize()
+        return float(self._loss_host[k])
 
     def profile(self, raw, reps=10, flush=None):
         """Per-kernel DEVICE times of the captured step: the same launch sequence captured once more on a single stream
