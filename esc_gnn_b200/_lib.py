@@ -91,6 +91,7 @@ SIGNATURES = {
     'escgnn_gemm_set_plan': (_i32, [_i32]),
     'escgnn_gemm_set_wide': (_i32, [_i32]),
     'escgnn_gemm_set_trace': (_i32, [_vp]),
+    'escgnn_gemm_trace_slots': (_i32, []),
     'escgnn_bn_set_trace': (_i32, [_vp]),
     'escgnn_gemm_set_split_warps': (_i32, [_i32]),
     'escgnn_gemm_set_staged_store': (_i32, [_i32]),

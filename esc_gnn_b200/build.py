@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libescgnn_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
-         '-Xcompiler', '-O2', '-Xcompiler', '-fopenmp', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-O2', '-Xcompiler', '-fopenmp', '--expt-relaxed-constexpr'] + os.environ.get('ESCGNN_NVCC_FLAGS', '').split()
 
 
 def sources():

@@ -92,11 +92,20 @@ struct Params {
     int stage_out;                // full tiles are written out row-contiguously through shared memory (escgnn_gemm_set_staged_store)
 };
 
+// 8 kernel-level stamps; a library built with -DESCGNN_TRACE_KB (ESCGNN_NVCC_FLAGS, see tools/trace_gemm.py) adds 4 per k-block for
+// the first 16 k-blocks of the TS kernel: 8+4i stage free (TMA issued), 9+4i landed, 10+4i split, 11+4i MMAs issued
+#ifdef ESCGNN_TRACE_KB
+constexpr int kTraceSlots = 72;
+#define ESC_TRACE_KB(cond, slot) do { if (cond) trace_stamp(p, slot); } while (0)
+#else
+constexpr int kTraceSlots = 8;
+#define ESC_TRACE_KB(cond, slot) do { } while (0)
+#endif
 __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
     if (p.trace) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+        p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kTraceSlots + slot] = t;
     }
 }
 
@@ -517,6 +526,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
+                ESC_TRACE_KB(i < 16, 8 + 4 * i);                                // stage free: TMA for k-block i issued
                 uint8_t* st = smem + (size_t)s * kStageBytes;
                 mbar_expect_tx(&full_bar[s], kStageBytes);
                 const int k0 = (kb_begin + i) * kBlockK;
@@ -557,6 +567,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
                 tcgen05_commit(&empty_bar[s]);
                 tcgen05_commit(&lo_free_bar[lb]);
+                ESC_TRACE_KB(i < 16, 11 + 4 * i);                               // MMAs of k-block i issued
             }
             tcgen05_commit(&tmem_full_bar);
             trace_stamp(p, 5);                                                // last MMA issued
@@ -576,6 +587,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int s = i % STAGES, lb = i % LO_BUFS;
             mbar_wait(&full_bar[s], (i / STAGES) & 1);
             if (i == 0 && t == 0) trace_stamp(p, 3);                            // first stage landed
+            ESC_TRACE_KB(i < 16 && tg == 0, 9 + 4 * i);                         // k-block i landed
             mbar_wait(&lo_free_bar[lb], ((i / LO_BUFS) & 1) ^ 1);     // MMAs that read TMEM A buffer / B_lo buffer `lb` are done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint8_t* stage = smem + (size_t)s * kStageBytes;
@@ -618,6 +630,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&split_bar[lb]);
+            ESC_TRACE_KB(i < 16 && tg == 0, 10 + 4 * i);                        // k-block i split
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * SW) : "memory");
         const int row = m0 + r;
@@ -1442,6 +1455,7 @@ int escgnn_gemm_set_split_target(int ctas) {
 int escgnn_gemm_set_plan(int plan) { g_gemm_plan = plan; return 0; }
 
 int escgnn_gemm_set_trace(unsigned long long* d_stamps) { g_gemm_trace = d_stamps; return 0; }
+int escgnn_gemm_trace_slots(void) { return kTraceSlots; }
 
 int escgnn_gemm_set_kb_groups(int groups) {
     const int was = g_gemm_kb_groups;

@@ -397,11 +397,14 @@ int escgnn_gemm_set_plan(int plan);
  * 64..148 row tiles -- the edge-level Linear layers of a reference batch (zinc_models.py:513-522, GINEConv.lin dgrad): on by default,
  * 0 = always 128-wide tiles (A/B timing and tests).  Returns the previous setting. */
 int escgnn_gemm_set_wide(int on);
-/* Debugging aid (tools/trace_gemm.py): when d_stamps is not NULL every CTA of the following escgnn_gemm_tf32x3* launches writes 8
- * %globaltimer values (ns) to d_stamps[(tile_n * tiles_m + tile_m) * 8 + i]: 0 CTA start, 1 prologue done, 2 predecessor complete
+/* Debugging aid (tools/trace_gemm.py): when d_stamps is not NULL every CTA of the following escgnn_gemm_tf32x3* launches writes
+ * %globaltimer values (ns): 0 CTA start, 1 prologue done, 2 predecessor complete
  * (griddepcontrol.wait returned), 3 first operand stage landed, 4 first k-block split, 5 last MMA issued, 6 accumulator complete,
- * 7 epilogue stored.  NULL switches it off (the default; one predictable branch per stamp). */
+ * 7 epilogue stored -- escgnn_gemm_trace_slots() words per CTA, d_stamps[(tile_n * tiles_m + tile_m) * slots + i].  A library built
+ * with -DESCGNN_TRACE_KB (72 slots) adds, for k-block i < 16: 8+4i stage free (TMA issued), 9+4i landed, 10+4i split, 11+4i MMAs
+ * issued.  NULL switches the trace off (the default; one predictable branch per stamp). */
 int escgnn_gemm_set_trace(unsigned long long* d_stamps);
+int escgnn_gemm_trace_slots(void);
 /* Warps that split the operand tiles into their tf32 planes during the main loop and drain the accumulator afterwards: 8 (default:
  * two per tensor-memory lane quarter; with the staged epilogue 1.072 against 1.116 ms per training step at batch 256) or 4 (A/B
  * timing and tests; the fused-BatchNorm epilogues always run with 4).  Returns the previous value. */

@@ -8,16 +8,17 @@ from esc_gnn_b200 import _lib
 L = _lib.lib()
 P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+SLOTS = L.escgnn_gemm_trace_slots()      # 72 with a library built by ESCGNN_NVCC_FLAGS=-DESCGNN_TRACE_KB python -m esc_gnn_b200.build --force
 NAMES = ['CTA start', 'prologue done', 'dependency wait returned', 'first stage landed', 'first k-block split', 'last MMA issued',
          'accumulator complete', 'epilogue stored']
 
 
-def chain(M, N, K, reps=12, b_mn=0):
+def chain(M, N, K, reps=12, b_mn=0, detail=False):
     X = torch.randn(M, K, device='cuda'); W = torch.randn(K, N, device='cuda') if b_mn else torch.randn(N, K, device='cuda')
     Y = torch.empty(M, N, device='cuda'); Z = torch.empty(M, K, device='cuda')
     rows = torch.tensor([M], dtype=torch.int32, device='cuda')
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
-    tr = torch.zeros(reps, tiles * 8, dtype=torch.int64, device='cuda')
+    tr = torch.zeros(reps, tiles * SLOTS, dtype=torch.int64, device='cuda')
     ws = torch.empty(1 << 20, device='cuda')
 
     def run():
@@ -34,11 +35,16 @@ def chain(M, N, K, reps=12, b_mn=0):
     for _ in range(3):
         g.replay()
     torch.cuda.synchronize()
-    t = tr[2:].view(reps - 2, tiles, 8).double() / 1e3            # us; the first launches warm up
+    t = tr[2:].view(reps - 2, tiles, SLOTS).double() / 1e3        # us; the first launches warm up
     rel = t - t[:, :, 2:3]
     print('M=%d N=%d K=%d (%d CTAs), B %s-major' % (M, N, K, tiles, 'MN' if b_mn else 'K'))
     for i, nm in enumerate(NAMES):
         print('   %-26s mean %7.2f   max over CTAs %7.2f' % (nm, rel[:, :, i].mean().item(), rel[:, :, i].max(dim=1).values.mean().item()))
+    kb = (K + 31) // 32
+    if kb <= 16 and detail and SLOTS >= 72:
+        print('   per k-block (mean over CTAs): stage free / landed / split / MMAs issued')
+        for i in range(kb):
+            print('     k-block %2d  %6.2f %6.2f %6.2f %6.2f' % ((i, ) + tuple(rel[:, :, 8 + 4 * i + j].mean().item() for j in range(4))))
     span = (t[:, :, 7].max(dim=1).values - t[:, :, 2].min(dim=1).values).mean().item()
     period = (t[1:, :, 2].min(dim=1).values - t[:-1, :, 2].min(dim=1).values).mean().item()
     gap = (t[1:, :, 2].min(dim=1).values - t[:-1, :, 7].max(dim=1).values).mean().item()
@@ -50,7 +56,7 @@ for sw, staged, kbg in ((4, 0, 1), (4, 1, 1), (8, 1, 1), (8, 1, 2)):
     L.escgnn_gemm_set_staged_store(staged)
     L.escgnn_gemm_set_kb_groups(kbg)
     print('---- %d splitter / epilogue warps, %s epilogue, %d k-block group(s)' % (sw, 'staged (row-contiguous)' if staged else 'register-row', kbg))
-    chain(5906, 256, 256)
+    chain(5906, 256, 256, detail=(kbg == 2))
     chain(5906, 256, 256, b_mn=1)
     chain(640, 256, 256)
 L.escgnn_gemm_set_split_warps(8)
