@@ -268,6 +268,27 @@ def test_pipelined_engine_matches_sequential_engine(name):
     np.testing.assert_allclose(got[3:], want[3:], rtol=3e-2, atol=1e-5)
 
 
+@pytest.mark.parametrize('pipeline', [False, True])
+def test_step_read_returns_every_loss_one_call_late(pipeline):
+    """engine.step_read: the host's copy of the loss comes from a pinned slot behind each step (no per-step device drain); the values
+    are exactly the device losses of step(), one call later, and last_read() hands out the final one."""
+    from esc_gnn_b200.pipeline import RawBatch
+    variant, config, count, kw = MU.MODEL_CASES['zinc']
+    torch.backends.cuda.matmul.allow_tf32 = False
+    a, _, raw0 = _engine_for(variant, config, count, kw, True, pipeline=pipeline)
+    b, _, _ = _engine_for(variant, config, count, kw, True, pipeline=pipeline)
+    order = [raw0, RawBatch.synth(config, 107, count), raw0, raw0, RawBatch.synth(config, 107, count), raw0]
+    order = [r for r in order if r.num_nodes <= a.c.caps['N'] and r.src.numel() <= a.c.caps['E_in']]
+    want = []
+    for r in order:
+        l = a.step(r)
+        want.append(None if l is None else float(l.item()))
+    got = [b.step_read(r) for r in order] + [b.last_read()]
+    assert got[0] is None                                   # nothing to hand out before the first step has run
+    assert got[1:] == want or np.allclose([x for x in got[1:] if x is not None], [x for x in want if x is not None], rtol=1e-3)
+    assert [x is None for x in got[1:]] == [x is None for x in want]
+
+
 @pytest.mark.parametrize('name,use_graph', [('zinc', False), ('zinc', True), ('count_h256', True), ('count_h64', False),
                                             ('zinc_l2', True)])
 def test_static_engine_train_steps_match_reference_fixture(name, use_graph):
