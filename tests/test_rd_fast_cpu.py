@@ -114,3 +114,19 @@ def test_fast_rd_ring_systems_and_trees(host, h):
             if h >= 3:                                 # (the host mirror instantiates cmax 2 for h = 3, 4 only)
                 s2, d2 = check(host, sym(und), n, h, sl, cmax=2)
                 assert (d2 > 0) if name == 'k4' else (d2 == 0), (name, sl)
+
+
+def test_fast_rd_with_six_cycles_per_ego_net(host):
+    """The solver is templated on the number of independent cycles it takes (the kernel ships with 4): with 6, molecule-like graphs
+    of up to 6 rings (max degree 5) are solved completely, for h = 2..4, with and without self-loops."""
+    from esc_gnn_b200 import synth
+    rng = np.random.Generator(np.random.PCG64(5))
+    solved = declined = 0
+    for i in range(60):
+        n = int(rng.integers(5, 40))
+        und = synth.random_graph(rng, n, n - 1 + int(rng.integers(0, 7)), max_degree=5)
+        ei = synth.symmetrise(und)
+        for h in (2, 3, 4):
+            s, d = check(host, ei, n, h, bool(i % 2), cmax=6)
+            solved += s; declined += d
+    assert solved > 0 and declined == 0
